@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Headline benchmark: ELBO + gradient (+ TF-1 Adam update) evaluations per second of the
+variational GP of BASELINE.json config 3 (N=65536, D=8, S=64 MC samples, RBF kernel, blocked
+Cholesky), on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
+
+A step = one pass of the hot path on one batch of synthetic inputs: K(X,X)+jI -> Cholesky ->
+reparameterised sampler + one-sample KL -> F = sqrt(k_var) L (s z) -> Gaussian log-likelihood ->
+full backward (incl. reverse-mode Cholesky and the lengthscale gradient) -> Adam.
+evals = S * N per step.  Multi-GPU: weak scaling in S (each rank draws its own S samples and
+replicates the factorisation), one NCCL all-reduce of the packed gradient per step.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "elbo_grad_evals_per_sec"
+UNIT = "evals/s (MC samples x data points / s)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--dim", type=int, default=8)
+    ap.add_argument("--samples", type=int, default=64)
+    ap.add_argument("--cpu-n", type=int, default=4096, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", type=int, default=0, help="GEMM engine: 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32")
+    return ap.parse_args()
+
+
+def cpu_baseline(n_full, D, S, n_sample, steps=2, warmup=1):
+    """Oracle (torch-CPU fp32) ELBO+grad+Adam step on a bounded sample, extrapolated ~N^3."""
+    import torch
+    from oracle import cpu_baseline as cb
+    n_sample = min(n_sample, n_full)
+    t, _, threads = cb.time_gpr_steps(n_sample, D, S, steps=steps, warmup=warmup)
+    scale = (n_full / n_sample) ** 3
+    t_full = t * scale
+    return {
+        "value": S * n_full / t_full, "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": (f"torch-CPU fp32 oracle, full ELBO+grad+Adam step at N={n_sample}, D={D}, S={S}: "
+                   f"{t:.3f} s/step (median of {steps}); extrapolated x(N/N_s)^3={scale:.0f} to N={n_full} "
+                   f"(99.7% of the FLOPs are the O(N^3) Cholesky and its reverse mode)"),
+        "sample_evals_per_sec": S * n_sample / t, "sample_s_per_step": t,
+    }
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(pw)), "samples": len(sm)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    times = []
+    from oracle import cpu_baseline as cb
+    n_s = min(a.cpu_n, a.n)
+    t, _, threads = cb.time_gpr_steps(n_s, a.dim, a.samples, steps=max(1, a.steps), warmup=max(1, min(a.warmup, 1)))
+    scale = (a.n / n_s) ** 3
+    val = a.samples * a.n / (t * scale)
+    sample = (f"torch-CPU fp32 restatement of the reference graph (TensorFlow is not installable here), "
+              f"ELBO+grad+Adam at N={n_s}: {t:.3f} s/step, extrapolated x{scale:.0f} (~N^3) to N={a.n}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * t * scale, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"variational GP regression N={a.n} D={a.dim} S={a.samples} RBF mean-field q (BASELINE config 3)",
+                   "timing": "host wall clock, CPU only"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    from henbun_b200 import _lib
+    from oracle import cpu_baseline as cb       # only for the synthetic problem generator + CPU leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    lib.hb_set_gemm_engine(a.engine)
+
+    n, D, S = a.n, a.dim, a.samples
+    X, Y, p = cb.make_gp_problem(n, D, S, seed=0)
+    order = ("q_mu", "q_sqrt", "scale", "lengthscales", "k_var", "var")
+    params_h = np.concatenate([np.asarray(p[k], np.float32).ravel() for k in order])
+    cfg = _lib.GpConfig(n, D, S, 1, 0, 1e-5, 1000 + rank, 0)
+    npar = lib.hb_gp_param_count(C.byref(cfg))
+    assert npar == params_h.size
+    dev = torch.device("cuda", local)
+    params = torch.from_numpy(params_h).to(dev)
+    grads = torch.zeros(npar, device=dev)
+    adam_m = torch.zeros(npar, device=dev); adam_v = torch.zeros(npar, device=dev)
+    step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+    out4 = torch.zeros(4, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    wsb = lib.hb_gp_elbo_workspace_bytes(C.byref(cfg))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    Xd = torch.from_numpy(X).to(dev); Yd = torch.from_numpy(Y).to(dev)
+    Xh = torch.from_numpy(X).pin_memory(); Yh = torch.from_numpy(Y).pin_memory()
+    out_h = torch.zeros(4).pin_memory()
+    st = _lib.stream
+
+    def step(it, host_io=False):
+        if host_io:      # the reference feeds Data through feed_dict on every session.run (param.py:701-705)
+            Xd.copy_(Xh, non_blocking=True); Yd.copy_(Yh, non_blocking=True)
+        cfg.offset = C.c_ulonglong(it * ((S * n + 3) // 4 * 4))
+        _lib.check(lib.hb_gp_elbo_step(C.byref(cfg), _lib.ptr(Xd), _lib.ptr(Yd), _lib.ptr(params), None, _lib.ptr(grads),
+                                       _lib.ptr(out4), _lib.ptr(ws), wsb, _lib.ptr(err), st()), "hb_gp_elbo_step")
+        if world > 1:
+            dist.all_reduce(grads)          # one NCCL all-reduce of the packed gradient (sum); mean below
+        _lib.check(lib.hb_increment_i32(_lib.ptr(step_ctr), st()), "hb_increment_i32")
+        _lib.check(lib.hb_adam_tf1(_lib.ptr(params), _lib.ptr(grads), _lib.ptr(adam_m), _lib.ptr(adam_v), npar,
+                                   -1.0 / world, 1e-3, 0.9, 0.999, 1e-8, _lib.ptr(step_ctr), 0, st()), "hb_adam_tf1")
+        if host_io:
+            out_h.copy_(out4, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, host_io, profile=False):
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        l0 = lib.hb_launch_count()
+        if profile:
+            lib.hb_profile_begin(200000)
+        ev0.record()
+        for i in range(nsteps):
+            step(timed.it, host_io); timed.it += 1
+        ev1.record()
+        barrier()
+        prof = None
+        if profile:
+            buf = (C.c_double * 4)()
+            lib.hb_profile_end(buf)
+            prof = list(buf)
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
+        return ms, lib.hb_launch_count() - l0, prof
+    timed.it = 0
+
+    for _ in range(a.warmup):
+        step(timed.it); timed.it += 1
+    barrier()
+    if err.item() != 0:
+        raise RuntimeError(f"Cholesky failed: non-positive pivot at row {err.item() - 1}")
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, launches, prof = timed(a.steps, host_io=False, profile=True)
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e, _, _ = timed(a.steps, host_io=True)
+    elbo = out4[0].item()
+    if not math.isfinite(elbo) or err.item() != 0:
+        raise RuntimeError(f"non-finite ELBO {elbo} / err flag {err.item()}")
+
+    if rank == 0:
+        evals = float(S) * n * world
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained")
+        peak_src = "measured bf16 dense sustained (MEASURED_PEAKS.json)"
+        if peak is None:
+            peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
+        n_gemm, gemm_ms, gemm_flop, _ = prof
+        achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        eng = lib.hb_get_gemm_engine()
+        line = {
+            "metric": METRIC, "value": evals * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"variational GP regression N={n} D={D} S={S}/GPU RBF mean-field q, ELBO+grad+Adam (BASELINE config 3)",
+                "parallelism": f"replicated factorisation, sample-sharded (weak scaling in S), {world} rank(s)",
+                "l2": "inputs larger than L2 (K/L and Lbar/Kbar are N^2 fp32 = %.1f GB each)" % (4.0 * n * n / 1e9),
+                "eps": "device Philox-4x32-10, regenerated in the backward",
+                "gemm_engine": {0: "auto", 1: "simt-fp32", 2: "tcgen05-3xtf32"}[eng],
+                "elbo_last": elbo,
+            },
+            "e2e": {"value": evals * a.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(Xh.numel() * 4 + Yh.numel() * 4), "d2h_bytes_per_step": 16,
+                    "ms_per_step": ms_e2e / a.steps,
+                    "api": "hb_gp_elbo_step + hb_adam_tf1 through the C ABI, X/Y fed from pinned host memory every step"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {
+                "bound": "tensor", "kernel": "hb::gemm (all level-3 work of potrf / potrf_bwd / TRMMs)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": None, "peak_source": peak_src,
+                "gemm_launches": int(n_gemm), "gemm_ms_per_step": gemm_ms / a.steps,
+                "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
+                "useful_gemm_flop_per_step": gemm_flop / a.steps,
+            },
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(n, D, S, a.cpu_n)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,139 @@
+"""ctypes binding of libhenbun_b200.so (the C ABI declared in include/henbun_b200.h).
+
+There is no CPU fallback: if the shared library is missing, ``load()`` raises, and every wrapper
+refuses tensors that are not fp32 CUDA tensors.  torch is used only to own device memory and the
+current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhenbun_b200.so")
+
+HB_OK, HB_ERR_ARG, HB_ERR_CUDA, HB_ERR_WORKSPACE = 0, 1, 2, 3
+ACT = {"none": 0, None: 0, "identity": 0, "sigmoid": 1, "relu": 2, "tanh": 3}
+
+_c_f = C.c_void_p        # device pointers travel as void*
+_ll = C.c_longlong
+_ull = C.c_ulonglong
+_i = C.c_int
+_fl = C.c_float
+_sz = C.c_size_t
+
+
+class GpConfig(C.Structure):
+    _fields_ = [("n", _i), ("D", _i), ("S", _i), ("n_ell", _i), ("q_fullrank", _i), ("jitter", _fl),
+                ("seed", _ull), ("offset", _ull)]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check that every symbol the header
+# declares is exported.
+SIGNATURES = {
+    "hb_version": (_i, []),
+    "hb_launch_count": (_ull, []),
+    "hb_reduce_workspace_bytes": (_sz, []),
+    "hb_set_gemm_engine": (_i, [_i]),
+    "hb_get_gemm_engine": (_i, []),
+    "hb_profile_begin": (_i, [_i]),
+    "hb_profile_end": (_i, [C.POINTER(C.c_double)]),
+    "hb_randn_philox": (_i, [_c_f, _ll, _ull, _ull, _c_f]),
+    "hb_sample_diag_fwd": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _c_f, _ull, _ull, _i, _c_f, _c_f, _c_f, _sz, _c_f]),
+    "hb_sample_diag_bwd": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _c_f, _ull, _ull, _i, _c_f, _c_f, _fl, _c_f, _ll,
+                                _c_f, _ll, _fl, _c_f]),
+    "hb_sample_tril_fwd": (_i, [_c_f, _c_f, _i, _i, _c_f, _i, _c_f, _c_f, _c_f, _sz, _c_f]),
+    "hb_sample_tril_bwd": (_i, [_c_f, _i, _i, _c_f, _c_f, _i, _c_f, _fl, _c_f, _c_f, _c_f, _c_f]),
+    "hb_gaussian_logpdf": (_i, [_c_f, _ll, _c_f, _ll, _c_f, _ll, _ll, _c_f, _c_f]),
+    "hb_gauss_loglik_fwd": (_i, [_c_f, _c_f, _c_f, _ll, _ll, _c_f, _fl, _c_f, _c_f, _c_f, _sz, _c_f]),
+    "hb_rbf_gram_fwd": (_i, [_c_f, _c_f, _i, _i, _i, _i, _c_f, _i, _c_f, _ll, _ll, _fl, _i, _i, _c_f]),
+    "hb_rbf_gram_bwd": (_i, [_c_f, _ll, _ll, _c_f, _c_f, _i, _i, _i, _i, _c_f, _i, _i, _i, _c_f, _c_f, _c_f, _sz,
+                             _c_f]),
+    "hb_potrf_workspace_bytes": (_sz, [_i]),
+    "hb_potrf_lower": (_i, [_c_f, _ll, _ll, _i, _i, _i, _c_f, _sz, _c_f, _c_f]),
+    "hb_potrf_lower_bwd": (_i, [_c_f, _ll, _ll, _c_f, _ll, _ll, _i, _i, _c_f, _sz, _c_f]),
+    "hb_trsm_workspace_bytes": (_sz, [_i, _i]),
+    "hb_trsm_right_lower": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _i, _c_f, _sz, _c_f]),
+    "hb_gemm": (_i, [_c_f, _ll, _ll, _i, _i, _c_f, _ll, _ll, _i, _i, _c_f, _ll, _ll, _i, _i, _i, _i, _i, _fl, _fl,
+                     _c_f, _ll, _i, _i, _fl, _fl, _c_f]),
+    "hb_act_bwd_colsum": (_i, [_c_f, _c_f, _c_f, _i, _i, _ll, _i, _i, _fl, _fl, _c_f, _c_f]),
+    "hb_colsum": (_i, [_c_f, _ll, _i, _i, _fl, _fl, _c_f, _c_f]),
+    "hb_adam_tf1": (_i, [_c_f, _c_f, _c_f, _c_f, _ll, _fl, _fl, _fl, _fl, _fl, _c_f, _i, _c_f]),
+    "hb_increment_i32": (_i, [_c_f, _c_f]),
+    "hb_transpose2d": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _fl, _c_f]),
+    "hb_zero_strict_upper": (_i, [_c_f, _ll, _i, _c_f]),
+    "hb_gp_param_count": (_sz, [C.POINTER(GpConfig)]),
+    "hb_gp_elbo_workspace_bytes": (_sz, [C.POINTER(GpConfig)]),
+    "hb_gp_elbo_step": (_i, [C.POINTER(GpConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f, _c_f]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class HenbunB200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; fail loudly if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HenbunB200Error(
+            f"{LIB_PATH} not found: build it with `make` (or __graft_entry__.build()). "
+            "henbun_b200 has no CPU or PyTorch fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+_ERR = {HB_ERR_ARG: "invalid argument", HB_ERR_CUDA: "CUDA launch/runtime failure",
+        HB_ERR_WORKSPACE: "workspace missing or too small"}
+
+
+def check(rc: int, what: str) -> None:
+    if rc == HB_ERR_ARG:
+        raise ValueError(f"{what}: {_ERR[rc]}")
+    if rc != HB_OK:
+        raise HenbunB200Error(f"{what}: {_ERR.get(rc, rc)}")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    """Device pointer of a contiguous-enough fp32/int32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise HenbunB200Error("henbun_b200 kernels need CUDA tensors (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise HenbunB200Error(f"expected a float32 CUDA tensor, got {t.dtype} on {t.device}")
+    return t
+
+
+_reduce_ws = {}
+
+
+def reduce_ws(device=None) -> torch.Tensor:
+    """Per-device scratch for reducing kernels (caller-owned, reused across calls on one stream)."""
+    dev = torch.device(device if device is not None else torch.cuda.current_device())
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    w = _reduce_ws.get(key)
+    if w is None:
+        w = torch.empty(load().hb_reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
+        _reduce_ws[key] = w
+    return w

@@ -1,0 +1,425 @@
+// extern "C" boundary of libhenbun_b200.so -- see include/henbun_b200.h for the contract.
+#include "../../include/henbun_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include <vector>
+
+namespace hb {
+
+static int g_engine = 0;
+void set_gemm_engine(int mode) { g_engine = mode; }
+int get_gemm_engine() { return g_engine; }
+
+int gemm_tc(const GemmParams& p, cudaStream_t stream);   // gemm_tc.cu
+bool gemm_tc_eligible(const GemmParams& p);
+
+static int gemm_dispatch(const GemmParams& p, cudaStream_t st) {
+  if (g_engine == 1) return gemm_simt(p, st);
+  if (gemm_tc_eligible(p)) return gemm_tc(p, st);
+  if (g_engine == 2) return HB_ERR_ARG;
+  return gemm_simt(p, st);
+}
+
+// Optional per-launch GEMM timing (CUDA events on the launching stream) for bench.py's roofline.
+struct GemmProfiler {
+  bool on = false;
+  size_t used = 0;
+  std::vector<cudaEvent_t> ev0, ev1;
+  std::vector<double> flops;
+} g_prof;
+
+static double gemm_useful_flops(const GemmParams& p) {
+  double f = 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch;
+  if (p.c_tri) f *= 0.5 * ((double)p.M + 1.0) / (double)p.M;
+  if (p.a_tri || p.b_tri) f *= 0.5;
+  return f;
+}
+
+int gemm(const GemmParams& p, cudaStream_t st) {
+  if (!g_prof.on || g_prof.used >= g_prof.ev0.size() || p.M <= 0 || p.N <= 0 || p.batch <= 0)
+    return gemm_dispatch(p, st);
+  const size_t i = g_prof.used++;
+  g_prof.flops[i] = gemm_useful_flops(p);
+  cudaEventRecord(g_prof.ev0[i], st);
+  const int rc = gemm_dispatch(p, st);
+  cudaEventRecord(g_prof.ev1[i], st);
+  return rc;
+}
+
+namespace {
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- scalar glue of the fused GP step (all on device, no host round trip) ----
+// sc layout: [0]=scale s, [1]=k_var, [2]=var, [3]=a=sqrt(k_var)*s, [4..4+n_ell)=ell
+__global__ void gp_prep_scalars_kernel(const float* __restrict__ p_scale, const float* __restrict__ p_ell, int n_ell,
+                                       const float* __restrict__ p_kvar, const float* __restrict__ p_var, float* sc) {
+  if (threadIdx.x == 0) {
+    const float s = softplus_f(*p_scale) + 1e-6f;
+    const float kv = softplus_f(*p_kvar) + 1e-6f;
+    const float v = softplus_f(*p_var) + 1e-6f;
+    sc[0] = s; sc[1] = kv; sc[2] = v; sc[3] = sqrtf(kv) * s;
+  }
+  for (int d = threadIdx.x; d < n_ell; d += blockDim.x) sc[4 + d] = softplus_f(p_ell[d]) + 1e-6f;
+}
+
+// ll3 = {loglik, sum E^2, sum E*F}; writes ELBO pieces and the scalar free-space gradients.
+__global__ void gp_scalar_bwd_kernel(const float* __restrict__ sc, const float* __restrict__ ll3,
+                                     const float* __restrict__ kl, long long total, int S, const float* p_scale,
+                                     const float* p_ell, int n_ell, const float* p_kvar, const float* p_var,
+                                     float* g_scale, float* g_ell, float* g_kvar, float* g_var, float* out4) {
+  if (threadIdx.x == 0) {
+    const double s = sc[0], kv = sc[1], v = sc[2], a = sc[3];
+    const double invS = 1.0 / (double)S;
+    const double sumE2 = ll3[1], sumEF = ll3[2];
+    // d ELBO / d a  = sum R .* Fraw,  R = -(1/S) E / v,  Fraw = F / a
+    const double ga = -invS * sumEF / (v * a);
+    const double gs = ga * sqrt(kv);
+    const double gkv = ga * s / (2.0 * sqrt(kv));
+    const double gv = invS * (-0.5 * (double)total / v + 0.5 * sumE2 / (v * v));
+    *g_scale = (float)(gs * (double)sigmoid_f(*p_scale));
+    *g_kvar = (float)(gkv * (double)sigmoid_f(*p_kvar));
+    *g_var = (float)(gv * (double)sigmoid_f(*p_var));
+    out4[0] = (float)(((double)ll3[0] - (double)*kl) * invS);
+    out4[1] = ll3[0];
+    out4[2] = *kl;
+    out4[3] = 0.f;
+  }
+  // lengthscale chain rule (g_ell currently holds d ELBO / d ell)
+  for (int d = threadIdx.x; d < n_ell; d += blockDim.x) g_ell[d] *= sigmoid_f(p_ell[d]);
+}
+
+// zt = a*wb - c*z (full-rank path)
+__global__ void gp_zbar_total_kernel(const float* __restrict__ wb, const float* __restrict__ z, const float* __restrict__ a,
+                                     float c, long long n, float* zt) {
+  const float aa = *a;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    zt[e] = aa * wb[e] - c * z[e];
+}
+
+struct GpLayout {
+  size_t off_K, off_G, off_Z, off_F, off_R, off_W, off_U, off_sc, off_red, off_potrf, total;
+  size_t potrf_bytes;
+};
+
+GpLayout gp_layout(const hb_gp_config& c) {
+  GpLayout L{};
+  const size_t nn = (size_t)c.n * c.n * sizeof(float), sn = (size_t)c.S * c.n * sizeof(float);
+  size_t o = 0;
+  L.off_K = o; o += align_up(nn);
+  L.off_G = o; o += align_up(nn);
+  L.off_Z = o; o += align_up(sn);
+  L.off_F = o; o += align_up(sn);
+  L.off_R = o; o += align_up(sn);
+  L.off_W = o; o += align_up(sn);
+  L.off_U = o; o += align_up(c.q_fullrank ? sn : 0);
+  L.off_sc = o; o += align_up((size_t)(16 + c.n_ell) * sizeof(float));
+  L.off_red = o; o += align_up(kReduceWsBytes);
+  L.potrf_bytes = potrf_workspace_bytes(c.n);
+  L.off_potrf = o; o += align_up(L.potrf_bytes);
+  L.total = o;
+  return L;
+}
+
+}  // namespace
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" {
+
+int hb_version(void) { return 100; }
+unsigned long long hb_launch_count(void) { return g_launches; }
+size_t hb_reduce_workspace_bytes(void) { return kReduceWsBytes; }
+int hb_set_gemm_engine(int mode) {
+  if (mode < 0 || mode > 2) return HB_ERR_ARG;
+  set_gemm_engine(mode);
+  return HB_OK;
+}
+int hb_get_gemm_engine(void) { return get_gemm_engine(); }
+
+int hb_profile_begin(int max_gemm_launches) {
+  if (max_gemm_launches < 0) return HB_ERR_ARG;
+  while ((int)g_prof.ev0.size() < max_gemm_launches) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return HB_ERR_CUDA;
+    g_prof.ev0.push_back(a); g_prof.ev1.push_back(b);
+  }
+  g_prof.flops.assign(g_prof.ev0.size(), 0.0);
+  g_prof.used = 0;
+  g_prof.on = true;
+  return HB_OK;
+}
+// Synchronises the device. out4 = {gemm launches timed, total gemm ms, total useful gemm FLOP, 0}.
+int hb_profile_end(double* out4_host) {
+  g_prof.on = false;
+  if (!out4_host) return HB_ERR_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return HB_ERR_CUDA;
+  double ms = 0.0, fl = 0.0;
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]) != cudaSuccess) return HB_ERR_CUDA;
+    ms += t; fl += g_prof.flops[i];
+  }
+  out4_host[0] = (double)g_prof.used; out4_host[1] = ms; out4_host[2] = fl; out4_host[3] = 0.0;
+  return HB_OK;
+}
+
+int hb_randn_philox(float* out, long long count, unsigned long long seed, unsigned long long offset, void* stream) {
+  return randn_philox(out, count, seed, offset, S(stream));
+}
+
+int hb_sample_diag_fwd(const float* mu, long long ld_mu, const float* omega, long long ld_omega, int rows, int cols,
+                       const float* eps, unsigned long long seed, unsigned long long offset, int Sn, float* z,
+                       float* kl_out, void* ws, size_t ws_bytes, void* stream) {
+  return sample_diag_fwd(mu, ld_mu, omega, ld_omega, rows, cols, eps, seed, offset, Sn, z, kl_out, ws, ws_bytes, S(stream));
+}
+
+int hb_sample_diag_bwd(const float* mu, long long ld_mu, const float* omega, long long ld_omega, int rows, int cols,
+                       const float* eps, unsigned long long seed, unsigned long long offset, int Sn,
+                       const float* zbar, const float* zbar_scale, float kl_coef, float* gmu, long long ld_gmu,
+                       float* gomega, long long ld_gomega, float beta, void* stream) {
+  return sample_diag_bwd(mu, ld_mu, omega, ld_omega, rows, cols, eps, seed, offset, Sn, zbar, zbar_scale, kl_coef, gmu,
+                         ld_gmu, gomega, ld_gomega, beta, S(stream));
+}
+
+int hb_sample_tril_fwd(const float* mu, const float* Lq, int n, int batch, const float* eps, int Sn, float* z,
+                       float* kl_out, void* ws, size_t ws_bytes, void* stream) {
+  if (n < 0 || batch < 0 || Sn < 0) return HB_ERR_ARG;
+  if ((long long)n * batch * Sn == 0) return kl_out ? fill_f32(kl_out, 1, 0.f, S(stream)) : HB_OK;
+  if (!mu || !Lq || !eps || !z) return HB_ERR_ARG;
+  // z[b] (S x n) = eps[b] (S x n) * tril(Lq[b])^T : op(B)[k][j] = Lq[j][k], keep k <= j (upper in (k,n))
+  GemmParams g;
+  g.A = eps; g.lda = n; g.sA = (long long)Sn * n;
+  g.B = Lq; g.ldb = n; g.sB = (long long)n * n; g.transB = 1; g.b_tri = 2;
+  g.C = z; g.ldc = n; g.sC = (long long)Sn * n;
+  g.M = Sn; g.N = n; g.K = n; g.batch = batch;
+  g.bias = mu; g.sBias = n;
+  HB_TRY(gemm(g, S(stream)));
+  if (kl_out)
+    HB_TRY(tril_logdet_kl(Lq, n, (long long)n * n, n, batch, eps, z, (long long)batch * Sn * n, Sn, kl_out, ws, ws_bytes, S(stream)));
+  return HB_OK;
+}
+
+int hb_sample_tril_bwd(const float* Lq, int n, int batch, const float* eps, const float* z, int Sn,
+                       const float* zbar, float kl_coef, float* gmu, float* gLq, float* scratch, void* stream) {
+  if (n < 0 || batch < 0 || Sn < 0) return HB_ERR_ARG;
+  const long long cnt = (long long)batch * Sn * n;
+  if (cnt == 0) return HB_OK;
+  if (!Lq || !eps || !z || !gmu || !gLq || !scratch) return HB_ERR_ARG;
+  cudaStream_t st = S(stream);
+  // zt = zbar - c*z
+  if (zbar) {
+    HB_TRY(copy2d(scratch, cnt, zbar, cnt, 1, (int)cnt, 1.f, st));
+    HB_TRY(axpby(scratch, z, cnt, -kl_coef, 1.f, st));
+  } else {
+    HB_TRY(axpby(scratch, z, cnt, -kl_coef, 0.f, st));
+  }
+  for (int b = 0; b < batch; ++b)
+    HB_TRY(colsum(scratch + (long long)b * Sn * n, n, Sn, n, 1.f, 0.f, gmu + (long long)b * n, st));
+  HB_TRY(fill_f32(gLq, (long long)batch * n * n, 0.f, st));
+  GemmParams g;   // gLq[b] = tril(zt[b]^T eps[b])
+  g.A = scratch; g.lda = n; g.sA = (long long)Sn * n; g.transA = 1;
+  g.B = eps; g.ldb = n; g.sB = (long long)Sn * n; g.transB = 0;
+  g.C = gLq; g.ldc = n; g.sC = (long long)n * n; g.c_tri = 1;
+  g.M = n; g.N = n; g.K = Sn; g.batch = batch;
+  HB_TRY(gemm(g, st));
+  return tril_diag_grad(gLq, n, (long long)n * n, Lq, n, (long long)n * n, n, batch, kl_coef * (float)Sn, st);
+}
+
+int hb_gaussian_logpdf(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
+                       long long var_period, long long total, float* out, void* stream) {
+  return gaussian_logpdf(x, x_period, mu, mu_period, var, var_period, total, out, S(stream));
+}
+
+int hb_gauss_loglik_fwd(const float* f, const float* f_scale, const float* y, long long total, long long y_period,
+                        const float* var, float rcoef, float* resid, float* out3, void* ws, size_t ws_bytes,
+                        void* stream) {
+  return gauss_loglik_fwd(f, f_scale, y, total, y_period, var, rcoef, resid, out3, ws, ws_bytes, S(stream));
+}
+
+int hb_rbf_gram_fwd(const float* X, const float* X2, int n, int n2, int D, int batch, const float* ell, int n_ell,
+                    float* K, long long ldk, long long strideK, float jitter, int lower_only, int csym, void* stream) {
+  return rbf_gram_fwd(X, X2, n, n2, D, (long long)n * D, (long long)n2 * D, ell, n_ell, K, ldk, strideK, batch, jitter,
+                      lower_only, csym, S(stream));
+}
+
+int hb_rbf_gram_bwd(const float* G, long long ldg, long long strideG, const float* X, const float* X2, int n, int n2,
+                    int D, int batch, const float* ell, int n_ell, int sym_lower, int csym, const float* out_scale,
+                    float* g_ell, void* ws, size_t ws_bytes, void* stream) {
+  return rbf_gram_bwd(G, ldg, strideG, X, X2, n, n2, D, (long long)n * D, (long long)n2 * D, ell, n_ell, batch, sym_lower,
+                      csym, out_scale, g_ell, ws, ws_bytes, S(stream));
+}
+
+size_t hb_potrf_workspace_bytes(int n) { return potrf_workspace_bytes(n); }
+int hb_potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
+                   size_t ws_bytes, int* err_flag, void* stream) {
+  return potrf_lower(A, lda, strideA, n, batch, zero_upper, ws, ws_bytes, err_flag, S(stream));
+}
+int hb_potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, long long ldg, long long strideG,
+                       int n, int batch, void* ws, size_t ws_bytes, void* stream) {
+  return potrf_lower_bwd(L, ldl, strideL, G, ldg, strideG, n, batch, ws, ws_bytes, S(stream));
+}
+size_t hb_trsm_workspace_bytes(int m, int n) { return trsm_workspace_bytes(m, n); }
+int hb_trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int m, int n, int trans, void* ws,
+                        size_t ws_bytes, void* stream) {
+  return trsm_right_lower(L, ldl, X, ldx, m, n, trans, ws, ws_bytes, S(stream));
+}
+
+int hb_gemm(const float* A, long long lda, long long strideA, int transA, int a_tri, const float* B, long long ldb,
+            long long strideB, int transB, int b_tri, float* C, long long ldc, long long strideC, int c_tri, int M,
+            int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
+            int clip, float clip_lo, float clip_hi, void* stream) {
+  GemmParams g;
+  g.A = A; g.lda = lda; g.sA = strideA; g.transA = transA; g.a_tri = a_tri;
+  g.B = B; g.ldb = ldb; g.sB = strideB; g.transB = transB; g.b_tri = b_tri;
+  g.C = C; g.ldc = ldc; g.sC = strideC; g.c_tri = c_tri;
+  g.M = M; g.N = N; g.K = K; g.batch = batch; g.alpha = alpha; g.beta = beta;
+  g.bias = bias; g.sBias = strideBias; g.act = act; g.clip = clip; g.clip_lo = clip_lo; g.clip_hi = clip_hi;
+  if (M > 0 && N > 0 && batch > 0) {
+    const long long minA = transA ? M : K, minB = transB ? K : N;
+    if ((K > 0 && (lda < minA || ldb < minB)) || ldc < N) return HB_ERR_ARG;
+  }
+  return gemm(g, S(stream));
+}
+
+int hb_act_bwd_colsum(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act, int clip,
+                      float clip_lo, float clip_hi, float* dbias, void* stream) {
+  return act_bwd_colsum(dy, y, dz, rows, cols, ld, act, clip, clip_lo, clip_hi, dbias, S(stream));
+}
+int hb_colsum(const float* a, long long lda, int rows, int cols, float alpha, float beta, float* out, void* stream) {
+  return colsum(a, lda, rows, cols, alpha, beta, out, S(stream));
+}
+
+int hb_adam_tf1(float* theta, const float* grad, float* m, float* v, long long n, float grad_scale, float lr, float b1,
+                float b2, float eps, const int* step_dev, int step_host, void* stream) {
+  return adam_tf1(theta, grad, m, v, n, grad_scale, lr, b1, b2, eps, step_dev, step_host, S(stream));
+}
+int hb_increment_i32(int* counter, void* stream) { return increment_i32(counter, S(stream)); }
+
+int hb_transpose2d(float* dst, long long ldd, const float* src, long long lds, int rows, int cols, float scale, void* stream) {
+  return transpose2d(dst, ldd, src, lds, rows, cols, scale, S(stream));
+}
+int hb_zero_strict_upper(float* a, long long lda, int n, void* stream) { return zero_strict_upper(a, lda, n, S(stream)); }
+
+// ---------------------------------------------------------------------------------------------
+// fused variational-GP ELBO + gradient
+// ---------------------------------------------------------------------------------------------
+size_t hb_gp_param_count(const hb_gp_config* c) {
+  if (!c) return 0;
+  return (size_t)c->n + (c->q_fullrank ? (size_t)c->n * c->n : (size_t)c->n) + 1 + c->n_ell + 2;
+}
+size_t hb_gp_elbo_workspace_bytes(const hb_gp_config* c) {
+  if (!c) return 0;
+  return gp_layout(*c).total + 256;
+}
+
+int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, const float* params, const float* eps,
+                    float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream) {
+  if (!cfg || !X || !Y || !params || !grads || !out4) return HB_ERR_ARG;
+  const hb_gp_config c = *cfg;
+  if (c.n <= 0 || c.D <= 0 || c.D > 32 || c.S <= 0 || (c.n_ell != 1 && c.n_ell != c.D)) return HB_ERR_ARG;
+  if (!eps && (c.offset & 3ull)) return HB_ERR_ARG;
+  const GpLayout L = gp_layout(c);
+  if (!ws || ws_bytes < L.total + 256) return HB_ERR_WORKSPACE;
+  cudaStream_t st = S(stream);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  float* K = reinterpret_cast<float*>(base + L.off_K);
+  float* G = reinterpret_cast<float*>(base + L.off_G);
+  float* Z = reinterpret_cast<float*>(base + L.off_Z);
+  float* F = reinterpret_cast<float*>(base + L.off_F);
+  float* R = reinterpret_cast<float*>(base + L.off_R);
+  float* W = reinterpret_cast<float*>(base + L.off_W);
+  float* U = reinterpret_cast<float*>(base + L.off_U);
+  float* sc = reinterpret_cast<float*>(base + L.off_sc);
+  void* red = base + L.off_red;
+  void* pws = base + L.off_potrf;
+  float* ll3 = sc + 8 + c.n_ell;       // 3 floats
+  float* kl = ll3 + 3;                 // 1 float
+
+  const int n = c.n, Sn = c.S;
+  const size_t nq = c.q_fullrank ? (size_t)n * n : (size_t)n;
+  const float* p_mu = params;
+  const float* p_sq = params + n;
+  const float* p_scale = p_sq + nq;
+  const float* p_ell = p_scale + 1;
+  const float* p_kvar = p_ell + c.n_ell;
+  const float* p_var = p_kvar + 1;
+  float* g_mu = grads;
+  float* g_sq = grads + n;
+  float* g_scale = g_sq + nq;
+  float* g_ell = g_scale + 1;
+  float* g_kvar = g_ell + c.n_ell;
+  float* g_var = g_kvar + 1;
+  const float invS = 1.f / (float)Sn;
+
+  gp_prep_scalars_kernel<<<1, 32, 0, st>>>(p_scale, p_ell, c.n_ell, p_kvar, p_var, sc);
+  HB_CHECK_LAUNCH();
+  const float* d_var = sc + 2;
+  const float* d_a = sc + 3;
+  const float* d_ell = sc + 4;
+
+  // K = rbf(X) + jitter I (lower tiles), L = chol(K) in place
+  HB_TRY(rbf_gram_fwd(X, nullptr, n, n, c.D, 0, 0, d_ell, c.n_ell, K, n, 0, 1, c.jitter, 1, 0, st));
+  HB_TRY(potrf_lower(K, n, 0, n, 1, 0, pws, L.potrf_bytes, err_flag, st));
+
+  // sampler + KL
+  const float* eps_used = eps;
+  if (!c.q_fullrank) {
+    HB_TRY(sample_diag_fwd(p_mu, n, p_sq, n, 1, n, eps, c.seed, c.offset, Sn, Z, kl, red, kReduceWsBytes, st));
+  } else {
+    if (!eps) {
+      HB_TRY(randn_philox(U, (long long)Sn * n, c.seed, c.offset, st));
+      eps_used = U;
+    }
+    HB_TRY(hb_sample_tril_fwd(p_mu, p_sq, n, 1, eps_used, Sn, Z, kl, red, kReduceWsBytes, stream));
+  }
+
+  // Fraw [S,n] = Z L^T : op(B)[k][j] = L[j][k], keep k <= j
+  {
+    GemmParams g;
+    g.A = Z; g.lda = n; g.B = K; g.ldb = n; g.transB = 1; g.b_tri = 2;
+    g.C = F; g.ldc = n; g.M = Sn; g.N = n; g.K = n;
+    HB_TRY(gemm(g, st));
+  }
+  HB_TRY(gauss_loglik_fwd(F, d_a, Y, (long long)Sn * n, n, d_var, invS, R, ll3, red, kReduceWsBytes, st));
+  // Wb_raw [S,n] = R L : op(B)[k][j] = L[k][j], keep k >= j (lower)
+  {
+    GemmParams g;
+    g.A = R; g.lda = n; g.B = K; g.ldb = n; g.transB = 0; g.b_tri = 1;
+    g.C = W; g.ldc = n; g.M = Sn; g.N = n; g.K = n;
+    HB_TRY(gemm(g, st));
+  }
+  if (!c.q_fullrank) {
+    HB_TRY(sample_diag_bwd(p_mu, n, p_sq, n, 1, n, eps, c.seed, c.offset, Sn, W, d_a, invS, g_mu, n, g_sq, n, 0.f, st));
+  } else {
+    // zt = a*W - Z/S (into F, which is free now); gmu = colsum(zt); gLq = tril(zt^T eps) + diag(1/Lq_ii)
+    gp_zbar_total_kernel<<<148 * 4, 256, 0, st>>>(W, Z, d_a, invS, (long long)Sn * n, F);
+    HB_CHECK_LAUNCH();
+    HB_TRY(colsum(F, n, Sn, n, 1.f, 0.f, g_mu, st));
+    HB_TRY(fill_f32(g_sq, (long long)n * n, 0.f, st));
+    GemmParams g;
+    g.A = F; g.lda = n; g.transA = 1; g.B = eps_used; g.ldb = n; g.transB = 0;
+    g.C = g_sq; g.ldc = n; g.c_tri = 1; g.M = n; g.N = n; g.K = Sn;
+    HB_TRY(gemm(g, st));
+    HB_TRY(tril_diag_grad(g_sq, n, 0, p_sq, n, 0, n, 1, 1.f, st));
+  }
+  // Lbar_raw = tril(R^T Z)  (the factor a = sqrt(k_var)*scale is applied at the very end: the
+  // reverse-mode Cholesky is linear in Lbar)
+  {
+    GemmParams g;
+    g.A = R; g.lda = n; g.transA = 1; g.B = Z; g.ldb = n; g.transB = 0;
+    g.C = G; g.ldc = n; g.c_tri = 1; g.M = n; g.N = n; g.K = Sn;
+    HB_TRY(gemm(g, st));
+  }
+  HB_TRY(potrf_lower_bwd(K, n, 0, G, n, 0, n, 1, pws, L.potrf_bytes, st));
+  HB_TRY(rbf_gram_bwd(G, n, 0, X, nullptr, n, n, c.D, 0, 0, d_ell, c.n_ell, 1, 1, 0, d_a, g_ell, red, kReduceWsBytes, st));
+  gp_scalar_bwd_kernel<<<1, 32, 0, st>>>(sc, ll3, kl, (long long)Sn * n, Sn, p_scale, p_ell, c.n_ell, p_kvar, p_var,
+                                         g_scale, g_ell, g_kvar, g_var, out4);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+}  // extern "C"

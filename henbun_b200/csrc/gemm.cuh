@@ -1,0 +1,39 @@
+// GEMM engine interface: C[MxN] = epi(alpha * op(A)[MxK] * op(B)[KxN] + beta * C), row-major fp32.
+#pragma once
+#include "common.cuh"
+
+namespace hb {
+
+// Triangular masks are expressed in the index space of op(A) (m,k) and op(B) (k,n):
+//   A: 1 keep k<=m (lower)   2 keep k>=m (upper)   3 keep k>m (strict upper)  4 keep k<m (strict lower)
+//   B: 1 keep n<=k (lower)   2 keep n>=k (upper)   3 keep n>k (strict upper)  4 keep n<k (strict lower)
+//   C: 1 compute/write only j<=i (tiles entirely above the diagonal are skipped)
+enum { ACT_NONE = 0, ACT_SIGMOID = 1, ACT_RELU = 2, ACT_TANH = 3 };
+
+struct GemmParams {
+  const float* A = nullptr;
+  const float* B = nullptr;
+  float* C = nullptr;
+  long long lda = 0, ldb = 0, ldc = 0;
+  long long sA = 0, sB = 0, sC = 0;  // batch strides (elements); 0 broadcasts
+  int batch = 1;
+  int M = 0, N = 0, K = 0;
+  float alpha = 1.f, beta = 0.f;
+  int transA = 0;  // 0: A stored [M x K]; 1: A stored [K x M]
+  int transB = 0;  // 0: B stored [K x N]; 1: B stored [N x K]
+  int a_tri = 0, b_tri = 0, c_tri = 0;
+  const float* bias = nullptr;  // optional [N] (+ batch stride sBias), added before the activation
+  long long sBias = 0;
+  int act = ACT_NONE;
+  int clip = 0;
+  float clip_lo = -50.f, clip_hi = 50.f;
+};
+
+// precision/engine selection: 0 = auto (tensor cores when the shape qualifies), 1 = force SIMT fp32,
+// 2 = force tcgen05 3xTF32 (error if the shape does not qualify)
+int gemm(const GemmParams& p, cudaStream_t stream);
+int gemm_simt(const GemmParams& p, cudaStream_t stream);
+void set_gemm_engine(int mode);
+int get_gemm_engine();
+
+}  // namespace hb

@@ -1,0 +1,254 @@
+// UnitRBF / UnitCsymRBF Gram matrix and its lengthscale gradient.
+//
+//   forward : K_ij = exp(-0.5 * sum_d ((x_id - x2_jd)/ell_d)^2)  [+ jitter on the diagonal]
+//             reference: UnitStationary.square_dist (Henbun/gp/kernels.py:54-84), UnitRBF.K (:110-111),
+//             UnitCsymRBF.K (:122-126), the jitter of UnitStationary.Cholesky (:100-101).
+//             The reference expands r^2 = -2 x.x' + |x|^2 + |x'|^2; we sum squared differences, which is
+//             the same quantity with less cancellation (parity is against the fp64 oracle).
+//   backward: g_ell_d = sum_ij G_ij K_ij (x_id - x2_jd)^2 / ell_d^3
+//
+// HBM-bound: the forward writes n*n2 floats once (lower-triangle tiles only on request), the
+// backward reads G once and recomputes K from X (D is small), so K is never re-read.
+#include "kernels.cuh"
+
+namespace hb {
+
+namespace {
+
+constexpr int TILE = 64;
+constexpr int DCH = 32;   // feature chunk staged in shared memory
+
+__device__ __forceinline__ float ell_at(const float* ell, int n_ell, int d) { return n_ell == 1 ? ell[0] : ell[d]; }
+
+template <bool CSYM>
+__global__ void __launch_bounds__(256) rbf_gram_fwd_kernel(const float* __restrict__ X, const float* __restrict__ X2,
+                                                           int n, int n2, int D, long long sX, long long sX2,
+                                                           const float* __restrict__ ell, int n_ell, float* K,
+                                                           long long ldk, long long sK, float jitter, int lower_only,
+                                                           int self) {
+  __shared__ float xs[TILE][DCH + 1];
+  __shared__ float ys[TILE][DCH + 1];
+  const int i0 = blockIdx.y * TILE, j0 = blockIdx.x * TILE;
+  if (lower_only && j0 > i0 + TILE - 1) return;
+  const int bz = blockIdx.z;
+  const float* Xb = X + (long long)bz * sX;
+  const float* Yb = X2 + (long long)bz * sX2;
+  float* Kb = K + (long long)bz * sK;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float r2[4][4], r2b[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { r2[a][b] = 0.f; r2b[a][b] = 0.f; }
+  for (int d0 = 0; d0 < D; d0 += DCH) {
+    const int dc = min(DCH, D - d0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < TILE * dc; e += 256) {
+      const int r = e / dc, d = e % dc;
+      const float il = 1.f / ell_at(ell, n_ell, d0 + d);
+      xs[r][d] = (i0 + r < n) ? Xb[(long long)(i0 + r) * D + d0 + d] * il : 0.f;
+      ys[r][d] = (j0 + r < n2) ? Yb[(long long)(j0 + r) * D + d0 + d] * il : 0.f;
+    }
+    __syncthreads();
+    for (int d = 0; d < dc; ++d) {
+      float xv[4], yv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xv[a] = xs[ty + 16 * a][d];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) yv[b] = ys[tx * 4 + b][d];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float df = xv[a] - yv[b];
+          r2[a][b] = fmaf(df, df, r2[a][b]);
+          if (CSYM) {
+            const float sf = xv[a] + yv[b];
+            r2b[a][b] = fmaf(sf, sf, r2b[a][b]);
+          }
+        }
+    }
+  }
+  const bool vec = ((ldk & 3) == 0) && ((sK & 3) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = i0 + ty + 16 * a;
+    if (i >= n) continue;
+    const int j = j0 + tx * 4;
+    float o[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      float k = expf(-0.5f * r2[a][b]);
+      if (CSYM) k += expf(-0.5f * r2b[a][b]);
+      if (self && i == j + b) k += jitter;
+      o[b] = k;
+    }
+    float* dst = Kb + (long long)i * ldk + j;
+    if (vec && j + 3 < n2) {
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (j + b < n2) dst[b] = o[b];
+    }
+  }
+}
+
+// Persistent over tiles; per-thread double accumulators per feature; one partial row per CTA.
+template <int DMAX>
+__global__ void __launch_bounds__(256) rbf_gram_bwd_kernel(const float* __restrict__ G, long long ldg, long long sG,
+                                                           const float* __restrict__ X, const float* __restrict__ X2,
+                                                           int n, int n2, int D, long long sX, long long sX2,
+                                                           const float* __restrict__ ell, int n_ell, int batch,
+                                                           int sym_lower, int csym, double* partials) {
+  __shared__ float xs[TILE][DMAX + 1];
+  __shared__ float ys[TILE][DMAX + 1];
+  __shared__ double red[32 * 8];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int tiles_i = (n + TILE - 1) / TILE, tiles_j = (n2 + TILE - 1) / TILE;
+  const long long ntiles = (long long)batch * tiles_i * tiles_j;
+  double dacc[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) dacc[d] = 0.0;
+  for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int bz = (int)(t / ((long long)tiles_i * tiles_j));
+    const int rem = (int)(t % ((long long)tiles_i * tiles_j));
+    const int i0 = (rem / tiles_j) * TILE, j0 = (rem % tiles_j) * TILE;
+    if (sym_lower && j0 > i0 + TILE - 1) continue;
+    const float* Xb = X + (long long)bz * sX;
+    const float* Yb = X2 + (long long)bz * sX2;
+    const float* Gb = G + (long long)bz * sG;
+    __syncthreads();
+    for (int e = threadIdx.x; e < TILE * D; e += 256) {
+      const int r = e / D, d = e % D;
+      const float il = 1.f / ell_at(ell, n_ell, d);
+      xs[r][d] = (i0 + r < n) ? Xb[(long long)(i0 + r) * D + d] * il : 0.f;
+      ys[r][d] = (j0 + r < n2) ? Yb[(long long)(j0 + r) * D + d] * il : 0.f;
+    }
+    __syncthreads();
+    float facc[DMAX];
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) facc[d] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int i = i0 + ty + 16 * a;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int j = j0 + tx * 4 + b;
+        if (i >= n || j >= n2) continue;
+        float w = 1.f;
+        if (sym_lower) {
+          if (j > i) continue;
+          w = (j == i) ? 1.f : 2.f;   // (the RBF diagonal has zero lengthscale derivative; Csym's does not)
+        }
+        float r2 = 0.f, r2b = 0.f;
+#pragma unroll
+        for (int d = 0; d < DMAX; ++d) {
+          if (d < D) {
+            const float df = xs[ty + 16 * a][d] - ys[tx * 4 + b][d];
+            r2 = fmaf(df, df, r2);
+            const float sf = xs[ty + 16 * a][d] + ys[tx * 4 + b][d];
+            r2b = fmaf(sf, sf, r2b);
+          }
+        }
+        const float g = w * __ldg(Gb + (long long)i * ldg + j);
+        const float gk = g * expf(-0.5f * r2);
+        const float gkb = csym ? g * expf(-0.5f * r2b) : 0.f;
+#pragma unroll
+        for (int d = 0; d < DMAX; ++d) {
+          if (d < D) {
+            const float df = xs[ty + 16 * a][d] - ys[tx * 4 + b][d];
+            facc[d] = fmaf(gk * df, df, facc[d]);
+            if (csym) {
+              const float sf = xs[ty + 16 * a][d] + ys[tx * 4 + b][d];
+              facc[d] = fmaf(gkb * sf, sf, facc[d]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) dacc[d] += (double)facc[d];
+  }
+  // block reduce, 8 features at a time
+  for (int d0 = 0; d0 < DMAX; d0 += 8) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (d0 + k < DMAX) ? dacc[d0 + k] : 0.0;
+    block_sum<8>(v, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (d0 + k < D) partials[(long long)blockIdx.x * DMAX + d0 + k] = v[k];
+    }
+  }
+}
+
+__global__ void gram_bwd_finalize_kernel(const double* __restrict__ partials, int nblocks, int D, int dmax,
+                                         const float* __restrict__ ell, int n_ell,
+                                         const float* __restrict__ out_scale, float* g_ell) {
+  // one warp; hat-space sums -> divide by ell_d (x was pre-divided by ell, so diff^2/ell^2 is already in)
+  double tot = 0.0;
+  const double osc = out_scale ? (double)*out_scale : 1.0;
+  for (int d = 0; d < D; ++d) {
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 32) s += partials[(long long)b * dmax + d];
+    s = warp_sum(s);
+    const double l = (double)ell_at(ell, n_ell, d);
+    if (n_ell == 1) tot += s / l;
+    else if (threadIdx.x == 0) g_ell[d] = (float)(osc * s / l);
+  }
+  if (n_ell == 1 && threadIdx.x == 0) g_ell[0] = (float)(osc * tot);
+}
+
+}  // namespace
+
+int rbf_gram_fwd(const float* X, const float* X2, int n, int n2, int D, long long sX, long long sX2,
+                 const float* ell, int n_ell, float* K, long long ldk, long long sK, int batch, float jitter,
+                 int lower_only, int csym, cudaStream_t st) {
+  if (n < 0 || n2 < 0 || D <= 0 || batch < 0) return HB_ERR_ARG;
+  if (n == 0 || n2 == 0 || batch == 0) return HB_OK;
+  if (!X || !ell || !K || ldk < n2 || (n_ell != 1 && n_ell != D)) return HB_ERR_ARG;
+  const int self = (X2 == nullptr);
+  if (self && n != n2) return HB_ERR_ARG;
+  if (!self && lower_only) return HB_ERR_ARG;
+  const float* Y = self ? X : X2;
+  const long long sY = self ? sX : sX2;
+  dim3 grid(cdiv(n2, TILE), cdiv(n, TILE), batch);
+  if (grid.y > 65535 || grid.z > 65535) return HB_ERR_ARG;
+  if (csym)
+    rbf_gram_fwd_kernel<true><<<grid, 256, 0, st>>>(X, Y, n, n2, D, sX, sY, ell, n_ell, K, ldk, sK, jitter, lower_only, self);
+  else
+    rbf_gram_fwd_kernel<false><<<grid, 256, 0, st>>>(X, Y, n, n2, D, sX, sY, ell, n_ell, K, ldk, sK, jitter, lower_only, self);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+int rbf_gram_bwd(const float* G, long long ldg, long long sG, const float* X, const float* X2, int n, int n2,
+                 int D, long long sX, long long sX2, const float* ell, int n_ell, int batch, int sym_lower,
+                 int csym, const float* out_scale, float* g_ell, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (n < 0 || n2 < 0 || D <= 0 || D > 32 || batch < 0) return HB_ERR_ARG;
+  if (!G || !X || !ell || !g_ell || ldg < n2 || (n_ell != 1 && n_ell != D)) return HB_ERR_ARG;
+  if (!ws || ws_bytes < kReduceWsBytes) return HB_ERR_WORKSPACE;
+  const int self = (X2 == nullptr);
+  if (self && n != n2) return HB_ERR_ARG;
+  if (sym_lower && !self) return HB_ERR_ARG;
+  const float* Y = self ? X : X2;
+  const long long sY = self ? sX : sX2;
+  const long long ntiles = (long long)batch * cdiv(n, TILE) * cdiv(n2, TILE);
+  int nb = (int)(ntiles < kReduceBlocks ? (ntiles > 0 ? ntiles : 1) : kReduceBlocks);
+  // grid: a multiple of the SM count when the problem is large
+  if (nb == kReduceBlocks) nb = 148 * 6;
+  double* partials = reinterpret_cast<double*>(ws);
+  const int dmax = D <= 8 ? 8 : 32;
+  if (dmax == 8)
+    rbf_gram_bwd_kernel<8><<<nb, 256, 0, st>>>(G, ldg, sG, X, Y, n, n2, D, sX, sY, ell, n_ell, batch, sym_lower, csym, partials);
+  else
+    rbf_gram_bwd_kernel<32><<<nb, 256, 0, st>>>(G, ldg, sG, X, Y, n, n2, D, sX, sY, ell, n_ell, batch, sym_lower, csym, partials);
+  HB_CHECK_LAUNCH();
+  gram_bwd_finalize_kernel<<<1, 32, 0, st>>>(partials, nb, D, dmax, ell, n_ell, out_scale, g_ell);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+}  // namespace hb

@@ -1,0 +1,420 @@
+// Blocked (recursive, all level-3) Cholesky, triangular solves and reverse-mode Cholesky.
+//
+//   reference ops replaced:  tf.cholesky                      (Henbun/gp/kernels.py:100-101)
+//                            tf.matrix_triangular_solve        (Henbun/gp/gp.py:162,169)
+//                            TF's _CholeskyGrad via minimize() (Henbun/model.py:220)
+//
+// Layout: row-major fp32, full-square storage, only the lower triangle is read/written.
+// The recursion splits on multiples of NB; leaves (<= NB) run in one CTA out of shared memory and
+// also emit the inverse of the diagonal block, so every triangular solve above the leaves is a GEMM.
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace hb {
+
+namespace {
+
+constexpr int NB = 128;          // leaf size
+constexpr int LDS = NB + 1;      // padded shared-memory leading dimension
+constexpr int LEAF_THREADS = 512;
+
+// ------------------------------------------------------------------------------------------
+// in-CTA helpers (matrices are NB x NB in shared memory, ld = LDS)
+// ------------------------------------------------------------------------------------------
+
+// Unblocked right-looking Cholesky of the n x n lower triangle held in S (rows/cols >= n are identity).
+// One __syncthreads per column: the scaling of column j-1 is deferred into phase j.
+__device__ void potrf_smem(float* S, int n, int* err_flag, int err_base) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  for (int j = 0; j <= n; ++j) {
+    __syncthreads();
+    if (j > 0) {  // finalise column j-1
+      const int q = j - 1;
+      const float d = S[q * LDS + q];
+      const float sd = sqrtf(d);
+      const float rs = 1.f / sd;
+      for (int i = q + 1 + tid; i < n; i += blockDim.x) S[i * LDS + q] *= rs;
+      // S[q][q] is rewritten only after everyone has read it: defer by one more phase (see below)
+      if (tid == 0 && !(d > 0.f) && err_flag) atomicCAS(err_flag, 0, err_base + q + 1);
+    }
+    if (j > 1) {  // diagonal of column j-2: nobody reads it any more
+      const int q = j - 2;
+      if (tid == 0) S[q * LDS + q] = sqrtf(S[q * LDS + q]);
+    }
+    if (j < n) {  // trailing update with (unscaled) column j
+      const float d = S[j * LDS + j];
+      const float invd = 1.f / d;
+      for (int i = j + 1 + warp; i < n; i += nwarp) {
+        const float ci = S[i * LDS + j] * invd;
+        for (int k = j + 1 + lane; k <= i; k += 32) S[i * LDS + k] = fmaf(-ci, S[k * LDS + j], S[i * LDS + k]);
+      }
+    }
+  }
+  __syncthreads();
+  if (n >= 1 && threadIdx.x == 0) S[(n - 1) * LDS + (n - 1)] = sqrtf(S[(n - 1) * LDS + (n - 1)]);
+  __syncthreads();
+}
+
+// X = L^{-1} for the lower-triangular L (NB x NB, identity padded). 4 lanes cooperate per column.
+__device__ void trinv_smem(const float* L, float* X) {
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * LDS; e += blockDim.x) X[e] = 0.f;
+  __syncthreads();
+  const int c = tid >> 2, sub = tid & 3;       // 512 threads -> 128 columns
+  const int cw = (tid & ~31) >> 2;              // first column handled by this warp
+  if (c < NB && sub == 0) X[c * LDS + c] = 1.f / L[c * LDS + c];
+  __syncwarp();
+  for (int i = cw + 1; i < NB; ++i) {
+    float part = 0.f;
+    if (c < NB && i > c)
+      for (int k = c + sub; k < i; k += 4) part = fmaf(L[i * LDS + k], X[k * LDS + c], part);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (c < NB && i > c && sub == 0) X[i * LDS + c] = -part / L[i * LDS + i];
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+// C = op(A) * op(B) on NB x NB shared-memory matrices; k restricted to [klo(i), khi(i)] by row.
+// KMODE 0: all k; 1: k >= i; 2: k <= i.
+template <bool TA, bool TB, int KMODE>
+__device__ void mm_smem(float* C, const float* A, const float* B) {
+  const int tid = threadIdx.x;
+  const int tr = tid >> 4, tc = tid & 15;   // 32 x 16 thread grid, 4 rows x 8 interleaved cols each
+  float acc[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+  const int i0 = tr * 4;
+  const int klo = (KMODE == 1) ? i0 : 0;
+  const int khi = (KMODE == 2) ? i0 + 3 : NB - 1;
+  for (int k = klo; k <= khi; ++k) {
+    float a[4], b[8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float v = TA ? A[k * LDS + i0 + r] : A[(i0 + r) * LDS + k];
+      if (KMODE == 1 && k < i0 + r) v = 0.f;
+      if (KMODE == 2 && k > i0 + r) v = 0.f;
+      a[r] = v;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) b[c] = TB ? B[(tc + 16 * c) * LDS + k] : B[k * LDS + tc + 16 * c];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) C[(i0 + r) * LDS + tc + 16 * c] = acc[r][c];
+}
+
+// load the n x n lower triangle of a global block into S; pad with `diag_pad` on the padded diagonal
+__device__ void load_lower(float* S, const float* G, long long ld, int n, float diag_pad) {
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int i = e / NB, j = e % NB;
+    float v = 0.f;
+    if (i < n && j <= i) v = G[(long long)i * ld + j];
+    else if (i == j) v = diag_pad;
+    S[i * LDS + j] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// leaf kernels (one CTA per matrix; blockIdx.x = batch index)
+// ------------------------------------------------------------------------------------------
+
+// Factor in place (lower), optionally zero the strict upper triangle, optionally emit Dinv = L^{-1}.
+__global__ void __launch_bounds__(LEAF_THREADS) potrf_leaf_kernel(float* A, long long lda, long long sA, int n,
+                                                                  float* Dinv, long long sD, int zero_upper,
+                                                                  int* err_flag, int err_base) {
+  extern __shared__ float sm[];
+  float* S = sm;
+  float* X = sm + NB * LDS;
+  float* Ab = A + (long long)blockIdx.x * sA;
+  load_lower(S, Ab, lda, n, 1.f);
+  potrf_smem(S, n, err_flag, err_base);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    if (j <= i) Ab[(long long)i * lda + j] = S[i * LDS + j];
+    else if (zero_upper) Ab[(long long)i * lda + j] = 0.f;
+  }
+  if (Dinv) {
+    trinv_smem(S, X);
+    float* Db = Dinv + (long long)blockIdx.x * sD;
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Db[e] = X[(e / NB) * LDS + (e % NB)];
+  }
+}
+
+// Dinv = L^{-1} for diagonal blocks of an already factored matrix; block b starts at (b*NB, b*NB).
+__global__ void __launch_bounds__(LEAF_THREADS) trinv_blocks_kernel(const float* L, long long ldl, int n,
+                                                                    float* Dinv) {
+  extern __shared__ float sm[];
+  float* S = sm;
+  float* X = sm + NB * LDS;
+  const int b = blockIdx.x;
+  const int nb = min(NB, n - b * NB);
+  load_lower(S, L + (long long)b * NB * ldl + (long long)b * NB, ldl, nb, 1.f);
+  __syncthreads();
+  trinv_smem(S, X);
+  float* Db = Dinv + (long long)b * NB * NB;
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Db[e] = X[(e / NB) * LDS + (e % NB)];
+}
+
+// Leaf of the reverse-mode recursion: G <- sym(L^{-T} Phi(L^T tril(G)) L^{-1}), written to both
+// triangles of the diagonal block.  Dinv = L^{-1} of this block (NB x NB, identity padded) or null.
+__global__ void __launch_bounds__(LEAF_THREADS) chol_rev_leaf_kernel(const float* L, long long ldl, long long sL,
+                                                                     float* G, long long ldg, long long sG, int n,
+                                                                     const float* Dinv, long long sD) {
+  extern __shared__ float sm[];
+  float* B0 = sm;
+  float* B1 = sm + NB * LDS;
+  float* B2 = sm + 2 * NB * LDS;
+  const float* Lb = L + (long long)blockIdx.x * sL;
+  float* Gb = G + (long long)blockIdx.x * sG;
+  load_lower(B0, Lb, ldl, n, 1.f);   // L
+  load_lower(B1, Gb, ldg, n, 0.f);   // tril(Lbar)
+  __syncthreads();
+  // P = Phi(L^T Lbar): (L^T)[i][k] = L[k][i], nonzero for k >= i
+  mm_smem<true, false, 1>(B2, B0, B1);
+  __syncthreads();
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int i = e / NB, j = e % NB;
+    float v = B2[i * LDS + j];
+    if (j > i) v = 0.f;
+    else if (j == i) v *= 0.5f;
+    B2[i * LDS + j] = v;
+  }
+  __syncthreads();
+  // Dinv into B0
+  if (Dinv) {
+    const float* Db = Dinv + (long long)blockIdx.x * sD;
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) B0[(e / NB) * LDS + (e % NB)] = Db[e];
+    __syncthreads();
+  } else {
+    // B0 holds L: invert into B1 then copy back
+    trinv_smem(B0, B1);
+    for (int e = threadIdx.x; e < NB * LDS; e += blockDim.x) B0[e] = B1[e];
+    __syncthreads();
+  }
+  // M1 = P * Dinv (lower x lower): k <= i
+  mm_smem<false, false, 2>(B1, B2, B0);
+  __syncthreads();
+  // S = Dinv^T * M1: (Dinv^T)[i][k] = Dinv[k][i], nonzero for k >= i
+  mm_smem<true, false, 1>(B2, B0, B1);
+  __syncthreads();
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    Gb[(long long)i * ldg + j] = 0.5f * (B2[i * LDS + j] + B2[j * LDS + i]);
+  }
+}
+
+constexpr size_t kLeafSmem2 = 2 * NB * LDS * sizeof(float);
+constexpr size_t kLeafSmem3 = 3 * NB * LDS * sizeof(float);
+
+int ensure_attrs() {
+  static bool done = false;
+  if (done) return HB_OK;
+  if (cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeafSmem2) != cudaSuccess) return HB_ERR_CUDA;
+  if (cudaFuncSetAttribute(trinv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeafSmem2) != cudaSuccess) return HB_ERR_CUDA;
+  if (cudaFuncSetAttribute(chol_rev_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeafSmem3) != cudaSuccess) return HB_ERR_CUDA;
+  done = true;
+  return HB_OK;
+}
+
+// split point: a multiple of NB, roughly half
+inline int split_point(int n) {
+  const int nblk = (n + NB - 1) / NB;
+  return ((nblk + 1) / 2) * NB;
+}
+
+struct Ctx {
+  cudaStream_t st;
+  float* dinv;        // [nblk][NB][NB]
+  float* tmp;         // [n][NB] scratch for leaf triangular solves
+  long long ldt;      // = NB
+  int* err;
+};
+
+inline float* dinv_slot(const Ctx& c, int off) { return c.dinv + (long long)(off / NB) * NB * NB; }
+
+// B (m x k at Bp) <- B * L^{-T},  L = k x k lower block whose diagonal starts at global offset `off`
+int trsm_rlt(const Ctx& c, const float* L, long long ldl, int off, float* Bp, long long ldb, int m, int k) {
+  if (m <= 0 || k <= 0) return HB_OK;
+  if (k <= NB) {
+    GemmParams g;
+    g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = 1;   // (B Dinv^T)
+    g.C = c.tmp; g.ldc = NB; g.M = m; g.N = k; g.K = k; g.alpha = 1.f; g.beta = 0.f;
+    HB_TRY(gemm(g, c.st));
+    return copy2d(Bp, ldb, c.tmp, NB, m, k, 1.f, c.st);
+  }
+  const int k1 = split_point(k), k2 = k - k1;
+  HB_TRY(trsm_rlt(c, L, ldl, off, Bp, ldb, m, k1));
+  GemmParams g;   // B2 -= B1 * L21^T
+  g.A = Bp; g.lda = ldb; g.B = L + (long long)k1 * ldl; g.ldb = ldl; g.transB = 1;
+  g.C = Bp + k1; g.ldc = ldb; g.M = m; g.N = k2; g.K = k1; g.alpha = -1.f; g.beta = 1.f;
+  HB_TRY(gemm(g, c.st));
+  return trsm_rlt(c, L + (long long)k1 * ldl + k1, ldl, off + k1, Bp + k1, ldb, m, k2);
+}
+
+// B <- B * L^{-1}
+int trsm_rln(const Ctx& c, const float* L, long long ldl, int off, float* Bp, long long ldb, int m, int k) {
+  if (m <= 0 || k <= 0) return HB_OK;
+  if (k <= NB) {
+    GemmParams g;
+    g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = 0;   // (B Dinv)
+    g.C = c.tmp; g.ldc = NB; g.M = m; g.N = k; g.K = k; g.alpha = 1.f; g.beta = 0.f;
+    HB_TRY(gemm(g, c.st));
+    return copy2d(Bp, ldb, c.tmp, NB, m, k, 1.f, c.st);
+  }
+  const int k1 = split_point(k), k2 = k - k1;
+  HB_TRY(trsm_rln(c, L + (long long)k1 * ldl + k1, ldl, off + k1, Bp + k1, ldb, m, k2));
+  GemmParams g;   // B1 -= B2 * L21
+  g.A = Bp + k1; g.lda = ldb; g.B = L + (long long)k1 * ldl; g.ldb = ldl; g.transB = 0;
+  g.C = Bp; g.ldc = ldb; g.M = m; g.N = k1; g.K = k2; g.alpha = -1.f; g.beta = 1.f;
+  HB_TRY(gemm(g, c.st));
+  return trsm_rln(c, L, ldl, off, Bp, ldb, m, k1);
+}
+
+int potrf_rec(const Ctx& c, float* A, long long lda, int off, int n) {
+  if (n <= NB) {
+    potrf_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem2, c.st>>>(A, lda, 0, n, dinv_slot(c, off), 0, 0, c.err, off);
+    HB_CHECK_LAUNCH();
+    return HB_OK;
+  }
+  const int n1 = split_point(n), m = n - n1;
+  float* A21 = A + (long long)n1 * lda;
+  float* A22 = A21 + n1;
+  HB_TRY(potrf_rec(c, A, lda, off, n1));
+  HB_TRY(trsm_rlt(c, A, lda, off, A21, lda, m, n1));
+  GemmParams g;   // A22 -= A21 A21^T (lower)
+  g.A = A21; g.lda = lda; g.B = A21; g.ldb = lda; g.transB = 1;
+  g.C = A22; g.ldc = lda; g.M = m; g.N = m; g.K = n1; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
+  HB_TRY(gemm(g, c.st));
+  return potrf_rec(c, A22, lda, off + n1, m);
+}
+
+int chol_rev_rec(const Ctx& c, const float* L, long long ldl, float* G, long long ldg, int off, int n) {
+  if (n <= NB) {
+    chol_rev_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.st>>>(L, ldl, 0, G, ldg, 0, n, dinv_slot(c, off), 0);
+    HB_CHECK_LAUNCH();
+    return HB_OK;
+  }
+  const int n1 = split_point(n), m = n - n1;
+  const float* L21 = L + (long long)n1 * ldl;
+  const float* L22 = L21 + n1;
+  float* G21 = G + (long long)n1 * ldg;
+  float* G22 = G21 + n1;
+  HB_TRY(chol_rev_rec(c, L22, ldl, G22, ldg, off + n1, m));
+  // G21 -= 2 sym(G22) L21, sym from the lower triangle: tril(G22) L21 + striu(G22^T) L21
+  {
+    GemmParams g;
+    g.A = G22; g.lda = ldg; g.a_tri = 1; g.B = L21; g.ldb = ldl; g.C = G21; g.ldc = ldg;
+    g.M = m; g.N = n1; g.K = m; g.alpha = -2.f; g.beta = 1.f;
+    HB_TRY(gemm(g, c.st));
+    g.transA = 1; g.a_tri = 3;
+    HB_TRY(gemm(g, c.st));
+  }
+  HB_TRY(trsm_rln(c, L, ldl, off, G21, ldg, m, n1));     // T = G21 L11^{-1}
+  {
+    GemmParams g;   // G11 -= tril(T^T L21)
+    g.A = G21; g.lda = ldg; g.transA = 1; g.B = L21; g.ldb = ldl; g.C = G; g.ldc = ldg;
+    g.M = n1; g.N = n1; g.K = m; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
+    HB_TRY(gemm(g, c.st));
+  }
+  HB_TRY(scale2d(G21, ldg, m, n1, 0.5f, c.st));
+  return chol_rev_rec(c, L, ldl, G, ldg, off, n1);
+}
+
+}  // namespace
+
+size_t potrf_workspace_bytes(int n) {
+  const long long nblk = (n + NB - 1) / NB;
+  return (size_t)(nblk * NB * NB + (long long)n * NB) * sizeof(float) + 256;
+}
+
+static int make_ctx(Ctx& c, int n, void* ws, size_t ws_bytes, int* err, cudaStream_t st) {
+  if (ws_bytes < potrf_workspace_bytes(n) || !ws) return HB_ERR_WORKSPACE;
+  const long long nblk = (n + NB - 1) / NB;
+  c.st = st;
+  c.dinv = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  c.tmp = c.dinv + nblk * NB * NB;
+  c.ldt = NB;
+  c.err = err;
+  return HB_OK;
+}
+
+// In-place lower Cholesky of `batch` n x n matrices.  Only the lower triangle is read.
+int potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
+                size_t ws_bytes, int* err_flag, cudaStream_t st) {
+  if (n < 0 || batch < 0 || (n > 0 && (!A || lda < n))) return HB_ERR_ARG;
+  if (n == 0 || batch == 0) return HB_OK;
+  HB_TRY(ensure_attrs());
+  if (n <= NB) {
+    potrf_leaf_kernel<<<batch, LEAF_THREADS, kLeafSmem2, st>>>(A, lda, strideA, n, nullptr, 0, zero_upper, err_flag, 0);
+    HB_CHECK_LAUNCH();
+    return HB_OK;
+  }
+  Ctx c;
+  HB_TRY(make_ctx(c, n, ws, ws_bytes, err_flag, st));
+  for (int b = 0; b < batch; ++b) {
+    float* Ab = A + (long long)b * strideA;
+    HB_TRY(potrf_rec(c, Ab, lda, 0, n));
+    if (zero_upper) HB_TRY(zero_strict_upper(Ab, lda, n, st));
+  }
+  return HB_OK;
+}
+
+// Reverse mode: on entry G's lower triangle holds dObj/dL, on exit dObj/dK (full-symmetric
+// convention, lower triangle valid).  L is the factor from potrf_lower (lower triangle read).
+int potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, long long ldg, long long strideG,
+                    int n, int batch, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (n < 0 || batch < 0 || (n > 0 && (!L || !G || ldl < n || ldg < n))) return HB_ERR_ARG;
+  if (n == 0 || batch == 0) return HB_OK;
+  HB_TRY(ensure_attrs());
+  if (n <= NB) {
+    chol_rev_leaf_kernel<<<batch, LEAF_THREADS, kLeafSmem3, st>>>(L, ldl, strideL, G, ldg, strideG, n, nullptr, 0);
+    HB_CHECK_LAUNCH();
+    return HB_OK;
+  }
+  Ctx c;
+  HB_TRY(make_ctx(c, n, ws, ws_bytes, nullptr, st));
+  const int nblk = (n + NB - 1) / NB;
+  for (int b = 0; b < batch; ++b) {
+    const float* Lb = L + (long long)b * strideL;
+    trinv_blocks_kernel<<<nblk, LEAF_THREADS, kLeafSmem2, st>>>(Lb, ldl, n, c.dinv);
+    HB_CHECK_LAUNCH();
+    HB_TRY(chol_rev_rec(c, Lb, ldl, G + (long long)b * strideG, ldg, 0, n));
+  }
+  return HB_OK;
+}
+
+// X <- X * L^{-T} (trans=1) or X * L^{-1} (trans=0), L n x n lower from potrf_lower, X m x n in place.
+int trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int m, int n, int trans, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
+  if (m < 0 || n < 0 || (n > 0 && m > 0 && (!L || !X || ldl < n || ldx < n))) return HB_ERR_ARG;
+  if (m == 0 || n == 0) return HB_OK;
+  HB_TRY(ensure_attrs());
+  const long long nblk = (n + NB - 1) / NB;
+  const size_t need = (size_t)(nblk * NB * NB + (long long)m * NB) * sizeof(float) + 256;
+  if (!ws || ws_bytes < need) return HB_ERR_WORKSPACE;
+  Ctx c;
+  c.st = st;
+  c.dinv = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  c.tmp = c.dinv + nblk * NB * NB;
+  c.ldt = NB;
+  c.err = nullptr;
+  trinv_blocks_kernel<<<(int)nblk, LEAF_THREADS, kLeafSmem2, st>>>(L, ldl, n, c.dinv);
+  HB_CHECK_LAUNCH();
+  return trans ? trsm_rlt(c, L, ldl, 0, X, ldx, m, n) : trsm_rln(c, L, ldl, 0, X, ldx, m, n);
+}
+
+size_t trsm_workspace_bytes(int m, int n) {
+  const long long nblk = (n + NB - 1) / NB;
+  return (size_t)(nblk * NB * NB + (long long)m * NB) * sizeof(float) + 256;
+}
+
+}  // namespace hb

@@ -1,0 +1,164 @@
+/* henbun_b200 -- C ABI of the B200-native Monte-Carlo ELBO hot path of Henbun.
+ *
+ * The reference (fujii-team/Henbun) has NO native/FFI boundary: ext_modules=[] (setup.py:28) and the
+ * only vestige is a commented-out tf.load_op_library block (Henbun/tf_wraps.py:50-71).  Every entry
+ * point below therefore replaces a group of TensorFlow ops that the reference's Python emits on the
+ * hot path; the reference call site each one stands for is cited per function.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name ends in _host.  Tensors are contiguous
+ *    row-major fp32 unless a leading dimension / stride argument says otherwise.
+ *  - The caller owns every buffer including workspaces; the library keeps no device state.
+ *  - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous and stream-ordered; no call
+ *    synchronises the host.  All calls are CUDA-graph capturable.
+ *  - Return value: 0 = launched, HB_ERR_ARG = bad argument (reference: ValueError/AssertionError,
+ *    e.g. Henbun/param.py:712-713, variationals.py:82), HB_ERR_CUDA = launch failure,
+ *    HB_ERR_WORKSPACE = workspace missing/too small.
+ *  - Numerical failure is reported asynchronously: a non-positive Cholesky pivot writes
+ *    (1 + global row index) into *err_flag (reference: InvalidArgumentError from tf.cholesky).
+ *  - Triangular matrices use full-square storage; only the lower triangle is read or written.
+ */
+#ifndef HENBUN_B200_H
+#define HENBUN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_ERR_ARG 1
+#define HB_ERR_CUDA 2
+#define HB_ERR_WORKSPACE 3
+
+#define HB_ACT_NONE 0
+#define HB_ACT_SIGMOID 1
+#define HB_ACT_RELU 2
+#define HB_ACT_TANH 3
+
+/* library / bookkeeping */
+int hb_version(void);
+unsigned long long hb_launch_count(void);           /* kernels launched by this library so far */
+size_t hb_reduce_workspace_bytes(void);             /* workspace every reducing call needs */
+int hb_set_gemm_engine(int mode);                   /* 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32 */
+int hb_get_gemm_engine(void);
+/* Optional instrumentation for bench.py: CUDA-event pairs around every GEMM launch on its stream.
+ * hb_profile_end synchronises and fills a HOST array {launches, total ms, useful FLOP, 0}. */
+int hb_profile_begin(int max_gemm_launches);
+int hb_profile_end(double* out4_host);
+
+/* tf.random_normal (variationals.py:107,127): Philox-4x32-10 + Box-Muller, counter based.
+ * Element i of the stream (seed, offset) is identical whether it is materialised here or
+ * regenerated inside hb_sample_diag_{fwd,bwd}.  offset must be a multiple of 4. */
+int hb_randn_philox(float* out, long long count, unsigned long long seed, unsigned long long offset, void* stream);
+
+/* Variational._sample 'diagonal' (variationals.py:138-142) fused with Normal._KL (:225-230) and
+ * logdet (:183-184).  mu/omega: [rows, cols] with row strides (LOCAL variationals read the two halves
+ * of an encoder row, param.py:529-537).  eps: [S, rows, cols] or NULL (Philox).  z: [S, rows, cols].
+ * kl_out (1 float, may be NULL) = -0.5*sum(2*omega + eps^2 - z^2) over all S samples. */
+int hb_sample_diag_fwd(const float* mu, long long ld_mu, const float* omega, long long ld_omega, int rows, int cols,
+                       const float* eps, unsigned long long seed, unsigned long long offset, int S, float* z,
+                       float* kl_out, void* ws, size_t ws_bytes, void* stream);
+/* Backward of the above for an objective  obj = g(z) - kl_coef*KL :  zbar = dg/dz [S,rows,cols]
+ * (NULL = 0), optionally multiplied by the device scalar *zbar_scale.  g* = beta*g* + grad. */
+int hb_sample_diag_bwd(const float* mu, long long ld_mu, const float* omega, long long ld_omega, int rows, int cols,
+                       const float* eps, unsigned long long seed, unsigned long long offset, int S,
+                       const float* zbar, const float* zbar_scale, float kl_coef, float* gmu, long long ld_gmu,
+                       float* gomega, long long ld_gomega, float beta, void* stream);
+
+/* Variational._sample 'fullrank' (variationals.py:144-146): z[b,s,:] = mu[b,:] + tril(Lq[b]) eps[b,s,:].
+ * Lq: [batch, n, n]; mu: [batch, n]; eps, z: [batch, S, n].  kl_out as above with
+ * logdet = log(diag(Lq)^2) (:185-186). */
+int hb_sample_tril_fwd(const float* mu, const float* Lq, int n, int batch, const float* eps, int S, float* z,
+                       float* kl_out, void* ws, size_t ws_bytes, void* stream);
+/* gmu [batch,n], gLq [batch,n,n] (lower triangle written, strict upper zeroed). zbar may be NULL. */
+int hb_sample_tril_bwd(const float* Lq, int n, int batch, const float* eps, const float* z, int S,
+                       const float* zbar, float kl_coef, float* gmu, float* gLq, float* scratch_Sn, void* stream);
+
+/* densities.gaussian (densities.py:25-27) elementwise with modular broadcasting:
+ * out[i] = logN(x[i % x_period]; mu[i % mu_period], var[i % var_period]). */
+int hb_gaussian_logpdf(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
+                       long long var_period, long long total, float* out, void* stream);
+/* reduce_sum(densities.gaussian(y, f_scale*f, var)) fused with the residual for the backward.
+ * f: [total]; y: [y_period] broadcast; var, f_scale: device scalars (f_scale may be NULL = 1).
+ * resid (may be NULL) = -rcoef*(f_scale*f - y)/var.  out3 = {loglik, sum E^2, sum E*(f_scale*f)}. */
+int hb_gauss_loglik_fwd(const float* f, const float* f_scale, const float* y, long long total, long long y_period,
+                        const float* var, float rcoef, float* resid, float* out3, void* ws, size_t ws_bytes,
+                        void* stream);
+
+/* UnitRBF.K / UnitCsymRBF.K (gp/kernels.py:54-84,110-111,122-126), + jitter*I when X2 == NULL
+ * (UnitStationary.Cholesky :100-101).  X [batch,n,D], X2 [batch,n2,D] or NULL, ell [n_ell] with
+ * n_ell in {1, D} (already transformed to the positive space).  lower_only skips tiles above the
+ * diagonal (requires X2 == NULL). */
+int hb_rbf_gram_fwd(const float* X, const float* X2, int n, int n2, int D, int batch, const float* ell, int n_ell,
+                    float* K, long long ldk, long long strideK, float jitter, int lower_only, int csym,
+                    void* stream);
+/* g_ell[n_ell] = *out_scale * sum_ij G_ij dK_ij/d ell.  sym_lower: G's lower triangle holds a symmetric
+ * gradient (full-symmetric convention), off-diagonal entries count twice. */
+int hb_rbf_gram_bwd(const float* G, long long ldg, long long strideG, const float* X, const float* X2, int n, int n2,
+                    int D, int batch, const float* ell, int n_ell, int sym_lower, int csym, const float* out_scale,
+                    float* g_ell, void* ws, size_t ws_bytes, void* stream);
+
+/* tf.cholesky (gp/kernels.py:101; gp/gp.py:135), batched, in place, lower. */
+size_t hb_potrf_workspace_bytes(int n);
+int hb_potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
+                   size_t ws_bytes, int* err_flag, void* stream);
+/* Reverse mode of tf.cholesky (TF's _CholeskyGrad, reached through Optimizer.compile, model.py:220).
+ * In: G lower = dObj/dL.  Out: G lower = dObj/dK for the symmetric input (off-diagonals of a
+ * symmetric perturbation count twice). */
+int hb_potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, long long ldg, long long strideG,
+                       int n, int batch, void* ws, size_t ws_bytes, void* stream);
+/* tf.matrix_triangular_solve from the right: X <- X L^{-T} (trans=1) or X L^{-1} (trans=0)
+ * (gp/gp.py:162,169 and densities.py:84 use the transposed-left forms of the same solves). */
+size_t hb_trsm_workspace_bytes(int m, int n);
+int hb_trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int m, int n, int trans, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* tf.matmul (GaussianProcess.ipynb:144, gp/gp.py:50, nn.py:32, variationals.py:146) with the fused
+ * MatBias epilogue clip(x w + b) -> activation (nn.py:32,83).
+ * C[M,N] = act(clip(alpha*op(A) op(B) + beta*C + bias)).  transA=0: A stored [M,K]; 1: [K,M].
+ * transB=0: B stored [K,N]; 1: [N,K].  Triangular masks: see csrc/gemm.cuh.  Batched by strides. */
+int hb_gemm(const float* A, long long lda, long long strideA, int transA, int a_tri, const float* B, long long ldb,
+            long long strideB, int transB, int b_tri, float* C, long long ldc, long long strideC, int c_tri, int M,
+            int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
+            int clip, float clip_lo, float clip_hi, void* stream);
+/* Backward helper of MatBias: dz = dy * act'(y) (through the output y), dbias[c] = sum_r dz[r,c]. */
+int hb_act_bwd_colsum(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act,
+                      int clip, float clip_lo, float clip_hi, float* dbias, void* stream);
+int hb_colsum(const float* a, long long lda, int rows, int cols, float alpha, float beta, float* out, void* stream);
+
+/* tf.train.AdamOptimizer.minimize(-objective) (model.py:206,220), TF-1 update rule:
+ * g = grad_scale*grad; lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps).
+ * t is read from *step_dev when non-NULL (graph-capturable), else step_host. */
+int hb_adam_tf1(float* theta, const float* grad, float* m, float* v, long long n, float grad_scale, float lr,
+                float b1, float b2, float eps, const int* step_dev, int step_host, void* stream);
+int hb_increment_i32(int* counter, void* stream);
+
+/* small utilities used by the host layer */
+int hb_transpose2d(float* dst, long long ldd, const float* src, long long lds, int rows, int cols, float scale, void* stream);
+int hb_zero_strict_upper(float* a, long long lda, int n, void* stream);
+
+/* ---- fused ELBO + gradient of the variational GP regression graph -------------------------------
+ * notebooks/GaussianProcess.ipynb:109-148 (ELBO_gaussian), S-sample mean:
+ *   y_fit = matmul(kern.Cholesky(X), q) * sqrt(k_var);  ELBO = sum gaussian(Y, y_fit, var) - KL()
+ * with q = variationals.Gaussian(shape=[n,1], q_shape) = scale * Normal.
+ * params / grads packing (free space, floats):
+ *   [ q_mu (n) | q_sqrt (n if mean-field else n*n) | scale (1) | lengthscales (n_ell) | k_var (1) | var (1) ]
+ * out4 = { ELBO, loglik_sum, kl_sum, 0 }.  eps: [S,n] or NULL (Philox(seed, offset)). */
+typedef struct {
+  int n, D, S, n_ell;
+  int q_fullrank;
+  float jitter;
+  unsigned long long seed, offset;
+} hb_gp_config;
+size_t hb_gp_param_count(const hb_gp_config* cfg);
+size_t hb_gp_elbo_workspace_bytes(const hb_gp_config* cfg);
+int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, const float* params, const float* eps,
+                    float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HENBUN_B200_H */
