@@ -179,9 +179,10 @@ int hb_sample_diag_fwd(const float* mu, long long ld_mu, const float* omega, lon
 
 int hb_sample_diag_bwd(const float* mu, long long ld_mu, const float* omega, long long ld_omega, int rows, int cols,
                        const float* eps, unsigned long long seed, unsigned long long offset, int Sn,
-                       const float* zbar, const float* zbar_scale, float kl_coef, float* gmu, long long ld_gmu,
+                       const float* zbar, const float* zbar_scale, float kl_coef, const float* kl_coef_dev, float* gmu,
+                       long long ld_gmu,
                        float* gomega, long long ld_gomega, float beta, void* stream) {
-  return sample_diag_bwd(mu, ld_mu, omega, ld_omega, rows, cols, eps, seed, offset, Sn, zbar, zbar_scale, kl_coef, gmu,
+  return sample_diag_bwd(mu, ld_mu, omega, ld_omega, rows, cols, eps, seed, offset, Sn, zbar, zbar_scale, kl_coef, kl_coef_dev, gmu,
                          ld_gmu, gomega, ld_gomega, beta, S(stream));
 }
 
@@ -232,6 +233,16 @@ int hb_sample_tril_bwd(const float* Lq, int n, int batch, const float* eps, cons
 int hb_gaussian_logpdf(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
                        long long var_period, long long total, float* out, void* stream) {
   return gaussian_logpdf(x, x_period, mu, mu_period, var, var_period, total, out, S(stream));
+}
+
+int hb_gaussian_logpdf_bwd(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
+                           long long var_period, long long total, const float* g, float* dmu, float* dvar,
+                           void* stream) {
+  return gaussian_logpdf_bwd(x, x_period, mu, mu_period, var, var_period, total, g, dmu, dvar, S(stream));
+}
+int hb_gather_rows(float* dst, const float* src, const long long* index, long long n_index, long long row_elems,
+                   void* stream) {
+  return gather_rows(dst, src, index, n_index, row_elems, S(stream));
 }
 
 int hb_gauss_loglik_fwd(const float* f, const float* f_scale, const float* y, long long total, long long y_period,
@@ -393,7 +404,7 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
     HB_TRY(gemm(g, st));
   }
   if (!c.q_fullrank) {
-    HB_TRY(sample_diag_bwd(p_mu, n, p_sq, n, 1, n, eps, c.seed, c.offset, Sn, W, d_a, invS, g_mu, n, g_sq, n, 0.f, st));
+    HB_TRY(sample_diag_bwd(p_mu, n, p_sq, n, 1, n, eps, c.seed, c.offset, Sn, W, d_a, invS, nullptr, g_mu, n, g_sq, n, 0.f, st));
   } else {
     // zt = a*W - Z/S (into F, which is free now); gmu = colsum(zt); gLq = tril(zt^T eps) + diag(1/Lq_ii)
     gp_zbar_total_kernel<<<148 * 4, 256, 0, st>>>(W, Z, d_a, invS, (long long)Sn * n, F);

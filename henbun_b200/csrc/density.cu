@@ -81,7 +81,34 @@ __global__ void gaussian_logpdf_kernel(const float* __restrict__ x, long long xp
   }
 }
 
+// d out / d mu and d out / d var of the elementwise log-density, times the incoming gradient g.
+__global__ void gaussian_logpdf_bwd_kernel(const float* __restrict__ x, long long xp, const float* __restrict__ mu,
+                                           long long mp, const float* __restrict__ var, long long vp, long long total,
+                                           const float* __restrict__ g, float* dmu, float* dvar) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const float v = var[e % vp];
+    const float d = x[e % xp] - mu[e % mp];
+    const float iv = 1.f / v;
+    const float gg = g[e];
+    if (dmu) dmu[e] = gg * d * iv;
+    if (dvar) dvar[e] = gg * (-0.5f * iv + 0.5f * d * d * iv * iv);
+  }
+}
+
 }  // namespace
+
+int gaussian_logpdf_bwd(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
+                        long long var_period, long long total, const float* g, float* dmu, float* dvar,
+                        cudaStream_t st) {
+  if (total < 0) return HB_ERR_ARG;
+  if (total == 0) return HB_OK;
+  if (!x || !mu || !var || !g || x_period <= 0 || mu_period <= 0 || var_period <= 0) return HB_ERR_ARG;
+  long long nb = (total + 255) / 256;
+  if (nb > 148 * 16) nb = 148 * 16;
+  gaussian_logpdf_bwd_kernel<<<(int)nb, 256, 0, st>>>(x, x_period, mu, mu_period, var, var_period, total, g, dmu, dvar);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
 
 int gauss_loglik_fwd(const float* f, const float* f_scale, const float* y, long long total, long long y_period,
                      const float* var, float rcoef, float* resid, float* out3, void* ws, size_t ws_bytes, cudaStream_t st) {

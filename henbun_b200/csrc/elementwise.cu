@@ -158,6 +158,16 @@ __global__ void adam_tf1_kernel(float* theta, const float* __restrict__ grad, fl
 
 __global__ void increment_kernel(int* p) { *p += 1; }
 
+// dst[i, :] = src[index[i], :]  (MinibatchData.get_feed_dict, Henbun/param.py:733-739, on device)
+__global__ void gather_rows_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                   const long long* __restrict__ index, long long n_index, long long row) {
+  const long long total = n_index * row;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / row, c = e % row;
+    dst[e] = src[index[i] * row + c];
+  }
+}
+
 }  // namespace
 
 int copy2d(float* dst, long long ldd, const float* src, long long lds, int rows, int cols, float scale, cudaStream_t st) {
@@ -229,6 +239,15 @@ int adam_tf1(float* theta, const float* grad, float* m, float* v, long long n, f
   if (n <= 0) return HB_OK;
   if (!theta || !grad || !m || !v) return HB_ERR_ARG;
   adam_tf1_kernel<<<grid_for(n, 256), 256, 0, st>>>(theta, grad, m, v, n, grad_scale, lr, b1, b2, eps, step_dev, step_host);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+int gather_rows(float* dst, const float* src, const long long* index, long long n_index, long long row_elems,
+                cudaStream_t st) {
+  if (n_index < 0 || row_elems < 0) return HB_ERR_ARG;
+  if (n_index * row_elems == 0) return HB_OK;
+  if (!dst || !src || !index) return HB_ERR_ARG;
+  gather_rows_kernel<<<grid_for(n_index * row_elems, 256), 256, 0, st>>>(dst, src, index, n_index, row_elems);
   HB_CHECK_LAUNCH();
   return HB_OK;
 }

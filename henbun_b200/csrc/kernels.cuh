@@ -21,7 +21,8 @@ int sample_diag_fwd(const float* mu, long long ld_mu, const float* omega, long l
                     float* kl_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int sample_diag_bwd(const float* mu, long long ld_mu, const float* omega, long long ld_om, int rows, int cols,
                     const float* eps, unsigned long long seed, unsigned long long offset, int S, const float* zbar,
-                    const float* zbar_scale, float kl_coef, float* gmu, long long ld_gmu, float* gom, long long ld_gom, float beta,
+                    const float* zbar_scale, float kl_coef, const float* kl_coef_dev, float* gmu, long long ld_gmu, float* gom,
+                    long long ld_gom, float beta,
                     cudaStream_t st);
 int tril_logdet_kl(const float* Lq, long long ld, long long stride, int n, int batch, const float* eps,
                    const float* z, long long count, int S, float* kl_out, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -36,6 +37,12 @@ int gauss_loglik_fwd(const float* f, const float* f_scale, const float* y, long 
                      const float* var, float rcoef, float* resid, float* out3, void* ws, size_t ws_bytes, cudaStream_t st);
 int gaussian_logpdf(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
                     long long var_period, long long total, float* out, cudaStream_t st);
+
+int gaussian_logpdf_bwd(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
+                        long long var_period, long long total, const float* g, float* dmu, float* dvar,
+                        cudaStream_t st);
+int gather_rows(float* dst, const float* src, const long long* index, long long n_index, long long row_elems,
+                cudaStream_t st);
 
 // ---- UnitRBF Gram (gram.cu) ----
 int rbf_gram_fwd(const float* X, const float* X2, int n, int n2, int D, long long sX, long long sX2,

@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(128) sample_diag_bwd_kernel(const float* __res
                                                               long long P, const float* __restrict__ eps,
                                                               unsigned long long seed, unsigned long long offset, int S,
                                                               const float* __restrict__ zbar,
-                                                              const float* __restrict__ zbar_scale, float c, float* gmu,
+                                                              const float* __restrict__ zbar_scale, float c_host,
+                                                              const float* __restrict__ c_dev, float* gmu,
                                                               long long ld_gmu, float* gom, long long ld_gom, float beta) {
   const long long p0 = 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
   if (p0 >= P) return;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(128) sample_diag_bwd_kernel(const float* __res
   }
   const bool grp = ((P & 3) == 0);   // Philox groups line up with p0
   const float zsc = zbar_scale ? __ldg(zbar_scale) : 1.f;
+  const float c = c_dev ? c_host * __ldg(c_dev) : c_host;
   for (int s = 0; s < S; ++s) {
     const long long base = (long long)s * P + p0;
     float e[4];
@@ -193,7 +195,8 @@ int sample_diag_fwd(const float* mu, long long ld_mu, const float* omega, long l
 
 int sample_diag_bwd(const float* mu, long long ld_mu, const float* omega, long long ld_om, int rows, int cols,
                     const float* eps, unsigned long long seed, unsigned long long offset, int S, const float* zbar,
-                    const float* zbar_scale, float kl_coef, float* gmu, long long ld_gmu, float* gom, long long ld_gom,
+                    const float* zbar_scale, float kl_coef, const float* kl_coef_dev, float* gmu, long long ld_gmu, float* gom,
+                    long long ld_gom,
                     float beta, cudaStream_t st) {
   if (rows < 0 || cols < 0 || S < 0) return HB_ERR_ARG;
   const long long P = (long long)rows * cols;
@@ -202,7 +205,7 @@ int sample_diag_bwd(const float* mu, long long ld_mu, const float* omega, long l
   if (!eps && (offset & 3ull)) return HB_ERR_ARG;
   const long long nthreads = (P + 3) / 4;
   sample_diag_bwd_kernel<<<(int)((nthreads + 127) / 128), 128, 0, st>>>(mu, ld_mu, omega, ld_om, cols, P, eps, seed,
-                                                                       offset, S, zbar, zbar_scale, kl_coef, gmu, ld_gmu, gom,
+                                                                       offset, S, zbar, zbar_scale, kl_coef, kl_coef_dev, gmu, ld_gmu, gom,
                                                                        ld_gom, beta);
   HB_CHECK_LAUNCH();
   return HB_OK;

@@ -1,0 +1,586 @@
+"""Autograd operators over the C ABI: what a user objective written against the Henbun API is
+made of when it runs on henbun_b200.  Every heavy op (matmul, Cholesky and its reverse mode, the RBF
+Gram matrix, the reparameterised sampler + KL, densities.gaussian, MatBias) launches this repo's CUDA
+kernels; torch only owns memory, the autograd tape and O(n) scalar glue.  No CPU path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ptr, stream, check, reduce_ws, ACT
+
+
+def _L():
+    return _lib.load()
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    t = _lib.f32(t)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def mark_lower(t: torch.Tensor) -> torch.Tensor:
+    """Tag a tensor as lower-triangular so matmul can skip the zero half."""
+    t._hb_lower = True
+    return t
+
+
+def is_lower(t) -> bool:
+    return bool(getattr(t, "_hb_lower", False))
+
+
+# --------------------------------------------------------------------------------------------
+# raw GEMM call on 2-D / 3-D contiguous tensors
+# --------------------------------------------------------------------------------------------
+def gemm_raw(A, B, C_out, M, N, K, transA=0, transB=0, a_tri=0, b_tri=0, c_tri=0, alpha=1.0, beta=0.0, batch=1,
+             sA=0, sB=0, sC=0, lda=None, ldb=None, ldc=None, bias=None, sBias=0, act=0, clip=0, lo=-50.0, hi=50.0):
+    lda = lda if lda is not None else (M if transA else K)
+    ldb = ldb if ldb is not None else (K if transB else N)
+    ldc = ldc if ldc is not None else N
+    check(_L().hb_gemm(ptr(A), lda, sA, transA, a_tri, ptr(B), ldb, sB, transB, b_tri, ptr(C_out), ldc, sC, c_tri,
+                       M, N, K, batch, float(alpha), float(beta), ptr(bias), sBias, act, clip, float(lo), float(hi),
+                       stream()), "hb_gemm")
+    return C_out
+
+
+class _MatMul2D(torch.autograd.Function):
+    """C = op(a) op(b) for 2-D (or row-flattened) operands with transpose flags handled by the GEMM
+    itself (no transposed copies).  Triangular flags refer to the *stored* matrices."""
+
+    @staticmethod
+    def forward(ctx, a, b, ta, tb, a_lower, b_lower):
+        a = _c(a); b = _c(b)
+        lead = tuple(a.shape[:-1]) if (a.dim() > 2 and not ta) else None
+        a2 = a.reshape(-1, a.shape[-1]) if lead is not None else a
+        M, K = (a2.shape[1], a2.shape[0]) if ta else a2.shape
+        N = b.shape[0] if tb else b.shape[1]
+        # op(A)(m,k): stored lower -> ta=0: keep k<=m (1); ta=1: keep k>=m (2)
+        a_tri = 0 if not a_lower else (2 if ta else 1)
+        # op(B)(k,n): stored lower -> tb=0: B[k][n], keep n<=k (1); tb=1: B[n][k], keep k<=n (2)
+        b_tri = 0 if not b_lower else (2 if tb else 1)
+        out = torch.empty(M, N, device=a.device)
+        gemm_raw(a2, b, out, M, N, K, transA=int(ta), transB=int(tb), a_tri=a_tri, b_tri=b_tri)
+        ctx.save_for_backward(a2, b)
+        ctx.meta = (ta, tb, a_lower, b_lower, M, N, K, lead, tuple(a.shape))
+        return out.reshape(lead + (N,)) if lead is not None else out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ta, tb, al, bl, M, N, K, lead, ashape = ctx.meta
+        g = _c(g).reshape(M, N)
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = torch.zeros_like(a) if al else torch.empty_like(a)
+            ct = 1 if al else 0
+            if not ta:      # dA[M,K] = G op(B)^T
+                bt = 0 if not bl else (1 if tb else 2)      # op'(B)(n,k): tb=1 uses B[n][k] (lower: k<=n -> mode 1 in (k=n_,n=k_) space)
+                gemm_raw(g, b, ga, M, K, N, transB=0 if tb else 1, b_tri=bt, c_tri=ct)
+            else:           # dA stored [K,M] = op(B) G^T
+                at = 0 if not bl else (2 if tb else 1)
+                gemm_raw(b, g, ga, K, M, N, transA=1 if tb else 0, transB=1, a_tri=at, c_tri=ct)
+            ga = ga.reshape(ashape)
+        if ctx.needs_input_grad[1]:
+            gb = torch.zeros_like(b) if bl else torch.empty_like(b)
+            ct = 1 if bl else 0
+            if not tb:      # dB[K,N] = op(A)^T G
+                at = 0 if not al else (1 if ta else 2)
+                gemm_raw(a, g, gb, K, N, M, transA=0 if ta else 1, a_tri=at, c_tri=ct)
+            else:           # dB stored [N,K] = G^T op(A)
+                bt = 0 if not al else (2 if ta else 1)
+                gemm_raw(g, a, gb, N, K, M, transA=1, transB=1 if ta else 0, b_tri=bt, c_tri=ct)
+        return ga, gb, None, None, None, None
+
+
+class _MatMulBatched(torch.autograd.Function):
+    """a [M,K] (optionally lower-triangular) @ b [S,K,1] / [S,K,N], and equal-batch a @ b."""
+
+    @staticmethod
+    def forward(ctx, a, b, a_lower):
+        a = _c(a); b = _c(b)
+        ctx.a_lower = a_lower
+        ctx.save_for_backward(a, b)
+        if a.dim() == 2 and b.dim() == 3 and b.shape[-1] == 1:
+            # fold the sample axis into the GEMM: out[S,M] = b[S,K] a^T
+            M, K = a.shape; S = b.shape[0]
+            out = torch.empty(S, M, 1, device=a.device)
+            gemm_raw(b, a, out, S, M, K, transB=1, b_tri=2 if a_lower else 0)
+            ctx.mode = "fold"
+            return out
+        if a.dim() == 2 and b.dim() == 3:
+            M, K = a.shape; S, _, N = b.shape
+            out = torch.empty(S, M, N, device=a.device)
+            gemm_raw(a, b, out, M, N, K, a_tri=1 if a_lower else 0, batch=S, sA=0, sB=K * N, sC=M * N)
+            ctx.mode = "bcast_a"
+            return out
+        if a.dim() == b.dim() and a.dim() >= 3 and a.shape[:-2] == b.shape[:-2]:
+            bs = a.shape[:-2]; nb = int(torch.Size(bs).numel())
+            M, K = a.shape[-2:]; N = b.shape[-1]
+            out = torch.empty(*bs, M, N, device=a.device)
+            gemm_raw(a, b, out, M, N, K, batch=nb, sA=M * K, sB=K * N, sC=M * N)
+            ctx.mode = "batched"
+            return out
+        raise ValueError(f"matmul: unsupported shapes {tuple(a.shape)} @ {tuple(b.shape)}")
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = _c(g)
+        ga = gb = None
+        lo = ctx.a_lower
+        if ctx.mode == "fold":
+            M, K = a.shape; S = b.shape[0]
+            if ctx.needs_input_grad[0]:      # ga[M,K] = g[S,M]^T b[S,K]
+                ga = torch.zeros(M, K, device=a.device) if lo else torch.empty(M, K, device=a.device)
+                gemm_raw(g, b, ga, M, K, S, transA=1, c_tri=1 if lo else 0)
+            if ctx.needs_input_grad[1]:      # gb[S,K] = g[S,M] a[M,K]
+                gb = torch.empty(S, K, 1, device=a.device)
+                gemm_raw(g, a, gb, S, K, M, b_tri=1 if lo else 0)
+        elif ctx.mode == "bcast_a":
+            M, K = a.shape; S, _, N = b.shape
+            if ctx.needs_input_grad[0]:
+                ga = torch.zeros(M, K, device=a.device)
+                for s in range(S):
+                    gemm_raw(g[s], b[s], ga, M, K, N, transB=1, beta=1.0, c_tri=1 if lo else 0)
+            if ctx.needs_input_grad[1]:
+                gb = torch.empty(S, K, N, device=a.device)
+                gemm_raw(a, g, gb, K, N, M, transA=1, a_tri=2 if lo else 0, batch=S, sA=0, sB=M * N, sC=K * N)
+        else:  # batched
+            bs = a.shape[:-2]; nb = int(torch.Size(bs).numel())
+            M, K = a.shape[-2:]; N = b.shape[-1]
+            if ctx.needs_input_grad[0]:
+                ga = torch.empty_like(a)
+                gemm_raw(g, b, ga, M, K, N, transB=1, batch=nb, sA=M * N, sB=K * N, sC=M * K)
+            if ctx.needs_input_grad[1]:
+                gb = torch.empty_like(b)
+                gemm_raw(a, g, gb, K, N, M, transA=1, batch=nb, sA=M * K, sB=M * N, sC=K * N)
+        return ga, gb, None
+
+
+def matmul(a, b, transpose_a=False, transpose_b=False):
+    """tf.matmul.  2-D (and row-flattened) products take the transpose flags natively."""
+    if b.dim() == 2 and (a.dim() == 2 or not transpose_a):
+        return _MatMul2D.apply(a, b, bool(transpose_a), bool(transpose_b), is_lower(a), is_lower(b))
+    lower = is_lower(a) and not transpose_a
+    if transpose_a:
+        a = a.transpose(-1, -2)
+    if transpose_b:
+        b = b.transpose(-1, -2)
+    return _MatMulBatched.apply(a, b, lower)
+
+
+# --------------------------------------------------------------------------------------------
+# Cholesky (generic) and the fused kernel-Cholesky
+# --------------------------------------------------------------------------------------------
+def _potrf_ws(n, device):
+    nbytes = _L().hb_potrf_workspace_bytes(int(n))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+_err_flags = {}
+
+
+def err_flag(device) -> torch.Tensor:
+    key = str(device)
+    if key not in _err_flags:
+        _err_flags[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _err_flags[key]
+
+
+def check_numerics(device=None):
+    """Raise if a Cholesky reported a non-positive pivot (the reference surfaces this as a TF
+    InvalidArgumentError from session.run).  Synchronises; call once per step or less."""
+    for key, f in list(_err_flags.items()):
+        v = int(f.item())
+        if v != 0:
+            f.zero_()
+            raise FloatingPointError(f"Cholesky decomposition was not successful: non-positive pivot at row {v - 1}")
+
+
+class _Cholesky(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A):
+        A = _lib.f32(A)
+        n = A.shape[-1]
+        batch = int(A.numel() // (n * n)) if n else 0
+        Lw = A.contiguous().clone()
+        ws, nb = _potrf_ws(n, A.device)
+        check(_L().hb_potrf_lower(ptr(Lw), n, n * n, n, batch, 1, ptr(ws), nb, ptr(err_flag(A.device)), stream()),
+              "hb_potrf_lower")
+        ctx.save_for_backward(Lw)
+        return mark_lower(Lw)
+
+    @staticmethod
+    def backward(ctx, g):
+        (Lw,) = ctx.saved_tensors
+        n = Lw.shape[-1]
+        batch = int(Lw.numel() // (n * n)) if n else 0
+        G = g.contiguous().clone()
+        ws, nb = _potrf_ws(n, Lw.device)
+        check(_L().hb_potrf_lower_bwd(ptr(Lw), n, n * n, ptr(G), n, n * n, n, batch, ptr(ws), nb, stream()),
+              "hb_potrf_lower_bwd")
+        Gl = torch.tril(G)
+        return Gl + torch.tril(G, -1).transpose(-1, -2)       # full symmetric gradient, like TF
+
+
+def cholesky(A):
+    return _Cholesky.apply(A)
+
+
+def _kern_shapes(X, X2):
+    if X.dim() == 2:
+        batch, n, D = 1, X.shape[0], X.shape[1]
+    elif X.dim() == 3:
+        batch, n, D = X.shape
+    else:
+        raise ValueError("X must be [n,d] or [N,n,d]")
+    n2 = n if X2 is None else X2.shape[-2]
+    return batch, n, n2, D
+
+
+class _RbfK(torch.autograd.Function):
+    """UnitRBF.K / UnitCsymRBF.K (gp/kernels.py:110-111,122-126)."""
+
+    @staticmethod
+    def forward(ctx, X, X2, ell, csym):
+        X = _c(X); X2c = None if X2 is None else _c(X2); ell = _c(ell).reshape(-1)
+        batch, n, n2, D = _kern_shapes(X, X2c)
+        K = torch.empty((batch, n, n2) if X.dim() == 3 else (n, n2), device=X.device)
+        check(_L().hb_rbf_gram_fwd(ptr(X), ptr(X2c), n, n2, D, batch, ptr(ell), ell.numel(), ptr(K), n2, n * n2, 0.0,
+                                   0, int(csym), stream()), "hb_rbf_gram_fwd")
+        ctx.save_for_backward(X, X2c if X2c is not None else X, ell)
+        ctx.has_x2 = X2 is not None
+        ctx.csym = int(csym)
+        return K
+
+    @staticmethod
+    def backward(ctx, g):
+        X, X2, ell = ctx.saved_tensors
+        if ctx.needs_input_grad[0] or (ctx.has_x2 and ctx.needs_input_grad[1]):
+            raise NotImplementedError("gradient w.r.t. kernel inputs X is not implemented (SparseGP.z is a 'next' row)")
+        batch, n, n2, D = _kern_shapes(X, X2 if ctx.has_x2 else None)
+        g = _c(g)
+        ws = reduce_ws(X.device)
+        gl = torch.empty(ell.numel(), device=X.device)
+        check(_L().hb_rbf_gram_bwd(ptr(g), n2, n * n2, ptr(X), ptr(X2) if ctx.has_x2 else None, n, n2, D, batch,
+                                   ptr(ell), ell.numel(), 0, ctx.csym, None, ptr(gl), ptr(ws), ws.numel(), stream()),
+              "hb_rbf_gram_bwd")
+        return None, None, gl, None
+
+
+def rbf_K(X, X2, ell, csym=False):
+    return _RbfK.apply(X, X2, ell, csym)
+
+
+class _KernCholesky(torch.autograd.Function):
+    """UnitStationary.Cholesky (gp/kernels.py:93-101) fused: Gram (lower tiles) + jitter + blocked
+    potrf in one buffer; backward = reverse-mode Cholesky in place + lengthscale contraction, K is
+    recomputed from X instead of being stored."""
+
+    @staticmethod
+    def forward(ctx, X, ell, jitter, csym):
+        X = _c(X); ell = _c(ell).reshape(-1)
+        batch, n, _, D = _kern_shapes(X, None)
+        Lw = torch.empty((batch, n, n) if X.dim() == 3 else (n, n), device=X.device)
+        lib = _L()
+        check(lib.hb_rbf_gram_fwd(ptr(X), None, n, n, D, batch, ptr(ell), ell.numel(), ptr(Lw), n, n * n, float(jitter),
+                                  1, int(csym), stream()), "hb_rbf_gram_fwd")
+        ws, nb = _potrf_ws(n, X.device)
+        check(lib.hb_potrf_lower(ptr(Lw), n, n * n, n, batch, 1, ptr(ws), nb, ptr(err_flag(X.device)), stream()),
+              "hb_potrf_lower")
+        ctx.save_for_backward(X, ell, Lw)
+        ctx.csym = int(csym)
+        return mark_lower(Lw)
+
+    @staticmethod
+    def backward(ctx, g):
+        X, ell, Lw = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("gradient w.r.t. kernel inputs X is not implemented")
+        batch, n, _, D = _kern_shapes(X, None)
+        G = g.contiguous().clone()
+        lib = _L()
+        ws, nb = _potrf_ws(n, X.device)
+        check(lib.hb_potrf_lower_bwd(ptr(Lw), n, n * n, ptr(G), n, n * n, n, batch, ptr(ws), nb, stream()),
+              "hb_potrf_lower_bwd")
+        rws = reduce_ws(X.device)
+        gl = torch.empty(ell.numel(), device=X.device)
+        check(lib.hb_rbf_gram_bwd(ptr(G), n, n * n, ptr(X), None, n, n, D, batch, ptr(ell), ell.numel(), 1, ctx.csym,
+                                  None, ptr(gl), ptr(rws), rws.numel(), stream()), "hb_rbf_gram_bwd")
+        return None, gl, None, None
+
+
+def kern_cholesky(X, ell, jitter, csym=False):
+    return _KernCholesky.apply(X, ell, jitter, csym)
+
+
+class _TrsmRight(torch.autograd.Function):
+    """X L^{-T} (trans=1) or X L^{-1} (trans=0); forward only is needed by the 'next' rows."""
+
+    @staticmethod
+    def forward(ctx, Lw, Xm, trans):
+        Lw = _c(Lw); out = _c(Xm).clone()
+        m, n = out.shape
+        nb = _L().hb_trsm_workspace_bytes(m, n)
+        ws = torch.empty(nb, dtype=torch.uint8, device=out.device)
+        check(_L().hb_trsm_right_lower(ptr(Lw), n, ptr(out), n, m, n, int(trans), ptr(ws), nb, stream()),
+              "hb_trsm_right_lower")
+        ctx.save_for_backward(Lw, out)
+        ctx.trans = int(trans)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        Lw, out = ctx.saved_tensors
+        # Y = X op(L)^{-1}:  dX = g op(L)^{-T} ; dL = -tril(...) -- computed with the same primitives
+        gx = _TrsmRight.apply(Lw, g, 1 - ctx.trans) if ctx.needs_input_grad[1] else None
+        gl = None
+        if ctx.needs_input_grad[0]:
+            gxx = gx if gx is not None else _TrsmRight.apply(Lw, g, 1 - ctx.trans)
+            # trans=1: Y = X L^{-T} -> dL = -tril(gX^T Y)... ; trans=0: Y = X L^{-1} -> dL = -tril(Y^T gX)
+            A, B = (gxx, out) if ctx.trans == 1 else (out, gxx)
+            n = Lw.shape[0]
+            gl = torch.zeros(n, n, device=Lw.device)
+            gemm_raw(A, B, gl, n, n, A.shape[0], transA=1, alpha=-1.0, c_tri=1)
+        return gl, gx, None
+
+
+def trsm_right(Lw, Xm, trans):
+    return _TrsmRight.apply(Lw, Xm, trans)
+
+
+# --------------------------------------------------------------------------------------------
+# Reparameterised sampler + one-sample KL
+# --------------------------------------------------------------------------------------------
+def _rows_cols(t: torch.Tensor):
+    """View t as [rows, cols] with a uniform row stride; returns (tensor, rows, cols, ld)."""
+    if t.dim() == 0:
+        t = t.reshape(1)
+    cols = t.shape[-1]
+    rows = int(t.numel() // cols) if cols else 0
+    if t.is_contiguous():
+        return t, rows, cols, cols
+    if t.dim() >= 2 and t.stride(-1) == 1:
+        # last-axis slice of a contiguous parent: uniform row stride if leading dims are packed
+        ld = t.stride(-2)
+        ok = True
+        exp = ld * t.shape[-2]
+        for d in range(t.dim() - 3, -1, -1):
+            if t.shape[d] != 1 and t.stride(d) != exp:
+                ok = False
+                break
+            exp *= t.shape[d]
+        if ok:
+            return t, rows, cols, ld
+    t = t.contiguous()
+    return t, rows, cols, cols
+
+
+class _SampleDiag(torch.autograd.Function):
+    """Variational._sample 'diagonal' + Normal-form KL pieces (variationals.py:138-142,183-184,225-230).
+    Returns z [S, *mu.shape] and kl = -0.5*sum(2*omega + eps^2 - z^2)."""
+
+    @staticmethod
+    def forward(ctx, mu, omega, eps, seed, offset, S):
+        mu = _lib.f32(mu); omega = _lib.f32(omega)
+        mu2, rows, cols, ld_mu = _rows_cols(mu)
+        om2, _, _, ld_om = _rows_cols(omega)
+        epsc = None if eps is None else _c(eps)
+        z = torch.empty((S,) + tuple(mu.shape), device=mu.device)
+        kl = torch.empty(1, device=mu.device)
+        ws = reduce_ws(mu.device)
+        check(_L().hb_sample_diag_fwd(ptr(mu2), ld_mu, ptr(om2), ld_om, rows, cols, ptr(epsc), seed, offset, S, ptr(z),
+                                      ptr(kl), ptr(ws), ws.numel(), stream()), "hb_sample_diag_fwd")
+        ctx.save_for_backward(mu2, om2, epsc if epsc is not None else torch.empty(0, device=mu.device))
+        ctx.meta = (rows, cols, ld_mu, ld_om, seed, offset, S, eps is not None, tuple(mu.shape))
+        return z, kl.reshape(())
+
+    @staticmethod
+    def backward(ctx, gz, gkl):
+        mu2, om2, epsc = ctx.saved_tensors
+        rows, cols, ld_mu, ld_om, seed, offset, S, has_eps, shape = ctx.meta
+        gmu = torch.empty(shape, device=mu2.device); gom = torch.empty(shape, device=mu2.device)
+        gzc = None if gz is None else _c(gz)
+        if gkl is None:
+            coef, coef_dev = 0.0, None
+        else:
+            coef, coef_dev = -1.0, _c(gkl.reshape(1))
+        check(_L().hb_sample_diag_bwd(ptr(mu2), ld_mu, ptr(om2), ld_om, rows, cols, ptr(epsc) if has_eps else None, seed,
+                                      offset, S, ptr(gzc), None, coef, ptr(coef_dev), ptr(gmu), cols, ptr(gom), cols,
+                                      0.0, stream()), "hb_sample_diag_bwd")
+        return gmu, gom, None, None, None, None
+
+
+def sample_diag(mu, omega, eps=None, seed=0, offset=0, S=1):
+    return _SampleDiag.apply(mu, omega, eps, int(seed), int(offset), int(S))
+
+
+class _SampleTril(torch.autograd.Function):
+    """Variational._sample 'fullrank' (variationals.py:144-146) + KL with logdet=log(diag^2) (:185-186).
+    mu [B,n], Lq [B,n,n], eps [B,S,n] -> z [B,S,n], kl scalar."""
+
+    @staticmethod
+    def forward(ctx, mu, Lq, eps):
+        mu = _c(mu); Lq = _c(Lq); eps = _c(eps)
+        B, S, n = eps.shape
+        z = torch.empty_like(eps)
+        kl = torch.empty(1, device=mu.device)
+        ws = reduce_ws(mu.device)
+        check(_L().hb_sample_tril_fwd(ptr(mu), ptr(Lq), n, B, ptr(eps), S, ptr(z), ptr(kl), ptr(ws), ws.numel(), stream()),
+              "hb_sample_tril_fwd")
+        ctx.save_for_backward(Lq, eps, z)
+        return z, kl.reshape(())
+
+    @staticmethod
+    def backward(ctx, gz, gkl):
+        Lq, eps, z = ctx.saved_tensors
+        B, S, n = eps.shape
+        c = torch.zeros((), device=z.device) if gkl is None else -gkl       # obj = g(z) - c*KL
+        zt = (-c) * z if gz is None else gz - c * z                        # O(S n) glue
+        zt = zt.contiguous()
+        gmu = zt.sum(1)
+        gL = torch.zeros_like(Lq)
+        gemm_raw(zt, eps, gL, n, n, S, transA=1, c_tri=1, batch=B, sA=S * n, sB=S * n, sC=n * n)
+        d = torch.diagonal(gL, dim1=-2, dim2=-1)
+        d += c * float(S) / torch.diagonal(Lq, dim1=-2, dim2=-1)
+        return gmu, gL, None
+
+
+def sample_tril(mu, Lq, eps):
+    return _SampleTril.apply(mu, Lq, eps)
+
+
+def randn_philox(shape, seed, offset, device):
+    out = torch.empty(shape, device=device)
+    check(_L().hb_randn_philox(ptr(out), out.numel(), int(seed), int(offset), stream()), "hb_randn_philox")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# densities.gaussian
+# --------------------------------------------------------------------------------------------
+def _period(t: torch.Tensor, out_shape) -> Optional[int]:
+    """numel if t broadcasts to out_shape 'modularly' (its shape is a suffix of out_shape), else None."""
+    ts = list(t.shape)
+    while ts and ts[0] == 1:
+        ts = ts[1:]
+    os_ = list(out_shape)
+    if len(ts) <= len(os_) and ts == os_[len(os_) - len(ts):]:
+        return max(1, int(t.numel()))
+    return None
+
+
+class _GaussianLogpdf(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mu, var):
+        shape = torch.broadcast_shapes(x.shape, mu.shape, var.shape)
+        ops_ = []
+        for t in (x, mu, var):
+            t = _lib.f32(t)
+            p = _period(t, shape)
+            if p is None:
+                t = t.expand(shape)
+                p = int(torch.Size(shape).numel())
+            ops_.append((_c(t), p))
+        total = int(torch.Size(shape).numel())
+        out = torch.empty(shape, device=x.device)
+        (xc, xp), (mc, mp), (vc, vp) = ops_
+        check(_L().hb_gaussian_logpdf(ptr(xc), xp, ptr(mc), mp, ptr(vc), vp, total, ptr(out), stream()),
+              "hb_gaussian_logpdf")
+        ctx.save_for_backward(xc, mc, vc)
+        ctx.meta = (xp, mp, vp, total, tuple(shape), tuple(x.shape), tuple(mu.shape), tuple(var.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, mc, vc = ctx.saved_tensors
+        xp, mp, vp, total, shape, xs, ms, vs = ctx.meta
+        g = _c(g.expand(shape))
+        need_mu = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        dmu = torch.empty(shape, device=g.device) if need_mu else None
+        dvar = torch.empty(shape, device=g.device) if ctx.needs_input_grad[2] else None
+        check(_L().hb_gaussian_logpdf_bwd(ptr(xc), xp, ptr(mc), mp, ptr(vc), vp, total, ptr(g), ptr(dmu), ptr(dvar),
+                                          stream()), "hb_gaussian_logpdf_bwd")
+        gx = (-dmu).sum_to_size(xs) if ctx.needs_input_grad[0] else None
+        gm = dmu.sum_to_size(ms) if ctx.needs_input_grad[1] else None
+        gv = dvar.sum_to_size(vs) if ctx.needs_input_grad[2] else None
+        return gx, gm, gv
+
+
+def gaussian_logpdf(x, mu, var):
+    return _GaussianLogpdf.apply(x, mu, var)
+
+
+# --------------------------------------------------------------------------------------------
+# MatBias: act(clip(x w + b))   (nn.py:31-32, 80-84)
+# --------------------------------------------------------------------------------------------
+class _MatBias(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act, clip, lo, hi):
+        x = _c(x); w = _c(w); b = _c(b)
+        K, N = w.shape[-2:]
+        nb = int(w.numel() // (K * N))
+        if w.dim() == 2:
+            rows = int(x.numel() // K)
+            out = torch.empty(*x.shape[:-1], N, device=x.device)
+            gemm_raw(x, w, out, rows, N, K, bias=b.reshape(-1), act=act, clip=clip, lo=lo, hi=hi)
+        else:
+            if x.shape[:-2] != w.shape[:-2]:
+                raise ValueError(f"MatBias: leading axes of x {tuple(x.shape)} must equal n_layers {tuple(w.shape[:-2])}")
+            rows = x.shape[-2]
+            out = torch.empty(*x.shape[:-1], N, device=x.device)
+            gemm_raw(x, w, out, rows, N, K, batch=nb, sA=rows * K, sB=K * N, sC=rows * N, bias=b.reshape(-1), sBias=N,
+                     act=act, clip=clip, lo=lo, hi=hi)
+        ctx.save_for_backward(x, w, out)
+        ctx.meta = (act, clip, lo, hi, nb, rows, K, N, tuple(b.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, out = ctx.saved_tensors
+        act, clip, lo, hi, nb, rows, K, N, bshape = ctx.meta
+        g = _c(g)
+        lib = _L()
+        dz = torch.empty_like(out)
+        db = torch.empty(bshape, device=g.device)
+        for i in range(nb):
+            off = i * rows * N
+            check(lib.hb_act_bwd_colsum(C.c_void_p(g.data_ptr() + 4 * off), C.c_void_p(out.data_ptr() + 4 * off),
+                                        C.c_void_p(dz.data_ptr() + 4 * off), rows, N, N, act, clip, lo, hi,
+                                        C.c_void_p(db.data_ptr() + 4 * i * N), stream()), "hb_act_bwd_colsum")
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            gemm_raw(dz, w, gx, rows, K, N, transB=1, batch=nb, sA=rows * N, sB=K * N, sC=rows * K)
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty_like(w)
+            gemm_raw(x, dz, gw, K, N, rows, transA=1, batch=nb, sA=rows * K, sB=rows * N, sC=K * N)
+        return gx, gw, db, None, None, None, None
+
+
+def matbias(x, w, b, act="none", clip=False, lo=-50.0, hi=50.0):
+    a = ACT[act]
+    if clip and a != 0:
+        # clip precedes the activation in the reference; keep its gradient mask exact by splitting
+        y = _MatBias.apply(x, w, b, 0, 1, float(lo), float(hi))
+        return {1: torch.sigmoid, 2: torch.relu, 3: torch.tanh}[a](y)
+    return _MatBias.apply(x, w, b, a, int(bool(clip)), float(lo), float(hi))
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """dst[i] = src[index[i]] on device (MinibatchData.get_feed_dict, param.py:733-739)."""
+    src = _c(src)
+    idx = index.to(device=src.device, dtype=torch.int64).contiguous()
+    row = int(src.numel() // src.shape[0]) if src.shape[0] else 0
+    out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), device=src.device)
+    check(_L().hb_gather_rows(ptr(out), ptr(src), ptr(idx), idx.numel(), row, stream()), "hb_gather_rows")
+    return out
+
+
+def adam_tf1_(theta, grad, m, v, step_dev, lr, b1, b2, eps, grad_scale=-1.0):
+    check(_L().hb_adam_tf1(ptr(theta), ptr(grad), ptr(m), ptr(v), theta.numel(), float(grad_scale), float(lr), float(b1),
+                           float(b2), float(eps), ptr(step_dev), 0, stream()), "hb_adam_tf1")

@@ -61,11 +61,13 @@ int hb_randn_philox(float* out, long long count, unsigned long long seed, unsign
 int hb_sample_diag_fwd(const float* mu, long long ld_mu, const float* omega, long long ld_omega, int rows, int cols,
                        const float* eps, unsigned long long seed, unsigned long long offset, int S, float* z,
                        float* kl_out, void* ws, size_t ws_bytes, void* stream);
-/* Backward of the above for an objective  obj = g(z) - kl_coef*KL :  zbar = dg/dz [S,rows,cols]
- * (NULL = 0), optionally multiplied by the device scalar *zbar_scale.  g* = beta*g* + grad. */
+/* Backward of the above for an objective  obj = g(z) - c*KL, c = kl_coef * (*kl_coef_dev if non-NULL):
+ * zbar = dg/dz [S,rows,cols] (NULL = 0), optionally multiplied by the device scalar *zbar_scale.
+ * g* = beta*g* + grad. */
 int hb_sample_diag_bwd(const float* mu, long long ld_mu, const float* omega, long long ld_omega, int rows, int cols,
                        const float* eps, unsigned long long seed, unsigned long long offset, int S,
-                       const float* zbar, const float* zbar_scale, float kl_coef, float* gmu, long long ld_gmu,
+                       const float* zbar, const float* zbar_scale, float kl_coef, const float* kl_coef_dev, float* gmu,
+                       long long ld_gmu,
                        float* gomega, long long ld_gomega, float beta, void* stream);
 
 /* Variational._sample 'fullrank' (variationals.py:144-146): z[b,s,:] = mu[b,:] + tril(Lq[b]) eps[b,s,:].
@@ -81,6 +83,14 @@ int hb_sample_tril_bwd(const float* Lq, int n, int batch, const float* eps, cons
  * out[i] = logN(x[i % x_period]; mu[i % mu_period], var[i % var_period]). */
 int hb_gaussian_logpdf(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
                        long long var_period, long long total, float* out, void* stream);
+/* Backward of hb_gaussian_logpdf: dmu[i] = g[i]*dlogN/dmu, dvar[i] = g[i]*dlogN/dvar (full size; the
+ * caller reduces over broadcast axes; dlogN/dx = -dlogN/dmu).  dmu / dvar may be NULL. */
+int hb_gaussian_logpdf_bwd(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
+                           long long var_period, long long total, const float* g, float* dmu, float* dvar,
+                           void* stream);
+/* MinibatchData.get_feed_dict (param.py:733-739) on device: dst[i,:] = src[index[i],:], index int64. */
+int hb_gather_rows(float* dst, const float* src, const long long* index, long long n_index, long long row_elems,
+                   void* stream);
 /* reduce_sum(densities.gaussian(y, f_scale*f, var)) fused with the residual for the backward.
  * f: [total]; y: [y_period] broadcast; var, f_scale: device scalars (f_scale may be NULL = 1).
  * resid (may be NULL) = -rcoef*(f_scale*f - y)/var.  out3 = {loglik, sum E^2, sum E*(f_scale*f)}. */

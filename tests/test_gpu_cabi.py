@@ -168,7 +168,7 @@ def test_sample_diag_fwd_bwd(lib, S, rows, cols, strided):
     assert abs(kl.item() - kl_ref.item()) <= 1e-5 * max(1.0, abs(kl_ref.item()))
     obj = torch.sum(z_ref * torch.tensor(zbar)) - c * kl_ref
     obj.backward()
-    rc = lib.hb_sample_diag_bwd(P(mu_d), ld, P(om_d), ld, rows, cols, P(dev(eps)), 0, 0, S, P(dev(zbar)), None, c,
+    rc = lib.hb_sample_diag_bwd(P(mu_d), ld, P(om_d), ld, rows, cols, P(dev(eps)), 0, 0, S, P(dev(zbar)), None, c, None,
                                 P(gmu_d), ldg, P(gom_d), ldg, 0.0, ST())
     assert rc == 0
     torch.cuda.synchronize()
@@ -191,8 +191,8 @@ def test_sample_diag_philox_matches_materialised_eps(lib):
     assert lib.hb_sample_diag_fwd(P(mu), n, P(om), n, 1, n, None, 42, 16, S, P(z2), P(k2), P(ws), ws.numel(), ST()) == 0
     zb = dev(rng.randn(S, n))
     g = [torch.zeros(1, n, device="cuda") for _ in range(4)]
-    assert lib.hb_sample_diag_bwd(P(mu), n, P(om), n, 1, n, P(eps), 0, 0, S, P(zb), None, 0.125, P(g[0]), n, P(g[1]), n, 0.0, ST()) == 0
-    assert lib.hb_sample_diag_bwd(P(mu), n, P(om), n, 1, n, None, 42, 16, S, P(zb), None, 0.125, P(g[2]), n, P(g[3]), n, 0.0, ST()) == 0
+    assert lib.hb_sample_diag_bwd(P(mu), n, P(om), n, 1, n, P(eps), 0, 0, S, P(zb), None, 0.125, None, P(g[0]), n, P(g[1]), n, 0.0, ST()) == 0
+    assert lib.hb_sample_diag_bwd(P(mu), n, P(om), n, 1, n, None, 42, 16, S, P(zb), None, 0.125, None, P(g[2]), n, P(g[3]), n, 0.0, ST()) == 0
     torch.cuda.synchronize()
     assert torch.equal(z1, z2) and torch.equal(k1, k2)
     assert torch.equal(g[0], g[2]) and torch.equal(g[1], g[3])
