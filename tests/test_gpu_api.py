@@ -139,12 +139,12 @@ def test_K_all_variants(kern_model):               # test_kernels.py:90-182 (ato
     with m.tf_mode():
         for A, B in ((X, None), (X, X2), (Xb, None), (Xb, X2b)):
             Bn = A if B is None else B
-            K1 = m.k1.K(A, B).cpu().numpy(); K2 = m.k2.K(A, B).cpu().numpy(); K3 = m.k3.K(A, B).cpu().numpy()
+            K1 = m.k1.K(A, B).detach().cpu().numpy(); K2 = m.k2.K(A, B).detach().cpu().numpy(); K3 = m.k3.K(A, B).detach().cpu().numpy()
             assert np.allclose(K1, np.exp(-0.5 * ref_sqdist(A, Bn, l1)), atol=1e-5)
             assert np.allclose(K2, np.exp(-0.5 * ref_sqdist(A, Bn, l2)), atol=1e-5)
             assert np.allclose(K3, np.exp(-0.5 * ref_sqdist(A, Bn, l1)) + np.exp(-0.5 * ref_sqdist(A, -Bn, l1)), atol=1e-5)
-        assert np.allclose(m.k1.Kdiag(torch.as_tensor(X).cuda()).cpu().numpy(), np.ones(5))
-        assert np.allclose(m.k1.K(X).cpu().numpy(), m.k1.K(X.reshape(1, -1, 2)).cpu().numpy()[0])   # :110-123
+        assert np.allclose(m.k1.Kdiag(torch.as_tensor(X).cuda()).detach().cpu().numpy(), np.ones(5))
+        assert np.allclose(m.k1.K(X).detach().cpu().numpy(), m.k1.K(X.reshape(1, -1, 2)).detach().cpu().numpy()[0])   # :110-123
         # gradients exist (test_kernels.py:134-139)
         loss = tf.reduce_sum(m.k2.K(X, X2))
         g = torch.autograd.grad(loss, m.get_tf_variables(), allow_unused=True)
@@ -156,10 +156,10 @@ def test_cholesky(kern_model):                     # test_kernels.py:184-226
     j = hb.settings.numerics.jitter_level
     with m.tf_mode():
         for k in (m.k1, m.k2, m.k3):
-            K = k.K(X).cpu().numpy(); L = k.Cholesky(X).cpu().numpy()
+            K = k.K(X).detach().cpu().numpy(); L = k.Cholesky(X).detach().cpu().numpy()
             assert L.shape == (5, 5) and np.allclose(np.triu(L, 1), 0)
             assert np.allclose(K + j * np.eye(5), L @ L.T, atol=1e-5)
-            Kb = k.K(Xb).cpu().numpy(); Lb = k.Cholesky(Xb).cpu().numpy()
+            Kb = k.K(Xb).detach().cpu().numpy(); Lb = k.Cholesky(Xb).detach().cpu().numpy()
             assert Lb.shape == (10, 5, 5)
             for i in range(10):
                 assert np.allclose(Kb[i] + j * np.eye(5), Lb[i] @ Lb[i].T, atol=1e-5)
@@ -169,7 +169,7 @@ def test_cholesky(kern_model):                     # test_kernels.py:184-226
         t = torch.tensor(np.log(np.expm1(l1 - 1e-6)), dtype=torch.float64, requires_grad=True)
         Lr = O.kern_cholesky(torch.tensor(X), O.log1pe_forward(t), j)
         Lr.sum().backward()
-        got = [x for x in g if x is not None][0].cpu().numpy()
+        got = [x for x in g if x is not None][0].detach().cpu().numpy()
         assert rel_err(got, t.grad.numpy()) < 1e-3      # 5 nearly collinear 2-D points: cond-limited in fp32
 
 
@@ -212,7 +212,7 @@ def test_nn_gradients_match_oracle():
                       [d['model.nn.matbias0.b'], d['model.nn.matbias1.b']], ['tanh'])
     (yr ** 2).sum().backward()
     for a, b in zip(g, tp):
-        assert rel_err(a.cpu().numpy(), b.grad.numpy()) < 1e-5
+        assert rel_err(a.detach().cpu().numpy(), b.grad.numpy()) < 1e-5
 
 
 # ------------------------------------------------------------------ model / Adam (test_model.py)
@@ -372,7 +372,7 @@ def test_amortised_model_matches_oracle():
     pairs = [('var', m.var)] + [(f'enc.w{i}', m.enc[i].w) for i in range(2)] + [(f'enc.b{i}', m.enc[i].b) for i in range(2)] \
         + [(f'dec.w{i}', m.dec[i].w) for i in range(2)] + [(f'dec.b{i}', m.dec[i].b) for i in range(2)]
     for name, var in pairs:
-        assert rel_err(var._tensor.grad.cpu().numpy(), gref[name]) < 2e-5, name
+        assert rel_err(var._tensor.grad.detach().cpu().numpy(), gref[name]) < 2e-5, name
     m.ELBO().optimize(maxiter=3, minibatch_size=B)      # the minibatch path runs end to end
 
 
@@ -407,4 +407,4 @@ def test_linear_operator_model_matches_oracle():
     ref, gref = O.value_and_grads(O.linear_operator_elbo, p, A.astype(np.float64), y.astype(np.float64), U.astype(np.float64))
     assert abs(float(val) - ref) <= 1e-5 * abs(ref)
     for name, var in (('q_mu', m.q.q_mu), ('q_sqrt', m.q.q_sqrt), ('var', m.var)):
-        assert rel_err(var._tensor.grad.cpu().numpy(), gref[name]) < 2e-5, name
+        assert rel_err(var._tensor.grad.detach().cpu().numpy(), gref[name]) < 2e-5, name

@@ -1,0 +1,128 @@
+"""CPU-side logic of the Henbun-shaped API mirror (no GPU, no kernels): parameter tree, naming,
+assignment, LOCAL feed sizes, settings, transforms, Indexer, and the "no silent fallback" rule.
+Ports of testing/test_param.py, test_data.py, test_transforms.py, test_model.py host-side checks."""
+import numpy as np
+import pytest
+import torch
+
+import henbun_b200 as hb
+
+
+def test_tree_names_and_parents():                   # test_param.py naming / parent links
+    m = hb.model.Model()
+    m.p = hb.param.Variable([2, 3])
+    m.k = hb.gp.kernels.UnitRBF(np.ones(2))
+    m.q = hb.variationals.Gaussian([4, 1], q_shape='fullrank')
+    assert m.p.long_name == 'model.p' and m.k.lengthscales.long_name == 'model.k.lengthscales'
+    assert m.q.q_mu._parent is m.q and m.q._parent is m and m.p.highest_parent is m
+    names = [v.long_name for v in m.get_variables()]
+    assert names == ['model.k.lengthscales', 'model.p', 'model.q.q_mu', 'model.q.q_sqrt', 'model.q.scale']   # name-sorted
+    assert m.q.q_sqrt.shape == [4, 4] and m.q.size == 4
+
+
+def test_truncated_normal_init_range():              # test_param.py:286-296
+    v = hb.param.Variable([2000], mean=1.0, stddev=0.5)
+    assert v._host.dtype == np.float32
+    assert np.all(np.abs(v._host - 1.0) <= 2 * 0.5 + 1e-6)
+    assert abs(v._host.mean() - 1.0) < 0.05
+
+
+def test_assignment_is_deferred_until_initialize():  # test_model.py:53-59, param.py docstring
+    m = hb.model.Model()
+    m.p = hb.param.Variable([2, 1])
+    m.initialize()
+    m.p = np.zeros((2, 1))
+    assert m.p._assigned
+    m.initialize()
+    assert not m.p._assigned and np.allclose(m.p.value, 0)
+    m.s = hb.param.Variable([1], transform=hb.transforms.positive)
+    m.s = 2.5
+    assert np.allclose(m.s.value, 2.5, atol=1e-5)            # stored in free space, read back transformed
+    assert np.allclose(m.s._free_numpy(), np.log(np.expm1(2.5 - 1e-6)), atol=1e-5)
+
+
+def test_variational_initialisation_rules():        # variationals.py:84-96, 266-273
+    g = hb.variationals.Gaussian([3], mean=0.1, stddev=2.0)
+    assert abs(g.q_mu._host.mean() - 0.05) < 0.3 and abs(g.q_sqrt._host.mean() - 0.0) < 0.3      # log(1)=0
+    g2 = hb.variationals.Gaussian([3], mean=5.0, stddev=1.0)                                     # |mean| >= stddev
+    assert abs(g2.q_mu._host.mean() - 1.0) < 0.1 and abs(g2.q_sqrt._host.mean() - np.log(0.2)) < 0.3
+    f = hb.variationals.Normal([5], q_shape='fullrank', stddev=0.5)
+    assert f.q_sqrt._host.shape == (5, 5) and np.all(f.q_sqrt._host > 0)                        # every entry ~ stddev
+    with pytest.raises(AssertionError):
+        hb.variationals.Normal([5], q_shape='lowrank')
+
+
+def test_local_feed_sizes_and_einsum_strings():      # test_variationals.py:15-24, param.py:281-289
+    LOCAL = hb.param.graph_key.LOCAL
+    v = hb.variationals.Normal((2, 3), n_layers=[2, 3], q_shape='fullrank')
+    vl = hb.variationals.Normal((2, 3), n_layers=[2, 3], q_shape='fullrank', collections=LOCAL)
+    assert v._einsum_matmul() == 'abcd,abd->abc' and vl._einsum_matmul() == 'abcde,abce->abcd'
+    assert vl.feed_size == 6 + 36 and v.feed_size == 0
+    d = hb.variationals.Gaussian([4], collections=LOCAL)
+    assert d.feed_size == 4 + 4 + 1                                     # q_mu | q_sqrt | scale, name-sorted
+    assert d.get_variables(LOCAL) and not d.get_variables(hb.param.graph_key.VARIABLES)
+    assert d.KL(hb.param.graph_key.VARIABLES).shape == ()               # zero for another collection
+
+
+def test_data_and_minibatch_data():                  # test_data.py, test_model.py:116-135
+    m = hb.model.Model()
+    m.d = hb.param.Data(np.arange(6.0).reshape(3, 2))
+    assert np.array_equal(m.d.value, np.arange(6.0).reshape(3, 2))
+    m.d = np.ones((3, 2))
+    assert np.array_equal(m.d.value, np.ones((3, 2)))
+    with pytest.raises(ValueError):
+        m.d = np.ones((4, 2))                                           # param.py:712-713
+    with pytest.raises(NotImplementedError):
+        hb.param.Data(np.array(['a']))
+    m.mb = hb.param.MinibatchData(np.zeros((100, 3)))
+    m.validate()
+    assert m._index.data_size == 100 and m._index.train_size == 90 and m._index.test_size == 10
+    idx = m._index.train_index(7)
+    assert idx.shape == (7,) and set(idx) <= set(m._index._train_index)
+    assert set(m._index.test_index(5)) <= set(m._index._test_index)
+    m.mb2 = hb.param.MinibatchData(np.zeros((50, 3)))
+    with pytest.raises(ValueError):
+        m.validate()                                                    # model.py:113
+
+
+def test_settings_temp_context():                    # _settings.py:26-63, Expert_GPR.ipynb:203,224
+    assert hb.settings.numerics.jitter_level == 1e-5 and hb.settings.numerics.clip_by_value is False
+    assert hb.settings.dtypes.float_type == 'float32'
+    cfg = hb.settings.get_settings()
+    cfg.numerics.jitter_level = 3e-4
+    with hb.settings.temp_settings(cfg):
+        assert hb.settings.numerics.jitter_level == 3e-4
+    assert hb.settings.numerics.jitter_level == 1e-5
+
+
+def test_transforms_numpy_roundtrip():               # test_transforms.py:49-53
+    x = np.random.RandomState(0).randn(10)
+    for t in (hb.transforms.Identity(), hb.transforms.Exp(), hb.transforms.Log1pe(), hb.transforms.Logistic(7.3, 19.4)):
+        assert np.allclose(t.backward(t.forward(x)), x, atol=1e-4)
+        xt = torch.tensor(x)
+        assert np.allclose(t.tf_forward(xt).numpy(), t.forward(x), atol=1e-12)      # test_transforms.py:39-47
+    assert hb.transforms.positive.__class__ is hb.transforms.Log1pe
+
+
+def test_paramlist_and_aliases():
+    pl = hb.param.ParamList([hb.param.Variable([1]), hb.param.Variable([2])])
+    assert len(pl) == 2 and pl[0].name == 'item0'
+    pl.append(hb.param.Variable([3]))
+    assert pl[2].name == 'item2'
+    assert hb.param.Param is hb.param.Variable and hb.gp.kern.RBF is hb.gp.kernels.UnitRBF
+    assert hb.gp.kern.Stationary is hb.gp.kernels.UnitStationary
+
+
+def test_no_silent_cpu_fallback():
+    """Evaluating anything needs the CUDA library and a device; without a GPU it must raise, not fall back."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = hb.model.Model()
+    m.q = hb.variationals.Normal([3])
+    with pytest.raises(Exception) as e:
+        with m.tf_mode():
+            m.q
+    assert 'CUDA' in str(e.value) or 'cuda' in str(e.value)
+    from henbun_b200 import _lib
+    with pytest.raises(_lib.HenbunB200Error):
+        _lib.ptr(torch.zeros(3))
