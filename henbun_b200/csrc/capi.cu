@@ -296,6 +296,17 @@ int hb_gemm(const float* A, long long lda, long long strideA, int transA, int a_
   return gemm(g, S(stream));
 }
 
+size_t hb_gemm_tc_workspace_bytes(int M, int N, int K) { return gemm_tc_workspace_bytes(M, N, K); }
+int hb_set_tc_option(int v) { set_tc_option(v); return HB_OK; }
+int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int c_tri, int M,
+                  int N, int K, float alpha, float beta, void* ws, size_t ws_bytes, void* stream) {
+  GemmParams g;
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.transB = 1; g.C = C; g.ldc = ldc; g.c_tri = c_tri;
+  g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.ws = ws; g.ws_bytes = ws_bytes;
+  if (!gemm_tc_eligible(g)) return HB_ERR_ARG;
+  return gemm_tc(g, S(stream));
+}
+
 int hb_act_bwd_colsum(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act, int clip,
                       float clip_lo, float clip_hi, float* dbias, void* stream) {
   return act_bwd_colsum(dy, y, dz, rows, cols, ld, act, clip, clip_lo, clip_hi, dbias, S(stream));

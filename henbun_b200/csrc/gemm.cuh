@@ -27,12 +27,16 @@ struct GemmParams {
   int act = ACT_NONE;
   int clip = 0;
   float clip_lo = -50.f, clip_hi = 50.f;
+  void* ws = nullptr;      // optional scratch for the tcgen05 engine (hi/lo operand copies)
+  size_t ws_bytes = 0;
 };
 
 // precision/engine selection: 0 = auto (tensor cores when the shape qualifies), 1 = force SIMT fp32,
 // 2 = force tcgen05 3xTF32 (error if the shape does not qualify)
 int gemm(const GemmParams& p, cudaStream_t stream);
 int gemm_simt(const GemmParams& p, cudaStream_t stream);
+size_t gemm_tc_workspace_bytes(int M, int N, int K);
+void set_tc_option(int v);
 void set_gemm_engine(int mode);
 int get_gemm_engine();
 

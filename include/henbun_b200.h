@@ -134,6 +134,14 @@ int hb_gemm(const float* A, long long lda, long long strideA, int transA, int a_
             long long strideB, int transB, int b_tri, float* C, long long ldc, long long strideC, int c_tri, int M,
             int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
             int clip, float clip_lo, float clip_hi, void* stream);
+/* The tcgen05 3xTF32 engine directly: C[M,N] = alpha*A[M,K]*B[N,K]^T + beta*C (both operands K-major), fp32-grade
+ * accuracy from three TF32 tensor-core passes.  Needs M,N >= 128, K >= 32, lda/ldb multiples of 4, 16-byte aligned
+ * A/B and a workspace of hb_gemm_tc_workspace_bytes(M,N,K); returns HB_ERR_ARG otherwise.
+ * hb_set_tc_option bit0: feed the raw fp32 operand as the "hi" TF32 operand (experiment). */
+size_t hb_gemm_tc_workspace_bytes(int M, int N, int K);
+int hb_set_tc_option(int v);
+int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int c_tri, int M,
+                  int N, int K, float alpha, float beta, void* ws, size_t ws_bytes, void* stream);
 /* Backward helper of MatBias: dz = dy * act'(y) (through the output y), dbias[c] = sum_r dz[r,c]. */
 int hb_act_bwd_colsum(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act,
                       int clip, float clip_lo, float clip_hi, float* dbias, void* stream);
