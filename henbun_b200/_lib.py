@@ -61,6 +61,8 @@ SIGNATURES = {
     "hb_trsm_right_lower": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _i, _c_f, _sz, _c_f]),
     "hb_gemm": (_i, [_c_f, _ll, _ll, _i, _i, _c_f, _ll, _ll, _i, _i, _c_f, _ll, _ll, _i, _i, _i, _i, _i, _fl, _fl,
                      _c_f, _ll, _i, _i, _fl, _fl, _c_f]),
+    "hb_gemm_ws": (_i, [_c_f, _ll, _ll, _i, _i, _c_f, _ll, _ll, _i, _i, _c_f, _ll, _ll, _i, _i, _i, _i, _i, _fl, _fl,
+                        _c_f, _ll, _i, _i, _fl, _fl, _c_f, _sz, _c_f]),
     "hb_gemm_tc_workspace_bytes": (_sz, [_i, _i, _i]),
     "hb_set_tc_option": (_i, [_i]),
     "hb_gemm_tn_tc": (_i, [_c_f, _ll, _c_f, _ll, _c_f, _ll, _i, _i, _i, _i, _fl, _fl, _c_f, _sz, _c_f]),

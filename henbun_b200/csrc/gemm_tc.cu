@@ -80,9 +80,19 @@ struct TcParams {
   int M, N, K;
   float alpha, beta;
   int c_tri;
+  int a_mode, b_mode;   // triangular structure in (row, k) space: 1 k<=r, 2 k>=r, 3 k>r, 4 k<r (elements are zeroed
+                        // by the split pass; here the modes only trim the k-range of each tile)
   int tiles_m, tiles_n;
   int vecC;
 };
+
+// k-block range [lo, hi) that can hold non-zeros for a tile whose rows start at r0 (extent ext)
+__device__ __forceinline__ void trim_range(int mode, int r0, int ext, int& lo, int& hi) {
+  if (mode == 1) hi = min(hi, (r0 + ext + BK - 1) / BK);            // k <= r  -> k < r0+ext
+  else if (mode == 2) lo = max(lo, r0 / BK);                          // k >= r
+  else if (mode == 3) lo = max(lo, (r0 + 1) / BK);                    // k >  r
+  else if (mode == 4) hi = min(hi, (r0 + ext - 1 + BK - 1) / BK);   // k <  r  -> k < r0+ext-1
+}
 
 template <int BN, int NSTAGE>
 struct Smem {
@@ -130,7 +140,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
   if (p.c_tri == 1 && n0 > m0 + BM - 1) return;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_k = (p.K + BK - 1) / BK;
+  int kb_lo = 0, kb_hi = (p.K + BK - 1) / BK;
+  trim_range(p.a_mode, m0, BM, kb_lo, kb_hi);
+  trim_range(p.b_mode, n0, BN, kb_lo, kb_hi);
+  const int num_k = max(kb_hi - kb_lo, 0);
   const int num_c = (num_k + CH - 1) / CH;
 
   if (warp == 0 && lane == 0) {
@@ -155,7 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t st = base + s * S::STAGE_BYTES;
         mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
-        const int k0 = kb * BK;
+        const int k0 = (kb_lo + kb) * BK;
         tma_load_2d(st, &tmAhi, full_bar(s), k0, m0);
         tma_load_2d(st + A_TILE_BYTES, &tmAlo, full_bar(s), k0, m0);
         tma_load_2d(st + 2 * A_TILE_BYTES, &tmBhi, full_bar(s), k0, n0);
@@ -267,28 +280,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
   }
 }
 
-// hi = a & 0xFFFFE000 (exactly representable in TF32), lo = a - hi (exact in fp32)
-__global__ void split_tf32_kernel(const float* __restrict__ src, long long lds, int rows, int cols, float* hi, float* lo,
-                                  long long ldw, int write_hi) {
-  const int c4 = (cols + 3) / 4;
+// ---- operand preparation: hi = a & 0xFFFFE000 (what the tf32 MMA reads from a raw fp32 word), lo = rna_tf32(a - hi) ----
+__device__ __forceinline__ bool tri_keep(int mode, long long r, long long k) {
+  return mode == 0 || (mode == 1 && k <= r) || (mode == 2 && k >= r) || (mode == 3 && k > r) || (mode == 4 && k < r);
+}
+__device__ __forceinline__ void split1(float v, float& h, float& l) {
+  h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  float d = v - h;                                   // exact
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(d));
+  l = __uint_as_float(t);
+}
+
+// source stored [rows x K] (K-major): element (r,k) = src[r*lds + k]
+__global__ void split_kmajor_kernel(const float* __restrict__ src, long long lds, int rows, int K, float* hi, float* lo,
+                                    long long ldw, int write_hi, int mode) {
+  const int c4 = (K + 3) / 4;
   const long long total = (long long)rows * c4;
+  const bool vec = ((lds & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long r = e / c4; const int c = (int)(e % c4) * 4;
     float v[4], h[4], l[4];
-    if (c + 3 < cols) {
+    if (vec && c + 3 < K) {
       const float4 t = *reinterpret_cast<const float4*>(src + r * lds + c);
       v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = (c + k < cols) ? src[r * lds + c + k] : 0.f;
+      for (int k = 0; k < 4; ++k) v[k] = (c + k < K) ? src[r * lds + c + k] : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      h[k] = __uint_as_float(__float_as_uint(v[k]) & 0xFFFFE000u);
-      l[k] = v[k] - h[k];
+      if (!tri_keep(mode, r, c + k)) v[k] = 0.f;
+      split1(v[k], h[k], l[k]);
     }
     if (write_hi) *reinterpret_cast<float4*>(hi + r * ldw + c) = make_float4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<float4*>(lo + r * ldw + c) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// source stored [K x rows] (row-index-major): element (r,k) = src[k*lds + r]; outputs K-major.  32x32 smem transpose.
+__global__ void split_transpose_kernel(const float* __restrict__ src, long long lds, int rows, int K, float* hi, float* lo,
+                                       long long ldw, int mode) {
+  __shared__ float t[32][33];
+  const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int k = k0 + j, r = r0 + threadIdx.x;
+    t[j][threadIdx.x] = (k < K && r < rows) ? src[(long long)k * lds + r] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, k = k0 + threadIdx.x;
+    if (r < rows && k < (int)ldw) {
+      float v = (k < K && tri_keep(mode, r, k)) ? t[threadIdx.x][j] : 0.f;
+      float h, l;
+      split1(v, h, l);
+      hi[(long long)r * ldw + k] = h;
+      lo[(long long)r * ldw + k] = l;
+    }
   }
 }
 
@@ -318,7 +366,7 @@ int make_map(CUtensorMap* map, const float* ptr, long long rows, long long cols,
   return r == CUDA_SUCCESS ? HB_OK : HB_ERR_CUDA;
 }
 
-int g_tc_option = 0;   // bit0: write an explicit masked "hi" copy instead of feeding the raw fp32 operand (measured: the
+int g_tc_option = 0;   // bit0: always write an explicit "hi" copy instead of feeding the raw fp32 operand (measured: the
                        // tf32 MMA ignores the 13 low mantissa bits, results are bit-identical)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -340,6 +388,29 @@ int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& b
   return HB_OK;
 }
 
+// One operand -> (hi, lo) K-major views.  `kmajor`: stored [rows x K]; otherwise stored [K x rows].
+struct Prepared { const float* hi; long long ld_hi; const float* lo; long long ld_lo; };
+
+int prepare_operand(const float* src, long long ld, int rows, int K, bool kmajor, int mode, float*& w, Prepared& out,
+                    cudaStream_t st) {
+  const long long kp = ((long long)K + 3) / 4 * 4;
+  const bool raw_hi = kmajor && mode == 0 && !(g_tc_option & 1) && aligned16(src) && (ld % 4 == 0);
+  float* hi = nullptr;
+  if (!raw_hi) { hi = w; w += (long long)rows * kp; }
+  float* lo = w; w += (long long)rows * kp;
+  if (kmajor) {
+    const long long tot = (long long)rows * (kp / 4);
+    int nb = (int)((tot + 255) / 256); if (nb > 148 * 8) nb = 148 * 8; if (nb < 1) nb = 1;
+    split_kmajor_kernel<<<nb, 256, 0, st>>>(src, ld, rows, K, hi, lo, kp, !raw_hi, mode);
+  } else {
+    dim3 grid((unsigned)cdiv(rows, 32), (unsigned)cdiv(kp, 32));
+    split_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, ld, rows, K, hi, lo, kp, mode);
+  }
+  HB_CHECK_LAUNCH();
+  out.hi = raw_hi ? src : hi; out.ld_hi = raw_hi ? ld : kp; out.lo = lo; out.ld_lo = kp;
+  return HB_OK;
+}
+
 }  // namespace
 
 void set_tc_option(int v) { g_tc_option = v; }
@@ -349,50 +420,35 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K) {
   return (size_t)(2 * ((long long)M + N) * kp) * sizeof(float) + 512;
 }
 
+// Shapes worth a tensor-core launch (plus its operand-preparation passes); everything else stays on the SIMT engine.
 bool gemm_tc_eligible(const GemmParams& p) {
   if (get_gemm_engine() == 1) return false;
-  if (p.transA != 0 || p.transB != 1 || p.a_tri || p.b_tri || p.batch != 1) return false;
-  if (p.bias || p.act != ACT_NONE || p.clip) return false;
+  if (p.batch != 1 || p.bias || p.act != ACT_NONE || p.clip) return false;
   if (p.M < 128 || p.N < 128 || p.K < 32) return false;
-  if ((p.lda & 3) || (p.ldb & 3) || !aligned16(p.A) || !aligned16(p.B)) return false;
+  if (get_gemm_engine() != 2 && (double)p.M * p.N * p.K < 256.0 * 256.0 * 256.0) return false;
   if (!p.ws || p.ws_bytes < gemm_tc_workspace_bytes(p.M, p.N, p.K)) return false;
   return true;
 }
 
 int gemm_tc(const GemmParams& p, cudaStream_t st) {
-  const long long kp = ((long long)p.K + 3) / 4 * 4;
   float* w = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.ws) + 255) & ~uintptr_t(255));
-  const bool same = (p.A == p.B && p.lda == p.ldb && p.M == p.N);
-  const int raw_hi = !(g_tc_option & 1);
-  float* a_hi = w; float* a_lo = a_hi + (long long)p.M * kp;
-  float* b_hi = same ? a_hi : a_lo + (long long)p.M * kp;
-  float* b_lo = same ? a_lo : b_hi + (long long)p.N * kp;
-  {
-    const long long tot = (long long)p.M * (kp / 4);
-    int nb = (int)((tot + 255) / 256); if (nb > 148 * 8) nb = 148 * 8; if (nb < 1) nb = 1;
-    split_tf32_kernel<<<nb, 256, 0, st>>>(p.A, p.lda, p.M, p.K, a_hi, a_lo, kp, !raw_hi);
-    HB_CHECK_LAUNCH();
-    if (!same) {
-      const long long tb = (long long)p.N * (kp / 4);
-      int nb2 = (int)((tb + 255) / 256); if (nb2 > 148 * 8) nb2 = 148 * 8; if (nb2 < 1) nb2 = 1;
-      split_tf32_kernel<<<nb2, 256, 0, st>>>(p.B, p.ldb, p.N, p.K, b_hi, b_lo, kp, !raw_hi);
-      HB_CHECK_LAUNCH();
-    }
-  }
+  static const int b2rk[5] = {0, 2, 1, 4, 3};      // mask of op(B)[k][n] expressed in (n, k) space
+  const int a_mode = p.a_tri, b_mode = b2rk[p.b_tri];
+  const bool a_kmajor = (p.transA == 0), b_kmajor = (p.transB == 1);
+  const bool same = (p.A == p.B && p.lda == p.ldb && p.M == p.N && a_kmajor == b_kmajor && a_mode == b_mode);
+  Prepared a, b;
+  HB_TRY(prepare_operand(p.A, p.lda, p.M, p.K, a_kmajor, a_mode, w, a, st));
+  if (same) b = a;
+  else HB_TRY(prepare_operand(p.B, p.ldb, p.N, p.K, b_kmajor, b_mode, w, b, st));
   const int BN = 256;
   CUtensorMap ah, al, bh, bl;
-  if (raw_hi) {
-    HB_TRY(make_map(&ah, p.A, p.M, p.K, p.lda, BM));
-    HB_TRY(make_map(&bh, p.B, p.N, p.K, p.ldb, BN));
-  } else {
-    HB_TRY(make_map(&ah, a_hi, p.M, p.K, kp, BM));
-    HB_TRY(make_map(&bh, b_hi, p.N, p.K, kp, BN));
-  }
-  HB_TRY(make_map(&al, a_lo, p.M, p.K, kp, BM));
-  HB_TRY(make_map(&bl, b_lo, p.N, p.K, kp, BN));
+  HB_TRY(make_map(&ah, a.hi, p.M, p.K, a.ld_hi, BM));
+  HB_TRY(make_map(&al, a.lo, p.M, p.K, a.ld_lo, BM));
+  HB_TRY(make_map(&bh, b.hi, p.N, p.K, b.ld_hi, BN));
+  HB_TRY(make_map(&bl, b.lo, p.N, p.K, b.ld_lo, BN));
   TcParams tp;
   tp.C = p.C; tp.ldc = p.ldc; tp.M = p.M; tp.N = p.N; tp.K = p.K; tp.alpha = p.alpha; tp.beta = p.beta;
-  tp.c_tri = p.c_tri; tp.tiles_m = 0; tp.tiles_n = 0;
+  tp.c_tri = p.c_tri; tp.a_mode = a_mode; tp.b_mode = b_mode; tp.tiles_m = 0; tp.tiles_n = 0;
   tp.vecC = aligned16(p.C) && (p.ldc % 4 == 0);
   return launch_tc<2>(ah, al, bh, bl, tp, st);
 }

@@ -237,7 +237,14 @@ struct Ctx {
   float* tmp;         // [n][NB] scratch for leaf triangular solves
   long long ldt;      // = NB
   int* err;
+  void* tcws;         // scratch of the tensor-core GEMM engine (hi/lo operand copies)
+  size_t tcws_bytes;
 };
+
+inline int gemm_ws(const Ctx& c, GemmParams& g) {
+  g.ws = c.tcws; g.ws_bytes = c.tcws_bytes;
+  return gemm(g, c.st);
+}
 
 inline float* dinv_slot(const Ctx& c, int off) { return c.dinv + (long long)(off / NB) * NB * NB; }
 
@@ -248,7 +255,7 @@ int trsm_rlt(const Ctx& c, const float* L, long long ldl, int off, float* Bp, lo
     GemmParams g;
     g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = 1;   // (B Dinv^T)
     g.C = c.tmp; g.ldc = NB; g.M = m; g.N = k; g.K = k; g.alpha = 1.f; g.beta = 0.f;
-    HB_TRY(gemm(g, c.st));
+    HB_TRY(gemm_ws(c, g));
     return copy2d(Bp, ldb, c.tmp, NB, m, k, 1.f, c.st);
   }
   const int k1 = split_point(k), k2 = k - k1;
@@ -256,7 +263,7 @@ int trsm_rlt(const Ctx& c, const float* L, long long ldl, int off, float* Bp, lo
   GemmParams g;   // B2 -= B1 * L21^T
   g.A = Bp; g.lda = ldb; g.B = L + (long long)k1 * ldl; g.ldb = ldl; g.transB = 1;
   g.C = Bp + k1; g.ldc = ldb; g.M = m; g.N = k2; g.K = k1; g.alpha = -1.f; g.beta = 1.f;
-  HB_TRY(gemm(g, c.st));
+  HB_TRY(gemm_ws(c, g));
   return trsm_rlt(c, L + (long long)k1 * ldl + k1, ldl, off + k1, Bp + k1, ldb, m, k2);
 }
 
@@ -267,7 +274,7 @@ int trsm_rln(const Ctx& c, const float* L, long long ldl, int off, float* Bp, lo
     GemmParams g;
     g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = 0;   // (B Dinv)
     g.C = c.tmp; g.ldc = NB; g.M = m; g.N = k; g.K = k; g.alpha = 1.f; g.beta = 0.f;
-    HB_TRY(gemm(g, c.st));
+    HB_TRY(gemm_ws(c, g));
     return copy2d(Bp, ldb, c.tmp, NB, m, k, 1.f, c.st);
   }
   const int k1 = split_point(k), k2 = k - k1;
@@ -275,7 +282,7 @@ int trsm_rln(const Ctx& c, const float* L, long long ldl, int off, float* Bp, lo
   GemmParams g;   // B1 -= B2 * L21
   g.A = Bp + k1; g.lda = ldb; g.B = L + (long long)k1 * ldl; g.ldb = ldl; g.transB = 0;
   g.C = Bp; g.ldc = ldb; g.M = m; g.N = k1; g.K = k2; g.alpha = -1.f; g.beta = 1.f;
-  HB_TRY(gemm(g, c.st));
+  HB_TRY(gemm_ws(c, g));
   return trsm_rln(c, L, ldl, off, Bp, ldb, m, k1);
 }
 
@@ -293,7 +300,7 @@ int potrf_rec(const Ctx& c, float* A, long long lda, int off, int n) {
   GemmParams g;   // A22 -= A21 A21^T (lower)
   g.A = A21; g.lda = lda; g.B = A21; g.ldb = lda; g.transB = 1;
   g.C = A22; g.ldc = lda; g.M = m; g.N = m; g.K = n1; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
-  HB_TRY(gemm(g, c.st));
+  HB_TRY(gemm_ws(c, g));
   return potrf_rec(c, A22, lda, off + n1, m);
 }
 
@@ -314,16 +321,16 @@ int chol_rev_rec(const Ctx& c, const float* L, long long ldl, float* G, long lon
     GemmParams g;
     g.A = G22; g.lda = ldg; g.a_tri = 1; g.B = L21; g.ldb = ldl; g.C = G21; g.ldc = ldg;
     g.M = m; g.N = n1; g.K = m; g.alpha = -2.f; g.beta = 1.f;
-    HB_TRY(gemm(g, c.st));
+    HB_TRY(gemm_ws(c, g));
     g.transA = 1; g.a_tri = 3;
-    HB_TRY(gemm(g, c.st));
+    HB_TRY(gemm_ws(c, g));
   }
   HB_TRY(trsm_rln(c, L, ldl, off, G21, ldg, m, n1));     // T = G21 L11^{-1}
   {
     GemmParams g;   // G11 -= tril(T^T L21)
     g.A = G21; g.lda = ldg; g.transA = 1; g.B = L21; g.ldb = ldl; g.C = G; g.ldc = ldg;
     g.M = n1; g.N = n1; g.K = m; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
-    HB_TRY(gemm(g, c.st));
+    HB_TRY(gemm_ws(c, g));
   }
   HB_TRY(scale2d(G21, ldg, m, n1, 0.5f, c.st));
   return chol_rev_rec(c, L, ldl, G, ldg, off, n1);
@@ -331,10 +338,18 @@ int chol_rev_rec(const Ctx& c, const float* L, long long ldl, float* G, long lon
 
 }  // namespace
 
-size_t potrf_workspace_bytes(int n) {
-  const long long nblk = (n + NB - 1) / NB;
-  return (size_t)(nblk * NB * NB + (long long)n * NB) * sizeof(float) + 256;
+static size_t tc_bytes_for(int m, int n) {   // largest GEMM of a recursion over an n x n triangle with m-row panels
+  if (n < 2 * NB) return 0;
+  const int h = split_point(n);
+  return gemm_tc_workspace_bytes(m < 0 ? h : m, h, h) + 256;
 }
+
+static size_t base_bytes(long long rows, int n) {
+  const long long nblk = (n + NB - 1) / NB;
+  return ((size_t)(nblk * NB * NB + rows * NB) * sizeof(float) + 256 + 255) / 256 * 256;
+}
+
+size_t potrf_workspace_bytes(int n) { return base_bytes(n, n) + tc_bytes_for(-1, n); }
 
 static int make_ctx(Ctx& c, int n, void* ws, size_t ws_bytes, int* err, cudaStream_t st) {
   if (ws_bytes < potrf_workspace_bytes(n) || !ws) return HB_ERR_WORKSPACE;
@@ -344,6 +359,8 @@ static int make_ctx(Ctx& c, int n, void* ws, size_t ws_bytes, int* err, cudaStre
   c.tmp = c.dinv + nblk * NB * NB;
   c.ldt = NB;
   c.err = err;
+  c.tcws = reinterpret_cast<char*>(c.dinv) + base_bytes(n, n) - 256;
+  c.tcws_bytes = tc_bytes_for(-1, n);
   return HB_OK;
 }
 
@@ -399,22 +416,20 @@ int trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int
   if (m == 0 || n == 0) return HB_OK;
   HB_TRY(ensure_attrs());
   const long long nblk = (n + NB - 1) / NB;
-  const size_t need = (size_t)(nblk * NB * NB + (long long)m * NB) * sizeof(float) + 256;
-  if (!ws || ws_bytes < need) return HB_ERR_WORKSPACE;
+  if (!ws || ws_bytes < trsm_workspace_bytes(m, n)) return HB_ERR_WORKSPACE;
   Ctx c;
   c.st = st;
   c.dinv = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
   c.tmp = c.dinv + nblk * NB * NB;
   c.ldt = NB;
   c.err = nullptr;
+  c.tcws = reinterpret_cast<char*>(c.dinv) + base_bytes(m, n) - 256;
+  c.tcws_bytes = tc_bytes_for(m, n);
   trinv_blocks_kernel<<<(int)nblk, LEAF_THREADS, kLeafSmem2, st>>>(L, ldl, n, c.dinv);
   HB_CHECK_LAUNCH();
   return trans ? trsm_rlt(c, L, ldl, 0, X, ldx, m, n) : trsm_rln(c, L, ldl, 0, X, ldx, m, n);
 }
 
-size_t trsm_workspace_bytes(int m, int n) {
-  const long long nblk = (n + NB - 1) / NB;
-  return (size_t)(nblk * NB * NB + (long long)m * NB) * sizeof(float) + 256;
-}
+size_t trsm_workspace_bytes(int m, int n) { return base_bytes(m, n) + tc_bytes_for(m, n); }
 
 }  // namespace hb

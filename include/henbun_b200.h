@@ -134,6 +134,13 @@ int hb_gemm(const float* A, long long lda, long long strideA, int transA, int a_
             long long strideB, int transB, int b_tri, float* C, long long ldc, long long strideC, int c_tri, int M,
             int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
             int clip, float clip_lo, float clip_hi, void* stream);
+/* hb_gemm with a scratch buffer: when ws holds hb_gemm_tc_workspace_bytes(M,N,K) bytes and the shape qualifies
+ * (batch 1, no bias/activation, M,N >= 128, large enough), the product runs on the tcgen05 3xTF32 engine (any
+ * transposition / triangular mask); otherwise exactly hb_gemm. */
+int hb_gemm_ws(const float* A, long long lda, long long strideA, int transA, int a_tri, const float* B, long long ldb,
+               long long strideB, int transB, int b_tri, float* C, long long ldc, long long strideC, int c_tri, int M,
+               int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
+               int clip, float clip_lo, float clip_hi, void* ws, size_t ws_bytes, void* stream);
 /* The tcgen05 3xTF32 engine directly: C[M,N] = alpha*A[M,K]*B[N,K]^T + beta*C (both operands K-major), fp32-grade
  * accuracy from three TF32 tensor-core passes.  Needs M,N >= 128, K >= 32, lda/ldb multiples of 4, 16-byte aligned
  * A/B and a workspace of hb_gemm_tc_workspace_bytes(M,N,K); returns HB_ERR_ARG otherwise.
