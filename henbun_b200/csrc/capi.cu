@@ -3,6 +3,8 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include <vector>
+#include <cstdio>
+#include <cstdlib>
 
 namespace hb {
 
@@ -13,10 +15,13 @@ int get_gemm_engine() { return g_engine; }
 int gemm_tc(const GemmParams& p, cudaStream_t stream);   // gemm_tc.cu
 bool gemm_tc_eligible(const GemmParams& p);
 
+// engine: 0 auto | 1 fp32 SIMT only (short-K kernel + k-looped kernel) | 2 force tcgen05 | 3 k-looped SIMT kernel only
 static int gemm_dispatch(const GemmParams& p, cudaStream_t st) {
-  if (g_engine == 1) return gemm_simt(p, st);
-  if (gemm_tc_eligible(p)) return gemm_tc(p, st);
-  if (g_engine == 2) return HB_ERR_ARG;
+  if (p.C == p.A && p.N > 128) return HB_ERR_ARG;      // in-place needs one column tile per row block
+  if (g_engine == 3) return gemm_simt(p, st);
+  if (g_engine == 2) return gemm_tc_eligible(p) ? gemm_tc(p, st) : HB_ERR_ARG;
+  if (gemm_small_eligible(p)) return gemm_small(p, st);
+  if (g_engine == 0 && gemm_tc_eligible(p)) return gemm_tc(p, st);
   return gemm_simt(p, st);
 }
 
@@ -26,6 +31,7 @@ struct GemmProfiler {
   size_t used = 0;
   std::vector<cudaEvent_t> ev0, ev1;
   std::vector<double> flops;
+  std::vector<long long> shape;   // M, N, K, engine(1 = tensor core) per launch
 } g_prof;
 
 static double gemm_useful_flops(const GemmParams& p) {
@@ -40,6 +46,8 @@ int gemm(const GemmParams& p, cudaStream_t st) {
     return gemm_dispatch(p, st);
   const size_t i = g_prof.used++;
   g_prof.flops[i] = gemm_useful_flops(p);
+  g_prof.shape[4 * i] = p.M; g_prof.shape[4 * i + 1] = p.N; g_prof.shape[4 * i + 2] = p.K;
+  g_prof.shape[4 * i + 3] = (g_engine == 2 || (g_engine == 0 && !gemm_small_eligible(p) && gemm_tc_eligible(p))) ? 1 : 0;
   cudaEventRecord(g_prof.ev0[i], st);
   const int rc = gemm_dispatch(p, st);
   cudaEventRecord(g_prof.ev1[i], st);
@@ -148,6 +156,7 @@ int hb_profile_begin(int max_gemm_launches) {
     g_prof.ev0.push_back(a); g_prof.ev1.push_back(b);
   }
   g_prof.flops.assign(g_prof.ev0.size(), 0.0);
+  g_prof.shape.assign(4 * g_prof.ev0.size(), 0);
   g_prof.used = 0;
   g_prof.on = true;
   return HB_OK;
@@ -158,11 +167,17 @@ int hb_profile_end(double* out4_host) {
   if (!out4_host) return HB_ERR_ARG;
   if (cudaDeviceSynchronize() != cudaSuccess) return HB_ERR_CUDA;
   double ms = 0.0, fl = 0.0;
+  const char* csv = getenv("HB_PROFILE_CSV");      // optional per-launch dump (debug aid for profiles/)
+  FILE* f = csv ? fopen(csv, "w") : nullptr;
+  if (f) fprintf(f, "M,N,K,tc,useful_flop,ms\n");
   for (size_t i = 0; i < g_prof.used; ++i) {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]) != cudaSuccess) return HB_ERR_CUDA;
+    if (cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]) != cudaSuccess) { if (f) fclose(f); return HB_ERR_CUDA; }
     ms += t; fl += g_prof.flops[i];
+    if (f) fprintf(f, "%lld,%lld,%lld,%lld,%.0f,%.6f\n", g_prof.shape[4 * i], g_prof.shape[4 * i + 1], g_prof.shape[4 * i + 2],
+                   g_prof.shape[4 * i + 3], g_prof.flops[i], t);
   }
+  if (f) fclose(f);
   out4_host[0] = (double)g_prof.used; out4_host[1] = ms; out4_host[2] = fl; out4_host[3] = 0.0;
   return HB_OK;
 }

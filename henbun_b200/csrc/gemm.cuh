@@ -35,6 +35,8 @@ struct GemmParams {
 // 2 = force tcgen05 3xTF32 (error if the shape does not qualify)
 int gemm(const GemmParams& p, cudaStream_t stream);
 int gemm_simt(const GemmParams& p, cudaStream_t stream);
+int gemm_small(const GemmParams& p, cudaStream_t stream);      // K <= 256, whole-K staging (latency-oriented); C may alias A if N <= 128
+bool gemm_small_eligible(const GemmParams& p);
 size_t gemm_tc_workspace_bytes(int M, int N, int K);
 void set_tc_option(int v);
 void set_gemm_engine(int mode);

@@ -22,58 +22,165 @@ constexpr int LEAF_THREADS = 512;
 // in-CTA helpers (matrices are NB x NB in shared memory, ld = LDS)
 // ------------------------------------------------------------------------------------------
 
-// Unblocked right-looking Cholesky of the n x n lower triangle held in S (rows/cols >= n are identity).
-// One __syncthreads per column: the scaling of column j-1 is deferred into phase j.
+// Column steps of the in-register 16x16 Cholesky (lane l holds row l); compile-time recursion keeps every array
+// index static so the rows stay in registers.
+template <int J>
+__device__ __forceinline__ void diag_steps(float (&a)[16], int l, int& bad) {
+  if constexpr (J < 16) {
+    const float d = __shfl_sync(0xffffffffu, a[J], J);
+    if (!(d > 0.f) && bad == 0) bad = J + 1;
+    const float sd = sqrtf(d), rs = 1.f / sd;
+    if (l == J) a[J] = sd;
+    else if (l > J) a[J] *= rs;
+#pragma unroll
+    for (int k = J + 1; k < 16; ++k) {
+      const float akj = __shfl_sync(0xffffffffu, a[J], k);
+      if (l >= k) a[k] = fmaf(-a[J], akj, a[k]);
+    }
+    diag_steps<J + 1>(a, l, bad);
+  }
+}
+
+// Blocked right-looking Cholesky of the NB x NB lower triangle held in S (rows/cols >= n are identity, so the
+// full padded matrix is factored).  16-wide panels: (1) warp 0 factors the 16x16 diagonal block in registers with
+// shuffles, (2) one thread per row solves its 16 panel entries, (3) all threads apply the rank-16 update out of a
+// transposed copy of the panel (conflict-free).  3 barriers per panel instead of one per column.
+constexpr int PB = 16;
 __device__ void potrf_smem(float* S, int n, int* err_flag, int err_base) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  for (int j = 0; j <= n; ++j) {
+  __shared__ float rinv[PB];
+  __shared__ float Pt[PB][NB + 1];      // Pt[j][i] = L[i][j0 + j] for the rows below the diagonal block
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __syncthreads();
+  for (int j0 = 0; j0 < NB; j0 += PB) {
+    if (warp == 0) {
+      float a[PB];
+      const int row = j0 + (lane & (PB - 1));
+#pragma unroll
+      for (int k = 0; k < PB; ++k) a[k] = S[row * LDS + j0 + k];
+      int bad = 0;
+      diag_steps<0>(a, lane & (PB - 1), bad);
+      if (bad) bad += j0;
+      if (lane < PB) {
+#pragma unroll
+        for (int k = 0; k < PB; ++k) if (k <= lane) S[row * LDS + j0 + k] = a[k];
+        rinv[lane] = 1.f / a[lane];
+      }
+      if (lane == 0 && bad != 0 && bad <= n && err_flag) atomicCAS(err_flag, 0, err_base + bad);
+    }
     __syncthreads();
-    if (j > 0) {  // finalise column j-1
-      const int q = j - 1;
-      const float d = S[q * LDS + q];
-      const float sd = sqrtf(d);
-      const float rs = 1.f / sd;
-      for (int i = q + 1 + tid; i < n; i += blockDim.x) S[i * LDS + q] *= rs;
-      // S[q][q] is rewritten only after everyone has read it: defer by one more phase (see below)
-      if (tid == 0 && !(d > 0.f) && err_flag) atomicCAS(err_flag, 0, err_base + q + 1);
+    const int base = j0 + PB;
+    if (base >= NB) break;
+    // (2) panel rows: x L11^T = a  (forward substitution, L11 broadcast from shared memory)
+    for (int i = base + tid; i < NB; i += blockDim.x) {
+      float x[PB];
+#pragma unroll
+      for (int k = 0; k < PB; ++k) x[k] = S[i * LDS + j0 + k];
+#pragma unroll
+      for (int j = 0; j < PB; ++j) {
+        float s = x[j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fmaf(-x[k], S[(j0 + j) * LDS + j0 + k], s);
+        x[j] = s * rinv[j];
+      }
+#pragma unroll
+      for (int k = 0; k < PB; ++k) { S[i * LDS + j0 + k] = x[k]; Pt[k][i] = x[k]; }
     }
-    if (j > 1) {  // diagonal of column j-2: nobody reads it any more
-      const int q = j - 2;
-      if (tid == 0) S[q * LDS + q] = sqrtf(S[q * LDS + q]);
-    }
-    if (j < n) {  // trailing update with (unscaled) column j
-      const float d = S[j * LDS + j];
-      const float invd = 1.f / d;
-      for (int i = j + 1 + warp; i < n; i += nwarp) {
-        const float ci = S[i * LDS + j] * invd;
-        for (int k = j + 1 + lane; k <= i; k += 32) S[i * LDS + k] = fmaf(-ci, S[k * LDS + j], S[i * LDS + k]);
+    __syncthreads();
+    // (3) trailing update S[i][k] -= sum_j Pt[j][i] Pt[j][k]  (k <= i), rows ty + 16 r, columns tx + 32 c
+    {
+      const int ty = tid >> 5, tx = tid & 31;          // 16 x 32 thread grid (512 threads)
+      constexpr int R = (NB - PB) / 16, Cc = NB / 32;
+      float acc[R][Cc];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < Cc; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < PB; ++j) {
+        float av[R], bv[Cc];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { const int i = base + ty + 16 * r; av[r] = (i < NB) ? Pt[j][i] : 0.f; }
+#pragma unroll
+        for (int c = 0; c < Cc; ++c) { const int k = base + tx + 32 * c; bv[c] = (k < NB) ? Pt[j][k] : 0.f; }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < Cc; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = base + ty + 16 * r;
+#pragma unroll
+        for (int c = 0; c < Cc; ++c) {
+          const int k = base + tx + 32 * c;
+          if (i < NB && k <= i) S[i * LDS + k] -= acc[r][c];
+        }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
-  if (n >= 1 && threadIdx.x == 0) S[(n - 1) * LDS + (n - 1)] = sqrtf(S[(n - 1) * LDS + (n - 1)]);
   __syncthreads();
 }
 
-// X = L^{-1} for the lower-triangular L (NB x NB, identity padded). 4 lanes cooperate per column.
-__device__ void trinv_smem(const float* L, float* X) {
+// One doubling level of the blocked triangular inverse: for every aligned 2S x 2S diagonal block whose two S x S
+// diagonal blocks are already inverted in X, X21 = -X22 * (L21 * X11).  T is scratch (same geometry as X).
+template <int S>
+__device__ __forceinline__ void trinv_level(const float* L, float* X, float* T) {
+  constexpr int NO = S / 8;                       // outputs per thread: rows rg + 8 r, one column j
   const int tid = threadIdx.x;
+  const int pair = tid / (8 * S), j = tid % S, rg = (tid / S) % 8;
+  const int r0 = 2 * S * pair;
+  float acc[NO];
+#pragma unroll
+  for (int r = 0; r < NO; ++r) acc[r] = 0.f;
+  for (int k = j; k < S; ++k) {                   // X11 is lower triangular: X11[k][j] = 0 for k < j
+    const float b = X[(r0 + k) * LDS + r0 + j];
+#pragma unroll
+    for (int r = 0; r < NO; ++r) acc[r] = fmaf(L[(r0 + S + rg + 8 * r) * LDS + r0 + k], b, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < NO; ++r) T[(r0 + S + rg + 8 * r) * LDS + r0 + j] = acc[r];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < NO; ++r) acc[r] = 0.f;
+  for (int k = 0; k < S; ++k) {                   // X22[i][k] = 0 for k > i
+    const float b = T[(r0 + S + k) * LDS + r0 + j];
+#pragma unroll
+    for (int r = 0; r < NO; ++r) {
+      const int i = rg + 8 * r;
+      const float a = (k <= i) ? X[(r0 + S + i) * LDS + r0 + S + k] : 0.f;
+      acc[r] = fmaf(a, b, acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NO; ++r) X[(r0 + S + rg + 8 * r) * LDS + r0 + j] = -acc[r];
+  __syncthreads();
+}
+
+// X = L^{-1} for the lower-triangular L (NB x NB, identity padded), blocked: 16x16 diagonal blocks by forward
+// substitution in registers (one lane per column), then three doubling levels (16 -> 32 -> 64 -> 128).
+// blockDim.x must be 512.  T is an NB x LDS scratch buffer.
+__device__ void trinv_smem(const float* L, float* X, float* T) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < NB * LDS; e += blockDim.x) X[e] = 0.f;
   __syncthreads();
-  const int c = tid >> 2, sub = tid & 3;       // 512 threads -> 128 columns
-  const int cw = (tid & ~31) >> 2;              // first column handled by this warp
-  if (c < NB && sub == 0) X[c * LDS + c] = 1.f / L[c * LDS + c];
-  __syncwarp();
-  for (int i = cw + 1; i < NB; ++i) {
-    float part = 0.f;
-    if (c < NB && i > c)
-      for (int k = c + sub; k < i; k += 4) part = fmaf(L[i * LDS + k], X[k * LDS + c], part);
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    if (c < NB && i > c && sub == 0) X[i * LDS + c] = -part / L[i * LDS + i];
-    __syncwarp();
+  if (warp < NB / 16 && lane < 16) {
+    const int b0 = 16 * warp, c = lane;
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float sacc = (i == c) ? 1.f : 0.f;
+#pragma unroll
+      for (int k = 0; k < i; ++k) sacc = fmaf(-L[(b0 + i) * LDS + b0 + k], x[k], sacc);
+      x[i] = sacc / L[(b0 + i) * LDS + b0 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) X[(b0 + i) * LDS + b0 + c] = x[i];
   }
   __syncthreads();
+  trinv_level<16>(L, X, T);
+  trinv_level<32>(L, X, T);
+  trinv_level<64>(L, X, T);
 }
 
 // C = op(A) * op(B) on NB x NB shared-memory matrices; k restricted to [klo(i), khi(i)] by row.
@@ -106,21 +213,72 @@ __device__ void mm_smem(float* C, const float* A, const float* B) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
   }
+  __syncthreads();   // C may alias an input
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 8; ++c) C[(i0 + r) * LDS + tc + 16 * c] = acc[r][c];
 }
 
-// load the n x n lower triangle of a global block into S; pad with `diag_pad` on the padded diagonal
+// load the n x n lower triangle of a global block into S; pad with `diag_pad` on the padded diagonal.
+// All global loads of a thread are issued before the first shared-memory store (one memory round trip).
 __device__ void load_lower(float* S, const float* G, long long ld, int n, float diag_pad) {
-  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+  const int tid = threadIdx.x;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(G) & 15) == 0) && blockDim.x == 512;
+  if (vec) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int q = tid + 512 * u, i = q >> 5, j4 = (q & 31) * 4;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n && j4 <= i) {
+        if (j4 + 3 < n) v[u] = *reinterpret_cast<const float4*>(G + (long long)i * ld + j4);
+        else {
+          const float* g = G + (long long)i * ld + j4;
+          v[u].x = g[0];
+          if (j4 + 1 < n) v[u].y = g[1];
+          if (j4 + 2 < n) v[u].z = g[2];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int q = tid + 512 * u, i = q >> 5, j4 = (q & 31) * 4;
+      const float t[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int jj = j4 + c;
+        float x = (i < n && jj <= i) ? t[c] : 0.f;
+        if (i >= n && jj == i) x = diag_pad;
+        S[i * LDS + jj] = x;
+      }
+    }
+    return;
+  }
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
     const int i = e / NB, j = e % NB;
     float v = 0.f;
     if (i < n && j <= i) v = G[(long long)i * ld + j];
     else if (i == j) v = diag_pad;
     S[i * LDS + j] = v;
   }
+}
+
+// load a dense NB x NB block (ld = NB, 16-byte aligned) with one memory round trip
+__device__ void load_full(float* S, const float* G) {
+  const int tid = threadIdx.x;
+  if (blockDim.x == 512 && (reinterpret_cast<uintptr_t>(G) & 15) == 0) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(G + 4 * (tid + 512 * u));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int q = tid + 512 * u, i = q >> 5, j4 = (q & 31) * 4;
+      S[i * LDS + j4] = v[u].x; S[i * LDS + j4 + 1] = v[u].y; S[i * LDS + j4 + 2] = v[u].z; S[i * LDS + j4 + 3] = v[u].w;
+    }
+    return;
+  }
+  for (int e = tid; e < NB * NB; e += blockDim.x) S[(e / NB) * LDS + (e % NB)] = G[e];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -134,6 +292,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) potrf_leaf_kernel(float* A, long
   extern __shared__ float sm[];
   float* S = sm;
   float* X = sm + NB * LDS;
+  float* T = sm + 2 * NB * LDS;
   float* Ab = A + (long long)blockIdx.x * sA;
   load_lower(S, Ab, lda, n, 1.f);
   potrf_smem(S, n, err_flag, err_base);
@@ -143,7 +302,7 @@ __global__ void __launch_bounds__(LEAF_THREADS) potrf_leaf_kernel(float* A, long
     else if (zero_upper) Ab[(long long)i * lda + j] = 0.f;
   }
   if (Dinv) {
-    trinv_smem(S, X);
+    trinv_smem(S, X, T);
     float* Db = Dinv + (long long)blockIdx.x * sD;
     for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Db[e] = X[(e / NB) * LDS + (e % NB)];
   }
@@ -155,11 +314,12 @@ __global__ void __launch_bounds__(LEAF_THREADS) trinv_blocks_kernel(const float*
   extern __shared__ float sm[];
   float* S = sm;
   float* X = sm + NB * LDS;
+  float* T = sm + 2 * NB * LDS;
   const int b = blockIdx.x;
   const int nb = min(NB, n - b * NB);
   load_lower(S, L + (long long)b * NB * ldl + (long long)b * NB, ldl, nb, 1.f);
   __syncthreads();
-  trinv_smem(S, X);
+  trinv_smem(S, X, T);
   float* Db = Dinv + (long long)b * NB * NB;
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) Db[e] = X[(e / NB) * LDS + (e % NB)];
 }
@@ -176,10 +336,16 @@ __global__ void __launch_bounds__(LEAF_THREADS) chol_rev_leaf_kernel(const float
   const float* Lb = L + (long long)blockIdx.x * sL;
   float* Gb = G + (long long)blockIdx.x * sG;
   load_lower(B0, Lb, ldl, n, 1.f);   // L
-  load_lower(B1, Gb, ldg, n, 0.f);   // tril(Lbar)
+  if (Dinv) {
+    load_full(B1, Dinv + (long long)blockIdx.x * sD);
+  } else {
+    __syncthreads();
+    trinv_smem(B0, B1, B2);          // B1 = L^{-1}, B2 scratch
+  }
+  load_lower(B2, Gb, ldg, n, 0.f);   // tril(Lbar)
   __syncthreads();
-  // P = Phi(L^T Lbar): (L^T)[i][k] = L[k][i], nonzero for k >= i
-  mm_smem<true, false, 1>(B2, B0, B1);
+  // P = Phi(L^T Lbar): (L^T)[i][k] = L[k][i], nonzero for k >= i.  Result overwrites Lbar (mm_smem syncs before storing).
+  mm_smem<true, false, 1>(B2, B0, B2);
   __syncthreads();
   for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
     const int i = e / NB, j = e % NB;
@@ -189,22 +355,11 @@ __global__ void __launch_bounds__(LEAF_THREADS) chol_rev_leaf_kernel(const float
     B2[i * LDS + j] = v;
   }
   __syncthreads();
-  // Dinv into B0
-  if (Dinv) {
-    const float* Db = Dinv + (long long)blockIdx.x * sD;
-    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) B0[(e / NB) * LDS + (e % NB)] = Db[e];
-    __syncthreads();
-  } else {
-    // B0 holds L: invert into B1 then copy back
-    trinv_smem(B0, B1);
-    for (int e = threadIdx.x; e < NB * LDS; e += blockDim.x) B0[e] = B1[e];
-    __syncthreads();
-  }
-  // M1 = P * Dinv (lower x lower): k <= i
-  mm_smem<false, false, 2>(B1, B2, B0);
+  // M1 = P * Dinv (lower x lower): k <= i   (L is dead: B0 receives M1)
+  mm_smem<false, false, 2>(B0, B2, B1);
   __syncthreads();
   // S = Dinv^T * M1: (Dinv^T)[i][k] = Dinv[k][i], nonzero for k >= i
-  mm_smem<true, false, 1>(B2, B0, B1);
+  mm_smem<true, false, 1>(B2, B1, B0);
   __syncthreads();
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e % n;
@@ -218,8 +373,8 @@ constexpr size_t kLeafSmem3 = 3 * NB * LDS * sizeof(float);
 int ensure_attrs() {
   static bool done = false;
   if (done) return HB_OK;
-  if (cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeafSmem2) != cudaSuccess) return HB_ERR_CUDA;
-  if (cudaFuncSetAttribute(trinv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeafSmem2) != cudaSuccess) return HB_ERR_CUDA;
+  if (cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeafSmem3) != cudaSuccess) return HB_ERR_CUDA;
+  if (cudaFuncSetAttribute(trinv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeafSmem3) != cudaSuccess) return HB_ERR_CUDA;
   if (cudaFuncSetAttribute(chol_rev_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLeafSmem3) != cudaSuccess) return HB_ERR_CUDA;
   done = true;
   return HB_OK;
@@ -253,10 +408,9 @@ int trsm_rlt(const Ctx& c, const float* L, long long ldl, int off, float* Bp, lo
   if (m <= 0 || k <= 0) return HB_OK;
   if (k <= NB) {
     GemmParams g;
-    g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = 1;   // (B Dinv^T)
-    g.C = c.tmp; g.ldc = NB; g.M = m; g.N = k; g.K = k; g.alpha = 1.f; g.beta = 0.f;
-    HB_TRY(gemm_ws(c, g));
-    return copy2d(Bp, ldb, c.tmp, NB, m, k, 1.f, c.st);
+    g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = 1;   // B <- B Dinv^T, in place
+    g.C = Bp; g.ldc = ldb; g.M = m; g.N = k; g.K = k; g.alpha = 1.f; g.beta = 0.f;
+    return gemm_ws(c, g);
   }
   const int k1 = split_point(k), k2 = k - k1;
   HB_TRY(trsm_rlt(c, L, ldl, off, Bp, ldb, m, k1));
@@ -272,10 +426,9 @@ int trsm_rln(const Ctx& c, const float* L, long long ldl, int off, float* Bp, lo
   if (m <= 0 || k <= 0) return HB_OK;
   if (k <= NB) {
     GemmParams g;
-    g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = 0;   // (B Dinv)
-    g.C = c.tmp; g.ldc = NB; g.M = m; g.N = k; g.K = k; g.alpha = 1.f; g.beta = 0.f;
-    HB_TRY(gemm_ws(c, g));
-    return copy2d(Bp, ldb, c.tmp, NB, m, k, 1.f, c.st);
+    g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = 0;   // B <- B Dinv, in place
+    g.C = Bp; g.ldc = ldb; g.M = m; g.N = k; g.K = k; g.alpha = 1.f; g.beta = 0.f;
+    return gemm_ws(c, g);
   }
   const int k1 = split_point(k), k2 = k - k1;
   HB_TRY(trsm_rln(c, L + (long long)k1 * ldl + k1, ldl, off + k1, Bp + k1, ldb, m, k2));
@@ -288,7 +441,7 @@ int trsm_rln(const Ctx& c, const float* L, long long ldl, int off, float* Bp, lo
 
 int potrf_rec(const Ctx& c, float* A, long long lda, int off, int n) {
   if (n <= NB) {
-    potrf_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem2, c.st>>>(A, lda, 0, n, dinv_slot(c, off), 0, 0, c.err, off);
+    potrf_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.st>>>(A, lda, 0, n, dinv_slot(c, off), 0, 0, c.err, off);
     HB_CHECK_LAUNCH();
     return HB_OK;
   }
@@ -371,7 +524,7 @@ int potrf_lower(float* A, long long lda, long long strideA, int n, int batch, in
   if (n == 0 || batch == 0) return HB_OK;
   HB_TRY(ensure_attrs());
   if (n <= NB) {
-    potrf_leaf_kernel<<<batch, LEAF_THREADS, kLeafSmem2, st>>>(A, lda, strideA, n, nullptr, 0, zero_upper, err_flag, 0);
+    potrf_leaf_kernel<<<batch, LEAF_THREADS, kLeafSmem3, st>>>(A, lda, strideA, n, nullptr, 0, zero_upper, err_flag, 0);
     HB_CHECK_LAUNCH();
     return HB_OK;
   }
@@ -402,7 +555,7 @@ int potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, 
   const int nblk = (n + NB - 1) / NB;
   for (int b = 0; b < batch; ++b) {
     const float* Lb = L + (long long)b * strideL;
-    trinv_blocks_kernel<<<nblk, LEAF_THREADS, kLeafSmem2, st>>>(Lb, ldl, n, c.dinv);
+    trinv_blocks_kernel<<<nblk, LEAF_THREADS, kLeafSmem3, st>>>(Lb, ldl, n, c.dinv);
     HB_CHECK_LAUNCH();
     HB_TRY(chol_rev_rec(c, Lb, ldl, G + (long long)b * strideG, ldg, 0, n));
   }
@@ -425,7 +578,7 @@ int trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int
   c.err = nullptr;
   c.tcws = reinterpret_cast<char*>(c.dinv) + base_bytes(m, n) - 256;
   c.tcws_bytes = tc_bytes_for(m, n);
-  trinv_blocks_kernel<<<(int)nblk, LEAF_THREADS, kLeafSmem2, st>>>(L, ldl, n, c.dinv);
+  trinv_blocks_kernel<<<(int)nblk, LEAF_THREADS, kLeafSmem3, st>>>(L, ldl, n, c.dinv);
   HB_CHECK_LAUNCH();
   return trans ? trsm_rlt(c, L, ldl, 0, X, ldx, m, n) : trsm_rln(c, L, ldl, 0, X, ldx, m, n);
 }

@@ -42,7 +42,7 @@ extern "C" {
 int hb_version(void);
 unsigned long long hb_launch_count(void);           /* kernels launched by this library so far */
 size_t hb_reduce_workspace_bytes(void);             /* workspace every reducing call needs */
-int hb_set_gemm_engine(int mode);                   /* 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32 */
+int hb_set_gemm_engine(int mode);                   /* 0 auto, 1 fp32 SIMT kernels only, 2 force tcgen05 3xTF32, 3 k-looped SIMT kernel only */
 int hb_get_gemm_engine(void);
 /* Optional instrumentation for bench.py: CUDA-event pairs around every GEMM launch on its stream.
  * hb_profile_end synchronises and fills a HOST array {launches, total ms, useful FLOP, 0}. */

@@ -96,8 +96,34 @@ def chol(n, reps=1):
               f"fwd {t[0]:.2f} ms ({fl_f / t[0] / 1e9:.1f} TF/s) bwd {t[1]:.2f} ms ({fl_b / t[1] / 1e9:.1f} TF/s)", flush=True)
 
 
+def inplace(m, k, trans):
+    rng = np.random.RandomState(m + k)
+    X = rng.randn(m, k + 8).astype(np.float32)
+    D = np.tril(rng.randn(128, 128)).astype(np.float32)
+    Xd, Dd = torch.from_numpy(X).cuda(), torch.from_numpy(D).cuda()
+    lib.hb_set_gemm_engine(1)
+    rc = lib.hb_gemm_ws(P(Xd), k + 8, 0, 0, 0, P(Dd), 128, 0, 1 if trans else 0, 0, P(Xd), k + 8, 0, 0, m, k, k, 1,
+                        1.0, 0.0, None, 0, 0, 0, -50.0, 50.0, None, 0, ST())
+    torch.cuda.synchronize(); lib.hb_set_gemm_engine(0)
+    Dk = D[:k, :k].astype(np.float64)
+    ref = X[:, :k].astype(np.float64) @ (Dk.T if trans else Dk)
+    out = Xd.cpu().numpy()
+    err = np.linalg.norm(out[:, :k] - ref) / np.linalg.norm(ref)
+    pad_ok = np.array_equal(out[:, k:], X[:, k:])
+    print(f"inplace m={m} k={k} trans={trans} rc={rc} err={err:.2e} pad_untouched={pad_ok}", flush=True)
+
+
 if __name__ == "__main__":
     worst = 0.0
+    for (m, k, t) in ((128, 128, 1), (1000, 128, 0), (5000, 96, 1), (64, 128, 0)):
+        inplace(m, k, t)
+    # short-K kernel (engine 1) against the k-looped kernel is covered by run(..., eng=1) vs fp64
+    for (tA, tB) in ((0, 1), (0, 0), (1, 0), (1, 1)):
+        run(200, 300, 128, tA, tB, eng=1); run(128, 128, 256, tA, tB, alpha=-1.0, beta=1.0, eng=1)
+        run(2000, 128, 100, tA, tB, a_tri=0, eng=1)
+    for tri in (1, 2, 3, 4):
+        run(256, 256, 256, 0, 0, a_tri=tri, eng=1); run(256, 256, 256, 1, 1, b_tri=tri, eng=1)
+    run(256, 256, 200, 1, 0, c_tri=1, alpha=-1.0, beta=1.0, eng=1)
     for (tA, tB) in ((0, 1), (0, 0), (1, 0), (1, 1)):
         worst = max(worst, run(256, 384, 200, tA, tB))
         worst = max(worst, run(300, 500, 100, tA, tB, alpha=-1.0, beta=1.0))
@@ -111,5 +137,5 @@ if __name__ == "__main__":
     worst = max(worst, run(640, 640, 384, 0, 1, c_tri=1, alpha=-1.0, beta=1.0))
     worst = max(worst, run(1000, 1000, 1000, 1, 0, a_tri=3))
     print("worst tc err", worst, flush=True)
-    for n in (1024, 4096, 8192, 16384):
+    for n in (128, 1024, 4096, 8192, 16384):
         chol(n)
