@@ -12,16 +12,37 @@ static int g_engine = 0;
 void set_gemm_engine(int mode) { g_engine = mode; }
 int get_gemm_engine() { return g_engine; }
 
-int gemm_tc(const GemmParams& p, cudaStream_t stream);   // gemm_tc.cu
+int gemm_tc(const GemmParams& p, cudaStream_t stream);   // gemm_tc.cu  (generation 1: operand-preparation pass + workspace)
 bool gemm_tc_eligible(const GemmParams& p);
+int gemm_tc2(const GemmParams& p, cudaStream_t stream);  // gemm_tc2.cu (generation 2: in-kernel split, no workspace)
+bool gemm_tc2_eligible(const GemmParams& p);
+int get_tc_option();
+
+// shapes worth a tensor-core launch
+static bool tc_worth(const GemmParams& p) {
+  return p.N >= 64 && p.K >= 32 && (double)p.M * p.N * p.K >= 256.0 * 256.0 * 256.0;
+}
+// short-K products: the whole-K SIMT kernel wins until there are enough 128-row tiles to fill the tensor-core grid
+static bool prefer_small(const GemmParams& p) {
+  if (!gemm_small_eligible(p)) return false;
+  const long long tiles = (long long)((p.M + 127) / 128) * ((p.N + 255) / 256);
+  return !(tiles >= 24 && gemm_tc2_eligible(p) && tc_worth(p));
+}
+static int tc_run(const GemmParams& p, cudaStream_t st, bool force) {
+  const bool v1 = (get_tc_option() & 2) != 0;
+  if (!v1 && gemm_tc2_eligible(p) && (force || tc_worth(p))) return gemm_tc2(p, st);
+  if (gemm_tc_eligible(p)) return gemm_tc(p, st);
+  return -1;
+}
 
 // engine: 0 auto | 1 fp32 SIMT only (short-K kernel + k-looped kernel) | 2 force tcgen05 | 3 k-looped SIMT kernel only
 static int gemm_dispatch(const GemmParams& p, cudaStream_t st) {
   if (p.C == p.A && p.N > 128) return HB_ERR_ARG;      // in-place needs one column tile per row block
   if (g_engine == 3) return gemm_simt(p, st);
-  if (g_engine == 2) return gemm_tc_eligible(p) ? gemm_tc(p, st) : HB_ERR_ARG;
+  if (g_engine == 2) { const int rc = tc_run(p, st, true); return rc < 0 ? HB_ERR_ARG : rc; }
+  if (g_engine == 1 ? gemm_small_eligible(p) : prefer_small(p)) return gemm_small(p, st);
+  if (g_engine == 0) { const int rc = tc_run(p, st, false); if (rc >= 0) return rc; }
   if (gemm_small_eligible(p)) return gemm_small(p, st);
-  if (g_engine == 0 && gemm_tc_eligible(p)) return gemm_tc(p, st);
   return gemm_simt(p, st);
 }
 
@@ -47,7 +68,7 @@ int gemm(const GemmParams& p, cudaStream_t st) {
   const size_t i = g_prof.used++;
   g_prof.flops[i] = gemm_useful_flops(p);
   g_prof.shape[4 * i] = p.M; g_prof.shape[4 * i + 1] = p.N; g_prof.shape[4 * i + 2] = p.K;
-  g_prof.shape[4 * i + 3] = (g_engine == 2 || (g_engine == 0 && !gemm_small_eligible(p) && gemm_tc_eligible(p))) ? 1 : 0;
+  g_prof.shape[4 * i + 3] = (g_engine == 2 || (g_engine == 0 && !prefer_small(p) && ((gemm_tc2_eligible(p) && tc_worth(p)) || gemm_tc_eligible(p)))) ? 1 : 0;
   cudaEventRecord(g_prof.ev0[i], st);
   const int rc = gemm_dispatch(p, st);
   cudaEventRecord(g_prof.ev1[i], st);
@@ -327,12 +348,8 @@ int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, 
   GemmParams g;
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.transB = 1; g.C = C; g.ldc = ldc; g.c_tri = c_tri;
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.ws = ws; g.ws_bytes = ws_bytes;
-  const int saved = get_gemm_engine();
-  set_gemm_engine(2);                       // bypass the size heuristic: this entry point always runs the tensor-core engine
-  const bool ok = gemm_tc_eligible(g);
-  set_gemm_engine(saved);
-  if (!ok) return HB_ERR_ARG;
-  return gemm_tc(g, S(stream));
+  const int rc = tc_run(g, S(stream), true);   // bypasses the size heuristic: always a tensor-core engine
+  return rc < 0 ? HB_ERR_ARG : rc;
 }
 
 int hb_act_bwd_colsum(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act, int clip,

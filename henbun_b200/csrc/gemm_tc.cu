@@ -414,6 +414,7 @@ int prepare_operand(const float* src, long long ld, int rows, int K, bool kmajor
 }  // namespace
 
 void set_tc_option(int v) { g_tc_option = v; }
+int get_tc_option() { return g_tc_option; }
 
 size_t gemm_tc_workspace_bytes(int M, int N, int K) {
   const long long kp = ((long long)K + 3) / 4 * 4;
@@ -426,6 +427,7 @@ bool gemm_tc_eligible(const GemmParams& p) {
   if (p.batch != 1 || p.bias || p.act != ACT_NONE || p.clip) return false;
   if (p.M < 128 || p.N < 128 || p.K < 32) return false;
   if (get_gemm_engine() != 2 && (double)p.M * p.N * p.K < 256.0 * 256.0 * 256.0) return false;
+  if (p.C == p.A || p.C == p.B) return false;
   if (!p.ws || p.ws_bytes < gemm_tc_workspace_bytes(p.M, p.N, p.K)) return false;
   return true;
 }

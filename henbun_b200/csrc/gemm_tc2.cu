@@ -1,0 +1,450 @@
+// tcgen05 3xTF32 GEMM engine, generation 2:  C[MxN] = alpha * op(A) * op(B) + beta * C   (fp32 in/out)
+//
+// What changed against gemm_tc.cu (generation 1):
+//   * the hi/lo operand split happens INSIDE the kernel: TMA brings the raw fp32 tile into shared memory once,
+//     four converter warps write lo = rn_tf32(x - trunc_tf32(x)) next to it (the raw words serve as "hi": the
+//     tf32 datapath ignores the 13 low mantissa bits).  No operand-preparation pass, no workspace, and half the
+//     L2->SM traffic (generation 1 streamed hi and lo copies and sat on the L2 bandwidth cap).
+//   * transposed operands are consumed in place through MN-major UMMA descriptors (SWIZZLE_128B_BASE32B boxes
+//     of 32 m x 16 k); K-major operands use SWIZZLE_64B rows of 16 floats.  Triangular masks are applied by the
+//     converter warps on the tiles that straddle the diagonal; fully masked k-blocks are never loaded.
+//   * BK = 16 with a 4-deep TMA ring (48 KB per stage for 128x256 tiles).
+//
+// Warp roles (512 threads, register budget re-balanced with setmaxnreg):
+//   warp 0      TMA producer                         warps 4..7   converters (hi/lo split, masks)
+//   warp 1      TMEM allocator + tcgen05.mma issuer  warps 8..15  epilogue (two-level fp32 accumulation, store)
+// Accumulation is two-level as in generation 1: the tensor core accumulates K=128 into one of two TMEM buffers,
+// the epilogue warps add each finished partial tile into fp32 registers with round-to-nearest.
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace hb {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 16;
+constexpr int NSTAGE = 4;
+constexpr int CHK = 8;                      // k-blocks per tensor-core accumulation chunk (K = 128)
+constexpr int NTHREADS = 512;
+constexpr int A_TILE = BM * BK * 4;         // 8 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// Shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version = 1 | [61,64) layout (2 = SW128, 4 = SW64)
+// K-major, SWIZZLE_64B : rows of 16 floats (64 B); 8-row atoms of 512 B -> SBO = 512; LBO unused.
+// MN-major tf32 has exactly one legal swizzled layout, SWIZZLE_128B_BASE32B (layout type 1; TMA name
+// SWIZZLE_128B_ATOM_32B): rows of 32 m (128 B), atoms of 4 k-rows (512 B) in which the 32-byte granules of a row
+// are XORed with (k row & 3).  Boxes of 32 m x 16 k -> SBO = 512 (next 4 k), LBO = 2048 (next 32 m = next box).
+template <bool KMAJOR>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  if (KMAJOR) {
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)4 << 61;
+  } else {
+    d |= (uint64_t)(2048 >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 61;
+  }
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+struct Tc2Params {
+  float* C;
+  long long ldc;
+  int M, N, K;
+  float alpha, beta;
+  int c_tri;
+  int a_mode, b_mode;   // triangular structure in (row, k) space: 1 k<=r, 2 k>=r, 3 k>r, 4 k<r
+  int tiles_m, tiles_n;
+  int vecC;
+};
+
+__device__ __forceinline__ bool keep_rk(int mode, int r, int k) {
+  return mode == 0 || (mode == 1 && k <= r) || (mode == 2 && k >= r) || (mode == 3 && k > r) || (mode == 4 && k < r);
+}
+// k-block range [lo, hi) that can hold non-zeros for a tile whose rows start at r0 (extent ext)
+__device__ __forceinline__ void trim_range(int mode, int r0, int ext, int& lo, int& hi) {
+  if (mode == 1) hi = min(hi, (r0 + ext + BK - 1) / BK);
+  else if (mode == 2) lo = max(lo, r0 / BK);
+  else if (mode == 3) lo = max(lo, (r0 + 1) / BK);
+  else if (mode == 4) hi = min(hi, (r0 + ext - 1 + BK - 1) / BK);
+}
+// does the mask zero anything inside rows [r0, r0+rows) x k [k0, k0+BK) ?
+__device__ __forceinline__ bool mask_crosses(int mode, int r0, int rows, int k0) {
+  switch (mode) {
+    case 0: return false;
+    case 1: return k0 + BK - 1 > r0;
+    case 2: return k0 < r0 + rows - 1;
+    case 3: return k0 <= r0 + rows - 1;
+    default: return k0 + BK - 1 >= r0;
+  }
+}
+
+// hi/lo split of one operand tile in shared memory (element-wise, so the swizzle does not matter); with MASK the
+// logical (row, k) of every 16-byte chunk is recovered from its swizzled position and masked elements are zeroed
+// in the raw tile as well.  ct = converter thread index (0..127).
+template <int ROWS, bool KMAJOR, bool MASK>
+__device__ __forceinline__ void convert_tile(uint32_t raw, uint32_t lo, int ct, int mode, int r0, int k0) {
+  constexpr int CHUNKS = ROWS * BK * 4 / 16;
+  constexpr int PER = CHUNKS / 128;
+  constexpr int BATCH = 4;
+  static_assert(PER % BATCH == 0, "tile size");
+#pragma unroll 1
+  for (int b = 0; b < PER; b += BATCH) {
+    float4 v[BATCH];
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const uint32_t o = (uint32_t)(ct + 128 * (b + i)) * 16u;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(raw + o));
+    }
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const uint32_t o = (uint32_t)(ct + 128 * (b + i)) * 16u;
+      float t[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      if (MASK) {
+        int r, k;
+        bool any = false;
+        if (KMAJOR) {       // row = o / 64, logical 16-byte chunk = physical ^ ((o >> 7) & 3)
+          r = (int)(o >> 6); k = (int)((((o >> 4) & 3u) ^ ((o >> 7) & 3u)) * 4u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (!keep_rk(mode, r0 + r, k0 + k + e)) { t[e] = 0.f; any = true; }
+        } else {            // box = o / 2048, k row = (o >> 7) & 15, logical 32-byte granule = physical ^ (krow & 3)
+          k = (int)((o >> 7) & 15u);
+          r = (int)((o >> 11) * 32u + ((((o >> 5) & 3u) ^ ((o >> 7) & 3u)) * 8u) + ((o >> 4) & 1u) * 4u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (!keep_rk(mode, r0 + r + e, k0 + k)) { t[e] = 0.f; any = true; }
+        }
+        if (any) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raw + o), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]) : "memory");
+      }
+      float l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float h = __uint_as_float(__float_as_uint(t[e]) & 0xFFFFE000u);
+        const float d = t[e] - h;                                        // exact
+        l[e] = __uint_as_float(__float_as_uint(d) + 0x1000u);            // round to nearest at the tf32 cut (MMA truncates)
+      }
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + o), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
+    }
+  }
+}
+
+template <int BN, bool AKM, bool BKM>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc2Params p) {
+  constexpr int B_TILE = BN * BK * 4;
+  constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+  constexpr int HALF = BN / 2;                       // columns per epilogue warp
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + NSTAGE * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto conv_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (2 * NSTAGE + s); };
+  auto tfull_bar = [&](int b) { return bars + 8u * (3 * NSTAGE + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (3 * NSTAGE + 2 + b); };
+  const uint32_t tmem_ptr_addr = bars + 8u * (3 * NSTAGE + 4);
+
+  constexpr int GROUP = 8;                            // grouped rasterisation: 8 row tiles share a B panel in L2
+  const int bid = blockIdx.x;
+  const int per_group = GROUP * p.tiles_n;
+  const int first_m = (bid / per_group) * GROUP;
+  const int gsz = min(p.tiles_m - first_m, GROUP);
+  const int tm = first_m + (bid % per_group) % gsz;
+  const int tn = (bid % per_group) / gsz;
+  const int m0 = tm * BM, n0 = tn * BN;
+  if (p.c_tri == 1 && n0 > m0 + BM - 1) return;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int kb_lo = 0, kb_hi = (p.K + BK - 1) / BK;
+  trim_range(p.a_mode, m0, BM, kb_lo, kb_hi);
+  trim_range(p.b_mode, n0, BN, kb_lo, kb_hi);
+  const int num_k = max(kb_hi - kb_lo, 0);
+  const int num_c = (num_k + CHK - 1) / CHK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 4); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)(2 * BN)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {          // ---------------- TMA producer ----------------
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t st = base + s * STAGE_BYTES;
+        mbar_expect_tx(full_bar(s), A_TILE + B_TILE);
+        const int k0 = (kb_lo + kb) * BK;
+        if (AKM) tma_load_2d(st, &tmA, full_bar(s), k0, m0);
+        else {
+#pragma unroll
+          for (int i = 0; i < BM / 32; ++i) tma_load_2d(st + i * 2048, &tmA, full_bar(s), m0 + 32 * i, k0);
+        }
+        const uint32_t sb = st + 2 * A_TILE;
+        if (BKM) tma_load_2d(sb, &tmB, full_bar(s), k0, n0);
+        else {
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i) tma_load_2d(sb + i * 2048, &tmB, full_bar(s), n0 + 32 * i, k0);
+        }
+        if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+      }
+    } else if (warp == 1 && lane == 0) {   // ---------------- MMA issuer ----------------
+      // instruction descriptor: D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), major bits 15/16 (1 = MN-major),
+      // N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (AKM ? 0u : (1u << 15)) | (BKM ? 0u : (1u << 16)) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      constexpr uint32_t ADV_A = AKM ? (32u >> 4) : (1024u >> 4);     // one K=8 step, in 16-byte units
+      constexpr uint32_t ADV_B = BKM ? (32u >> 4) : (1024u >> 4);
+      int s = 0; uint32_t ph = 0;
+      for (int c = 0; c < num_c; ++c) {
+        const int buf = c & 1;
+        mbar_wait(tempty_bar(buf), (uint32_t)(((c >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        const int kb_end = min(num_k, (c + 1) * CHK);
+        for (int kb = c * CHK; kb < kb_end; ++kb) {
+          mbar_wait(conv_bar(s), ph);
+          tc_fence_after();
+          const uint32_t st = base + s * STAGE_BYTES;
+          const uint64_t a_hi = make_desc<AKM>(st), a_lo = make_desc<AKM>(st + A_TILE);
+          const uint64_t b_hi = make_desc<BKM>(st + 2 * A_TILE), b_lo = make_desc<BKM>(st + 2 * A_TILE + B_TILE);
+          const bool first_kb = (kb == c * CHK);
+#pragma unroll
+          for (int k2 = 0; k2 < BK / 8; ++k2) {
+            const uint64_t da = (uint64_t)(ADV_A * k2), db = (uint64_t)(ADV_B * k2);
+            tc_mma_tf32(d_tmem, a_lo + da, b_hi + db, idesc, (first_kb && k2 == 0) ? 0u : 1u);   // small terms first
+            tc_mma_tf32(d_tmem, a_hi + da, b_lo + db, idesc, 1u);
+            tc_mma_tf32(d_tmem, a_hi + da, b_hi + db, idesc, 1u);
+          }
+          tc_commit(empty_bar(s));
+          if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+        }
+        tc_commit(tfull_bar(buf));
+      }
+    }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    // ---------------- converters ----------------
+    const int ct = threadIdx.x - 128;
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < num_k; ++kb) {
+      const int k0 = (kb_lo + kb) * BK;
+      mbar_wait(full_bar(s), ph);
+      const uint32_t st = base + s * STAGE_BYTES;
+      if (mask_crosses(p.a_mode, m0, BM, k0)) convert_tile<BM, AKM, true>(st, st + A_TILE, ct, p.a_mode, m0, k0);
+      else convert_tile<BM, AKM, false>(st, st + A_TILE, ct, 0, 0, 0);
+      if (mask_crosses(p.b_mode, n0, BN, k0)) convert_tile<BN, BKM, true>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ct, p.b_mode, n0, k0);
+      else convert_tile<BN, BKM, false>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ct, 0, 0, 0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(conv_bar(s));
+      if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    // ---------------- epilogue: warp (w & 3) owns TMEM lanes [32 (w&3), +32), column half (w - 8) / 4 ----------------
+    const int q = warp & 3;
+    const int half = (warp - 8) >> 2;
+    float acc[HALF];
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+    for (int c = 0; c < num_c; ++c) {
+      const int buf = c & 1;
+      mbar_wait(tfull_bar(buf), (uint32_t)((c >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < HALF / 32; ++i) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF + i * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[i * 32 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+    const int gi = m0 + q * 32 + lane;
+    if (gi < p.M) {
+      float* crow = p.C + (long long)gi * p.ldc;
+      const int gj0 = n0 + half * HALF;
+#pragma unroll
+      for (int v = 0; v < HALF / 4; ++v) {
+        const int gj = gj0 + v * 4;
+        if (gj < p.N) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = p.alpha * acc[v * 4 + e];
+          const bool full = (gj + 3 < p.N) && !(p.c_tri == 1 && gj + 3 > gi);
+          if (full && p.vecC) {
+            if (p.beta != 0.f) {
+              const float4 old = *reinterpret_cast<const float4*>(crow + gj);
+              o[0] = fmaf(p.beta, old.x, o[0]); o[1] = fmaf(p.beta, old.y, o[1]);
+              o[2] = fmaf(p.beta, old.z, o[2]); o[3] = fmaf(p.beta, old.w, o[3]);
+            }
+            *reinterpret_cast<float4*>(crow + gj) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (gj + e < p.N && !(p.c_tri == 1 && gj + e > gi)) {
+                float x = o[e];
+                if (p.beta != 0.f) x = fmaf(p.beta, crow[gj + e], x);
+                crow[gj + e] = x;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode2() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// Tensor map of one operand.  K-major: stored [rows x K], box {16 k, box_rows} SWIZZLE_64B.
+//                              MN-major: stored [K x rows], box {32 rows, 16 k} SWIZZLE_128B_ATOM_32B.
+int make_map2(CUtensorMap* map, const float* ptr, long long rows, long long K, long long ld, bool kmajor, int box_rows) {
+  auto enc = get_encode2();
+  if (!enc) return HB_ERR_CUDA;
+  cuuint64_t gdim[2], gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2], estr[2] = {1, 1};
+  CUtensorMapSwizzle sw;
+  if (kmajor) { gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows; box[0] = BK; box[1] = (cuuint32_t)box_rows; sw = CU_TENSOR_MAP_SWIZZLE_64B; }
+  else { gdim[0] = (cuuint64_t)rows; gdim[1] = (cuuint64_t)K; box[0] = 32; box[1] = BK; sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? HB_OK : HB_ERR_CUDA;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BN, bool AKM, bool BKM>
+int launch3(const CUtensorMap& ta, const CUtensorMap& tb, Tc2Params tp, cudaStream_t st) {
+  constexpr int SMEM = NSTAGE * (2 * A_TILE + 2 * BN * BK * 4) + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(gemm_tc2_kernel<BN, AKM, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+      return HB_ERR_CUDA;
+    attr_done = true;
+  }
+  tp.tiles_m = cdiv(tp.M, BM);
+  tp.tiles_n = cdiv(tp.N, BN);
+  gemm_tc2_kernel<BN, AKM, BKM><<<tp.tiles_m * tp.tiles_n, NTHREADS, SMEM, st>>>(ta, tb, tp);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+template <int BN>
+int launch2(bool akm, bool bkm, const CUtensorMap& ta, const CUtensorMap& tb, const Tc2Params& tp, cudaStream_t st) {
+  if (akm) return bkm ? launch3<BN, true, true>(ta, tb, tp, st) : launch3<BN, true, false>(ta, tb, tp, st);
+  return bkm ? launch3<BN, false, true>(ta, tb, tp, st) : launch3<BN, false, false>(ta, tb, tp, st);
+}
+
+}  // namespace
+
+// No workspace: operands are consumed where they lie.  Needs 16-byte aligned operands with ld % 4 == 0 (TMA).
+bool gemm_tc2_eligible(const GemmParams& p) {
+  if (p.batch != 1 || p.bias || p.act != ACT_NONE || p.clip) return false;
+  if (p.M < 1 || p.N < 1 || p.K < 1) return false;
+  if (!aligned16(p.A) || !aligned16(p.B) || (p.lda & 3) || (p.ldb & 3)) return false;
+  if (p.C == p.A && p.N > 256) return false;
+  return true;
+}
+
+int gemm_tc2(const GemmParams& p, cudaStream_t st) {
+  static const int b2rk[5] = {0, 2, 1, 4, 3};      // mask of op(B)[k][n] expressed in (n, k) space
+  const bool akm = (p.transA == 0), bkm = (p.transB == 1);
+  const int BN = (p.N <= 128) ? 128 : 256;
+  CUtensorMap ta, tb;
+  HB_TRY(make_map2(&ta, p.A, p.M, p.K, p.lda, akm, BM));
+  HB_TRY(make_map2(&tb, p.B, p.N, p.K, p.ldb, bkm, BN));
+  Tc2Params tp;
+  tp.C = p.C; tp.ldc = p.ldc; tp.M = p.M; tp.N = p.N; tp.K = p.K; tp.alpha = p.alpha; tp.beta = p.beta;
+  tp.c_tri = p.c_tri; tp.a_mode = p.a_tri; tp.b_mode = b2rk[p.b_tri]; tp.tiles_m = 0; tp.tiles_n = 0;
+  tp.vecC = aligned16(p.C) && (p.ldc % 4 == 0);
+  if (BN == 128) return launch2<128>(akm, bkm, ta, tb, tp, st);
+  return launch2<256>(akm, bkm, ta, tb, tp, st);
+}
+
+}  // namespace hb

@@ -491,11 +491,9 @@ int chol_rev_rec(const Ctx& c, const float* L, long long ldl, float* G, long lon
 
 }  // namespace
 
-static size_t tc_bytes_for(int m, int n) {   // largest GEMM of a recursion over an n x n triangle with m-row panels
-  if (n < 2 * NB) return 0;
-  const int h = split_point(n);
-  return gemm_tc_workspace_bytes(m < 0 ? h : m, h, h) + 256;
-}
+// The generation-2 tensor-core engine consumes operands in place, so the factorisations need no GEMM scratch
+// (generation 1 needed hi/lo copies of the largest operand pair: n^2 floats).
+static size_t tc_bytes_for(int, int) { return 0; }
 
 static size_t base_bytes(long long rows, int n) {
   const long long nblk = (n + NB - 1) / NB;
