@@ -22,6 +22,8 @@
 
 namespace hb {
 
+int get_tc_option();   // gemm_tc.cu
+
 namespace {
 
 constexpr int BM = 128;
@@ -370,6 +372,248 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs owns one 256 x 256 output tile.  CTA r holds the A
+// rows [m0 + 128 r, +128) and the B rows [n0 + 128 r, +128) of every k-block plus the accumulator rows of its own
+// A half; the leader CTA issues one M=256 MMA that reads both CTAs' shared memory.  Per SM and MMA this halves the
+// B-operand shared-memory reads (the 1-CTA kernel is shared-memory-bandwidth bound: MMA operand reads 96 B/clk +
+// TMA 32 + converters 64 against 128 B/clk -- ncu: tensor pipe 67 % busy) and halves TMA / converter work per flop.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int NSTAGE_P = 6;
+constexpr int P_STAGE_BYTES = 4 * A_TILE;           // A raw | A lo | B-half raw | B-half lo, 8 KB each
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default (.release.cta)
+// semantics on purpose: a .release.cluster arrive compiles to MEMBAR.ALL.GPU + CCTL.IVALL per call, which made the
+// converter warps the bottleneck (131 vs 200 TFLOP/s).  The data it publishes is shared memory written before a
+// fence.proxy.async by the same warp, or TMEM reads completed by tcgen05.wait::ld.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+template <bool AKM, bool BKM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc2Params p) {
+  constexpr int BN = 256, PM = 256;                  // pair tile
+  constexpr int HALF = BN / 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + NSTAGE_P * P_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto conv_bar = [&](int s) { return bars + 8u * (NSTAGE_P + s); };          // used in the leader: 4 local + 4 remote warps
+  auto empty_bar = [&](int s) { return bars + 8u * (2 * NSTAGE_P + s); };
+  auto tfull_bar = [&](int b) { return bars + 8u * (3 * NSTAGE_P + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (3 * NSTAGE_P + 2 + b); };  // used in the leader: 8 local + 8 remote warps
+  const uint32_t tmem_ptr_addr = bars + 8u * (3 * NSTAGE_P + 4);
+
+  const uint32_t rank = cluster_ctarank();
+  constexpr int GROUP = 4;                            // 4 pair-rows (1024 rows) share a B panel in L2
+  const int bid = blockIdx.x >> 1;
+  const int per_group = GROUP * p.tiles_n;
+  const int first_m = (bid / per_group) * GROUP;
+  const int gsz = min(p.tiles_m - first_m, GROUP);
+  const int tm = first_m + (bid % per_group) % gsz;
+  const int tn = (bid % per_group) / gsz;
+  const int pm0 = tm * PM, n0 = tn * BN;              // pair tile origin
+  if (p.c_tri == 1 && n0 > pm0 + PM - 1) return;      // same decision in both CTAs
+  const int m0 = pm0 + 128 * (int)rank;               // this CTA's A / accumulator rows
+  const int nb0 = n0 + 128 * (int)rank;               // this CTA's B rows
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int kb_lo = 0, kb_hi = (p.K + BK - 1) / BK;
+  trim_range(p.a_mode, pm0, PM, kb_lo, kb_hi);
+  trim_range(p.b_mode, n0, BN, kb_lo, kb_hi);
+  const int num_k = max(kb_hi - kb_lo, 0);
+  const int num_c = (num_k + CHK - 1) / CHK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NSTAGE_P; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 8); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                 // barriers of both CTAs are initialised before any remote arrive
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {          // ---------------- TMA producer (each CTA loads its own halves) ----------------
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t st = base + s * P_STAGE_BYTES;
+        mbar_expect_tx(full_bar(s), 2 * A_TILE);
+        const int k0 = (kb_lo + kb) * BK;
+        if (AKM) tma_load_2d(st, &tmA, full_bar(s), k0, m0);
+        else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_load_2d(st + i * 2048, &tmA, full_bar(s), m0 + 32 * i, k0);
+        }
+        const uint32_t sb = st + 2 * A_TILE;
+        if (BKM) tma_load_2d(sb, &tmB, full_bar(s), k0, nb0);
+        else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_load_2d(sb + i * 2048, &tmB, full_bar(s), nb0 + 32 * i, k0);
+        }
+        if (++s == NSTAGE_P) { s = 0; ph ^= 1u; }
+      }
+    } else if (warp == 1 && lane == 0 && rank == 0) {   // ---------------- MMA issuer (leader CTA only) ----------------
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (AKM ? 0u : (1u << 15)) | (BKM ? 0u : (1u << 16)) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
+      constexpr uint32_t ADV_A = AKM ? (32u >> 4) : (1024u >> 4);
+      constexpr uint32_t ADV_B = BKM ? (32u >> 4) : (1024u >> 4);
+      int s = 0; uint32_t ph = 0;
+      for (int c = 0; c < num_c; ++c) {
+        const int buf = c & 1;
+        mbar_wait(tempty_bar(buf), (uint32_t)(((c >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        const int kb_end = min(num_k, (c + 1) * CHK);
+        for (int kb = c * CHK; kb < kb_end; ++kb) {
+          mbar_wait(conv_bar(s), ph);
+          tc_fence_after();
+          const uint32_t st = base + s * P_STAGE_BYTES;
+          const uint64_t a_hi = make_desc<AKM>(st), a_lo = make_desc<AKM>(st + A_TILE);
+          const uint64_t b_hi = make_desc<BKM>(st + 2 * A_TILE), b_lo = make_desc<BKM>(st + 3 * A_TILE);
+          const bool first_kb = (kb == c * CHK);
+#pragma unroll
+          for (int k2 = 0; k2 < BK / 8; ++k2) {
+            const uint64_t da = (uint64_t)(ADV_A * k2), db = (uint64_t)(ADV_B * k2);
+            tc_mma_tf32_pair(d_tmem, a_lo + da, b_hi + db, idesc, (first_kb && k2 == 0) ? 0u : 1u);
+            tc_mma_tf32_pair(d_tmem, a_hi + da, b_lo + db, idesc, 1u);
+            tc_mma_tf32_pair(d_tmem, a_hi + da, b_hi + db, idesc, 1u);
+          }
+          tc_commit_pair(empty_bar(s));              // frees stage s in both CTAs
+          if (++s == NSTAGE_P) { s = 0; ph ^= 1u; }
+        }
+        tc_commit_pair(tfull_bar(buf));              // both CTAs' epilogues may drain their half
+      }
+    }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    // ---------------- converters: own A tile and own B half, then tell the leader ----------------
+    const int ct = threadIdx.x - 128;
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < num_k; ++kb) {
+      const int k0 = (kb_lo + kb) * BK;
+      mbar_wait(full_bar(s), ph);
+      const uint32_t st = base + s * P_STAGE_BYTES;
+      if (mask_crosses(p.a_mode, m0, 128, k0)) convert_tile<128, AKM, true>(st, st + A_TILE, ct, p.a_mode, m0, k0);
+      else convert_tile<128, AKM, false>(st, st + A_TILE, ct, 0, 0, 0);
+      if (mask_crosses(p.b_mode, nb0, 128, k0)) convert_tile<128, BKM, true>(st + 2 * A_TILE, st + 3 * A_TILE, ct, p.b_mode, nb0, k0);
+      else convert_tile<128, BKM, false>(st + 2 * A_TILE, st + 3 * A_TILE, ct, 0, 0, 0);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(conv_bar(s), 0);
+      if (++s == NSTAGE_P) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    // ---------------- epilogue: this CTA's 128 accumulator rows ----------------
+    const int q = warp & 3;
+    const int half = (warp - 8) >> 2;
+    float acc[HALF];
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+    for (int c = 0; c < num_c; ++c) {
+      const int buf = c & 1;
+      mbar_wait(tfull_bar(buf), (uint32_t)((c >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < HALF / 32; ++i) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF + i * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[i * 32 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(tempty_bar(buf), 0);
+    }
+    const int gi = m0 + q * 32 + lane;
+    if (gi < p.M) {
+      float* crow = p.C + (long long)gi * p.ldc;
+      const int gj0 = n0 + half * HALF;
+#pragma unroll
+      for (int v = 0; v < HALF / 4; ++v) {
+        const int gj = gj0 + v * 4;
+        if (gj < p.N) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = p.alpha * acc[v * 4 + e];
+          const bool full = (gj + 3 < p.N) && !(p.c_tri == 1 && gj + 3 > gi);
+          if (full && p.vecC) {
+            if (p.beta != 0.f) {
+              const float4 old = *reinterpret_cast<const float4*>(crow + gj);
+              o[0] = fmaf(p.beta, old.x, o[0]); o[1] = fmaf(p.beta, old.y, o[1]);
+              o[2] = fmaf(p.beta, old.z, o[2]); o[3] = fmaf(p.beta, old.w, o[3]);
+            }
+            *reinterpret_cast<float4*>(crow + gj) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (gj + e < p.N && !(p.c_tri == 1 && gj + e > gi)) {
+                float x = o[e];
+                if (p.beta != 0.f) x = fmaf(p.beta, crow[gj + e], x);
+                crow[gj + e] = x;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                 // no CTA leaves (or frees TMEM) while its partner may still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode2() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -415,6 +659,27 @@ int launch3(const CUtensorMap& ta, const CUtensorMap& tb, Tc2Params tp, cudaStre
   return HB_OK;
 }
 
+template <bool AKM, bool BKM>
+int launch_pair2(const CUtensorMap& ta, const CUtensorMap& tb, Tc2Params tp, cudaStream_t st) {
+  constexpr int SMEM = NSTAGE_P * P_STAGE_BYTES + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(gemm_tc2_pair_kernel<AKM, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+      return HB_ERR_CUDA;
+    attr_done = true;
+  }
+  tp.tiles_m = cdiv(tp.M, 256);
+  tp.tiles_n = cdiv(tp.N, 256);
+  gemm_tc2_pair_kernel<AKM, BKM><<<2 * tp.tiles_m * tp.tiles_n, NTHREADS, SMEM, st>>>(ta, tb, tp);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+int launch_pair(bool akm, bool bkm, const CUtensorMap& ta, const CUtensorMap& tb, const Tc2Params& tp, cudaStream_t st) {
+  if (akm) return bkm ? launch_pair2<true, true>(ta, tb, tp, st) : launch_pair2<true, false>(ta, tb, tp, st);
+  return bkm ? launch_pair2<false, true>(ta, tb, tp, st) : launch_pair2<false, false>(ta, tb, tp, st);
+}
+
 template <int BN>
 int launch2(bool akm, bool bkm, const CUtensorMap& ta, const CUtensorMap& tb, const Tc2Params& tp, cudaStream_t st) {
   if (akm) return bkm ? launch3<BN, true, true>(ta, tb, tp, st) : launch3<BN, true, false>(ta, tb, tp, st);
@@ -436,13 +701,17 @@ int gemm_tc2(const GemmParams& p, cudaStream_t st) {
   static const int b2rk[5] = {0, 2, 1, 4, 3};      // mask of op(B)[k][n] expressed in (n, k) space
   const bool akm = (p.transA == 0), bkm = (p.transB == 1);
   const int BN = (p.N <= 128) ? 128 : 256;
+  // CTA pairs (256 x 256 tiles) once there are enough of them to fill the GPU; bit 2 of the option word disables them
+  const bool pair = BN == 256 && !(get_tc_option() & 4) && (long long)cdiv(p.M, 256) * cdiv(p.N, 256) >= 64 &&
+                    !(p.C == p.A);
   CUtensorMap ta, tb;
   HB_TRY(make_map2(&ta, p.A, p.M, p.K, p.lda, akm, BM));
-  HB_TRY(make_map2(&tb, p.B, p.N, p.K, p.ldb, bkm, BN));
+  HB_TRY(make_map2(&tb, p.B, p.N, p.K, p.ldb, bkm, pair ? 128 : BN));
   Tc2Params tp;
   tp.C = p.C; tp.ldc = p.ldc; tp.M = p.M; tp.N = p.N; tp.K = p.K; tp.alpha = p.alpha; tp.beta = p.beta;
   tp.c_tri = p.c_tri; tp.a_mode = p.a_tri; tp.b_mode = b2rk[p.b_tri]; tp.tiles_m = 0; tp.tiles_n = 0;
   tp.vecC = aligned16(p.C) && (p.ldc % 4 == 0);
+  if (pair) return launch_pair(akm, bkm, ta, tb, tp, st);
   if (BN == 128) return launch2<128>(akm, bkm, ta, tb, tp, st);
   return launch2<256>(akm, bkm, ta, tb, tp, st);
 }

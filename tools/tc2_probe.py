@@ -24,7 +24,7 @@ def timeit(M, N, K, tA, tB, a_tri=0, c_tri=0, opt=0, reps=5, beta=0.0):
     lib.hb_set_tc_option(0); lib.hb_set_gemm_engine(0)
     ms = e0.elapsed_time(e1) / reps
     fl = 2.0 * M * N * K * (0.5 if (c_tri or a_tri) else 1.0)
-    print(f"time M={M} N={N} K={K} tA={tA} tB={tB} a_tri={a_tri} c_tri={c_tri} gen={'1' if opt & 2 else '2'} rc={rc}: {ms:.3f} ms {fl / ms / 1e9:.1f} TF/s", flush=True)
+    print(f"time M={M} N={N} K={K} tA={tA} tB={tB} a_tri={a_tri} c_tri={c_tri} gen={'1' if opt & 2 else ('2-single' if opt & 4 else '2-pair')} rc={rc}: {ms:.3f} ms {fl / ms / 1e9:.1f} TF/s", flush=True)
 
 if __name__ == "__main__":
     worst = 0.0
@@ -43,8 +43,20 @@ if __name__ == "__main__":
     worst = max(worst, run(640, 640, 384, 0, 1, c_tri=1, alpha=-1.0, beta=1.0))
     worst = max(worst, run(1000, 1000, 1000, 1, 0, a_tri=3))
     worst = max(worst, run(2048, 2048, 2048, 0, 1))
-    print("worst tc2 err", worst, flush=True)
-    for opt in (0, 2):
+    print("worst tc2 err (1-CTA shapes)", worst, flush=True)
+    worst = 0.0
+    for (tA, tB) in ((0, 1), (0, 0), (1, 0), (1, 1)):      # CTA-pair kernel: >= 64 tiles of 256 x 256
+        worst = max(worst, run(2100, 2180, 520, tA, tB, alpha=-1.0, beta=1.0))
+    for a_tri in (1, 2, 3, 4):
+        worst = max(worst, run(2048, 2048, 2048, 0, 0, a_tri=a_tri, alpha=-2.0, beta=1.0))
+        worst = max(worst, run(2048, 2048, 2048, 1, 0, a_tri=a_tri))
+    for b_tri in (1, 2, 3, 4):
+        worst = max(worst, run(2048, 2304, 2304, 0, 1, b_tri=b_tri))
+        worst = max(worst, run(2048, 2304, 2304, 0, 0, b_tri=b_tri))
+    worst = max(worst, run(3000, 3000, 700, 1, 0, c_tri=1, alpha=-1.0, beta=1.0))
+    worst = max(worst, run(3000, 3000, 700, 0, 1, c_tri=1, alpha=-1.0, beta=1.0))
+    print("worst tc2 err (pair shapes)", worst, flush=True)
+    for opt in (0, 4):
         timeit(4096, 4096, 4096, 0, 1, opt=opt)
         timeit(8192, 8192, 8192, 0, 1, c_tri=1, opt=opt)
         timeit(8192, 8192, 8192, 1, 0, opt=opt)
