@@ -41,6 +41,8 @@ SIGNATURES = {
     "hb_get_gemm_engine": (_i, []),
     "hb_profile_begin": (_i, [_i]),
     "hb_profile_end": (_i, [C.POINTER(C.c_double)]),
+    "hb_phase_begin": (_i, []),
+    "hb_phase_end": (_i, [C.POINTER(C.c_double), _i]),
     "hb_randn_philox": (_i, [_c_f, _ll, _ull, _ull, _c_f]),
     "hb_sample_diag_fwd": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _c_f, _ull, _ull, _i, _c_f, _c_f, _c_f, _sz, _c_f]),
     "hb_sample_diag_bwd": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _c_f, _ull, _ull, _i, _c_f, _c_f, _fl, _c_f, _c_f, _ll,

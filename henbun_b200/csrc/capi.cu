@@ -20,7 +20,9 @@ int get_tc_option();
 
 // shapes worth a tensor-core launch
 static bool tc_worth(const GemmParams& p) {
-  return p.N >= 64 && p.K >= 32 && (double)p.M * p.N * p.K >= 256.0 * 256.0 * 256.0;
+  if (p.N < 64 || p.K < 32) return false;
+  if ((double)p.M * p.N * p.K >= 256.0 * 256.0 * 256.0) return true;
+  return p.K >= 512 && p.M >= 64 && p.ws != nullptr;     // long-K reductions into a small tile: split-K on tensor cores
 }
 // short-K products: the whole-K SIMT kernel wins until there are enough 128-row tiles to fill the tensor-core grid
 static bool prefer_small(const GemmParams& p) {
@@ -54,6 +56,17 @@ struct GemmProfiler {
   std::vector<double> flops;
   std::vector<long long> shape;   // M, N, K, engine(1 = tensor core) per launch
 } g_prof;
+
+// Optional phase timing of the fused GP step (events on the launching stream; enabled by hb_phase_begin).
+struct PhaseProfiler {
+  bool on = false;
+  int used = 0;
+  cudaEvent_t ev[16];
+  bool made = false;
+} g_phase;
+static void phase_mark(cudaStream_t st) {
+  if (g_phase.on && g_phase.used < 16) cudaEventRecord(g_phase.ev[g_phase.used++], st);
+}
 
 static double gemm_useful_flops(const GemmParams& p) {
   double f = 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch;
@@ -201,6 +214,29 @@ int hb_profile_end(double* out4_host) {
   if (f) fclose(f);
   out4_host[0] = (double)g_prof.used; out4_host[1] = ms; out4_host[2] = fl; out4_host[3] = 0.0;
   return HB_OK;
+}
+
+// Phase timing of ONE hb_gp_elbo_step call: hb_phase_begin(); step; hb_phase_end(out) -> ms of
+// {prep+Gram fwd, potrf, sampler+F+loglik+W, sampler bwd + Lbar, potrf_bwd, Gram bwd + scalars}; returns #phases.
+int hb_phase_begin(void) {
+  if (!g_phase.made) {
+    for (int i = 0; i < 16; ++i) if (cudaEventCreate(&g_phase.ev[i]) != cudaSuccess) return HB_ERR_CUDA;
+    g_phase.made = true;
+  }
+  g_phase.used = 0; g_phase.on = true;
+  return HB_OK;
+}
+int hb_phase_end(double* out_ms, int capacity) {
+  g_phase.on = false;
+  if (!out_ms) return -1;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  int n = 0;
+  for (int i = 0; i + 1 < g_phase.used && n < capacity; ++i, ++n) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_phase.ev[i], g_phase.ev[i + 1]) != cudaSuccess) return -1;
+    out_ms[n] = t;
+  }
+  return n;
 }
 
 int hb_randn_philox(float* out, long long count, unsigned long long seed, unsigned long long offset, void* stream) {
@@ -422,6 +458,7 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
   float* g_var = g_kvar + 1;
   const float invS = 1.f / (float)Sn;
 
+  phase_mark(st);
   gp_prep_scalars_kernel<<<1, 32, 0, st>>>(p_scale, p_ell, c.n_ell, p_kvar, p_var, sc);
   HB_CHECK_LAUNCH();
   const float* d_var = sc + 2;
@@ -430,7 +467,9 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
 
   // K = rbf(X) + jitter I (lower tiles), L = chol(K) in place
   HB_TRY(rbf_gram_fwd(X, nullptr, n, n, c.D, 0, 0, d_ell, c.n_ell, K, n, 0, 1, c.jitter, 1, 0, st));
+  phase_mark(st);
   HB_TRY(potrf_lower(K, n, 0, n, 1, 0, pws, L.potrf_bytes, err_flag, st));
+  phase_mark(st);
 
   // sampler + KL
   const float* eps_used = eps;
@@ -459,6 +498,7 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
     g.C = W; g.ldc = n; g.M = Sn; g.N = n; g.K = n;
     HB_TRY(gemm(g, st));
   }
+  phase_mark(st);
   if (!c.q_fullrank) {
     HB_TRY(sample_diag_bwd(p_mu, n, p_sq, n, 1, n, eps, c.seed, c.offset, Sn, W, d_a, invS, nullptr, g_mu, n, g_sq, n, 0.f, st));
   } else {
@@ -481,11 +521,14 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
     g.C = G; g.ldc = n; g.c_tri = 1; g.M = n; g.N = n; g.K = Sn;
     HB_TRY(gemm(g, st));
   }
+  phase_mark(st);
   HB_TRY(potrf_lower_bwd(K, n, 0, G, n, 0, n, 1, pws, L.potrf_bytes, st));
+  phase_mark(st);
   HB_TRY(rbf_gram_bwd(G, n, 0, X, nullptr, n, n, c.D, 0, 0, d_ell, c.n_ell, 1, 1, 0, d_a, g_ell, red, kReduceWsBytes, st));
   gp_scalar_bwd_kernel<<<1, 32, 0, st>>>(sc, ll3, kl, (long long)Sn * n, Sn, p_scale, p_ell, c.n_ell, p_kvar, p_var,
                                          g_scale, g_ell, g_kvar, g_var, out4);
   HB_CHECK_LAUNCH();
+  phase_mark(st);
   return HB_OK;
 }
 

@@ -105,6 +105,8 @@ struct Tc2Params {
   int a_mode, b_mode;   // triangular structure in (row, k) space: 1 k<=r, 2 k>=r, 3 k>r, 4 k<r
   int tiles_m, tiles_n;
   int vecC;
+  int ksplit;             // k-blocks per split (blockIdx.y = split index); 0 = no split
+  long long csplit;       // element stride between the partial outputs of consecutive splits
 };
 
 __device__ __forceinline__ bool keep_rk(int mode, int r, int k) {
@@ -206,6 +208,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   int kb_lo = 0, kb_hi = (p.K + BK - 1) / BK;
   trim_range(p.a_mode, m0, BM, kb_lo, kb_hi);
   trim_range(p.b_mode, n0, BN, kb_lo, kb_hi);
+  float* const Cout = p.C + (long long)blockIdx.y * p.csplit;   // split-K: this split's partial output
+  if (p.ksplit > 0) {
+    kb_lo = max(kb_lo, (int)blockIdx.y * p.ksplit);
+    kb_hi = min(kb_hi, ((int)blockIdx.y + 1) * p.ksplit);
+  }
   const int num_k = max(kb_hi - kb_lo, 0);
   const int num_c = (num_k + CHK - 1) / CHK;
 
@@ -333,7 +340,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     const int gi = m0 + q * 32 + lane;
     if (gi < p.M) {
-      float* crow = p.C + (long long)gi * p.ldc;
+      float* crow = Cout + (long long)gi * p.ldc;
       const int gj0 = n0 + half * HALF;
 #pragma unroll
       for (int v = 0; v < HALF / 4; ++v) {
@@ -614,6 +621,20 @@ gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// C = beta * C + sum_s partial[s]   (deterministic split-K reduction; c_tri: only j <= i)
+__global__ void splitk_reduce_kernel(float* C, long long ldc, const float* __restrict__ part, long long pstride, int M, int N,
+                                     int S, float beta, int c_tri) {
+  const long long total = (long long)M * N;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / N), j = (int)(e % N);
+    if (c_tri && j > i) continue;
+    float acc = 0.f;
+    for (int sidx = 0; sidx < S; ++sidx) acc += part[sidx * pstride + e];
+    float* c = C + (long long)i * ldc + j;
+    *c = (beta != 0.f) ? fmaf(beta, *c, acc) : acc;
+  }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 get_encode2() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -654,7 +675,8 @@ int launch3(const CUtensorMap& ta, const CUtensorMap& tb, Tc2Params tp, cudaStre
   }
   tp.tiles_m = cdiv(tp.M, BM);
   tp.tiles_n = cdiv(tp.N, BN);
-  gemm_tc2_kernel<BN, AKM, BKM><<<tp.tiles_m * tp.tiles_n, NTHREADS, SMEM, st>>>(ta, tb, tp);
+  const int nsplit = tp.ksplit > 0 ? cdiv(cdiv(tp.K, BK), tp.ksplit) : 1;
+  gemm_tc2_kernel<BN, AKM, BKM><<<dim3((unsigned)(tp.tiles_m * tp.tiles_n), (unsigned)nsplit), NTHREADS, SMEM, st>>>(ta, tb, tp);
   HB_CHECK_LAUNCH();
   return HB_OK;
 }
@@ -711,7 +733,33 @@ int gemm_tc2(const GemmParams& p, cudaStream_t st) {
   tp.C = p.C; tp.ldc = p.ldc; tp.M = p.M; tp.N = p.N; tp.K = p.K; tp.alpha = p.alpha; tp.beta = p.beta;
   tp.c_tri = p.c_tri; tp.a_mode = p.a_tri; tp.b_mode = b2rk[p.b_tri]; tp.tiles_m = 0; tp.tiles_n = 0;
   tp.vecC = aligned16(p.C) && (p.ldc % 4 == 0);
+  tp.ksplit = 0; tp.csplit = 0;
   if (pair) return launch_pair(akm, bkm, ta, tb, tp, st);
+  // split-K for "tall reductions" (small output, long K): partial tiles into the caller's scratch, then one
+  // deterministic reduction pass.  Used when the output has too few tiles to occupy the GPU.
+  const long long tiles = (long long)cdiv(p.M, BM) * cdiv(p.N, BN);
+  if (p.ws && tiles < 74 && p.K >= 512 && !p.a_tri && !p.b_tri) {
+    int want = (int)((148 + tiles - 1) / tiles);
+    const int kblocks = cdiv(p.K, BK);
+    int per = cdiv(kblocks, want);
+    per = (per + CHK - 1) / CHK * CHK;                     // whole accumulation chunks per split
+    if (per < 16) per = 16;                                // >= 256 of K per split
+    const int nsplit = cdiv(kblocks, per);
+    float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p.ws) + 255) & ~uintptr_t(255));
+    const size_t need = (size_t)nsplit * p.M * p.N * sizeof(float) + 256;
+    if (nsplit > 1 && p.ws_bytes >= need) {
+      Tc2Params sp = tp;
+      sp.C = part; sp.ldc = p.N; sp.beta = 0.f; sp.c_tri = p.c_tri; sp.ksplit = per; sp.csplit = (long long)p.M * p.N;
+      sp.vecC = (p.N % 4 == 0);
+      int rc = (BN == 128) ? launch2<128>(akm, bkm, ta, tb, sp, st) : launch2<256>(akm, bkm, ta, tb, sp, st);
+      if (rc != HB_OK) return rc;
+      const long long tot = (long long)p.M * p.N;
+      int nb = (int)((tot + 255) / 256); if (nb > 148 * 8) nb = 148 * 8;
+      splitk_reduce_kernel<<<nb, 256, 0, st>>>(p.C, p.ldc, part, sp.csplit, p.M, p.N, nsplit, p.beta, p.c_tri);
+      HB_CHECK_LAUNCH();
+      return HB_OK;
+    }
+  }
   if (BN == 128) return launch2<128>(akm, bkm, ta, tb, tp, st);
   return launch2<256>(akm, bkm, ta, tb, tp, st);
 }

@@ -129,6 +129,50 @@ __global__ void __launch_bounds__(256) rbf_gram_bwd_kernel(const float* __restri
     float facc[DMAX];
 #pragma unroll
     for (int d = 0; d < DMAX; ++d) facc[d] = 0.f;
+    if (DMAX <= 8) {
+      // small feature count: the thread's 4 x-rows and 4 y-rows live in registers (the shared-memory version
+      // issued 4 LDS per element and feature and was LDS-bound: 18 ms at n = 65536, D = 8)
+      float xr[4][DMAX], yr[4][DMAX];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int d = 0; d < DMAX; ++d) { xr[a][d] = (d < D) ? xs[ty + 16 * a][d] : 0.f; yr[a][d] = (d < D) ? ys[tx * 4 + a][d] : 0.f; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = i0 + ty + 16 * a;
+        if (i >= n) continue;
+        const float4 g4 = (j0 + tx * 4 + 3 < n2 && (ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(Gb) & 15) == 0)
+                              ? __ldg(reinterpret_cast<const float4*>(Gb + (long long)i * ldg + j0 + tx * 4))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool vec = (j0 + tx * 4 + 3 < n2 && (ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(Gb) & 15) == 0);
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int j = j0 + tx * 4 + b;
+          if (j >= n2) continue;
+          float w = 1.f;
+          if (sym_lower) {
+            if (j > i) continue;
+            w = (j == i) ? 1.f : 2.f;
+          }
+          float df[DMAX], r2 = 0.f, r2b = 0.f;
+#pragma unroll
+          for (int d = 0; d < DMAX; ++d) { df[d] = xr[a][d] - yr[b][d]; r2 = fmaf(df[d], df[d], r2); }
+          const float g = w * (vec ? gv[b] : __ldg(Gb + (long long)i * ldg + j));
+          const float gk = g * expf(-0.5f * r2);
+#pragma unroll
+          for (int d = 0; d < DMAX; ++d) facc[d] = fmaf(gk * df[d], df[d], facc[d]);
+          if (csym) {
+            float sf[DMAX];
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d) { sf[d] = xr[a][d] + yr[b][d]; r2b = fmaf(sf[d], sf[d], r2b); }
+            const float gkb = g * expf(-0.5f * r2b);
+#pragma unroll
+            for (int d = 0; d < DMAX; ++d) facc[d] = fmaf(gkb * sf[d], sf[d], facc[d]);
+          }
+        }
+      }
+    } else {
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const int i = i0 + ty + 16 * a;
@@ -166,6 +210,7 @@ __global__ void __launch_bounds__(256) rbf_gram_bwd_kernel(const float* __restri
           }
         }
       }
+    }
     }
 #pragma unroll
     for (int d = 0; d < DMAX; ++d) dacc[d] += (double)facc[d];

@@ -439,61 +439,114 @@ int trsm_rln(const Ctx& c, const float* L, long long ldl, int off, float* Bp, lo
   return trsm_rln(c, L, ldl, off, Bp, ldb, m, k1);
 }
 
-int potrf_rec(const Ctx& c, float* A, long long lda, int off, int n) {
-  if (n <= NB) {
-    potrf_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.st>>>(A, lda, 0, n, dinv_slot(c, off), 0, 0, c.err, off);
+// Column-recursive blocked Cholesky: factor columns [c0, c0+w) of the n x n matrix (rows c0..n-1), all updates
+// from columns < c0 already applied.  Every step works on ALL rows below the diagonal block at once, so a level-w
+// update is one tall GEMM and a leaf is one potrf kernel plus one in-place solve of the whole panel
+// (2 n/NB - 1 GEMM launches in total; the square-recursive form needed (n/NB) log2(n/NB)).
+int potrf_cols(const Ctx& c, float* A, long long lda, int c0, int w, int n) {
+  float* D = A + (long long)c0 * lda + c0;            // diagonal block of this column range
+  if (w <= NB) {
+    potrf_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.st>>>(D, lda, 0, w, dinv_slot(c, c0), 0, 0, c.err, c0);
     HB_CHECK_LAUNCH();
-    return HB_OK;
+    const int below = n - (c0 + w);
+    if (below <= 0) return HB_OK;
+    GemmParams g;                                      // panel <- panel * Dinv^T, in place
+    float* Pn = D + (long long)w * lda;
+    g.A = Pn; g.lda = lda; g.B = dinv_slot(c, c0); g.ldb = NB; g.transB = 1;
+    g.C = Pn; g.ldc = lda; g.M = below; g.N = w; g.K = w; g.alpha = 1.f; g.beta = 0.f;
+    return gemm_ws(c, g);
   }
-  const int n1 = split_point(n), m = n - n1;
-  float* A21 = A + (long long)n1 * lda;
-  float* A22 = A21 + n1;
-  HB_TRY(potrf_rec(c, A, lda, off, n1));
-  HB_TRY(trsm_rlt(c, A, lda, off, A21, lda, m, n1));
-  GemmParams g;   // A22 -= A21 A21^T (lower)
-  g.A = A21; g.lda = lda; g.B = A21; g.ldb = lda; g.transB = 1;
-  g.C = A22; g.ldc = lda; g.M = m; g.N = m; g.K = n1; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
-  HB_TRY(gemm_ws(c, g));
-  return potrf_rec(c, A22, lda, off + n1, m);
+  const int w1 = split_point(w), w2 = w - w1;
+  HB_TRY(potrf_cols(c, A, lda, c0, w1, n));
+  {
+    // A[c0+w1 .. n, c0+w1 .. c0+w) -= L[c0+w1 .. n, c0 .. c0+w1) * L[c0+w1 .. c0+w, c0 .. c0+w1)^T  (lower trapezoid)
+    float* P = A + (long long)(c0 + w1) * lda + c0;
+    GemmParams g;
+    g.A = P; g.lda = lda; g.B = P; g.ldb = lda; g.transB = 1;
+    g.C = P + w1; g.ldc = lda; g.M = n - (c0 + w1); g.N = w2; g.K = w1; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
+    HB_TRY(gemm_ws(c, g));
+  }
+  return potrf_cols(c, A, lda, c0 + w1, w2, n);
 }
 
-int chol_rev_rec(const Ctx& c, const float* L, long long ldl, float* G, long long ldg, int off, int n) {
-  if (n <= NB) {
-    chol_rev_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.st>>>(L, ldl, 0, G, ldg, 0, n, dinv_slot(c, off), 0);
+int potrf_rec(const Ctx& c, float* A, long long lda, int off, int n) {
+  (void)off;
+  return potrf_cols(c, A, lda, 0, n, n);
+}
+
+// Column-recursive reverse mode, the mirror image of potrf_cols.  rev_cols(c0, w) owns G[c0 .. n, c0 .. c0+w):
+// on entry it holds dObj/dL for these columns with every contribution of the columns to the right already applied,
+// on exit dObj/dK in the full-symmetric convention (an off-diagonal entry holds half of the lower-triangle gradient).
+//   w <= NB :  S  = G_below * L_DD^{-1} / 2              (in place, all rows below the diagonal block)
+//              G_DD -= 2 tril(S^T L_below)               (tall reduction, K = rows below)
+//              G_DD  = leaf reverse of chol(L_DD)
+//   else    :  rev_cols(right half);  with R = rows below this column range, T = the right half's diagonal rows:
+//              G[R, left] -= 2 G[R, right] L[T, left]              (reverse of the tall update, rows below)
+//              G[T, left] -= 2 G[R, right]^T L[R, left]            (tall reduction)
+//              G[T, left] -= 2 sym(G[T, right]) L[T, left]
+//              rev_cols(left half)
+// Launch count ~ 4 n/NB (the square recursion needed ~ 3 (n/NB) log2(n/NB)) and every GEMM spans all rows below.
+int chol_rev_cols(const Ctx& c, const float* L, long long ldl, float* G, long long ldg, int c0, int w, int n) {
+  float* GD = G + (long long)c0 * ldg + c0;
+  const float* LD = L + (long long)c0 * ldl + c0;
+  if (w <= NB) {
+    const int below = n - (c0 + w);
+    if (below > 0) {
+      float* Gp = GD + (long long)w * ldg;
+      const float* Lp = LD + (long long)w * ldl;
+      GemmParams g;
+      g.A = Gp; g.lda = ldg; g.B = dinv_slot(c, c0); g.ldb = NB; g.transB = 0;
+      g.C = Gp; g.ldc = ldg; g.M = below; g.N = w; g.K = w; g.alpha = 0.5f; g.beta = 0.f;
+      HB_TRY(gemm_ws(c, g));
+      GemmParams h;
+      h.A = Gp; h.lda = ldg; h.transA = 1; h.B = Lp; h.ldb = ldl; h.transB = 0;
+      h.C = GD; h.ldc = ldg; h.M = w; h.N = w; h.K = below; h.alpha = -2.f; h.beta = 1.f; h.c_tri = 1;
+      HB_TRY(gemm_ws(c, h));
+    }
+    chol_rev_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.st>>>(LD, ldl, 0, GD, ldg, 0, w, dinv_slot(c, c0), 0);
     HB_CHECK_LAUNCH();
     return HB_OK;
   }
-  const int n1 = split_point(n), m = n - n1;
-  const float* L21 = L + (long long)n1 * ldl;
-  const float* L22 = L21 + n1;
-  float* G21 = G + (long long)n1 * ldg;
-  float* G22 = G21 + n1;
-  HB_TRY(chol_rev_rec(c, L22, ldl, G22, ldg, off + n1, m));
-  // G21 -= 2 sym(G22) L21, sym from the lower triangle: tril(G22) L21 + striu(G22^T) L21
+  const int w1 = split_point(w), w2 = w - w1;
+  const int r1 = c0 + w1, rb = c0 + w, nb = n - rb;
+  HB_TRY(chol_rev_cols(c, L, ldl, G, ldg, r1, w2, n));
+  float* G_T_left = G + (long long)r1 * ldg + c0;           // [w2 x w1]
+  const float* L_T_left = L + (long long)r1 * ldl + c0;     // [w2 x w1]
+  if (nb > 0) {
+    float* G_R_right = G + (long long)rb * ldg + r1;        // [nb x w2]
+    float* G_R_left = G + (long long)rb * ldg + c0;         // [nb x w1]
+    const float* L_R_left = L + (long long)rb * ldl + c0;   // [nb x w1]
+    GemmParams a;
+    a.A = G_R_right; a.lda = ldg; a.B = L_T_left; a.ldb = ldl; a.transB = 0;
+    a.C = G_R_left; a.ldc = ldg; a.M = nb; a.N = w1; a.K = w2; a.alpha = -2.f; a.beta = 1.f;
+    HB_TRY(gemm_ws(c, a));
+    GemmParams b;
+    b.A = G_R_right; b.lda = ldg; b.transA = 1; b.B = L_R_left; b.ldb = ldl; b.transB = 0;
+    b.C = G_T_left; b.ldc = ldg; b.M = w2; b.N = w1; b.K = nb; b.alpha = -2.f; b.beta = 1.f;
+    HB_TRY(gemm_ws(c, b));
+  }
   {
-    GemmParams g;
-    g.A = G22; g.lda = ldg; g.a_tri = 1; g.B = L21; g.ldb = ldl; g.C = G21; g.ldc = ldg;
-    g.M = m; g.N = n1; g.K = m; g.alpha = -2.f; g.beta = 1.f;
+    GemmParams g;   // G[T, left] -= 2 sym(G[T, right]) L[T, left], sym from the lower triangle
+    g.A = G + (long long)r1 * ldg + r1; g.lda = ldg; g.a_tri = 1; g.B = L_T_left; g.ldb = ldl; g.transB = 0;
+    g.C = G_T_left; g.ldc = ldg; g.M = w2; g.N = w1; g.K = w2; g.alpha = -2.f; g.beta = 1.f;
     HB_TRY(gemm_ws(c, g));
     g.transA = 1; g.a_tri = 3;
     HB_TRY(gemm_ws(c, g));
   }
-  HB_TRY(trsm_rln(c, L, ldl, off, G21, ldg, m, n1));     // T = G21 L11^{-1}
-  {
-    GemmParams g;   // G11 -= tril(T^T L21)
-    g.A = G21; g.lda = ldg; g.transA = 1; g.B = L21; g.ldb = ldl; g.C = G; g.ldc = ldg;
-    g.M = n1; g.N = n1; g.K = m; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
-    HB_TRY(gemm_ws(c, g));
-  }
-  HB_TRY(scale2d(G21, ldg, m, n1, 0.5f, c.st));
-  return chol_rev_rec(c, L, ldl, G, ldg, off, n1);
+  return chol_rev_cols(c, L, ldl, G, ldg, c0, w1, n);
+}
+
+int chol_rev_rec(const Ctx& c, const float* L, long long ldl, float* G, long long ldg, int off, int n) {
+  (void)off;
+  return chol_rev_cols(c, L, ldl, G, ldg, 0, n, n);
 }
 
 }  // namespace
 
 // The generation-2 tensor-core engine consumes operands in place, so the factorisations need no GEMM scratch
 // (generation 1 needed hi/lo copies of the largest operand pair: n^2 floats).
-static size_t tc_bytes_for(int, int) { return 0; }
+// What remains is the split-K scratch of the tall reductions in the reverse mode (partial output tiles).
+static size_t tc_bytes_for(int, int n) { return n >= 8 * NB ? (size_t)40 << 20 : 0; }
 
 static size_t base_bytes(long long rows, int n) {
   const long long nblk = (n + NB - 1) / NB;

@@ -48,6 +48,10 @@ int hb_get_gemm_engine(void);
  * hb_profile_end synchronises and fills a HOST array {launches, total ms, useful FLOP, 0}. */
 int hb_profile_begin(int max_gemm_launches);
 int hb_profile_end(double* out4_host);
+/* Phase timing of one hb_gp_elbo_step: hb_phase_begin(); step; n = hb_phase_end(ms, cap) fills ms[0..n) with
+ * {scalars + Gram fwd, potrf, sampler + F + log-lik + W, sampler bwd + Lbar, potrf_bwd, Gram bwd + scalar grads}. */
+int hb_phase_begin(void);
+int hb_phase_end(double* out_ms_host, int capacity);
 
 /* tf.random_normal (variationals.py:107,127): Philox-4x32-10 + Box-Muller, counter based.
  * Element i of the stream (seed, offset) is identical whether it is materialised here or
