@@ -41,6 +41,7 @@ SIGNATURES = {
     "hb_get_gemm_engine": (_i, []),
     "hb_profile_begin": (_i, [_i]),
     "hb_profile_end": (_i, [C.POINTER(C.c_double)]),
+    "hb_profile_end_ex": (_i, [C.POINTER(C.c_double)]),
     "hb_phase_begin": (_i, []),
     "hb_phase_end": (_i, [C.POINTER(C.c_double), _i]),
     "hb_randn_philox": (_i, [_c_f, _ll, _ull, _ull, _c_f]),

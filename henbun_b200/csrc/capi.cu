@@ -16,6 +16,7 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream);   // gemm_tc.cu  (generat
 bool gemm_tc_eligible(const GemmParams& p);
 int gemm_tc2(const GemmParams& p, cudaStream_t stream);  // gemm_tc2.cu (generation 2: in-kernel split, no workspace)
 bool gemm_tc2_eligible(const GemmParams& p);
+bool gemm_tc2_uses_pair(const GemmParams& p);
 int get_tc_option();
 
 // shapes worth a tensor-core launch
@@ -70,7 +71,11 @@ static void phase_mark(cudaStream_t st) {
 
 static double gemm_useful_flops(const GemmParams& p) {
   double f = 2.0 * (double)p.M * (double)p.N * (double)p.K * (double)p.batch;
-  if (p.c_tri) f *= 0.5 * ((double)p.M + 1.0) / (double)p.M;
+  if (p.c_tri) {   // lower trapezoid: M*N - N(N-1)/2 outputs when M >= N
+    const double M = p.M, N = p.N;
+    const double outs = (M >= N) ? M * N - 0.5 * N * (N - 1.0) : 0.5 * M * (M + 1.0);
+    f *= outs / (M * N);
+  }
   if (p.a_tri || p.b_tri) f *= 0.5;
   return f;
 }
@@ -82,6 +87,7 @@ int gemm(const GemmParams& p, cudaStream_t st) {
   g_prof.flops[i] = gemm_useful_flops(p);
   g_prof.shape[4 * i] = p.M; g_prof.shape[4 * i + 1] = p.N; g_prof.shape[4 * i + 2] = p.K;
   g_prof.shape[4 * i + 3] = (g_engine == 2 || (g_engine == 0 && !prefer_small(p) && ((gemm_tc2_eligible(p) && tc_worth(p)) || gemm_tc_eligible(p)))) ? 1 : 0;
+  if (g_prof.shape[4 * i + 3] && !(get_tc_option() & 2) && gemm_tc2_eligible(p) && gemm_tc2_uses_pair(p)) g_prof.shape[4 * i + 3] = 2;
   cudaEventRecord(g_prof.ev0[i], st);
   const int rc = gemm_dispatch(p, st);
   cudaEventRecord(g_prof.ev1[i], st);
@@ -213,6 +219,23 @@ int hb_profile_end(double* out4_host) {
   }
   if (f) fclose(f);
   out4_host[0] = (double)g_prof.used; out4_host[1] = ms; out4_host[2] = fl; out4_host[3] = 0.0;
+  return HB_OK;
+}
+// Same, but also splits out the launches that ran the CTA-pair tcgen05 kernel (the dominant kernel):
+// out8 = {launches, ms, useful FLOP, pair launches, pair ms, pair useful FLOP, 0, 0}.  Call INSTEAD of hb_profile_end.
+int hb_profile_end_ex(double* out8_host) {
+  if (!out8_host) return HB_ERR_ARG;
+  const size_t used = g_prof.used;
+  const int rc = hb_profile_end(out8_host);
+  if (rc != HB_OK) return rc;
+  double pn = 0.0, pms = 0.0, pfl = 0.0;
+  for (size_t i = 0; i < used; ++i) {
+    if (g_prof.shape[4 * i + 3] != 2) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]) != cudaSuccess) return HB_ERR_CUDA;
+    pn += 1.0; pms += t; pfl += g_prof.flops[i];
+  }
+  out8_host[3] = pn; out8_host[4] = pms; out8_host[5] = pfl; out8_host[6] = 0.0; out8_host[7] = 0.0;
   return HB_OK;
 }
 

@@ -107,7 +107,82 @@ struct Tc2Params {
   int vecC;
   int ksplit;             // k-blocks per split (blockIdx.y = split index); 0 = no split
   long long csplit;       // element stride between the partial outputs of consecutive splits
+  const float* bias;      // optional [N], added before the activation (MatBias: Henbun/nn.py:31-32)
+  int act, clip;
+  float clip_lo, clip_hi;
 };
+
+__device__ __forceinline__ float tc2_act(float x, int act, int clip, float lo, float hi) {
+  if (clip) x = fminf(fmaxf(x, lo), hi);
+  switch (act) {
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-x));
+    case ACT_RELU: return fmaxf(x, 0.f);
+    case ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+
+// Epilogue of one output tile.  Each epilogue thread holds one accumulator ROW (TMEM lane) -- storing from that
+// layout writes 16 bytes per row per instruction, 32 rows (ldc apart) per warp: half-used sectors and no DRAM page
+// locality, which dominated short-K products (M=65280, N=K=256: 153 us against ~30 us of HBM time).  So the tile is
+// staged through the (now idle) pipeline shared memory and written with one 512-byte contiguous row segment per
+// warp instruction; beta*C is read with the same pattern.  ew = epilogue warp 0..7, q = ew & 3, half = ew >> 2.
+template <int BN>
+__device__ __forceinline__ void store_tile(const float (&acc)[BN / 2], const Tc2Params& p, float* Cbase, uint32_t sm_tile,
+                                           int m0, int n0, int ew, int lane) {
+  constexpr int HALF = BN / 2;
+  constexpr int LDT = BN + 4;                       // padded row (floats)
+  const int q = ew & 3, half = ew >> 2;
+  {
+    const uint32_t row = sm_tile + (uint32_t)((q * 32 + lane) * LDT + half * HALF) * 4u;
+#pragma unroll
+    for (int v = 0; v < HALF / 4; ++v)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + v * 16), "f"(acc[4 * v]), "f"(acc[4 * v + 1]),
+                   "f"(acc[4 * v + 2]), "f"(acc[4 * v + 3]) : "memory");
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
+  const bool post = (p.bias != nullptr) || p.act != ACT_NONE || p.clip;
+#pragma unroll 1
+  for (int r = ew; r < BM; r += 8) {
+    const int gi = m0 + r;
+    if (gi >= p.M) break;
+    float* crow = Cbase + (long long)gi * p.ldc;
+#pragma unroll
+    for (int seg = 0; seg < BN / 128; ++seg) {
+      const int cj = seg * 128 + lane * 4;
+      const int gj = n0 + cj;
+      if (gj >= p.N) continue;
+      float o[4];
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                   : "r"(sm_tile + (uint32_t)(r * LDT + cj) * 4u));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] *= p.alpha;
+      const bool full = (gj + 3 < p.N) && !(p.c_tri == 1 && gj + 3 > gi);
+      if (full && p.vecC) {
+        if (p.beta != 0.f) {
+          const float4 old = *reinterpret_cast<const float4*>(crow + gj);
+          o[0] = fmaf(p.beta, old.x, o[0]); o[1] = fmaf(p.beta, old.y, o[1]);
+          o[2] = fmaf(p.beta, old.z, o[2]); o[3] = fmaf(p.beta, old.w, o[3]);
+        }
+        if (post) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = tc2_act(o[e] + (p.bias ? __ldg(p.bias + gj + e) : 0.f), p.act, p.clip, p.clip_lo, p.clip_hi);
+        }
+        *reinterpret_cast<float4*>(crow + gj) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (gj + e < p.N && !(p.c_tri == 1 && gj + e > gi)) {
+            float x = o[e];
+            if (p.beta != 0.f) x = fmaf(p.beta, crow[gj + e], x);
+            if (post) x = tc2_act(x + (p.bias ? __ldg(p.bias + gj + e) : 0.f), p.act, p.clip, p.clip_lo, p.clip_hi);
+            crow[gj + e] = x;
+          }
+        }
+      }
+    }
+  }
+}
 
 __device__ __forceinline__ bool keep_rk(int mode, int r, int k) {
   return mode == 0 || (mode == 1 && k <= r) || (mode == 2 && k >= r) || (mode == 3 && k > r) || (mode == 4 && k < r);
@@ -338,38 +413,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(buf));
     }
-    const int gi = m0 + q * 32 + lane;
-    if (gi < p.M) {
-      float* crow = Cout + (long long)gi * p.ldc;
-      const int gj0 = n0 + half * HALF;
-#pragma unroll
-      for (int v = 0; v < HALF / 4; ++v) {
-        const int gj = gj0 + v * 4;
-        if (gj < p.N) {
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = p.alpha * acc[v * 4 + e];
-          const bool full = (gj + 3 < p.N) && !(p.c_tri == 1 && gj + 3 > gi);
-          if (full && p.vecC) {
-            if (p.beta != 0.f) {
-              const float4 old = *reinterpret_cast<const float4*>(crow + gj);
-              o[0] = fmaf(p.beta, old.x, o[0]); o[1] = fmaf(p.beta, old.y, o[1]);
-              o[2] = fmaf(p.beta, old.z, o[2]); o[3] = fmaf(p.beta, old.w, o[3]);
-            }
-            *reinterpret_cast<float4*>(crow + gj) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (gj + e < p.N && !(p.c_tri == 1 && gj + e > gi)) {
-                float x = o[e];
-                if (p.beta != 0.f) x = fmaf(p.beta, crow[gj + e], x);
-                crow[gj + e] = x;
-              }
-            }
-          }
-        }
-      }
-    }
+    store_tile<BN>(acc, p, Cout, base, m0, n0, warp - 8, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -579,38 +623,7 @@ gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(tempty_bar(buf), 0);
     }
-    const int gi = m0 + q * 32 + lane;
-    if (gi < p.M) {
-      float* crow = p.C + (long long)gi * p.ldc;
-      const int gj0 = n0 + half * HALF;
-#pragma unroll
-      for (int v = 0; v < HALF / 4; ++v) {
-        const int gj = gj0 + v * 4;
-        if (gj < p.N) {
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = p.alpha * acc[v * 4 + e];
-          const bool full = (gj + 3 < p.N) && !(p.c_tri == 1 && gj + 3 > gi);
-          if (full && p.vecC) {
-            if (p.beta != 0.f) {
-              const float4 old = *reinterpret_cast<const float4*>(crow + gj);
-              o[0] = fmaf(p.beta, old.x, o[0]); o[1] = fmaf(p.beta, old.y, o[1]);
-              o[2] = fmaf(p.beta, old.z, o[2]); o[3] = fmaf(p.beta, old.w, o[3]);
-            }
-            *reinterpret_cast<float4*>(crow + gj) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (gj + e < p.N && !(p.c_tri == 1 && gj + e > gi)) {
-                float x = o[e];
-                if (p.beta != 0.f) x = fmaf(p.beta, crow[gj + e], x);
-                crow[gj + e] = x;
-              }
-            }
-          }
-        }
-      }
-    }
+    store_tile<BN>(acc, p, p.C, base, m0, n0, warp - 8, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -712,11 +725,16 @@ int launch2(bool akm, bool bkm, const CUtensorMap& ta, const CUtensorMap& tb, co
 
 // No workspace: operands are consumed where they lie.  Needs 16-byte aligned operands with ld % 4 == 0 (TMA).
 bool gemm_tc2_eligible(const GemmParams& p) {
-  if (p.batch != 1 || p.bias || p.act != ACT_NONE || p.clip) return false;
+  if (p.batch != 1) return false;
   if (p.M < 1 || p.N < 1 || p.K < 1) return false;
   if (!aligned16(p.A) || !aligned16(p.B) || (p.lda & 3) || (p.ldb & 3)) return false;
   if (p.C == p.A && p.N > 256) return false;
   return true;
+}
+
+// shapes that run the CTA-pair kernel: N > 128, at least 64 tiles of 256 x 256, not in place
+bool gemm_tc2_uses_pair(const GemmParams& p) {
+  return p.N > 128 && !(get_tc_option() & 4) && (long long)cdiv(p.M, 256) * cdiv(p.N, 256) >= 64 && !(p.C == p.A);
 }
 
 int gemm_tc2(const GemmParams& p, cudaStream_t st) {
@@ -724,8 +742,7 @@ int gemm_tc2(const GemmParams& p, cudaStream_t st) {
   const bool akm = (p.transA == 0), bkm = (p.transB == 1);
   const int BN = (p.N <= 128) ? 128 : 256;
   // CTA pairs (256 x 256 tiles) once there are enough of them to fill the GPU; bit 2 of the option word disables them
-  const bool pair = BN == 256 && !(get_tc_option() & 4) && (long long)cdiv(p.M, 256) * cdiv(p.N, 256) >= 64 &&
-                    !(p.C == p.A);
+  const bool pair = gemm_tc2_uses_pair(p);
   CUtensorMap ta, tb;
   HB_TRY(make_map2(&ta, p.A, p.M, p.K, p.lda, akm, BM));
   HB_TRY(make_map2(&tb, p.B, p.N, p.K, p.ldb, bkm, pair ? 128 : BN));
@@ -734,11 +751,12 @@ int gemm_tc2(const GemmParams& p, cudaStream_t st) {
   tp.c_tri = p.c_tri; tp.a_mode = p.a_tri; tp.b_mode = b2rk[p.b_tri]; tp.tiles_m = 0; tp.tiles_n = 0;
   tp.vecC = aligned16(p.C) && (p.ldc % 4 == 0);
   tp.ksplit = 0; tp.csplit = 0;
+  tp.bias = p.bias; tp.act = p.act; tp.clip = p.clip; tp.clip_lo = p.clip_lo; tp.clip_hi = p.clip_hi;
   if (pair) return launch_pair(akm, bkm, ta, tb, tp, st);
   // split-K for "tall reductions" (small output, long K): partial tiles into the caller's scratch, then one
   // deterministic reduction pass.  Used when the output has too few tiles to occupy the GPU.
   const long long tiles = (long long)cdiv(p.M, BM) * cdiv(p.N, BN);
-  if (p.ws && tiles < 74 && p.K >= 512 && !p.a_tri && !p.b_tri) {
+  if (p.ws && tiles < 74 && p.K >= 512 && !p.a_tri && !p.b_tri && !p.bias && p.act == ACT_NONE && !p.clip) {
     int want = (int)((148 + tiles - 1) / tiles);
     const int kblocks = cdiv(p.K, BK);
     int per = cdiv(kblocks, want);

@@ -41,10 +41,28 @@ def gemm_raw(A, B, C_out, M, N, K, transA=0, transB=0, a_tri=0, b_tri=0, c_tri=0
     lda = lda if lda is not None else (M if transA else K)
     ldb = ldb if ldb is not None else (K if transB else N)
     ldc = ldc if ldc is not None else N
-    check(_L().hb_gemm(ptr(A), lda, sA, transA, a_tri, ptr(B), ldb, sB, transB, b_tri, ptr(C_out), ldc, sC, c_tri,
-                       M, N, K, batch, float(alpha), float(beta), ptr(bias), sBias, act, clip, float(lo), float(hi),
-                       stream()), "hb_gemm")
+    ws, wsb = _gemm_scratch(C_out.device, M, N, K, batch)
+    check(_L().hb_gemm_ws(ptr(A), lda, sA, transA, a_tri, ptr(B), ldb, sB, transB, b_tri, ptr(C_out), ldc, sC, c_tri,
+                          M, N, K, batch, float(alpha), float(beta), ptr(bias), sBias, act, clip, float(lo), float(hi),
+                          ptr(ws), wsb, stream()), "hb_gemm_ws")
     return C_out
+
+
+_SCRATCH = {}
+
+
+def _gemm_scratch(device, M, N, K, batch):
+    """Split-K scratch of the tensor-core engine (long-K products with a small output, e.g. dW = x^T dz of MatBias).
+    One 64 MiB buffer per device, only handed over for shapes that can use it; stream-ordered reuse is safe because
+    every product runs on torch's current stream."""
+    if batch != 1 or K < 512 or M * N > 74 * 128 * 256:
+        return None, 0
+    key = (device.type, device.index)
+    buf = _SCRATCH.get(key)
+    if buf is None:
+        buf = torch.empty(64 << 20, dtype=torch.uint8, device=device)
+        _SCRATCH[key] = buf
+    return buf, buf.numel()
 
 
 class _MatMul2D(torch.autograd.Function):

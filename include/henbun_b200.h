@@ -48,6 +48,9 @@ int hb_get_gemm_engine(void);
  * hb_profile_end synchronises and fills a HOST array {launches, total ms, useful FLOP, 0}. */
 int hb_profile_begin(int max_gemm_launches);
 int hb_profile_end(double* out4_host);
+/* As hb_profile_end, plus the share of the CTA-pair tcgen05 kernel: out8 = {launches, ms, useful FLOP, pair launches,
+ * pair ms, pair useful FLOP, 0, 0}. */
+int hb_profile_end_ex(double* out8_host);
 /* Phase timing of one hb_gp_elbo_step: hb_phase_begin(); step; n = hb_phase_end(ms, cap) fills ms[0..n) with
  * {scalars + Gram fwd, potrf, sampler + F + log-lik + W, sampler bwd + Lbar, potrf_bwd, Gram bwd + scalar grads}. */
 int hb_phase_begin(void);
