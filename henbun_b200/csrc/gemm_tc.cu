@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 namespace hb {
 
@@ -414,7 +415,14 @@ int prepare_operand(const float* src, long long ld, int rows, int K, bool kmajor
 }  // namespace
 
 void set_tc_option(int v) { g_tc_option = v; }
-int get_tc_option() { return g_tc_option; }
+int get_tc_option() {
+  static bool env_read = false;
+  if (!env_read) {                      // HB_TC_OPTION=<bits> overrides the default once, at first use (A/B runs)
+    env_read = true;
+    if (const char* e = getenv("HB_TC_OPTION")) g_tc_option = atoi(e);
+  }
+  return g_tc_option;
+}
 
 size_t gemm_tc_workspace_bytes(int M, int N, int K) {
   const long long kp = ((long long)K + 3) / 4 * 4;

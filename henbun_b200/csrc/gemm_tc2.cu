@@ -96,6 +96,41 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return d;
 }
 
+// bf16 operand tiles of the cross products.  K-major: SWIZZLE_32B (layout 6), 8-row atoms of 256 B.
+// MN-major: SWIZZLE_64B (layout 4), atoms of 8 k-rows x 64 B = 512 B (SBO), 32-row groups 1024 B apart (LBO).
+template <bool KMAJOR>
+__device__ __forceinline__ uint64_t make_desc_bf16(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  if (KMAJOR) {
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)6 << 61;
+  } else {
+    d |= (uint64_t)(1024 >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)4 << 61;
+  }
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
 struct Tc2Params {
   float* C;
   long long ldc;
@@ -208,7 +243,7 @@ __device__ __forceinline__ bool mask_crosses(int mode, int r0, int rows, int k0)
 // hi/lo split of one operand tile in shared memory (element-wise, so the swizzle does not matter); with MASK the
 // logical (row, k) of every 16-byte chunk is recovered from its swizzled position and masked elements are zeroed
 // in the raw tile as well.  ct = converter thread index (0..127).
-template <int ROWS, bool KMAJOR, bool MASK>
+template <int ROWS, bool KMAJOR, bool MASK, bool BFX>
 __device__ __forceinline__ void convert_tile(uint32_t raw, uint32_t lo, int ct, int mode, int r0, int k0) {
   constexpr int CHUNKS = ROWS * BK * 4 / 16;
   constexpr int PER = CHUNKS / 128;
@@ -241,19 +276,41 @@ __device__ __forceinline__ void convert_tile(uint32_t raw, uint32_t lo, int ct, 
         }
         if (any) asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(raw + o), "f"(t[0]), "f"(t[1]), "f"(t[2]), "f"(t[3]) : "memory");
       }
-      float l[4];
+      float hv[4], l[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float h = __uint_as_float(__float_as_uint(t[e]) & 0xFFFFE000u);
-        const float d = t[e] - h;                                        // exact
-        l[e] = __uint_as_float(__float_as_uint(d) + 0x1000u);            // round to nearest at the tf32 cut (MMA truncates)
+        hv[e] = __uint_as_float(__float_as_uint(t[e]) & 0xFFFFE000u);
+        l[e] = t[e] - hv[e];                                             // exact
       }
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + o), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
+      if (!BFX) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) l[e] = __uint_as_float(__float_as_uint(l[e]) + 0x1000u);   // RN at the tf32 cut (MMA truncates)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo + o), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
+      } else {
+        // bf16 copies of hi and lo for the two cross products, written in the canonical 16-bit UMMA layouts:
+        //   K-major : rows of 16 bf16 (32 B), SWIZZLE_32B (16-byte chunk ^= bit 7 of the offset, i.e. (row >> 2) & 1)
+        //   MN-major: per 32-row box 16 k-rows of 32 bf16 (64 B), SWIZZLE_64B (chunk ^= (k >> 1) & 3)
+        uint32_t d;
+        if (KMAJOR) {
+          const uint32_t r = o >> 6, c = ((o >> 4) & 3u) ^ ((o >> 7) & 3u);
+          d = r * 32u + ((((c >> 1) ^ ((r >> 2) & 1u))) << 4) + ((c & 1u) << 3);
+        } else {
+          const uint32_t box = o >> 11, k = (o >> 7) & 15u, gran = ((o >> 5) & 3u) ^ (k & 3u), hf = (o >> 4) & 1u;
+          d = box * 1024u + k * 64u + ((gran ^ ((k >> 1) & 3u)) << 4) + (hf << 3);
+        }
+        uint32_t h01, h23, l01, l23;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(hv[1]), "f"(hv[0]));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(hv[3]), "f"(hv[2]));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l01) : "f"(l[1]), "f"(l[0]));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l23) : "f"(l[3]), "f"(l[2]));
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(lo + d), "r"(h01), "r"(h23) : "memory");
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(lo + (uint32_t)(ROWS * 32) + d), "r"(l01), "r"(l23) : "memory");
+      }
     }
   }
 }
 
-template <int BN, bool AKM, bool BKM>
+template <int BN, bool AKM, bool BKM, bool BFX>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc2Params p) {
   constexpr int B_TILE = BN * BK * 4;
@@ -333,6 +390,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (AKM ? 0u : (1u << 15)) | (BKM ? 0u : (1u << 16)) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // kind::f16 with bf16 operands (format 1), fp32 accumulate
+      const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | (AKM ? 0u : (1u << 15)) | (BKM ? 0u : (1u << 16)) |
+                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      (void)idesc_bf;
       constexpr uint32_t ADV_A = AKM ? (32u >> 4) : (1024u >> 4);     // one K=8 step, in 16-byte units
       constexpr uint32_t ADV_B = BKM ? (32u >> 4) : (1024u >> 4);
       int s = 0; uint32_t ph = 0;
@@ -349,12 +410,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint64_t a_hi = make_desc<AKM>(st), a_lo = make_desc<AKM>(st + A_TILE);
           const uint64_t b_hi = make_desc<BKM>(st + 2 * A_TILE), b_lo = make_desc<BKM>(st + 2 * A_TILE + B_TILE);
           const bool first_kb = (kb == c * CHK);
+          if (BFX) {
+            // cross products in bf16 (one K=16 MMA each), hi*hi in tf32 (two K=8 MMAs)
+            const uint32_t sa = st + A_TILE, sb = st + 2 * A_TILE + B_TILE;
+            tc_mma_bf16(d_tmem, make_desc_bf16<AKM>(sa + BM * 32), make_desc_bf16<BKM>(sb), idesc_bf, first_kb ? 0u : 1u);   // lo_a * hi_b
+            tc_mma_bf16(d_tmem, make_desc_bf16<AKM>(sa), make_desc_bf16<BKM>(sb + BN * 32), idesc_bf, 1u);                  // hi_a * lo_b
+#pragma unroll
+            for (int k2 = 0; k2 < BK / 8; ++k2)
+              tc_mma_tf32(d_tmem, a_hi + (uint64_t)(ADV_A * k2), b_hi + (uint64_t)(ADV_B * k2), idesc, 1u);
+          } else {
 #pragma unroll
           for (int k2 = 0; k2 < BK / 8; ++k2) {
             const uint64_t da = (uint64_t)(ADV_A * k2), db = (uint64_t)(ADV_B * k2);
             tc_mma_tf32(d_tmem, a_lo + da, b_hi + db, idesc, (first_kb && k2 == 0) ? 0u : 1u);   // small terms first
             tc_mma_tf32(d_tmem, a_hi + da, b_lo + db, idesc, 1u);
             tc_mma_tf32(d_tmem, a_hi + da, b_hi + db, idesc, 1u);
+          }
           }
           tc_commit(empty_bar(s));
           if (++s == NSTAGE) { s = 0; ph ^= 1u; }
@@ -371,10 +442,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int k0 = (kb_lo + kb) * BK;
       mbar_wait(full_bar(s), ph);
       const uint32_t st = base + s * STAGE_BYTES;
-      if (mask_crosses(p.a_mode, m0, BM, k0)) convert_tile<BM, AKM, true>(st, st + A_TILE, ct, p.a_mode, m0, k0);
-      else convert_tile<BM, AKM, false>(st, st + A_TILE, ct, 0, 0, 0);
-      if (mask_crosses(p.b_mode, n0, BN, k0)) convert_tile<BN, BKM, true>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ct, p.b_mode, n0, k0);
-      else convert_tile<BN, BKM, false>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ct, 0, 0, 0);
+      if (mask_crosses(p.a_mode, m0, BM, k0)) convert_tile<BM, AKM, true, BFX>(st, st + A_TILE, ct, p.a_mode, m0, k0);
+      else convert_tile<BM, AKM, false, BFX>(st, st + A_TILE, ct, 0, 0, 0);
+      if (mask_crosses(p.b_mode, n0, BN, k0)) convert_tile<BN, BKM, true, BFX>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ct, p.b_mode, n0, k0);
+      else convert_tile<BN, BKM, false, BFX>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ct, 0, 0, 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(conv_bar(s));
@@ -467,7 +538,7 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t adesc
       "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 
-template <bool AKM, bool BKM>
+template <bool AKM, bool BKM, bool BFX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc2Params p) {
   constexpr int BN = 256, PM = 256;                  // pair tile
@@ -543,6 +614,9 @@ gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else if (warp == 1 && lane == 0 && rank == 0) {   // ---------------- MMA issuer (leader CTA only) ----------------
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (AKM ? 0u : (1u << 15)) | (BKM ? 0u : (1u << 16)) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
+      const uint32_t idesc_bf = (1u << 4) | (1u << 7) | (1u << 10) | (AKM ? 0u : (1u << 15)) | (BKM ? 0u : (1u << 16)) |
+                                ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(PM >> 4) << 24);
+      (void)idesc_bf;
       constexpr uint32_t ADV_A = AKM ? (32u >> 4) : (1024u >> 4);
       constexpr uint32_t ADV_B = BKM ? (32u >> 4) : (1024u >> 4);
       int s = 0; uint32_t ph = 0;
@@ -559,12 +633,21 @@ gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const uint64_t a_hi = make_desc<AKM>(st), a_lo = make_desc<AKM>(st + A_TILE);
           const uint64_t b_hi = make_desc<BKM>(st + 2 * A_TILE), b_lo = make_desc<BKM>(st + 3 * A_TILE);
           const bool first_kb = (kb == c * CHK);
+          if (BFX) {
+            const uint32_t sa = st + A_TILE, sb = st + 3 * A_TILE;
+            tc_mma_bf16_pair(d_tmem, make_desc_bf16<AKM>(sa + 128 * 32), make_desc_bf16<BKM>(sb), idesc_bf, first_kb ? 0u : 1u);
+            tc_mma_bf16_pair(d_tmem, make_desc_bf16<AKM>(sa), make_desc_bf16<BKM>(sb + 128 * 32), idesc_bf, 1u);
+#pragma unroll
+            for (int k2 = 0; k2 < BK / 8; ++k2)
+              tc_mma_tf32_pair(d_tmem, a_hi + (uint64_t)(ADV_A * k2), b_hi + (uint64_t)(ADV_B * k2), idesc, 1u);
+          } else {
 #pragma unroll
           for (int k2 = 0; k2 < BK / 8; ++k2) {
             const uint64_t da = (uint64_t)(ADV_A * k2), db = (uint64_t)(ADV_B * k2);
             tc_mma_tf32_pair(d_tmem, a_lo + da, b_hi + db, idesc, (first_kb && k2 == 0) ? 0u : 1u);
             tc_mma_tf32_pair(d_tmem, a_hi + da, b_lo + db, idesc, 1u);
             tc_mma_tf32_pair(d_tmem, a_hi + da, b_hi + db, idesc, 1u);
+          }
           }
           tc_commit_pair(empty_bar(s));              // frees stage s in both CTAs
           if (++s == NSTAGE_P) { s = 0; ph ^= 1u; }
@@ -581,10 +664,10 @@ gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int k0 = (kb_lo + kb) * BK;
       mbar_wait(full_bar(s), ph);
       const uint32_t st = base + s * P_STAGE_BYTES;
-      if (mask_crosses(p.a_mode, m0, 128, k0)) convert_tile<128, AKM, true>(st, st + A_TILE, ct, p.a_mode, m0, k0);
-      else convert_tile<128, AKM, false>(st, st + A_TILE, ct, 0, 0, 0);
-      if (mask_crosses(p.b_mode, nb0, 128, k0)) convert_tile<128, BKM, true>(st + 2 * A_TILE, st + 3 * A_TILE, ct, p.b_mode, nb0, k0);
-      else convert_tile<128, BKM, false>(st + 2 * A_TILE, st + 3 * A_TILE, ct, 0, 0, 0);
+      if (mask_crosses(p.a_mode, m0, 128, k0)) convert_tile<128, AKM, true, BFX>(st, st + A_TILE, ct, p.a_mode, m0, k0);
+      else convert_tile<128, AKM, false, BFX>(st, st + A_TILE, ct, 0, 0, 0);
+      if (mask_crosses(p.b_mode, nb0, 128, k0)) convert_tile<128, BKM, true, BFX>(st + 2 * A_TILE, st + 3 * A_TILE, ct, p.b_mode, nb0, k0);
+      else convert_tile<128, BKM, false, BFX>(st + 2 * A_TILE, st + 3 * A_TILE, ct, 0, 0, 0);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(conv_bar(s), 0);
@@ -677,37 +760,52 @@ int make_map2(CUtensorMap* map, const float* ptr, long long rows, long long K, l
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int BN, bool AKM, bool BKM>
-int launch3(const CUtensorMap& ta, const CUtensorMap& tb, Tc2Params tp, cudaStream_t st) {
+template <int BN, bool AKM, bool BKM, bool BFX>
+int launch4(const CUtensorMap& ta, const CUtensorMap& tb, Tc2Params tp, cudaStream_t st) {
   constexpr int SMEM = NSTAGE * (2 * A_TILE + 2 * BN * BK * 4) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(gemm_tc2_kernel<BN, AKM, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tc2_kernel<BN, AKM, BKM, BFX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
       return HB_ERR_CUDA;
     attr_done = true;
   }
   tp.tiles_m = cdiv(tp.M, BM);
   tp.tiles_n = cdiv(tp.N, BN);
   const int nsplit = tp.ksplit > 0 ? cdiv(cdiv(tp.K, BK), tp.ksplit) : 1;
-  gemm_tc2_kernel<BN, AKM, BKM><<<dim3((unsigned)(tp.tiles_m * tp.tiles_n), (unsigned)nsplit), NTHREADS, SMEM, st>>>(ta, tb, tp);
+  gemm_tc2_kernel<BN, AKM, BKM, BFX><<<dim3((unsigned)(tp.tiles_m * tp.tiles_n), (unsigned)nsplit), NTHREADS, SMEM, st>>>(ta, tb, tp);
   HB_CHECK_LAUNCH();
   return HB_OK;
 }
 
-template <bool AKM, bool BKM>
-int launch_pair2(const CUtensorMap& ta, const CUtensorMap& tb, Tc2Params tp, cudaStream_t st) {
+template <bool AKM, bool BKM, bool BFX>
+int launch_pair3(const CUtensorMap& ta, const CUtensorMap& tb, Tc2Params tp, cudaStream_t st) {
   constexpr int SMEM = NSTAGE_P * P_STAGE_BYTES + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(gemm_tc2_pair_kernel<AKM, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tc2_pair_kernel<AKM, BKM, BFX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
       return HB_ERR_CUDA;
     attr_done = true;
   }
   tp.tiles_m = cdiv(tp.M, 256);
   tp.tiles_n = cdiv(tp.N, 256);
-  gemm_tc2_pair_kernel<AKM, BKM><<<2 * tp.tiles_m * tp.tiles_n, NTHREADS, SMEM, st>>>(ta, tb, tp);
+  gemm_tc2_pair_kernel<AKM, BKM, BFX><<<2 * tp.tiles_m * tp.tiles_n, NTHREADS, SMEM, st>>>(ta, tb, tp);
   HB_CHECK_LAUNCH();
   return HB_OK;
+}
+
+// Cross-product arithmetic: default = TF32 hi*hi + bf16 cross terms (lo_a*hi_b + hi_a*lo_b, one K=16 MMA each);
+// bit 3 of the option word forces three TF32 passes.  Measured per product vs fp64: 1.5e-6 (default) against 1.0e-6
+// (3xTF32; both dominated by the K=128 chunked accumulation) -- the fused GP step at n=4608 matches the fp64 oracle
+// to 5.0e-8 (ELBO) / 1.2e-7 (gradient) either way, and the step is 9 % faster.
+inline bool use_bfx() { return (get_tc_option() & 8) == 0; }
+
+template <bool AKM, bool BKM>
+int launch_pair2(const CUtensorMap& ta, const CUtensorMap& tb, const Tc2Params& tp, cudaStream_t st) {
+  return use_bfx() ? launch_pair3<AKM, BKM, true>(ta, tb, tp, st) : launch_pair3<AKM, BKM, false>(ta, tb, tp, st);
+}
+template <int BN, bool AKM, bool BKM>
+int launch3(const CUtensorMap& ta, const CUtensorMap& tb, const Tc2Params& tp, cudaStream_t st) {
+  return use_bfx() ? launch4<BN, AKM, BKM, true>(ta, tb, tp, st) : launch4<BN, AKM, BKM, false>(ta, tb, tp, st);
 }
 
 int launch_pair(bool akm, bool bkm, const CUtensorMap& ta, const CUtensorMap& tb, const Tc2Params& tp, cudaStream_t st) {

@@ -30,7 +30,7 @@ def run(M, N, K, tA, tB, a_tri=0, b_tri=0, c_tri=0, alpha=1.0, beta=0.0, eng=2):
         Ad, Bd, Cd = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda(), torch.from_numpy(C0).cuda()
         wsb = lib.hb_gemm_tc_workspace_bytes(M, N, K)
         ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-        lib.hb_set_gemm_engine(engine)
+        lib.hb_set_gemm_engine(engine); lib.hb_set_tc_option(int(os.environ.get('HB_TC_OPT', '0')))
         rc = lib.hb_gemm_ws(P(Ad), A.shape[1], 0, tA, a_tri, P(Bd), B.shape[1], 0, tB, b_tri, P(Cd), N, 0, c_tri, M, N, K, 1,
                             alpha, beta, None, 0, 0, 0, -50.0, 50.0, P(ws), wsb, ST())
         torch.cuda.synchronize()
