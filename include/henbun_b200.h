@@ -141,17 +141,23 @@ int hb_gemm(const float* A, long long lda, long long strideA, int transA, int a_
             long long strideB, int transB, int b_tri, float* C, long long ldc, long long strideC, int c_tri, int M,
             int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
             int clip, float clip_lo, float clip_hi, void* stream);
-/* hb_gemm with a scratch buffer: when ws holds hb_gemm_tc_workspace_bytes(M,N,K) bytes and the shape qualifies
- * (batch 1, no bias/activation, M,N >= 128, large enough), the product runs on the tcgen05 3xTF32 engine (any
- * transposition / triangular mask); otherwise exactly hb_gemm. */
+/* hb_gemm with an optional scratch buffer.  Engine choice (hb_set_gemm_engine(0), the default):
+ *   - K <= 256 and few output tiles          -> short-K fp32 SIMT kernel (whole K staged in one round trip)
+ *   - batch 1, 16-byte aligned A/B, ld % 4 == 0, N >= 64, K >= 32 and M*N*K >= 256^3 (or K >= 512 with ws given)
+ *                                            -> tcgen05 engine (gemm_tc2.cu): any transposition, triangular masks,
+ *                                               alpha/beta/bias/activation epilogue, C may alias A when N <= 256;
+ *                                               CTA-pair kernel from 64 tiles of 256x256, split-K (needs ws: partial
+ *                                               tiles, <= 40 MiB) for long-K products with a small output
+ *   - everything else (batched, unaligned)   -> k-looped fp32 SIMT kernel.
+ * Results are fp32-grade on every path (product error vs fp64 <= 3e-6 relative, tests/test_gpu_tc.py). */
 int hb_gemm_ws(const float* A, long long lda, long long strideA, int transA, int a_tri, const float* B, long long ldb,
                long long strideB, int transB, int b_tri, float* C, long long ldc, long long strideC, int c_tri, int M,
                int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
                int clip, float clip_lo, float clip_hi, void* ws, size_t ws_bytes, void* stream);
-/* The tcgen05 3xTF32 engine directly: C[M,N] = alpha*A[M,K]*B[N,K]^T + beta*C (both operands K-major), fp32-grade
- * accuracy from three TF32 tensor-core passes.  Needs M,N >= 128, K >= 32, lda/ldb multiples of 4, 16-byte aligned
- * A/B and a workspace of hb_gemm_tc_workspace_bytes(M,N,K); returns HB_ERR_ARG otherwise.
- * hb_set_tc_option bit0: feed the raw fp32 operand as the "hi" TF32 operand (experiment). */
+/* Force the tensor-core engine on C[M,N] = alpha*A[M,K]*B[N,K]^T + beta*C (both operands K-major); HB_ERR_ARG if the
+ * operands do not qualify.  hb_set_tc_option bits (A/B experiments; also read once from the environment variable
+ * HB_TC_OPTION): 1 = generation-1 engine writes explicit hi copies, 2 = use generation 1 (operand-preparation pass,
+ * needs hb_gemm_tc_workspace_bytes of ws), 4 = no CTA pairs, 8 = three TF32 passes instead of TF32 + bf16 cross terms. */
 size_t hb_gemm_tc_workspace_bytes(int M, int N, int K);
 int hb_set_tc_option(int v);
 int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int c_tri, int M,
