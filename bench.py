@@ -259,6 +259,18 @@ def main():
         if peak is None:
             peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
         n_gemm, gemm_ms, gemm_flop, n_pair, pair_ms, pair_flop = prof[:6]
+        traffic = None
+        try:    # DRAM bytes of one captured launch of the dominant kernel (ncu --set full, summary committed in profiles/)
+            tr = {}
+            for ln in open(os.path.join(ROOT, "profiles", "r1_ncu_prof_tc2_pair_bfx_r1.csv")):
+                c = ln.strip().split(",")
+                if len(c) >= 3 and c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tr[c[0]] = float(c[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(c[2], 1.0)
+            if len(tr) == 2:
+                traffic = {"bytes_per_launch": sum(tr.values()), "launch": "gemm_tc2_pair_kernel, M=N=K=8192 (tools/gemm_one.py)",
+                           "algorithmic_bytes": 3 * 8192 * 8192 * 4, "source": "profiles/r1_ncu_prof_tc2_pair_bfx_r1.csv"}
+        except Exception:
+            traffic = None
         achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         pair_achieved = pair_flop / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0
         eng = lib.hb_get_gemm_engine()
@@ -283,7 +295,7 @@ def main():
             "roofline": {
                 "bound": "tensor", "kernel": "hb::gemm = gemm_tc2_pair_kernel / gemm_tc2_kernel (tcgen05 3xTF32) + short-K SIMT kernel: all level-3 work of potrf / potrf_bwd / sample projections",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "gemm_launches": int(n_gemm), "gemm_ms_per_step": gemm_ms,
                 "gemm_share_of_step": gemm_ms / ms_prof if ms_prof > 0 else None,
                 "useful_gemm_flop_per_step": gemm_flop,
@@ -291,8 +303,9 @@ def main():
                                 "ms_per_step": pair_ms, "useful_flop_per_step": pair_flop, "achieved": pair_achieved,
                                 "frac": pair_achieved / peak if peak else None,
                                 "share_of_step": pair_ms / ms_prof if ms_prof > 0 else None},
-                "note": ("fp32 parity (1e-5) needs three TF32 tensor-core passes per product (hi*hi + hi*lo + lo*hi): the ceiling of "
-                         "this formulation is the dense TF32 rate / 3 = bf16 rate / 6, i.e. frac <= 0.167 against the bf16 peak"),
+                "note": ("fp32 parity (1e-5) needs a split product: hi*hi in TF32 (two K=8 MMAs per 16-wide k-block) + lo*hi and hi*lo "
+                         "in bf16 (one K=16 MMA each) = 4 tensor-pipe slots where a bf16 GEMM needs 1, i.e. frac <= 0.25 against the "
+                         "bf16 peak for this formulation"),
                 "how": "CUDA-event pair around every GEMM launch of one extra (untimed) step; achieved = useful FLOP / summed launch time",
             },
             "phases_ms": phases,

@@ -359,6 +359,12 @@ int hb_rbf_gram_bwd(const float* G, long long ldg, long long strideG, const floa
                       csym, out_scale, g_ell, ws, ws_bytes, S(stream));
 }
 
+int hb_rbf_gram_bwd_x2(const float* G, long long ldg, long long strideG, const float* X, const float* X2, int n, int n2,
+                       int D, int batch, const float* ell, int n_ell, int sym_lower, float scale, float* dX2, void* stream) {
+  return rbf_gram_bwd_x2(G, ldg, strideG, X, X2 ? X2 : X, n, n2, D, (long long)n * D, (long long)n2 * D, ell, n_ell, batch,
+                         sym_lower, scale, dX2, S(stream));
+}
+
 size_t hb_potrf_workspace_bytes(int n) { return potrf_workspace_bytes(n); }
 int hb_potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
                    size_t ws_bytes, int* err_flag, void* stream) {

@@ -554,7 +554,7 @@ gemm_tc2_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tmem_ptr_addr = bars + 8u * (3 * NSTAGE_P + 4);
 
   const uint32_t rank = cluster_ctarank();
-  constexpr int GROUP = 4;                            // 4 pair-rows (1024 rows) share a B panel in L2
+  constexpr int GROUP = 8;                            // 8 pair-rows (2048 rows): a wave of 74 pair tiles is ~8 x 9, near-square
   const int bid = blockIdx.x >> 1;
   const int per_group = GROUP * p.tiles_n;
   const int first_m = (bid / per_group) * GROUP;

@@ -246,6 +246,65 @@ __global__ void gram_bwd_finalize_kernel(const double* __restrict__ partials, in
   if (n_ell == 1 && threadIdx.x == 0) g_ell[0] = (float)(osc * tot);
 }
 
+
+// Gradient w.r.t. the kernel inputs ("next" row SparseGP: inducing points are trainable, Henbun/gp/gp.py:95-98):
+//   dX2[j,d] = sum_i Geff[i,j] K(x_i, y_j) (x_id - y_jd) / ell_d^2
+// with Geff = G, or (sym_lower) the symmetric matrix whose lower triangle G holds.  One block owns 32 points y_j and
+// streams G in 32-row tiles (coalesced along j); K is recomputed from X, X2.  D <= DMAX features.
+template <int DMAX>
+__global__ void __launch_bounds__(256) rbf_gram_bwd_x2_kernel(const float* __restrict__ G, long long ldg, long long sG,
+                                                              const float* __restrict__ X, const float* __restrict__ X2,
+                                                              int n, int n2, int D, long long sX, long long sX2,
+                                                              const float* __restrict__ ell, int n_ell, int sym_lower,
+                                                              float scale, float* dX2, long long sD) {
+  __shared__ float xs[32][DMAX + 1];
+  __shared__ float red[8][32][DMAX + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int bz = blockIdx.y;
+  const float* Gb = G + (long long)bz * sG;
+  const float* Xb = X + (long long)bz * sX;
+  const float* Yb = X2 + (long long)bz * sX2;
+  const int j = blockIdx.x * 32 + tx;
+  float y[DMAX], acc[DMAX];
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) {
+    y[d] = (d < D && j < n2) ? Yb[(long long)j * D + d] / ell_at(ell, n_ell, d) : 0.f;
+    acc[d] = 0.f;
+  }
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * D; e += 256) {
+      const int r = e / D, d = e % D;
+      xs[r][d] = (i0 + r < n) ? Xb[(long long)(i0 + r) * D + d] / ell_at(ell, n_ell, d) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = ty + 8 * k, i = i0 + r;
+      if (i >= n || j >= n2) continue;
+      const float g = (sym_lower && j > i) ? __ldg(Gb + (long long)j * ldg + i) : __ldg(Gb + (long long)i * ldg + j);
+      float df[DMAX], r2 = 0.f;
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) { df[d] = (d < D) ? xs[r][d] - y[d] : 0.f; r2 = fmaf(df[d], df[d], r2); }
+      const float gk = g * expf(-0.5f * r2);
+#pragma unroll
+      for (int d = 0; d < DMAX; ++d) acc[d] = fmaf(gk, df[d], acc[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < DMAX; ++d) red[ty][tx][d] = acc[d];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * D; e += 256) {
+    const int c = e / D, d = e % D;
+    const int jj = blockIdx.x * 32 + c;
+    if (jj >= n2) continue;
+    float sacc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) sacc += red[t][c][d];
+    dX2[(long long)bz * sD + (long long)jj * D + d] = scale * sacc / ell_at(ell, n_ell, d);
+  }
+}
+
 }  // namespace
 
 int rbf_gram_fwd(const float* X, const float* X2, int n, int n2, int D, long long sX, long long sX2,
@@ -292,6 +351,24 @@ int rbf_gram_bwd(const float* G, long long ldg, long long sG, const float* X, co
     rbf_gram_bwd_kernel<32><<<nb, 256, 0, st>>>(G, ldg, sG, X, Y, n, n2, D, sX, sY, ell, n_ell, batch, sym_lower, csym, partials);
   HB_CHECK_LAUNCH();
   gram_bwd_finalize_kernel<<<1, 32, 0, st>>>(partials, nb, D, dmax, ell, n_ell, out_scale, g_ell);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+// dX2 = scale * d/dX2 of sum_ij Geff_ij K(X, X2)_ij  (see rbf_gram_bwd_x2_kernel); D <= 32.
+int rbf_gram_bwd_x2(const float* G, long long ldg, long long sG, const float* X, const float* X2, int n, int n2, int D,
+                    long long sX, long long sX2, const float* ell, int n_ell, int batch, int sym_lower, float scale,
+                    float* dX2, cudaStream_t st) {
+  if (n < 0 || n2 < 0 || D <= 0 || D > 32 || batch < 0 || (n_ell != 1 && n_ell != D)) return HB_ERR_ARG;
+  if (n2 == 0 || batch == 0) return HB_OK;
+  if (!G || !X || !X2 || !ell || !dX2 || ldg < n2 || batch > 65535) return HB_ERR_ARG;
+  if (sym_lower && n != n2) return HB_ERR_ARG;
+  dim3 grid((unsigned)cdiv(n2, 32), (unsigned)batch);
+  const long long sD = (long long)n2 * D;
+  if (D <= 8)
+    rbf_gram_bwd_x2_kernel<8><<<grid, 256, 0, st>>>(G, ldg, sG, X, X2, n, n2, D, sX, sX2, ell, n_ell, sym_lower, scale, dX2, sD);
+  else
+    rbf_gram_bwd_x2_kernel<32><<<grid, 256, 0, st>>>(G, ldg, sG, X, X2, n, n2, D, sX, sX2, ell, n_ell, sym_lower, scale, dX2, sD);
   HB_CHECK_LAUNCH();
   return HB_OK;
 }

@@ -52,6 +52,10 @@ int rbf_gram_bwd(const float* G, long long ldg, long long sG, const float* X, co
                  int D, long long sX, long long sX2, const float* ell, int n_ell, int batch, int sym_lower,
                  int csym, const float* out_scale, float* g_ell, void* ws, size_t ws_bytes, cudaStream_t st);
 
+int rbf_gram_bwd_x2(const float* G, long long ldg, long long sG, const float* X, const float* X2, int n, int n2, int D,
+                    long long sX, long long sX2, const float* ell, int n_ell, int batch, int sym_lower, float scale,
+                    float* dX2, cudaStream_t st);
+
 // ---- NN helpers (nn.cu) ----
 int act_bwd_colsum(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act, int clip,
                    float clip_lo, float clip_hi, float* dbias, cudaStream_t st);

@@ -24,8 +24,8 @@ class GP(Parameterized):
 
 class SparseGP(GP):
     """Sparse GP with inducing points z [m,d] (gp/gp.py:53-192).  Listed as a 'next' row in
-    SURVEY.md 8f: built from the same kernels (Gram, potrf, TRSM, GEMM); gradients w.r.t. z are not
-    implemented yet, so z is held fixed."""
+    SURVEY.md 8f: built from the same kernels (Gram, potrf, TRSM, GEMM); the inducing points z are trainable
+    (gradient through K(x, z) and chol(K(z, z)) via hb_rbf_gram_bwd_x2)."""
 
     def __init__(self, kern, z, collections=[graph_key.VARIABLES]):
         GP.__init__(self, kern)
@@ -34,7 +34,7 @@ class SparseGP(GP):
         self.m = len(z)
 
     def _z(self):
-        return object.__getattribute__(self, 'z').tensor().detach()
+        return object.__getattribute__(self, 'z').tensor()
 
     def samples(self, x, u, q_shape='diagonal'):
         assert (q_shape in ['diagonal', 'neglected', 'fullrank'])

@@ -278,16 +278,34 @@ class _RbfK(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         X, X2, ell = ctx.saved_tensors
-        if ctx.needs_input_grad[0] or (ctx.has_x2 and ctx.needs_input_grad[1]):
-            raise NotImplementedError("gradient w.r.t. kernel inputs X is not implemented (SparseGP.z is a 'next' row)")
         batch, n, n2, D = _kern_shapes(X, X2 if ctx.has_x2 else None)
         g = _c(g)
-        ws = reduce_ws(X.device)
-        gl = torch.empty(ell.numel(), device=X.device)
-        check(_L().hb_rbf_gram_bwd(ptr(g), n2, n * n2, ptr(X), ptr(X2) if ctx.has_x2 else None, n, n2, D, batch,
-                                   ptr(ell), ell.numel(), 0, ctx.csym, None, ptr(gl), ptr(ws), ws.numel(), stream()),
-              "hb_rbf_gram_bwd")
-        return None, None, gl, None
+        gX = gX2 = gl = None
+        lib = _L()
+        want_x = ctx.needs_input_grad[0]
+        want_x2 = ctx.has_x2 and ctx.needs_input_grad[1]
+        if want_x or want_x2:
+            if ctx.csym:
+                raise NotImplementedError("gradient w.r.t. the inputs of UnitCsymRBF is not implemented")
+            gT = g.transpose(-1, -2).contiguous()
+            if want_x2 or not ctx.has_x2:       # second-argument part: dX2_j = sum_i G_ij K_ij (x_i - x2_j)/ell^2
+                d2 = torch.empty_like(X2)
+                check(lib.hb_rbf_gram_bwd_x2(ptr(g), n2, n * n2, ptr(X), ptr(X2), n, n2, D, batch, ptr(ell), ell.numel(), 0,
+                                             1.0, ptr(d2), stream()), "hb_rbf_gram_bwd_x2")
+                if ctx.has_x2:
+                    gX2 = d2
+            if want_x:                          # first-argument part: the same contraction on G^T with swapped roles
+                d1 = torch.empty_like(X)
+                check(lib.hb_rbf_gram_bwd_x2(ptr(gT), n, n * n2, ptr(X2), ptr(X), n2, n, D, batch, ptr(ell), ell.numel(), 0,
+                                             1.0, ptr(d1), stream()), "hb_rbf_gram_bwd_x2")
+                gX = d1 if ctx.has_x2 else d1 + d2      # K(X, X): both arguments are X
+        if ctx.needs_input_grad[2]:
+            ws = reduce_ws(X.device)
+            gl = torch.empty(ell.numel(), device=X.device)
+            check(lib.hb_rbf_gram_bwd(ptr(g), n2, n * n2, ptr(X), ptr(X2) if ctx.has_x2 else None, n, n2, D, batch,
+                                      ptr(ell), ell.numel(), 0, ctx.csym, None, ptr(gl), ptr(ws), ws.numel(), stream()),
+                  "hb_rbf_gram_bwd")
+        return gX, gX2, gl, None
 
 
 def rbf_K(X, X2, ell, csym=False):
@@ -317,8 +335,8 @@ class _KernCholesky(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         X, ell, Lw = ctx.saved_tensors
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("gradient w.r.t. kernel inputs X is not implemented")
+        if ctx.needs_input_grad[0] and ctx.csym:
+            raise NotImplementedError("gradient w.r.t. the inputs of UnitCsymRBF is not implemented")
         batch, n, _, D = _kern_shapes(X, None)
         G = g.contiguous().clone()
         lib = _L()
@@ -329,7 +347,13 @@ class _KernCholesky(torch.autograd.Function):
         gl = torch.empty(ell.numel(), device=X.device)
         check(lib.hb_rbf_gram_bwd(ptr(G), n, n * n, ptr(X), None, n, n, D, batch, ptr(ell), ell.numel(), 1, ctx.csym,
                                   None, ptr(gl), ptr(rws), rws.numel(), stream()), "hb_rbf_gram_bwd")
-        return None, gl, None, None
+        gX = None
+        if ctx.needs_input_grad[0]:
+            # K-bar is symmetric (lower triangle stored): both kernel arguments are X -> twice the second-argument part
+            gX = torch.empty_like(X)
+            check(lib.hb_rbf_gram_bwd_x2(ptr(G), n, n * n, ptr(X), None, n, n, D, batch, ptr(ell), ell.numel(), 1, 2.0,
+                                         ptr(gX), stream()), "hb_rbf_gram_bwd_x2")
+        return gX, gl, None, None
 
 
 def kern_cholesky(X, ell, jitter, csym=False):

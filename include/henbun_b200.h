@@ -112,6 +112,12 @@ int hb_gauss_loglik_fwd(const float* f, const float* f_scale, const float* y, lo
 int hb_rbf_gram_fwd(const float* X, const float* X2, int n, int n2, int D, int batch, const float* ell, int n_ell,
                     float* K, long long ldk, long long strideK, float jitter, int lower_only, int csym,
                     void* stream);
+/* Gradient w.r.t. the SECOND kernel argument (SparseGP inducing points, Henbun/gp/gp.py:95-98, 146-174):
+ * dX2[b][j][d] = scale * sum_i Geff_ij K(x_i, x2_j) (x_id - x2_jd) / ell_d^2, Geff = G or (sym_lower, n == n2) the
+ * symmetric matrix whose lower triangle G holds.  X2 == NULL means X.  The gradient w.r.t. the first argument is the
+ * same call on G^T with the arguments swapped.  UnitRBF only (no Csym term); D <= 32. */
+int hb_rbf_gram_bwd_x2(const float* G, long long ldg, long long strideG, const float* X, const float* X2, int n, int n2,
+                       int D, int batch, const float* ell, int n_ell, int sym_lower, float scale, float* dX2, void* stream);
 /* g_ell[n_ell] = *out_scale * sum_ij G_ij dK_ij/d ell.  sym_lower: G's lower triangle holds a symmetric
  * gradient (full-symmetric convention), off-diagonal entries count twice. */
 int hb_rbf_gram_bwd(const float* G, long long ldg, long long strideG, const float* X, const float* X2, int n, int n2,
