@@ -9,6 +9,7 @@
 // also emit the inverse of the diagonal block, so every triangular solve above the leaves is a GEMM.
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include <cstdlib>
 
 namespace hb {
 
@@ -392,9 +393,47 @@ struct Ctx {
   float* tmp;         // [n][NB] scratch for leaf triangular solves
   long long ldt;      // = NB
   int* err;
-  void* tcws;         // scratch of the tensor-core GEMM engine (hi/lo operand copies)
+  void* tcws;         // scratch of the tensor-core GEMM engine (split-K partial tiles)
   size_t tcws_bytes;
+  // look-ahead: the single-CTA leaf kernels run on a high-priority side stream while the main stream continues with
+  // products that do not depend on them (null side stream = everything on the main stream)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+  mutable bool side_pending = false;     // a leaf is in flight on the side stream and the main stream has not joined it
 };
+
+// Side stream and its two events, created once per device (the only state this library keeps besides cuFuncAttributes;
+// HB_LOOKAHEAD=0 in the environment disables the look-ahead).
+struct SideState { cudaStream_t st = nullptr; cudaEvent_t a = nullptr, b = nullptr; bool tried = false; };
+static SideState g_side[64];
+static void attach_side(Ctx& c) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  SideState& s = g_side[dev];
+  if (!s.tried) {
+    s.tried = true;
+    const char* e = getenv("HB_LOOKAHEAD");
+    if (!(e && e[0] == '0')) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, hi) != cudaSuccess) s.st = nullptr;
+      if (s.st && (cudaEventCreateWithFlags(&s.a, cudaEventDisableTiming) != cudaSuccess ||
+                   cudaEventCreateWithFlags(&s.b, cudaEventDisableTiming) != cudaSuccess)) s.st = nullptr;
+    }
+  }
+  c.side = s.st; c.ev_main = s.a; c.ev_side = s.b;
+}
+// side stream picks up everything issued on the main stream so far
+static inline void fork_side(const Ctx& c) {
+  cudaEventRecord(c.ev_main, c.st);
+  cudaStreamWaitEvent(c.side, c.ev_main, 0);
+}
+// main stream waits for the leaf in flight on the side stream (no-op if none)
+static inline void join_side(const Ctx& c) {
+  if (!c.side_pending) return;
+  cudaStreamWaitEvent(c.st, c.ev_side, 0);
+  c.side_pending = false;
+}
 
 inline int gemm_ws(const Ctx& c, GemmParams& g) {
   g.ws = c.tcws; g.ws_bytes = c.tcws_bytes;
@@ -443,11 +482,14 @@ int trsm_rln(const Ctx& c, const float* L, long long ldl, int off, float* Bp, lo
 // from columns < c0 already applied.  Every step works on ALL rows below the diagonal block at once, so a level-w
 // update is one tall GEMM and a leaf is one potrf kernel plus one in-place solve of the whole panel
 // (2 n/NB - 1 GEMM launches in total; the square-recursive form needed (n/NB) log2(n/NB)).
-int potrf_cols(const Ctx& c, float* A, long long lda, int c0, int w, int n) {
+int potrf_cols(const Ctx& c, float* A, long long lda, int c0, int w, int n, bool leaf_done = false) {
   float* D = A + (long long)c0 * lda + c0;            // diagonal block of this column range
   if (w <= NB) {
-    potrf_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.st>>>(D, lda, 0, w, dinv_slot(c, c0), 0, 0, c.err, c0);
-    HB_CHECK_LAUNCH();
+    if (!leaf_done) {
+      potrf_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.st>>>(D, lda, 0, w, dinv_slot(c, c0), 0, 0, c.err, c0);
+      HB_CHECK_LAUNCH();
+    }
+    join_side(c);                                      // the look-ahead leaf (if any) must be done before the solve
     const int below = n - (c0 + w);
     if (below <= 0) return HB_OK;
     GemmParams g;                                      // panel <- panel * Dinv^T, in place
@@ -457,16 +499,39 @@ int potrf_cols(const Ctx& c, float* A, long long lda, int c0, int w, int n) {
     return gemm_ws(c, g);
   }
   const int w1 = split_point(w), w2 = w - w1;
-  HB_TRY(potrf_cols(c, A, lda, c0, w1, n));
-  {
-    // A[c0+w1 .. n, c0+w1 .. c0+w) -= L[c0+w1 .. n, c0 .. c0+w1) * L[c0+w1 .. c0+w, c0 .. c0+w1)^T  (lower trapezoid)
-    float* P = A + (long long)(c0 + w1) * lda + c0;
-    GemmParams g;
-    g.A = P; g.lda = lda; g.B = P; g.ldb = lda; g.transB = 1;
-    g.C = P + w1; g.ldc = lda; g.M = n - (c0 + w1); g.N = w2; g.K = w1; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
+  HB_TRY(potrf_cols(c, A, lda, c0, w1, n, leaf_done));
+  // A[c0+w1 .. n, c0+w1 .. c0+w) -= L[c0+w1 .. n, c0 .. c0+w1) * L[c0+w1 .. c0+w, c0 .. c0+w1)^T  (lower trapezoid)
+  float* P = A + (long long)(c0 + w1) * lda + c0;
+  const int M = n - (c0 + w1);
+  GemmParams g;
+  g.A = P; g.lda = lda; g.B = P; g.ldb = lda; g.transB = 1;
+  g.C = P + w1; g.ldc = lda; g.M = M; g.N = w2; g.K = w1; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
+  if (!c.side || w1 > 1024) {   // splitting a long-K update costs more than hiding one 76 us leaf behind it
     HB_TRY(gemm_ws(c, g));
+    return potrf_cols(c, A, lda, c0 + w1, w2, n);
   }
-  return potrf_cols(c, A, lda, c0 + w1, w2, n);
+  // look-ahead: update the next diagonal block first, factor it on the side stream, update the rest meanwhile
+  const int nb = min(NB, w2);
+  GemmParams d = g;                                    // rows [0, nb) x cols [0, nb), lower triangle
+  d.M = nb; d.N = nb;
+  HB_TRY(gemm_ws(c, d));
+  fork_side(c);
+  potrf_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.side>>>(P + w1, lda, 0, nb, dinv_slot(c, c0 + w1), 0, 0, c.err, c0 + w1);
+  HB_CHECK_LAUNCH();
+  cudaEventRecord(c.ev_side, c.side);
+  c.side_pending = true;
+  if (M > nb) {
+    GemmParams r = g;                                  // rows [nb, M) x cols [0, nb): full block
+    r.A = P + (long long)nb * lda; r.C = P + w1 + (long long)nb * lda; r.M = M - nb; r.N = nb; r.c_tri = 0;
+    HB_TRY(gemm_ws(c, r));
+    if (w2 > nb) {
+      GemmParams t = g;                                // rows [nb, M) x cols [nb, w2): lower trapezoid of its own
+      t.A = P + (long long)nb * lda; t.B = P + (long long)nb * lda;
+      t.C = P + w1 + (long long)nb * lda + nb; t.M = M - nb; t.N = w2 - nb; t.c_tri = 1;
+      HB_TRY(gemm_ws(c, t));
+    }
+  }
+  return potrf_cols(c, A, lda, c0 + w1, w2, n, /*leaf_done=*/true);
 }
 
 int potrf_rec(const Ctx& c, float* A, long long lda, int off, int n) {
@@ -503,6 +568,17 @@ int chol_rev_cols(const Ctx& c, const float* L, long long ldl, float* G, long lo
       h.C = GD; h.ldc = ldg; h.M = w; h.N = w; h.K = below; h.alpha = -2.f; h.beta = 1.f; h.c_tri = 1;
       HB_TRY(gemm_ws(c, h));
     }
+    // the leaf result (the diagonal block of K-bar) is only read by sym(G[T, right]) products further up and by the
+    // Gram backward: run it on the side stream and join right before those
+    if (c.side) {
+      join_side(c);                                    // one leaf in flight at a time (a single pair of events)
+      fork_side(c);
+      chol_rev_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.side>>>(LD, ldl, 0, GD, ldg, 0, w, dinv_slot(c, c0), 0);
+      HB_CHECK_LAUNCH();
+      cudaEventRecord(c.ev_side, c.side);
+      c.side_pending = true;
+      return HB_OK;
+    }
     chol_rev_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.st>>>(LD, ldl, 0, GD, ldg, 0, w, dinv_slot(c, c0), 0);
     HB_CHECK_LAUNCH();
     return HB_OK;
@@ -525,6 +601,7 @@ int chol_rev_cols(const Ctx& c, const float* L, long long ldl, float* G, long lo
     b.C = G_T_left; b.ldc = ldg; b.M = w2; b.N = w1; b.K = nb; b.alpha = -2.f; b.beta = 1.f;
     HB_TRY(gemm_ws(c, b));
   }
+  join_side(c);     // the next products read the diagonal blocks of G[T, right]
   {
     GemmParams g;   // G[T, left] -= 2 sym(G[T, right]) L[T, left], sym from the lower triangle
     g.A = G + (long long)r1 * ldg + r1; g.lda = ldg; g.a_tri = 1; g.B = L_T_left; g.ldb = ldl; g.transB = 0;
@@ -581,9 +658,11 @@ int potrf_lower(float* A, long long lda, long long strideA, int n, int batch, in
   }
   Ctx c;
   HB_TRY(make_ctx(c, n, ws, ws_bytes, err_flag, st));
+  attach_side(c);
   for (int b = 0; b < batch; ++b) {
     float* Ab = A + (long long)b * strideA;
     HB_TRY(potrf_rec(c, Ab, lda, 0, n));
+    join_side(c);
     if (zero_upper) HB_TRY(zero_strict_upper(Ab, lda, n, st));
   }
   return HB_OK;
@@ -603,12 +682,14 @@ int potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, 
   }
   Ctx c;
   HB_TRY(make_ctx(c, n, ws, ws_bytes, nullptr, st));
+  attach_side(c);
   const int nblk = (n + NB - 1) / NB;
   for (int b = 0; b < batch; ++b) {
     const float* Lb = L + (long long)b * strideL;
     trinv_blocks_kernel<<<nblk, LEAF_THREADS, kLeafSmem3, st>>>(Lb, ldl, n, c.dinv);
     HB_CHECK_LAUNCH();
     HB_TRY(chol_rev_rec(c, Lb, ldl, G + (long long)b * strideG, ldg, 0, n));
+    join_side(c);
   }
   return HB_OK;
 }
