@@ -177,41 +177,61 @@ __device__ __forceinline__ void store_tile(const float (&acc)[BN / 2], const Tc2
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
   const bool post = (p.bias != nullptr) || p.act != ACT_NONE || p.clip;
+  // rows ew, ew+8, ...: RB rows per trip so that RB * (BN/128) reads of the old C are in flight per lane (one read per
+  // trip made the beta = 1 epilogue latency-bound: 16 dependent DRAM round trips per warp)
+  constexpr int RB = 4, SEGS = BN / 128;
 #pragma unroll 1
-  for (int r = ew; r < BM; r += 8) {
-    const int gi = m0 + r;
-    if (gi >= p.M) break;
-    float* crow = Cbase + (long long)gi * p.ldc;
+  for (int r0 = ew; r0 < BM; r0 += 8 * RB) {
+    float4 oldv[RB][SEGS];
+    const bool fastC = p.vecC && p.beta != 0.f;
 #pragma unroll
-    for (int seg = 0; seg < BN / 128; ++seg) {
-      const int cj = seg * 128 + lane * 4;
-      const int gj = n0 + cj;
-      if (gj >= p.N) continue;
-      float o[4];
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
-                   : "r"(sm_tile + (uint32_t)(r * LDT + cj) * 4u));
+    for (int b = 0; b < RB; ++b) {
+      const int gi = m0 + r0 + 8 * b;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] *= p.alpha;
-      const bool full = (gj + 3 < p.N) && !(p.c_tri == 1 && gj + 3 > gi);
-      if (full && p.vecC) {
-        if (p.beta != 0.f) {
-          const float4 old = *reinterpret_cast<const float4*>(crow + gj);
-          o[0] = fmaf(p.beta, old.x, o[0]); o[1] = fmaf(p.beta, old.y, o[1]);
-          o[2] = fmaf(p.beta, old.z, o[2]); o[3] = fmaf(p.beta, old.w, o[3]);
-        }
-        if (post) {
+      for (int seg = 0; seg < SEGS; ++seg) {
+        const int gj = n0 + seg * 128 + lane * 4;
+        oldv[b][seg] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fastC && r0 + 8 * b < BM && gi < p.M && gj + 3 < p.N && !(p.c_tri == 1 && gj + 3 > gi))
+          oldv[b][seg] = *reinterpret_cast<const float4*>(Cbase + (long long)gi * p.ldc + gj);
+      }
+    }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = tc2_act(o[e] + (p.bias ? __ldg(p.bias + gj + e) : 0.f), p.act, p.clip, p.clip_lo, p.clip_hi);
-        }
-        *reinterpret_cast<float4*>(crow + gj) = make_float4(o[0], o[1], o[2], o[3]);
-      } else {
+    for (int b = 0; b < RB; ++b) {
+      const int r = r0 + 8 * b;
+      const int gi = m0 + r;
+      if (r >= BM || gi >= p.M) continue;
+      float* crow = Cbase + (long long)gi * p.ldc;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (gj + e < p.N && !(p.c_tri == 1 && gj + e > gi)) {
-            float x = o[e];
-            if (p.beta != 0.f) x = fmaf(p.beta, crow[gj + e], x);
-            if (post) x = tc2_act(x + (p.bias ? __ldg(p.bias + gj + e) : 0.f), p.act, p.clip, p.clip_lo, p.clip_hi);
-            crow[gj + e] = x;
+      for (int seg = 0; seg < SEGS; ++seg) {
+        const int cj = seg * 128 + lane * 4;
+        const int gj = n0 + cj;
+        if (gj >= p.N) continue;
+        float o[4];
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                     : "r"(sm_tile + (uint32_t)(r * LDT + cj) * 4u));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] *= p.alpha;
+        const bool full = (gj + 3 < p.N) && !(p.c_tri == 1 && gj + 3 > gi);
+        if (full && p.vecC) {
+          if (p.beta != 0.f) {
+            const float4 old = oldv[b][seg];
+            o[0] = fmaf(p.beta, old.x, o[0]); o[1] = fmaf(p.beta, old.y, o[1]);
+            o[2] = fmaf(p.beta, old.z, o[2]); o[3] = fmaf(p.beta, old.w, o[3]);
+          }
+          if (post) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = tc2_act(o[e] + (p.bias ? __ldg(p.bias + gj + e) : 0.f), p.act, p.clip, p.clip_lo, p.clip_hi);
+          }
+          *reinterpret_cast<float4*>(crow + gj) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (gj + e < p.N && !(p.c_tri == 1 && gj + e > gi)) {
+              float x = o[e];
+              if (p.beta != 0.f) x = fmaf(p.beta, crow[gj + e], x);
+              if (post) x = tc2_act(x + (p.bias ? __ldg(p.bias + gj + e) : 0.f), p.act, p.clip, p.clip_lo, p.clip_hi);
+              crow[gj + e] = x;
+            }
           }
         }
       }

@@ -24,7 +24,7 @@ def timeit(M, N, K, tA, tB, a_tri=0, c_tri=0, opt=0, reps=5, beta=0.0):
     lib.hb_set_tc_option(0); lib.hb_set_gemm_engine(0)
     ms = e0.elapsed_time(e1) / reps
     fl = 2.0 * M * N * K * (0.5 if (c_tri or a_tri) else 1.0)
-    print(f"time M={M} N={N} K={K} tA={tA} tB={tB} a_tri={a_tri} c_tri={c_tri} gen={'1' if opt & 2 else ('2-single' if opt & 4 else '2-pair')}{'-3xtf32' if opt & 8 else '-bf16x'} rc={rc}: {ms:.3f} ms {fl / ms / 1e9:.1f} TF/s", flush=True)
+    print(f"time M={M} N={N} K={K} tA={tA} tB={tB} a_tri={a_tri} c_tri={c_tri} gen={'1' if opt & 2 else ('2-single' if opt & 4 else '2-pair')}{'-3xtf32' if opt & 8 else '-bf16x'}{'-nonpers' if opt & 16 else ''} rc={rc}: {ms:.3f} ms {fl / ms / 1e9:.1f} TF/s", flush=True)
 
 if __name__ == "__main__":
     worst = 0.0
@@ -56,7 +56,11 @@ if __name__ == "__main__":
     worst = max(worst, run(3000, 3000, 700, 1, 0, c_tri=1, alpha=-1.0, beta=1.0))
     worst = max(worst, run(3000, 3000, 700, 0, 1, c_tri=1, alpha=-1.0, beta=1.0))
     print("worst tc2 err (pair shapes)", worst, flush=True)
-    for opt in (8, 0):
+    for opt in (0,):
+        timeit(65280, 256, 256, 0, 1, opt=opt, reps=20, beta=1.0)
+        timeit(32768, 512, 512, 0, 1, opt=opt, reps=20, beta=1.0)
+        timeit(32768, 1024, 1024, 0, 0, opt=opt, reps=10, beta=1.0)
+        timeit(16384, 2048, 2048, 1, 0, opt=opt, reps=10, beta=1.0)
         timeit(4096, 4096, 4096, 0, 1, opt=opt)
         timeit(8192, 8192, 8192, 0, 1, c_tri=1, opt=opt)
         timeit(8192, 8192, 8192, 1, 0, opt=opt)
