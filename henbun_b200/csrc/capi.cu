@@ -417,6 +417,11 @@ int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, 
   return rc < 0 ? HB_ERR_ARG : rc;
 }
 
+size_t hb_act_bwd_colsum_workspace_bytes(int rows, int cols) { return act_bwd_colsum_workspace_bytes(rows, cols); }
+int hb_act_bwd_colsum_ws(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act, int clip,
+                         float clip_lo, float clip_hi, float* dbias, void* ws, size_t ws_bytes, void* stream) {
+  return act_bwd_colsum_ws(dy, y, dz, rows, cols, ld, act, clip, clip_lo, clip_hi, dbias, ws, ws_bytes, S(stream));
+}
 int hb_act_bwd_colsum(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act, int clip,
                       float clip_lo, float clip_hi, float* dbias, void* stream) {
   return act_bwd_colsum(dy, y, dz, rows, cols, ld, act, clip, clip_lo, clip_hi, dbias, S(stream));

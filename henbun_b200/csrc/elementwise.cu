@@ -142,6 +142,63 @@ __global__ void act_bwd_colsum_kernel(const float* __restrict__ dy, const float*
   }
 }
 
+// Full-grid version: the one-block-per-32-columns kernel above runs on cols/32 SMs (25 of 148 for a 784-wide layer:
+// 27 ms of a 34 ms config-4 step).  Here a block owns a [rows_per_block x 128] slab (float4 per lane along the
+// columns), writes dz and a per-block column partial (double) into `partials[blockIdx.y][col]`; a second small kernel
+// sums the partials in a fixed order (deterministic, no atomics).
+__global__ void __launch_bounds__(256) act_bwd_tile_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* dz,
+                                                           int rows, int cols, long long ld, int act, int clip, float lo, float hi,
+                                                           int rows_per_block, double* partials) {
+  __shared__ double red[8][128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int r_begin = blockIdx.y * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  double dacc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < cols) {
+    int n = 0;
+    for (int r = r_begin + w; r < r_end; r += 8) {
+      const long long idx = (long long)r * ld + c;
+      const float4 yy = *reinterpret_cast<const float4*>(y + idx);
+      const float4 dd = *reinterpret_cast<const float4*>(dy + idx);
+      float g[4] = {dd.x * act_grad_from_output(yy.x, act), dd.y * act_grad_from_output(yy.y, act),
+                    dd.z * act_grad_from_output(yy.z, act), dd.w * act_grad_from_output(yy.w, act)};
+      if (clip) {
+        const float yv[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (yv[e] <= lo || yv[e] >= hi) g[e] = 0.f;
+      }
+      *reinterpret_cast<float4*>(dz + idx) = make_float4(g[0], g[1], g[2], g[3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] += g[e];
+      if (++n == 64) {      // bound the fp32 running sums
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { dacc[e] += (double)acc[e]; acc[e] = 0.f; }
+        n = 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) red[w][lane * 4 + e] = dacc[e] + (double)acc[e];
+  __syncthreads();
+  if (partials && threadIdx.x < 128) {
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < cols) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+      partials[(long long)blockIdx.y * cols + cc] = t;
+    }
+  }
+}
+__global__ void colsum_partials_kernel(const double* __restrict__ partials, int nb, int cols, float* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double t = 0.0;
+  for (int b = 0; b < nb; ++b) t += partials[(long long)b * cols + c];
+  out[c] = (float)t;
+}
+
 // tf.train.AdamOptimizer on loss = -objective: g = grad_scale * grad (grad_scale = -1 for maximise).
 __global__ void adam_tf1_kernel(float* theta, const float* __restrict__ grad, float* m, float* v, long long n,
                                 float gs, float lr, float b1, float b2, float eps, const int* step_dev, int step_host) {
@@ -225,6 +282,34 @@ int axpby(float* y, const float* x, long long n, float a, float b, cudaStream_t 
   if (n <= 0) return HB_OK;
   axpby_kernel<<<grid_for(n, 256), 256, 0, st>>>(y, x, n, a, b);
   HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+size_t act_bwd_colsum_workspace_bytes(int rows, int cols) {
+  (void)rows;
+  return (size_t)148 * 8 * (size_t)(cols > 0 ? cols : 0) * sizeof(double) + 256;
+}
+int act_bwd_colsum_ws(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act, int clip,
+                      float clip_lo, float clip_hi, float* dbias, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return HB_OK;
+  const bool vec = (cols % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dz) & 15) == 0);
+  if (!vec || !ws || ws_bytes < act_bwd_colsum_workspace_bytes(rows, cols) || rows < 512)
+    return act_bwd_colsum(dy, y, dz, rows, cols, ld, act, clip, clip_lo, clip_hi, dbias, st);
+  const int col_tiles = cdiv(cols, 128);
+  int row_blocks = (148 * 8) / col_tiles;                       // ~8 blocks per SM in total
+  if (row_blocks < 1) row_blocks = 1;
+  int rpb = cdiv(rows, row_blocks);
+  if (rpb < 64) rpb = 64;
+  rpb = (rpb + 7) / 8 * 8;
+  row_blocks = cdiv(rows, rpb);
+  double* part = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  act_bwd_tile_kernel<<<dim3((unsigned)col_tiles, (unsigned)row_blocks), 256, 0, st>>>(dy, y, dz, rows, cols, ld, act, clip, clip_lo,
+                                                                                      clip_hi, rpb, dbias ? part : nullptr);
+  HB_CHECK_LAUNCH();
+  if (dbias) {
+    colsum_partials_kernel<<<cdiv(cols, 128), 128, 0, st>>>(part, row_blocks, cols, dbias);
+    HB_CHECK_LAUNCH();
+  }
   return HB_OK;
 }
 int act_bwd_colsum(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act, int clip,

@@ -57,6 +57,9 @@ int rbf_gram_bwd_x2(const float* G, long long ldg, long long sG, const float* X,
                     float* dX2, cudaStream_t st);
 
 // ---- NN helpers (nn.cu) ----
+size_t act_bwd_colsum_workspace_bytes(int rows, int cols);
+int act_bwd_colsum_ws(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act, int clip,
+                      float clip_lo, float clip_hi, float* dbias, void* ws, size_t ws_bytes, cudaStream_t st);
 int act_bwd_colsum(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act, int clip,
                    float clip_lo, float clip_hi, float* dbias, cudaStream_t st);
 

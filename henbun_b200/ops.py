@@ -57,12 +57,17 @@ def _gemm_scratch(device, M, N, K, batch):
     every product runs on torch's current stream."""
     if batch != 1 or K < 512 or M * N > 74 * 128 * 256:
         return None, 0
+    buf = _scratch64(device)
+    return buf, buf.numel()
+
+
+def _scratch64(device):
     key = (device.type, device.index)
     buf = _SCRATCH.get(key)
     if buf is None:
         buf = torch.empty(64 << 20, dtype=torch.uint8, device=device)
         _SCRATCH[key] = buf
-    return buf, buf.numel()
+    return buf
 
 
 class _MatMul2D(torch.autograd.Function):
@@ -589,11 +594,13 @@ class _MatBias(torch.autograd.Function):
         lib = _L()
         dz = torch.empty_like(out)
         db = torch.empty(bshape, device=g.device)
+        ws = _scratch64(g.device)
         for i in range(nb):
             off = i * rows * N
-            check(lib.hb_act_bwd_colsum(C.c_void_p(g.data_ptr() + 4 * off), C.c_void_p(out.data_ptr() + 4 * off),
-                                        C.c_void_p(dz.data_ptr() + 4 * off), rows, N, N, act, clip, lo, hi,
-                                        C.c_void_p(db.data_ptr() + 4 * i * N), stream()), "hb_act_bwd_colsum")
+            check(lib.hb_act_bwd_colsum_ws(C.c_void_p(g.data_ptr() + 4 * off), C.c_void_p(out.data_ptr() + 4 * off),
+                                           C.c_void_p(dz.data_ptr() + 4 * off), rows, N, N, act, clip, lo, hi,
+                                           C.c_void_p(db.data_ptr() + 4 * i * N), ptr(ws), ws.numel(), stream()),
+                  "hb_act_bwd_colsum_ws")
         gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)

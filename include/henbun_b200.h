@@ -169,6 +169,11 @@ int hb_set_tc_option(int v);
 int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int c_tri, int M,
                   int N, int K, float alpha, float beta, void* ws, size_t ws_bytes, void* stream);
 /* Backward helper of MatBias: dz = dy * act'(y) (through the output y), dbias[c] = sum_r dz[r,c]. */
+/* Same with a scratch buffer of hb_act_bwd_colsum_workspace_bytes(rows, cols): full-grid kernel + deterministic partial
+ * reduction (the scratch-free entry point uses one block per 32 columns).  Falls back to it when ws is NULL / too small. */
+size_t hb_act_bwd_colsum_workspace_bytes(int rows, int cols);
+int hb_act_bwd_colsum_ws(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act,
+                         int clip, float clip_lo, float clip_hi, float* dbias, void* ws, size_t ws_bytes, void* stream);
 int hb_act_bwd_colsum(const float* dy, const float* y, float* dz, int rows, int cols, long long ld, int act,
                       int clip, float clip_lo, float clip_hi, float* dbias, void* stream);
 int hb_colsum(const float* a, long long lda, int rows, int cols, float alpha, float beta, float* out, void* stream);
