@@ -850,9 +850,10 @@ bool gemm_tc2_eligible(const GemmParams& p) {
   return true;
 }
 
-// shapes that run the CTA-pair kernel: N > 128, at least 64 tiles of 256 x 256, not in place
+// shapes that run the CTA-pair kernel: M > 128 (a 256-row pair tile would be mostly padding otherwise), N > 128,
+// at least 64 tiles of 256 x 256, not in place
 bool gemm_tc2_uses_pair(const GemmParams& p) {
-  return p.N > 128 && !(get_tc_option() & 4) && (long long)cdiv(p.M, 256) * cdiv(p.N, 256) >= 64 && !(p.C == p.A);
+  return p.M > 128 && p.N > 128 && !(get_tc_option() & 4) && (long long)cdiv(p.M, 256) * cdiv(p.N, 256) >= 64 && !(p.C == p.A);
 }
 
 int gemm_tc2(const GemmParams& p, cudaStream_t st) {
