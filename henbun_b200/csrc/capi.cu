@@ -182,7 +182,7 @@ int hb_version(void) { return 100; }
 unsigned long long hb_launch_count(void) { return g_launches; }
 size_t hb_reduce_workspace_bytes(void) { return kReduceWsBytes; }
 int hb_set_gemm_engine(int mode) {
-  if (mode < 0 || mode > 2) return HB_ERR_ARG;
+  if (mode < 0 || mode > 3) return HB_ERR_ARG;
   set_gemm_engine(mode);
   return HB_OK;
 }
