@@ -52,6 +52,9 @@ SIGNATURES = {
     "hb_sample_tril_bwd": (_i, [_c_f, _i, _i, _c_f, _c_f, _i, _c_f, _fl, _c_f, _c_f, _c_f, _c_f]),
     "hb_gaussian_logpdf": (_i, [_c_f, _ll, _c_f, _ll, _c_f, _ll, _ll, _c_f, _c_f]),
     "hb_gaussian_logpdf_bwd": (_i, [_c_f, _ll, _c_f, _ll, _c_f, _ll, _ll, _c_f, _c_f, _c_f, _c_f]),
+    "hb_density_nargs": (_i, [_i]),
+    "hb_density_logpdf": (_i, [_i, _c_f, _c_f, _ll, _c_f, _c_f]),
+    "hb_density_logpdf_bwd": (_i, [_i, _c_f, _c_f, _ll, _c_f, _ll, _c_f, _c_f, _sz, _c_f]),
     "hb_gather_rows": (_i, [_c_f, _c_f, _c_f, _ll, _ll, _c_f]),
     "hb_gauss_loglik_fwd": (_i, [_c_f, _c_f, _c_f, _ll, _ll, _c_f, _fl, _c_f, _c_f, _c_f, _sz, _c_f]),
     "hb_rbf_gram_fwd": (_i, [_c_f, _c_f, _i, _i, _i, _i, _c_f, _i, _c_f, _ll, _ll, _fl, _i, _i, _c_f]),

@@ -335,6 +335,18 @@ int hb_gaussian_logpdf_bwd(const float* x, long long x_period, const float* mu, 
                            void* stream) {
   return gaussian_logpdf_bwd(x, x_period, mu, mu_period, var, var_period, total, g, dmu, dvar, S(stream));
 }
+int hb_density_nargs(int kind) { return density_nargs_host(kind); }
+
+int hb_density_logpdf(int kind, const float* const* args, const long long* periods, long long total, float* out,
+                      void* stream) {
+  return density_logpdf(kind, args, periods, total, out, S(stream));
+}
+
+int hb_density_logpdf_bwd(int kind, const float* const* args, const long long* periods, long long total, const float* g,
+                          long long g_period, float* const* dargs, void* ws, size_t ws_bytes, void* stream) {
+  return density_logpdf_bwd(kind, args, periods, total, g, g_period, dargs, ws, ws_bytes, S(stream));
+}
+
 int hb_gather_rows(float* dst, const float* src, const long long* index, long long n_index, long long row_elems,
                    void* stream) {
   return gather_rows(dst, src, index, n_index, row_elems, S(stream));

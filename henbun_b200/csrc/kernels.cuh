@@ -41,6 +41,12 @@ int gaussian_logpdf(const float* x, long long x_period, const float* mu, long lo
 int gaussian_logpdf_bwd(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
                         long long var_period, long long total, const float* g, float* dmu, float* dvar,
                         cudaStream_t st);
+// ---- the whole densities.py family (density_family.cu) ----
+int density_nargs_host(int kind);
+int density_logpdf(int kind, const float* const* args, const long long* periods, long long total, float* out,
+                   cudaStream_t st);
+int density_logpdf_bwd(int kind, const float* const* args, const long long* periods, long long total, const float* g,
+                       long long g_period, float* const* dargs, void* ws, size_t ws_bytes, cudaStream_t st);
 int gather_rows(float* dst, const float* src, const long long* index, long long n_index, long long row_elems,
                 cudaStream_t st);
 

@@ -1,18 +1,17 @@
-"""Log-densities, mirror of Henbun/densities.py.  ``gaussian`` (:25-27) is the hot-path one and runs
-this repo's CUDA kernels forward and backward; the others (:30-103) are elementwise epilogue
-variants kept for API completeness and evaluated with torch elementwise ops."""
+"""Log-densities, mirror of Henbun/densities.py.  Every elementwise density (:25-74, :95-103) is one CUDA
+kernel forward and one backward from the same family (csrc/density_family.cu, C ABI hb_density_logpdf /
+hb_density_logpdf_bwd); ``multivariate_normal`` (:75-91) runs on the blocked triangular solve."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 
 from . import ops
-from .tf_wraps import log_sum_exp
 
 
 def _t(x, like):
     if isinstance(x, torch.Tensor):
-        return x
+        return x if x.dtype == torch.float32 else x.to(torch.float32)
     return torch.as_tensor(np.asarray(x, dtype=np.float32), device=like.device)
 
 
@@ -23,52 +22,45 @@ def _like(*xs):
     raise TypeError("at least one argument must be a device tensor")
 
 
+def _call(name, *args):
+    like = _like(*args)
+    return ops.density(name, *[_t(a, like) for a in args])
+
+
 def gaussian(x, mu, var):
-    like = _like(x, mu, var)
-    return ops.gaussian_logpdf(_t(x, like), _t(mu, like), _t(var, like))
+    return _call("gaussian", x, mu, var)
 
 
 def lognormal(x, mu, var):
-    lnx = torch.log(x)
-    return gaussian(lnx, mu, var) - lnx
+    return _call("lognormal", x, mu, var)
 
 
 def bernoulli(p, y):
-    return torch.log(torch.where(y == 1, p, 1 - p))
+    return _call("bernoulli", p, y)
 
 
 def poisson(lamb, y):
-    return y * torch.log(lamb) - lamb - torch.lgamma(y + 1.)
+    return _call("poisson", lamb, y)
 
 
 def exponential(lamb, y):
-    return - y / lamb - torch.log(lamb)
+    return _call("exponential", lamb, y)
 
 
 def gamma(shape, scale, x):
-    like = _like(shape, scale, x)
-    shape, scale, x = _t(shape, like), _t(scale, like), _t(x, like)
-    return -shape * torch.log(scale) - torch.lgamma(shape) + (shape - 1.) * torch.log(x) - x / scale
+    return _call("gamma", shape, scale, x)
 
 
 def student_t(x, mean, scale, deg_free):
-    like = _like(x, mean, scale, deg_free)
-    x, mean, scale, deg_free = _t(x, like), _t(mean, like), _t(scale, like), _t(deg_free, like)
-    const = torch.lgamma((deg_free + 1.) * 0.5) - torch.lgamma(deg_free * 0.5) \
-        - 0.5 * (torch.log(torch.square(scale)) + torch.log(deg_free) + float(np.log(np.pi)))
-    return const - 0.5 * (deg_free + 1.) * torch.log(1. + (1. / deg_free) * (torch.square((x - mean) / scale)))
+    return _call("student_t", x, mean, scale, deg_free)
 
 
 def beta(alpha, beta, y):
-    y = torch.clamp(y, 1e-6, 1 - 1e-6)
-    return (alpha - 1.) * torch.log(y) + (beta - 1.) * torch.log(1. - y) + torch.lgamma(alpha + beta) \
-        - torch.lgamma(alpha) - torch.lgamma(beta)
+    return _call("beta", alpha, beta, y)
 
 
 def laplace(mu, sigma, y):
-    like = _like(mu, sigma, y)
-    mu, sigma, y = _t(mu, like), _t(sigma, like), _t(y, like)
-    return - torch.abs(mu - y) / sigma - torch.log(2. * sigma)
+    return _call("laplace", mu, sigma, y)
 
 
 def multivariate_normal(x, mu, L):
@@ -87,4 +79,6 @@ def multivariate_normal(x, mu, L):
 
 
 def bimixture(fraction, logp0, logp1):
-    return log_sum_exp(torch.stack([logp0 + torch.log(fraction), logp1 + torch.log(1.0 - fraction)], dim=-1), axis=-1)
+    """log(fraction*exp(logp0) + (1-fraction)*exp(logp1)) (densities.py:95-103), one fused kernel instead of
+    log / stack / reduce_max / exp / reduce_sum / log."""
+    return _call("bimixture", fraction, logp0, logp1)

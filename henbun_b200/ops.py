@@ -521,45 +521,81 @@ def _period(t: torch.Tensor, out_shape) -> Optional[int]:
     return None
 
 
-class _GaussianLogpdf(torch.autograd.Function):
+DENSITY_KINDS = {"gaussian": 0, "lognormal": 1, "bernoulli": 2, "poisson": 3, "exponential": 4, "gamma": 5,
+                 "student_t": 6, "beta": 7, "laplace": 8, "bimixture": 9}
+
+
+def _ptr_array(tensors):
+    return (C.c_void_p * 4)(*[(t.data_ptr() if t is not None else None) for t in tensors] + [None] * (4 - len(tensors)))
+
+
+class _Density(torch.autograd.Function):
+    """One densities.py log-density (densities.py:25-103) = one kernel forward, one backward
+    (csrc/density_family.cu).  Operands in the reference's argument order; broadcasting is modular
+    (suffix-shaped operands / scalars are read in place, anything else is expanded first)."""
+
     @staticmethod
-    def forward(ctx, x, mu, var):
-        shape = torch.broadcast_shapes(x.shape, mu.shape, var.shape)
-        ops_ = []
-        for t in (x, mu, var):
+    def forward(ctx, kind, *args):
+        shape = torch.broadcast_shapes(*[a.shape for a in args])
+        total = int(torch.Size(shape).numel())
+        ops_, periods = [], []
+        for t in args:
             t = _lib.f32(t)
             p = _period(t, shape)
             if p is None:
                 t = t.expand(shape)
-                p = int(torch.Size(shape).numel())
-            ops_.append((_c(t), p))
-        total = int(torch.Size(shape).numel())
-        out = torch.empty(shape, device=x.device)
-        (xc, xp), (mc, mp), (vc, vp) = ops_
-        check(_L().hb_gaussian_logpdf(ptr(xc), xp, ptr(mc), mp, ptr(vc), vp, total, ptr(out), stream()),
-              "hb_gaussian_logpdf")
-        ctx.save_for_backward(xc, mc, vc)
-        ctx.meta = (xp, mp, vp, total, tuple(shape), tuple(x.shape), tuple(mu.shape), tuple(var.shape))
+                p = total
+            ops_.append(_c(t)); periods.append(min(p, max(total, 1)))
+        out = torch.empty(shape, device=args[0].device)
+        if total:
+            check(_L().hb_density_logpdf(kind, _ptr_array(ops_), (C.c_longlong * 4)(*periods + [1] * (4 - len(periods))),
+                                         total, ptr(out), stream()), "hb_density_logpdf")
+        ctx.save_for_backward(*ops_)
+        ctx.meta = (kind, periods, total, tuple(shape), [tuple(a.shape) for a in args])
         return out
 
     @staticmethod
     def backward(ctx, g):
-        xc, mc, vc = ctx.saved_tensors
-        xp, mp, vp, total, shape, xs, ms, vs = ctx.meta
-        g = _c(g.expand(shape))
-        need_mu = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        dmu = torch.empty(shape, device=g.device) if need_mu else None
-        dvar = torch.empty(shape, device=g.device) if ctx.needs_input_grad[2] else None
-        check(_L().hb_gaussian_logpdf_bwd(ptr(xc), xp, ptr(mc), mp, ptr(vc), vp, total, ptr(g), ptr(dmu), ptr(dvar),
-                                          stream()), "hb_gaussian_logpdf_bwd")
-        gx = (-dmu).sum_to_size(xs) if ctx.needs_input_grad[0] else None
-        gm = dmu.sum_to_size(ms) if ctx.needs_input_grad[1] else None
-        gv = dvar.sum_to_size(vs) if ctx.needs_input_grad[2] else None
-        return gx, gm, gv
+        ops_ = ctx.saved_tensors
+        kind, periods, total, shape, arg_shapes = ctx.meta
+        n = len(ops_)
+        if total == 0:
+            return (None,) + tuple(torch.zeros(s, device=g.device) if ctx.needs_input_grad[i + 1] else None
+                                   for i, s in enumerate(arg_shapes))
+        if all(st == 0 for st in g.stride()) and g.numel() > 0:      # the broadcast scalar a reduce_sum sends back
+            gc, gp = g.reshape(-1)[:1].contiguous(), 1
+        else:
+            gc, gp = _c(g.expand(shape)), total
+        outs = []
+        for i in range(n):
+            if not ctx.needs_input_grad[i + 1]:
+                outs.append(None)
+            elif periods[i] == 1 and total > 1:
+                outs.append(torch.empty(1, device=g.device))            # reduced in-kernel
+            else:
+                outs.append(torch.empty(shape, device=g.device))
+        ws = _lib.reduce_ws(g.device)
+        check(_L().hb_density_logpdf_bwd(kind, _ptr_array(ops_), (C.c_longlong * 4)(*periods + [1] * (4 - n)), total,
+                                         ptr(gc), gp, _ptr_array(outs), ptr(ws), ws.numel(), stream()),
+              "hb_density_logpdf_bwd")
+        grads = []
+        for i in range(n):
+            o = outs[i]
+            if o is None:
+                grads.append(None)
+            elif o.numel() == 1 and total > 1:
+                grads.append(o.reshape(arg_shapes[i]) if int(torch.Size(arg_shapes[i]).numel()) == 1 else o.expand(arg_shapes[i]))
+            else:
+                grads.append(o.sum_to_size(arg_shapes[i]))
+        return (None,) + tuple(grads)
+
+
+def density(name, *args):
+    return _Density.apply(DENSITY_KINDS[name], *args)
 
 
 def gaussian_logpdf(x, mu, var):
-    return _GaussianLogpdf.apply(x, mu, var)
+    return _Density.apply(0, x, mu, var)
 
 
 # --------------------------------------------------------------------------------------------

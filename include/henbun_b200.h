@@ -95,6 +95,35 @@ int hb_gaussian_logpdf(const float* x, long long x_period, const float* mu, long
 int hb_gaussian_logpdf_bwd(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
                            long long var_period, long long total, const float* g, float* dmu, float* dvar,
                            void* stream);
+/* The log-densities of Henbun/densities.py as one elementwise family (csrc/density_family.cu).
+ * kind (operands in the reference function's argument order, file:line in densities.py):
+ *   HB_DENSITY_GAUSSIAN 0 (x, mu, var) :25-27      HB_DENSITY_GAMMA 5 (shape, scale, x) :49-51
+ *   HB_DENSITY_LOGNORMAL 1 (x, mu, var) :30-32     HB_DENSITY_STUDENT_T 6 (x, mean, scale, deg_free) :54-61
+ *   HB_DENSITY_BERNOULLI 2 (p, y) :35-36           HB_DENSITY_BETA 7 (alpha, beta, y) :64-70
+ *   HB_DENSITY_POISSON 3 (lamb, y) :39-40          HB_DENSITY_LAPLACE 8 (mu, sigma, y) :73-74
+ *   HB_DENSITY_EXPONENTIAL 4 (lamb, y) :43-44      HB_DENSITY_BIMIXTURE 9 (fraction, logp0, logp1) :95-103
+ * args / periods: HOST arrays of hb_density_nargs(kind) device pointers and their modular periods
+ * (operand i is read at flat index e % periods[i]; 1 = scalar, total = full tensor).  out[e], e < total. */
+#define HB_DENSITY_GAUSSIAN 0
+#define HB_DENSITY_LOGNORMAL 1
+#define HB_DENSITY_BERNOULLI 2
+#define HB_DENSITY_POISSON 3
+#define HB_DENSITY_EXPONENTIAL 4
+#define HB_DENSITY_GAMMA 5
+#define HB_DENSITY_STUDENT_T 6
+#define HB_DENSITY_BETA 7
+#define HB_DENSITY_LAPLACE 8
+#define HB_DENSITY_BIMIXTURE 9
+int hb_density_nargs(int kind);   /* -1 for an unknown kind */
+int hb_density_logpdf(int kind, const float* const* args, const long long* periods, long long total, float* out,
+                      void* stream);
+/* Backward of hb_density_logpdf (what tf.gradients emits for the same graph).  g: incoming gradient read at
+ * e % g_period (1 = the scalar a reduce_sum sends back).  dargs: HOST array of device pointers, NULL = not wanted.
+ * For an operand with period 1 (and total > 1) dargs[i][0] = sum_e g[e] * dlogp/d operand_i, reduced in-kernel
+ * (deterministic; needs ws of hb_reduce_workspace_bytes()); otherwise dargs[i][e] = g[e] * dlogp/d operand_i at
+ * full size and the caller sums over the broadcast axes. */
+int hb_density_logpdf_bwd(int kind, const float* const* args, const long long* periods, long long total, const float* g,
+                          long long g_period, float* const* dargs, void* ws, size_t ws_bytes, void* stream);
 /* MinibatchData.get_feed_dict (param.py:733-739) on device: dst[i,:] = src[index[i],:], index int64. */
 int hb_gather_rows(float* dst, const float* src, const long long* index, long long n_index, long long row_elems,
                    void* stream);

@@ -163,6 +163,56 @@ def student_t(x, mean, scale, deg_free):
         1.0 + (1.0 / deg_free) * torch.square((x - mean) / scale))
 
 
+def lognormal(x, mu, var):
+    """densities.lognormal (densities.py:30-32)."""
+    lnx = torch.log(x)
+    return gaussian(lnx, mu, var) - lnx
+
+
+def bernoulli(p, y):
+    """densities.bernoulli (densities.py:35-36; tf.select = where)."""
+    return torch.log(torch.where(y == 1, p, 1 - p))
+
+
+def poisson(lamb, y):
+    """densities.poisson (densities.py:39-40)."""
+    return y * torch.log(lamb) - lamb - torch.lgamma(y + 1.0)
+
+
+def exponential(lamb, y):
+    """densities.exponential (densities.py:43-44)."""
+    return -y / lamb - torch.log(lamb)
+
+
+def gamma(shape, scale, x):
+    """densities.gamma (densities.py:47-49)."""
+    return -shape * torch.log(scale) - torch.lgamma(shape) + (shape - 1.0) * torch.log(x) - x / scale
+
+
+def beta(alpha, beta_, y):
+    """densities.beta (densities.py:62-68), y clipped to [1e-6, 1-1e-6]."""
+    y = torch.clamp(y, 1e-6, 1 - 1e-6)
+    return ((alpha - 1.0) * torch.log(y) + (beta_ - 1.0) * torch.log(1.0 - y)
+            + torch.lgamma(alpha + beta_) - torch.lgamma(alpha) - torch.lgamma(beta_))
+
+
+def laplace(mu, sigma, y):
+    """densities.laplace (densities.py:71-72)."""
+    return -torch.abs(mu - y) / sigma - torch.log(2.0 * sigma)
+
+
+def bimixture(fraction, logp0, logp1):
+    """densities.bimixture (densities.py:94-103) with tf_wraps.log_sum_exp (tf_wraps.py:42-48)."""
+    t = torch.stack([logp0 + torch.log(fraction), logp1 + torch.log(1.0 - fraction)], dim=-1)
+    m = torch.amax(t, dim=-1, keepdim=True)
+    return m.squeeze(-1) + torch.log(torch.sum(torch.exp(t - m), dim=-1))
+
+
+DENSITIES = {"gaussian": gaussian, "lognormal": lognormal, "bernoulli": bernoulli, "poisson": poisson,
+             "exponential": exponential, "gamma": gamma, "student_t": student_t, "beta": beta, "laplace": laplace,
+             "bimixture": bimixture}
+
+
 def multivariate_normal(x, mu, L):
     """densities.multivariate_normal (densities.py:75-91)."""
     d = x - mu
@@ -196,6 +246,18 @@ def square_dist(X, lengthscales, X2=None):
 def rbf_K(X, lengthscales, X2=None):
     """UnitRBF.K (gp/kernels.py:110-111)."""
     return torch.exp(-square_dist(X, lengthscales, X2) / 2.0)
+
+
+def rbf_K_direct(X, lengthscales, X2=None):
+    """Same function as rbf_K with r^2 summed from squared differences instead of the reference's
+    -2 x.x' + |x|^2 + |x'|^2 expansion (gp/kernels.py:71-84).  Identical in exact arithmetic; in fp32 the
+    expansion loses ~|x|^2 * 2^-24 absolute per entry, which at N=2000 on the 1-D notebook grid with l=0.2
+    already breaks positive-definiteness at jitter 3e-4.  Only used as the fp32 comparator of the config-2
+    full-size test (the CUDA kernel sums differences as well, csrc/gram.cu)."""
+    Xe = X / lengthscales
+    X2e = Xe if X2 is None else X2 / lengthscales
+    d = Xe.unsqueeze(-2) - X2e.unsqueeze(-3)
+    return torch.exp(-0.5 * torch.sum(torch.square(d), -1))
 
 
 def csym_rbf_K(X, lengthscales, X2=None):
@@ -432,7 +494,7 @@ def chol_rev_recursive(L, Lbar, nb=32):
 # Other BASELINE configs
 # --------------------------------------------------------------------------
 
-def expert_gpr_elbo(p, X, Y, U3, q_shapes=("fullrank", "fullrank", "fullrank"), jitter=3e-4):
+def expert_gpr_elbo(p, X, Y, U3, q_shapes=("fullrank", "fullrank", "fullrank"), jitter=3e-4, K_fn=rbf_K):
     """notebooks/Expert_GPR.ipynb:101-149 (``ELBO``), S-sample mean.
     p: 'q_{s,l,r}.q_mu' [n], 'q_{s,l,r}.q_sqrt', 'q_{s,l,r}.scale' [1],
        'kern_{s,l,r}.lengthscales' [1], 'k_var','k_var_r','var' [1] (all free).
@@ -441,7 +503,7 @@ def expert_gpr_elbo(p, X, Y, U3, q_shapes=("fullrank", "fullrank", "fullrank"), 
     fs, kl = {}, 0.0
     for name, qs in zip(("s", "l", "r"), q_shapes):
         ell = log1pe_forward(p[f"kern_{name}.lengthscales"])
-        L = kern_cholesky(X, ell, jitter)
+        L = kern_cholesky(X, ell, jitter, K_fn)
         mu, sq = p[f"q_{name}.q_mu"], p[f"q_{name}.q_sqrt"]
         U = U3[name]
         if qs == "diagonal":

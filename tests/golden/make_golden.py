@@ -167,6 +167,40 @@ def golden_densities_transforms():
          logistic_fwd=fwl, logistic_logjac=ljl, exp_fwd=fwe)
 
 
+def golden_densities_all():
+    """Every non-Gaussian density of Henbun/densities.py:30-103 and its tf.gradients w.r.t. each tensor
+    argument (d sum(w * logp) with a fixed random weighting w, so that every element's derivative is pinned)."""
+    rng = np.random.RandomState(0)
+    shp = (3, 5, 4)
+    pos = lambda *s: np.exp(0.5 * rng.randn(*s))
+    cases = {
+        # name: (function, [argument arrays in the reference's order])
+        "lognormal": (hb.densities.lognormal, [pos(*shp), rng.randn(5, 4), pos(4)]),
+        "bernoulli": (hb.densities.bernoulli, [rng.uniform(0.05, 0.95, shp), (rng.rand(*shp) < 0.5).astype(np.float64)]),
+        "poisson": (hb.densities.poisson, [pos(*shp), rng.poisson(3.0, shp).astype(np.float64)]),
+        "exponential": (hb.densities.exponential, [pos(5, 4), pos(*shp)]),
+        "gamma": (hb.densities.gamma, [pos(4) + 0.5, pos(5, 4), pos(*shp)]),
+        "student_t": (hb.densities.student_t, [rng.randn(*shp), rng.randn(5, 4), pos(4), pos(*shp) * 3.0]),
+        "beta": (hb.densities.beta, [pos(5, 4) + 0.5, pos(4) + 0.5,
+                                     np.concatenate([rng.uniform(0.02, 0.98, (3, 5, 3)), np.array([0.0, 1.0, 0.5] * 5).reshape(3, 5, 1)], -1)]),
+        "laplace": (hb.densities.laplace, [rng.randn(5, 4), pos(4), rng.randn(*shp)]),
+        "bimixture": (hb.densities.bimixture, [rng.uniform(0.05, 0.95, (5, 4)), rng.randn(*shp) * 3, rng.randn(*shp) * 3]),
+    }
+    out = {}
+    with tf.Session() as sess:
+        for name, (fn, args) in cases.items():
+            w = rng.randn(*shp)
+            ts = [tf.constant(a) for a in args]
+            val = fn(*ts)
+            out[name + "/out"] = sess.run(val)
+            out[name + "/w"] = w
+            gs = sess.run(tf.gradients(tf.reduce_sum(val * tf.constant(w)), ts))
+            for i, (a, g) in enumerate(zip(args, gs)):
+                out[f"{name}/arg{i}"] = a
+                out[f"{name}/grad{i}"] = np.zeros_like(a) if g is None else np.asarray(g)
+    save("densities_all", **out)
+
+
 def _gpr_class(X, Y, q_shape):
     class GPR(hb.model.Model):                 # notebooks/GaussianProcess.ipynb:109-148, verbatim structure
         def setUp(self):
@@ -311,6 +345,7 @@ if __name__ == "__main__":
     golden_kernels()
     golden_nn()
     golden_densities_transforms()
+    golden_densities_all()
     golden_gpr()
     golden_amortised()
     golden_expert_gpr()

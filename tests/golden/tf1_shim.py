@@ -360,6 +360,8 @@ def multiply(a, b, name=None): return _bin(torch.mul, a, b)
 def cast(x, dtype, name=None): return _un(lambda t: t.to(dtype.torch), x)
 def clip_by_value(x, lo, hi, name=None): return _un(lambda t: torch.clamp(t, lo, hi), x)
 def equal(a, b): return _bin(torch.eq, a, b)
+def select(cond, a, b):                                        # TF <= 0.12 name of tf.where (densities.py:36)
+    return Tensor(lambda c, x, y: torch.where(_v(c), _as_t(_v(x)), _as_t(_v(y))), [cond, a, b], None)
 
 
 def _red(f):

@@ -103,6 +103,22 @@ def test_neural_net():
         assert np.allclose(v.grad.numpy(), g["grad_sumsq_y1"][k], rtol=1e-10, atol=1e-12)
 
 
+def test_all_densities_and_their_gradients():
+    """Every density of densities.py:30-103 and tf.gradients of it, as the unmodified reference computed them."""
+    d = np.load(os.path.join(G, "densities_all.npz"))
+    for name, fn in O.DENSITIES.items():
+        if name == "gaussian":
+            continue
+        n_args = len([k for k in d.files if k.startswith(name + "/arg")])
+        args = [torch.tensor(d[f"{name}/arg{i}"], dtype=torch.float64, requires_grad=True) for i in range(n_args)]
+        out = fn(*args)
+        assert np.allclose(out.detach().numpy(), d[name + "/out"], rtol=1e-12, atol=1e-12), name
+        (out * torch.tensor(d[name + "/w"])).sum().backward()
+        for i, a in enumerate(args):
+            got = np.zeros_like(d[f"{name}/grad{i}"]) if a.grad is None else a.grad.numpy()
+            assert np.allclose(got, d[f"{name}/grad{i}"], rtol=1e-10, atol=1e-12), (name, i)
+
+
 def test_densities_and_transforms():
     g = load("densities_transforms")
     assert np.allclose(O.gaussian(T(g["a"]), T(0.0), T(2.0)).numpy(), g["gauss_scalar"], atol=1e-12)

@@ -1,0 +1,37 @@
+"""Config 2 (Expert GPR, N=2000, jitter 3e-4, cond ~3e6) gradient error vs the fp64 oracle under each GEMM engine
+setting, next to the fp32-CPU restatement's error.  Evidence for the accuracy discussion in DESIGN.md."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+import henbun_b200 as hb
+from henbun_b200 import _lib
+from oracle import henbun_oracle as O
+import test_gpu_configs as T
+
+n, S = int(sys.argv[1]) if len(sys.argv) > 1 else 2000, 4
+jitter = float(sys.argv[2]) if len(sys.argv) > 2 else 3e-4
+rng = np.random.RandomState(0)
+X = np.linspace(0, 6, n).reshape(-1, 1)
+Y = np.sin(0.1 * X * X * X) + rng.randn(*X.shape) * 0.1
+q_shapes = ('fullrank', 'fullrank', 'diagonal')
+m = T.ExpertGPR(X=X, Y=Y, q_shapes=q_shapes)
+for nm in ("q_s", "q_l"):
+    getattr(m, nm).q_sqrt = 0.3 * np.eye(n) + (0.2 / np.sqrt(n)) * np.tril(rng.randn(n, n))
+opt = T._compile(m, jitter, S)
+p = T._free(m, q_shapes)
+U = {nm: rng.randn(S, n).astype(np.float32) for nm in ("s", "l", "r")}
+eps = {object.__getattribute__(m, "q_" + nm): U[nm].reshape(S, n, 1) for nm in U}
+fn = lambda pp, X_, Y_, U_: O.expert_gpr_elbo(pp, X_, Y_, U_, q_shapes=q_shapes, jitter=jitter)
+fn32 = lambda pp, X_, Y_, U_: O.expert_gpr_elbo(pp, X_, Y_, U_, q_shapes=q_shapes, jitter=jitter, K_fn=O.rbf_K_direct)
+ref, gref = O.value_and_grads(fn, p, X, Y[:, 0], U)
+ref32, gref32 = O.value_and_grads(fn32, p, X, Y[:, 0], U, dtype=torch.float32)
+keys = list(gref)
+print("fp32-CPU   ELBO rel %.1e  grads %s" % (abs(ref32 - ref) / abs(ref), " ".join("%.0e" % T.rel_err(gref32[k], gref[k]) for k in keys)))
+lib = _lib.load()
+for label, eng, opt_bits in (("auto", 0, 0), ("simt", 1, 0), ("all-tf32", 0, 8), ("kloop", 3, 0)):
+    lib.hb_set_gemm_engine(eng); lib.hb_set_tc_option(opt_bits)
+    val, grads = T._value_and_grads(m, opt, eps)
+    errs = [T.rel_err(grads["model." + k].reshape(gref[k].shape), gref[k]) for k in keys]
+    print("%-10s ELBO rel %.1e  grads %s" % (label, abs(val - ref) / abs(ref), " ".join("%.0e" % e for e in errs)))
+print(keys)

@@ -1,4 +1,4 @@
-"""BASELINE configs 4 and 5 at full size through the Henbun-shaped Python API (model.optimize): ms per Adam step.
+"""BASELINE configs 1, 2, 4 and 5 at full size through the Henbun-shaped Python API (model.optimize): ms per Adam step.
 Not bench lines (bench.py measures config 3) -- evidence that the other configs run at their named sizes."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,7 +17,62 @@ def timed(opt, steps, **kw):
     return (time.perf_counter() - t0) / steps * 1e3
 
 
-if which == "4":
+if which in ("1", "2"):
+    # config 1: notebooks/GaussianProcess.ipynb:109-148 at N=100, full-covariance q, S=10
+    # config 2: notebooks/Expert_GPR.ipynb:101-149 at N=2000, 3 experts (q_s, q_l full-covariance, q_r mean-field)
+    rng = np.random.RandomState(0)
+    if which == "1":
+        n, S, jitter = 100, 10, 1e-5
+        X = np.linspace(0, 6, n).reshape(-1, 1); Y = np.sin(X) + 0.3 * rng.randn(n, 1)
+
+        class GPR(hb.model.Model):
+            def setUp(self):
+                self.X = hb.param.Data(X); self.Y = hb.param.Data(Y)
+                self.q = hb.variationals.Gaussian(shape=X.shape, q_shape='fullrank')
+                self.kern = hb.gp.kernels.UnitRBF()
+                self.k_var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+                self.var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+
+            @hb.model.AutoOptimize()
+            def ELBO(self):
+                y_fit = tf.matmul(self.kern.Cholesky(self.X), self.q) * tf.sqrt(self.k_var)
+                return tf.reduce_sum(hb.densities.gaussian(self.Y, y_fit, self.var)) - self.KL()
+        m = GPR()
+    else:
+        n, S, jitter = 2000, 10, 3e-4
+        X = np.linspace(0, 6, n).reshape(-1, 1); Y = np.sin(0.1 * X ** 3) + 0.1 * rng.randn(n, 1)
+
+        class ExpertGPR(hb.model.Model):
+            def setUp(self):
+                self.X = hb.param.Data(X); self.Y = hb.param.Data(Y)
+                self.q_s = hb.variationals.Gaussian(shape=X.shape, q_shape='fullrank')
+                self.q_l = hb.variationals.Gaussian(shape=X.shape, q_shape='fullrank')
+                self.q_r = hb.variationals.Gaussian(shape=X.shape, q_shape='diagonal')
+                self.kern_s = hb.gp.kernels.UnitRBF(np.ones(1) * 0.2)
+                self.kern_l = hb.gp.kernels.UnitRBF(np.ones(1) * 1)
+                self.kern_r = hb.gp.kernels.UnitRBF(np.ones(1) * 1)
+                self.k_var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+                self.k_var_r = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+                self.var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+
+            @hb.model.AutoOptimize()
+            def ELBO(self):
+                f_s = tf.matmul(self.kern_s.Cholesky(self.X), self.q_s)
+                f_l = tf.matmul(self.kern_l.Cholesky(self.X), self.q_l)
+                f_r = tf.matmul(self.kern_r.Cholesky(self.X), self.q_r) * tf.sqrt(self.k_var_r)
+                fraction = tf.sigmoid(f_r)
+                f = (fraction * f_s + (1 - fraction) * f_l) * self.k_var
+                return tf.reduce_sum(hb.densities.gaussian(self.Y, f, self.var)) - self.KL()
+        m = ExpertGPR()
+        for nm in ("q_s", "q_l"):
+            getattr(m, nm).q_sqrt = 0.3 * np.eye(n) + (0.2 / np.sqrt(n)) * np.tril(rng.randn(n, n))
+    cfg = hb.settings.get_settings(); cfg.numerics.jitter_level = jitter
+    with hb.settings.temp_settings(cfg):
+        m.ELBO().compile(n_samples=S, verbose=False)
+    ms = timed(m.ELBO(), 20)
+    print(f"config {which} (N={n}, S={S}, jitter {jitter:g}): {ms:.3f} ms/step = {S * n / ms * 1e3:.3e} evals/s; "
+          f"ELBO {float(m.ELBO().run()):.4f}", flush=True)
+elif which == "4":
     class Amortised(hb.model.Model):
         def setUp(self, X=None, latent=64):
             self.X = hb.param.MinibatchData(X)
