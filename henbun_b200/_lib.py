@@ -31,6 +31,10 @@ class GpConfig(C.Structure):
                 ("seed", _ull), ("offset", _ull)]
 
 
+class LinopConfig(C.Structure):
+    _fields_ = [("M", _i), ("M_total", _ll), ("n", _i), ("S", _i), ("seed", _ull), ("offset", _ull)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check that every symbol the header
 # declares is exported.
 SIGNATURES = {
@@ -81,6 +85,11 @@ SIGNATURES = {
     "hb_increment_i32": (_i, [_c_f, _c_f]),
     "hb_transpose2d": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _fl, _c_f]),
     "hb_zero_strict_upper": (_i, [_c_f, _ll, _i, _c_f]),
+    "hb_linop_param_count": (_sz, [C.POINTER(LinopConfig)]),
+    "hb_linop_workspace_bytes": (_sz, [C.POINTER(LinopConfig)]),
+    "hb_linop_elbo_local": (_i, [C.POINTER(LinopConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f]),
+    "hb_linop_elbo_update": (_i, [C.POINTER(LinopConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _fl, _fl, _fl, _fl, _c_f, _i,
+                                  _c_f, _c_f, _sz, _c_f]),
     "hb_gp_param_count": (_sz, [C.POINTER(GpConfig)]),
     "hb_gp_elbo_workspace_bytes": (_sz, [C.POINTER(GpConfig)]),
     "hb_gp_elbo_step": (_i, [C.POINTER(GpConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f, _c_f]),

@@ -75,10 +75,12 @@ __device__ __forceinline__ float density_eval(const float (&v)[kMaxArgs]) {
     const float t = (v[0] - v[1]) / v[2];
     return (float)(c - 0.5 * (nu + 1.0) * (double)log1pf(t * t / v[3]));
   } else if (KIND == 7) {                            // beta(alpha, beta, y), y clipped to [1e-6, 1-1e-6]
-    const float y = fminf(fmaxf(v[2], 1e-6f), 1.f - 1e-6f);
+    // the clip bound 1 - 1e-6 is not an fp32 number (nearest: 1 - 1.013e-6, a 1.3 % error on 1 - y): clip and take
+    // the logs in double
+    const double y = fmin(fmax((double)v[2], 1e-6), 1.0 - 1e-6);
     const double a = (double)v[0], b = (double)v[1];
     const double c = lgamma(a + b) - lgamma(a) - lgamma(b);
-    return (float)((a - 1.0) * (double)logf(y) + (b - 1.0) * (double)logf(1.f - y) + c);
+    return (float)((a - 1.0) * log(y) + (b - 1.0) * log1p(-y) + c);
   } else if (KIND == 8) {                            // laplace(mu, sigma, y)
     return -fabsf(v[0] - v[2]) / v[1] - logf(2.f * v[1]);
   } else {                                           // bimixture(fraction, logp0, logp1)
@@ -121,13 +123,13 @@ __device__ __forceinline__ void density_grad(const float (&v)[kMaxArgs], float (
                       0.5 * (double)log1pf(t * t / nu) + 0.5 * (double)w * (double)t / (double)nu;
     dv[3] = (float)dn;
   } else if (KIND == 7) {
-    const bool inside = v[2] >= 1e-6f && v[2] <= 1.f - 1e-6f;
-    const float y = fminf(fmaxf(v[2], 1e-6f), 1.f - 1e-6f);
+    const bool inside = (double)v[2] >= 1e-6 && (double)v[2] <= 1.0 - 1e-6;
+    const double y = fmin(fmax((double)v[2], 1e-6), 1.0 - 1e-6);
     const double a = (double)v[0], b = (double)v[1];
     const double pab = digamma_d(a + b);
-    dv[0] = (float)((double)logf(y) + pab - digamma_d(a));
-    dv[1] = (float)((double)logf(1.f - y) + pab - digamma_d(b));
-    dv[2] = inside ? (v[0] - 1.f) / y - (v[1] - 1.f) / (1.f - y) : 0.f;
+    dv[0] = (float)(log(y) + pab - digamma_d(a));
+    dv[1] = (float)(log1p(-y) + pab - digamma_d(b));
+    dv[2] = inside ? (float)((a - 1.0) / y - (b - 1.0) / (1.0 - y)) : 0.f;
   } else if (KIND == 8) {
     const float is = 1.f / v[1], d = v[0] - v[2];
     const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);

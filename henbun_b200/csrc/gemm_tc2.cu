@@ -859,7 +859,7 @@ bool gemm_tc2_uses_pair(const GemmParams& p) {
 int gemm_tc2(const GemmParams& p, cudaStream_t st) {
   static const int b2rk[5] = {0, 2, 1, 4, 3};      // mask of op(B)[k][n] expressed in (n, k) space
   const bool akm = (p.transA == 0), bkm = (p.transB == 1);
-  const int BN = (p.N <= 128) ? 128 : 256;
+  const int BN = (p.N <= 128 || p.hint_bn128) ? 128 : 256;
   // CTA pairs (256 x 256 tiles) once there are enough of them to fill the GPU; bit 2 of the option word disables them
   const bool pair = gemm_tc2_uses_pair(p);
   CUtensorMap ta, tb;
@@ -878,6 +878,17 @@ int gemm_tc2(const GemmParams& p, cudaStream_t st) {
   if (p.ws && tiles < 74 && p.K >= 512 && !p.a_tri && !p.b_tri && !p.bias && p.act == ACT_NONE && !p.clip) {
     int want = (int)((148 + tiles - 1) / tiles);
     const int kblocks = cdiv(p.K, BK);
+    if (tiles >= 32) {
+      // many tiles, few splits: the rounding to whole waves of 148 CTAs dominates (64 tiles x 3 splits = 1.3 waves
+      // ran at 65 % efficiency).  Take the split count with the best wave efficiency that the scratch allows.
+      const int max_split = p.ws_bytes > 256 ? (int)((p.ws_bytes - 256) / ((size_t)p.M * p.N * sizeof(float))) : 0;
+      double best = 0.0;
+      for (int ns = 1; ns <= 16 && ns <= max_split && kblocks / ns >= 16; ++ns) {
+        const long long ctas = tiles * ns;
+        const double eff = (double)ctas / (148.0 * (double)((ctas + 147) / 148));
+        if (eff > best + 0.02) { best = eff; want = ns; }
+      }
+    }
     int per = cdiv(kblocks, want);
     per = (per + CHK - 1) / CHK * CHK;                     // whole accumulation chunks per split
     if (per < 16) per = 16;                                // >= 256 of K per split

@@ -1,0 +1,341 @@
+// Fused ELBO + gradient + Adam step of BASELINE config 5: a full-covariance Normal([n]) posterior observed through a
+// dense forward operator A [M, n] with a Gaussian likelihood,
+//     z = mu + tril(L_q) u            variationals.py:144-146 (matrix_band_part + matmul)
+//     KL = -1/2 sum(logdet + u^2 - z^2), logdet = log diag(L_q)^2   variationals.py:185-186, 225-230
+//     ELBO = sum gaussian(y, A z, var) - KL                          densities.py:25-27
+// S-sample mean, maximised by tf.train.AdamOptimizer on -ELBO (model.py:206,220).
+//
+// HBM-bound: per step A is streamed twice (F = Z A^T, Zbar = R A), tril(L_q) is read once by the
+// sampler, and the update of L_q never materialises its n x n gradient: `tril_rank_adam_kernel` forms
+// Lbar_ij = sum_s Zt[s,i] U[s,j] (+ 1/L_ii on the diagonal) tile by tile in registers and applies the TF-1 Adam rule
+// to L_q, m, v in the same pass, touching only the lower triangle (the strict upper triangle of the reference's
+// [n,n] variable gets zero gradient, so its Adam update is exactly zero -- SURVEY.md section 9).
+// Algorithmic bytes per step: 2*4*M*n (A twice) + 4*n^2/2 (sampler) + 6*4*n^2/2 (Adam on tril) + O((M+n) S).
+//
+// Split in two calls so that a row-sharded A (M/G rows per GPU) needs exactly one collective in between:
+//   hb_linop_elbo_local   : sampler, F, log-lik, partial Zbar = R_g A_g          -> zbar_stats [S*n + 4]
+//   (all-reduce zbar_stats over the ranks; nothing to do on one GPU)
+//   hb_linop_elbo_update  : mu-bar, var-bar, fused Lbar + Adam                    (replicated on every rank)
+#include <stdlib.h>
+#include "kernels.cuh"
+#include "gemm.cuh"
+#include "../../include/henbun_b200.h"
+
+namespace hb {
+
+namespace {
+
+struct LinopLayout {
+  size_t off_U, off_Z, off_F, off_Zt, off_sc, off_gt, off_red, off_gemm, gemm_bytes, total;
+};
+
+inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
+
+LinopLayout linop_layout(const hb_linop_config& c) {
+  LinopLayout L;
+  const size_t sn = (size_t)c.S * c.n * 4;
+  size_t o = 0;
+  L.off_U = o; o += al256(sn);
+  L.off_Z = o; o += al256(sn);
+  L.off_F = o; o += al256((size_t)c.S * (size_t)(c.M > 0 ? c.M : 1) * 4);
+  L.off_Zt = o; o += al256(sn);
+  L.off_sc = o; o += 256;
+  L.off_gt = o; o += al256(((size_t)c.n + 4) * 4);
+  L.off_red = o; o += al256(kReduceWsBytes);
+  // split-K partial tiles of Zbar = R A (up to 10 partial [S, n] outputs)
+  L.gemm_bytes = al256((size_t)10 * c.S * c.n * 4 + 256);
+  if (L.gemm_bytes > ((size_t)40 << 20)) L.gemm_bytes = (size_t)40 << 20;
+  L.off_gemm = o; o += L.gemm_bytes;
+  L.total = o;
+  return L;
+}
+
+// sc[0] = var = softplus(free) + 1e-6 (transforms.py:133-134), sc[1] = d var / d free = sigmoid(free)
+__global__ void linop_prep_kernel(const float* __restrict__ p_var, float* sc) {
+  if (threadIdx.x == 0) {
+    const float x = *p_var;
+    sc[0] = softplus_f(x) + 1e-6f;
+    sc[1] = sigmoid_f(x);
+  }
+}
+
+// stats4 = {loglik, sum E^2, 0, 0} appended to the partial Zbar (one all-reduce carries both)
+__global__ void linop_pack_stats_kernel(const float* __restrict__ ll3, float* stats4) {
+  if (threadIdx.x == 0) { stats4[0] = ll3[0]; stats4[1] = ll3[1]; stats4[2] = 0.f; stats4[3] = 0.f; }
+}
+
+// Zt = Zbar - Z/S  (d ELBO_mean / d z: likelihood part minus the KL's z/S), elementwise.
+__global__ void __launch_bounds__(256) linop_zt_kernel(const float* __restrict__ zbar, const float* __restrict__ z,
+                                                       float invS, long long cnt, float* __restrict__ zt) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < cnt; e += (long long)gridDim.x * blockDim.x)
+    zt[e] = zbar[e] - invS * z[e];
+}
+
+// Scalar part of the update: d ELBO_mean / d var_free from the all-reduced {loglik, sum E^2}; out4 = {ELBO, ll, kl, 0}.
+// The log-likelihood each rank reported used its own row count; the -1/2 log var term is linear in the row count, so
+// the all-reduced ll is already that of the full operator.
+__global__ void linop_scalars_kernel(const float* __restrict__ stats4, const float* __restrict__ kl, const float* __restrict__ sc,
+                                     double total_elems, float invS, float* g_var, float* out4) {
+  if (threadIdx.x == 0) {
+    const double v = (double)sc[0];
+    const double dll_dv = -0.5 * total_elems / v + 0.5 * (double)stats4[1] / (v * v);
+    *g_var = (float)(dll_dv * (double)invS * (double)sc[1]);
+    out4[0] = (stats4[0] - *kl) * invS;
+    out4[1] = stats4[0];
+    out4[2] = *kl;
+    out4[3] = 0.f;
+  }
+}
+
+// Fused gradient-of-L_q + TF-1 Adam over the lower triangle.  64x64 tile of (i, j) per CTA, 4x4 per thread.
+//   g_ij = sum_s Zt[s,i] U[s,j] + (i == j) / L_ii                 (d ELBO_mean / d L_ij, j <= i)
+//   Adam on loss = -ELBO:  gl = -g;  m = b1 m + (1-b1) gl;  v = b2 v + (1-b2) gl^2;  L -= lr_t m / (sqrt(v) + eps)
+// m == NULL: no update (gradient only).  gout != NULL: also store g (tiles that touch the lower triangle; entries with
+// j > i inside them are written as 0).
+template <bool PREFETCH>
+__global__ void __launch_bounds__(256) tril_rank_adam_kernel(float* __restrict__ Lq, float* __restrict__ m, float* __restrict__ v,
+                                                             float* __restrict__ gout, const float* __restrict__ Zt,
+                                                             const float* __restrict__ U, int n, int S, float lr, float b1,
+                                                             float b2, float eps, const int* step_dev, int step_host) {
+  // one CTA per lower-triangle tile: linear index k -> (ti, tj), tj <= ti, rows of tiles consecutive
+  const long long kblk = blockIdx.x;
+  int ti = (int)((sqrt(8.0 * (double)kblk + 1.0) - 1.0) * 0.5);
+  while ((long long)ti * (ti + 1) / 2 > kblk) --ti;
+  while ((long long)(ti + 1) * (ti + 2) / 2 <= kblk) ++ti;
+  const int tj = (int)(kblk - (long long)ti * (ti + 1) / 2);
+  __shared__ __align__(16) float Zs[64][64];
+  __shared__ __align__(16) float Us[64][64];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int i0 = ti * 64, j0 = tj * 64;
+  // The parameter / moment tiles are requested BEFORE the rank-S product so that their HBM latency hides under the
+  // 1024 FMAs per thread (the product reads only the L2-resident Zt and U).
+  const bool vec = ((n & 3) == 0);
+  float4 pl[4], pm[4], pv[4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    pl[x] = pm[x] = pv[x] = make_float4(1.f, 1.f, 1.f, 1.f);
+    const int i = i0 + ty * 4 + x, jb = j0 + tx * 4;
+    if (PREFETCH && vec && i < n && jb < n && jb <= i) {
+      const long long off = (long long)i * n + jb;
+      pl[x] = __ldcs(reinterpret_cast<const float4*>(Lq + off));
+      if (m) { pm[x] = __ldcs(reinterpret_cast<const float4*>(m + off)); pv[x] = __ldcs(reinterpret_cast<const float4*>(v + off)); }
+    }
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int s0 = 0; s0 < S; s0 += 64) {
+    // stage Zt[s0..s0+63, i0..i0+63] and U[s0..s0+63, j0..j0+63] (zero-padded)
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+      const int s = idx >> 6, c = idx & 63;
+      const bool sv = (s0 + s) < S;
+      Zs[s][c] = (sv && (i0 + c) < n) ? __ldg(Zt + (long long)(s0 + s) * n + i0 + c) : 0.f;
+      Us[s][c] = (sv && (j0 + c) < n) ? __ldg(U + (long long)(s0 + s) * n + j0 + c) : 0.f;
+    }
+    __syncthreads();
+    const int sl = min(64, S - s0);
+    for (int s = 0; s < sl; ++s) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&Zs[s][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Us[s][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+    }
+    __syncthreads();
+  }
+  float lr_t = 0.f;
+  if (m) {
+    const int t = step_dev ? *step_dev : step_host;
+    lr_t = lr * sqrtf(1.f - powf(b2, (float)t)) / (1.f - powf(b1, (float)t));
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int i = i0 + ty * 4 + x;
+    if (i >= n) continue;
+    const int jb = j0 + tx * 4;
+    if (jb >= n || jb > i) continue;
+    const long long off = (long long)i * n + jb;
+    float l[4], mm[4], vv[4], g[4];
+    if (vec) {
+      if (!PREFETCH) {
+        pl[x] = __ldcs(reinterpret_cast<const float4*>(Lq + off));
+        if (m) { pm[x] = __ldcs(reinterpret_cast<const float4*>(m + off)); pv[x] = __ldcs(reinterpret_cast<const float4*>(v + off)); }
+      }
+      l[0] = pl[x].x; l[1] = pl[x].y; l[2] = pl[x].z; l[3] = pl[x].w;
+      mm[0] = pm[x].x; mm[1] = pm[x].y; mm[2] = pm[x].z; mm[3] = pm[x].w;
+      vv[0] = pv[x].x; vv[1] = pv[x].y; vv[2] = pv[x].z; vv[3] = pv[x].w;
+    } else {
+#pragma unroll
+      for (int y = 0; y < 4; ++y) {
+        const bool ok = (jb + y) < n;
+        l[y] = ok ? Lq[off + y] : 1.f;
+        if (m) { mm[y] = ok ? m[off + y] : 0.f; vv[y] = ok ? v[off + y] : 0.f; }
+      }
+    }
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const int j = jb + y;
+      const bool live = (j <= i) && (j < n);
+      g[y] = live ? acc[x][y] + ((j == i) ? 1.f / l[y] : 0.f) : 0.f;
+      if (m && live) {
+        const float gl = -g[y];
+        mm[y] = b1 * mm[y] + (1.f - b1) * gl;
+        vv[y] = b2 * vv[y] + (1.f - b2) * gl * gl;
+        l[y] -= lr_t * mm[y] / (sqrtf(vv[y]) + eps);
+      }
+    }
+    if (vec) {
+      if (m) {
+        __stcs(reinterpret_cast<float4*>(Lq + off), make_float4(l[0], l[1], l[2], l[3]));
+        __stcs(reinterpret_cast<float4*>(m + off), make_float4(mm[0], mm[1], mm[2], mm[3]));
+        __stcs(reinterpret_cast<float4*>(v + off), make_float4(vv[0], vv[1], vv[2], vv[3]));
+      }
+      if (gout) *reinterpret_cast<float4*>(gout + off) = make_float4(g[0], g[1], g[2], g[3]);
+    } else {
+#pragma unroll
+      for (int y = 0; y < 4; ++y) {
+        if ((jb + y) >= n) continue;
+        if (m && (jb + y) <= i) { Lq[off + y] = l[y]; m[off + y] = mm[y]; v[off + y] = vv[y]; }
+        if (gout) gout[off + y] = g[y];
+      }
+    }
+  }
+}
+
+inline cudaStream_t ST(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline bool cfg_ok(const hb_linop_config& c) {
+  return c.M >= 0 && c.n > 0 && c.S > 0 && c.M_total >= c.M;
+}
+
+}  // namespace
+
+int tril_rank_adam(float* Lq, float* m, float* v, float* gout, const float* Zt, const float* U, int n, int S, float lr,
+                   float b1, float b2, float eps, const int* step_dev, int step_host, cudaStream_t st) {
+  if (n <= 0 || S <= 0) return HB_OK;
+  if (!Lq || !Zt || !U || ((m == nullptr) != (v == nullptr))) return HB_ERR_ARG;
+  const long long t = cdiv(n, 64);
+  const unsigned blocks = (unsigned)(t * (t + 1) / 2);
+  // HB_LINOP_PREFETCH=1: request the L/m/v tiles before the rank-S product (128 registers, 2 CTAs/SM) -- measured
+  // slower than relying on 4 resident CTAs/SM for the overlap (1.26 vs 1.02 ms at n=16384), kept for A/B runs.
+  static const bool prefetch = [] { const char* e = getenv("HB_LINOP_PREFETCH"); return e && e[0] == '1'; }();
+  if (prefetch) tril_rank_adam_kernel<true><<<blocks, 256, 0, st>>>(Lq, m, v, gout, Zt, U, n, S, lr, b1, b2, eps, step_dev, step_host);
+  else tril_rank_adam_kernel<false><<<blocks, 256, 0, st>>>(Lq, m, v, gout, Zt, U, n, S, lr, b1, b2, eps, step_dev, step_host);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" {
+
+size_t hb_linop_param_count(const hb_linop_config* c) {
+  if (!c) return 0;
+  return (size_t)c->n * c->n + (size_t)c->n + 1;
+}
+
+size_t hb_linop_workspace_bytes(const hb_linop_config* c) {
+  if (!c || !cfg_ok(*c)) return 0;
+  return linop_layout(*c).total + 256;
+}
+
+int hb_linop_elbo_local(const hb_linop_config* cfg, const float* A, const float* y, const float* params, const float* eps,
+                        float* zbar_stats, void* ws, size_t ws_bytes, void* stream) {
+  if (!cfg || !params || !zbar_stats) return HB_ERR_ARG;
+  const hb_linop_config c = *cfg;
+  if (!cfg_ok(c) || (c.M > 0 && (!A || !y))) return HB_ERR_ARG;
+  if (!eps && (c.offset & 3ull)) return HB_ERR_ARG;
+  const LinopLayout L = linop_layout(c);
+  if (!ws || ws_bytes < L.total + 256) return HB_ERR_WORKSPACE;
+  cudaStream_t st = ST(stream);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  float* U = reinterpret_cast<float*>(base + L.off_U);
+  float* Z = reinterpret_cast<float*>(base + L.off_Z);
+  float* F = reinterpret_cast<float*>(base + L.off_F);
+  float* sc = reinterpret_cast<float*>(base + L.off_sc);
+  void* red = base + L.off_red;
+  void* gws = base + L.off_gemm;
+  float* ll3 = sc + 4;
+  float* kl = sc + 8;
+  const int n = c.n, Sn = c.S, M = c.M;
+  const float* p_sq = params;
+  const float* p_mu = params + (size_t)n * n;
+  const float* p_var = p_mu + n;
+
+  linop_prep_kernel<<<1, 32, 0, st>>>(p_var, sc);
+  HB_CHECK_LAUNCH();
+  // eps always ends up in the workspace: the update call reads it again
+  if (eps) HB_TRY(copy2d(U, (long long)Sn * n, eps, (long long)Sn * n, 1, Sn * n, 1.f, st));
+  else HB_TRY(randn_philox(U, (long long)Sn * n, c.seed, c.offset, st));
+  {  // Z [S, n] = mu + U tril(L_q)^T : op(B)[k][j] = L_q[j][k], keep k <= j.  S <= 128 rows = one tile row, and the
+     // triangular mask + bias epilogue rule out split-K: 128-wide tiles double the number of CTAs streaming L_q.
+    GemmParams g;
+    g.A = U; g.lda = n; g.B = p_sq; g.ldb = n; g.transB = 1; g.b_tri = 2;
+    g.C = Z; g.ldc = n; g.M = Sn; g.N = n; g.K = n; g.bias = p_mu; g.hint_bn128 = 1;
+    HB_TRY(gemm(g, st));
+  }
+  HB_TRY(tril_logdet_kl(p_sq, n, (long long)n * n, n, 1, U, Z, (long long)Sn * n, Sn, kl, red, kReduceWsBytes, st));
+  if (M > 0) {
+    {  // F [S, M] = Z A^T
+      GemmParams g;
+      g.A = Z; g.lda = n; g.B = A; g.ldb = n; g.transB = 1;
+      g.C = F; g.ldc = M; g.M = Sn; g.N = M; g.K = n; g.ws = gws; g.ws_bytes = L.gemm_bytes;
+      HB_TRY(gemm(g, st));
+    }
+    // log-lik + R = (1/S) d ll / d F, in place over F
+    HB_TRY(gauss_loglik_fwd(F, nullptr, y, (long long)Sn * M, M, sc, 1.f / (float)Sn, F, ll3, red, kReduceWsBytes, st));
+    {  // partial Zbar [S, n] = R A   (long-K, small output: split-K through the scratch)
+      GemmParams g;
+      g.A = F; g.lda = M; g.B = A; g.ldb = n; g.transB = 0;
+      g.C = zbar_stats; g.ldc = n; g.M = Sn; g.N = n; g.K = M; g.ws = gws; g.ws_bytes = L.gemm_bytes;
+      HB_TRY(gemm(g, st));
+    }
+  } else {
+    HB_TRY(fill_f32(zbar_stats, (long long)Sn * n, 0.f, st));
+    HB_TRY(fill_f32(ll3, 3, 0.f, st));
+  }
+  linop_pack_stats_kernel<<<1, 32, 0, st>>>(ll3, zbar_stats + (size_t)Sn * n);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+int hb_linop_elbo_update(const hb_linop_config* cfg, float* params, const float* zbar_stats, float* grads, float* m, float* v,
+                         float lr, float b1, float b2, float eps_adam, const int* step_dev, int step_host, float* out4,
+                         void* ws, size_t ws_bytes, void* stream) {
+  if (!cfg || !params || !zbar_stats || !out4) return HB_ERR_ARG;
+  const hb_linop_config c = *cfg;
+  if (!cfg_ok(c) || ((m == nullptr) != (v == nullptr))) return HB_ERR_ARG;
+  const LinopLayout L = linop_layout(c);
+  if (!ws || ws_bytes < L.total + 256) return HB_ERR_WORKSPACE;
+  cudaStream_t st = ST(stream);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  float* U = reinterpret_cast<float*>(base + L.off_U);
+  float* Z = reinterpret_cast<float*>(base + L.off_Z);
+  float* Zt = reinterpret_cast<float*>(base + L.off_Zt);
+  float* sc = reinterpret_cast<float*>(base + L.off_sc);
+  float* gt = reinterpret_cast<float*>(base + L.off_gt);      // [ mu-bar (n) | var-bar (1) ]
+  float* kl = sc + 8;
+  const int n = c.n, Sn = c.S;
+  const size_t nn = (size_t)n * n;
+  const float invS = 1.f / (float)Sn;
+  const long long cnt = (long long)Sn * n;
+
+  linop_zt_kernel<<<148 * 4, 256, 0, st>>>(zbar_stats, Z, invS, cnt, Zt);
+  HB_CHECK_LAUNCH();
+  HB_TRY(colsum(Zt, n, Sn, n, 1.f, 0.f, gt, st));
+  linop_scalars_kernel<<<1, 32, 0, st>>>(zbar_stats + cnt, kl, sc, (double)Sn * (double)c.M_total, invS, gt + n, out4);
+  HB_CHECK_LAUNCH();
+  if (grads) HB_TRY(copy2d(grads + nn, n + 1, gt, n + 1, 1, n + 1, 1.f, st));
+  // fused Lbar + Adam over the lower triangle of L_q (gradient-only when m is NULL)
+  HB_TRY(tril_rank_adam(params, m, v, grads, Zt, U, n, Sn, lr, b1, b2, eps_adam, step_dev, step_host, st));
+  if (m) HB_TRY(adam_tf1(params + nn, gt, m + nn, v + nn, (long long)n + 1, -1.f, lr, b1, b2, eps_adam, step_dev, step_host, st));
+  return HB_OK;
+}
+
+}  // extern "C"

@@ -236,6 +236,31 @@ size_t hb_gp_elbo_workspace_bytes(const hb_gp_config* cfg);
 int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, const float* params, const float* eps,
                     float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream);
 
+/* ---- fused ELBO + gradient + Adam of the linear-operator model (BASELINE config 5) ---------------------
+ * q = variationals.Normal([n], q_shape='fullrank') (variationals.py:94-96,144-146,185-186,225-230) observed through a
+ * dense operator A [M, n]:  ELBO = sum gaussian(y, A z, var) - KL  (densities.py:25-27), S-sample mean.
+ * params / grads / m / v packing (free space, floats):  [ q_sqrt (n*n, row-major, lower triangle used) | q_mu (n) | var (1) ]
+ * Row-sharded across ranks: each rank holds M rows of the M_total-row operator and calls hb_linop_elbo_local, the
+ * ranks all-reduce (sum) zbar_stats [S*n + 4], every rank calls hb_linop_elbo_update.  On one GPU M == M_total
+ * and the two calls run back to back.  Both calls take the SAME workspace (it carries eps and z between them).
+ *   local : eps [S,n] or NULL (Philox(seed, offset), identical on every rank).
+ *   update: grads may be NULL; when given it receives d ELBO_mean / d params (strict upper triangle of q_sqrt
+ *           untouched).  m, v NULL -> gradient only; otherwise the TF-1 Adam rule of hb_adam_tf1 on -ELBO is applied
+ *           in the same pass that forms the q_sqrt gradient (never materialised).  out4 = {ELBO, loglik, kl, 0}. */
+typedef struct {
+  int M;                 /* rows of A held by this rank */
+  long long M_total;     /* rows of the whole operator (== M on one GPU) */
+  int n, S;
+  unsigned long long seed, offset;
+} hb_linop_config;
+size_t hb_linop_param_count(const hb_linop_config* cfg);
+size_t hb_linop_workspace_bytes(const hb_linop_config* cfg);
+int hb_linop_elbo_local(const hb_linop_config* cfg, const float* A, const float* y, const float* params, const float* eps,
+                        float* zbar_stats, void* ws, size_t ws_bytes, void* stream);
+int hb_linop_elbo_update(const hb_linop_config* cfg, float* params, const float* zbar_stats, float* grads, float* m, float* v,
+                         float lr, float b1, float b2, float eps_adam, const int* step_dev, int step_host, float* out4,
+                         void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

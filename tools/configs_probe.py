@@ -72,6 +72,41 @@ if which in ("1", "2"):
     ms = timed(m.ELBO(), 20)
     print(f"config {which} (N={n}, S={S}, jitter {jitter:g}): {ms:.3f} ms/step = {S * n / ms * 1e3:.3e} evals/s; "
           f"ELBO {float(m.ELBO().run()):.4f}", flush=True)
+elif which == "5f":
+    # config 5 through the fused C entry points (hb_linop_elbo_local / _update): per-phase CUDA-event times and the
+    # HBM roofline of the step (algorithmic bytes: SURVEY.md 8d / csrc/linop.cu header)
+    from henbun_b200.fused import LinearOperatorStep
+    M, n, S = 65536, 16384, 64
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(M, n, device="cuda", generator=gen) / np.sqrt(n)
+    y = A[:, :256] @ torch.randn(256, device="cuda", generator=gen) + 0.1 * torch.randn(M, device="cuda", generator=gen)
+    st = LinearOperatorStep(A, y, S, lr=1e-3)
+    st.q_sqrt.copy_(0.1 * torch.eye(n, device="cuda") + 1e-3 * torch.tril(torch.randn(n, n, device="cuda", generator=gen)))
+    for i in range(3):
+        st.step(None, i)
+    steps = 10
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(steps):
+        st.local(None, 3 + i); ev[2 * i + 1].record()
+        st.update(); ev[2 * i + 2].record()
+    torch.cuda.synchronize()
+    t_local = np.median([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)])
+    t_upd = np.median([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps)])
+    ms = ev[0].elapsed_time(ev[-1]) / steps
+    tri = n * (n + 1) / 2
+    bytes_local = 2 * 4.0 * M * n + 4 * tri + 4.0 * S * (3 * M + 4 * n)
+    bytes_upd = 6 * 4 * tri + 4.0 * S * n * 4
+    peak = 6550.1e9
+    print(f"config 5 fused (n={n}, A {M}x{n}, S={S}): {ms:.3f} ms/step = {S * M / ms * 1e3:.3e} evals/s; ELBO {float(st.out4[0]):.1f}")
+    print(f"  local  (sampler + F=ZA^T + loglik + Zbar=RA): {t_local:.3f} ms, {bytes_local / 1e9:.2f} GB algorithmic -> "
+          f"{bytes_local / t_local / 1e6:.0f} GB/s = {bytes_local / t_local / 1e-3 / peak:.2f} of HBM peak")
+    print(f"  update (mu-bar, var-bar, fused Lbar+Adam on tril): {t_upd:.3f} ms, {bytes_upd / 1e9:.2f} GB algorithmic -> "
+          f"{bytes_upd / t_upd / 1e6:.0f} GB/s = {bytes_upd / t_upd / 1e-3 / peak:.2f} of HBM peak")
+    print(f"  step: {(bytes_local + bytes_upd) / 1e9:.2f} GB algorithmic -> {(bytes_local + bytes_upd) / ms / 1e6:.0f} GB/s = "
+          f"{(bytes_local + bytes_upd) / ms / 1e-3 / peak:.2f} of HBM peak (6550 GB/s measured copy)", flush=True)
+    m = None
 elif which == "4":
     class Amortised(hb.model.Model):
         def setUp(self, X=None, latent=64):
@@ -116,7 +151,14 @@ else:
     ms = timed(m.ELBO(), 5)
     print(f"config 5 (n=16384 full-covariance q, A 65536x16384, S=64): {ms:.2f} ms/step = {S * M / ms * 1e3:.3e} evals/s", flush=True)
 
-if os.environ.get("HB_TORCH_PROF") == "1":
+if os.environ.get("HB_TORCH_PROF") == "1" and which == "5f":
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(3):
+            st.step(None, 20 + i)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=16, max_name_column_width=90))
+elif os.environ.get("HB_TORCH_PROF") == "1":
     from torch.profiler import profile, ProfilerActivity
     opt = m.ELBO()
     kw = dict(minibatch_size=4096) if which == "4" else {}
