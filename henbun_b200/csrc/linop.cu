@@ -121,11 +121,11 @@ __global__ void __launch_bounds__(256) tril_rank_adam_kernel(float* __restrict__
       if (m) { pm[x] = __ldcs(reinterpret_cast<const float4*>(m + off)); pv[x] = __ldcs(reinterpret_cast<const float4*>(v + off)); }
     }
   }
-  float acc[4][4];
+  // rank-S product on packed fp32 FMAs (FFMA2: two lanes of one 64-bit register pair per instruction): the kernel is
+  // issue-bound, not FMA-pipe-bound, so halving the FMA instruction count is what matters
+  unsigned long long acc2[4][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int a = 0; a < 4; ++a) { acc2[a][0] = 0ull; acc2[a][1] = 0ull; }
   for (int s0 = 0; s0 < S; s0 += 64) {
     // stage Zt[s0..s0+63, i0..i0+63] and U[s0..s0+63, j0..j0+63] (zero-padded)
     for (int idx = tid; idx < 64 * 64; idx += 256) {
@@ -136,16 +136,26 @@ __global__ void __launch_bounds__(256) tril_rank_adam_kernel(float* __restrict__
     }
     __syncthreads();
     const int sl = min(64, S - s0);
+#pragma unroll 4
     for (int s = 0; s < sl; ++s) {
       const float4 a4 = *reinterpret_cast<const float4*>(&Zs[s][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Us[s][tx * 4]);
-      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+      const ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(&Us[s][tx * 4]);    // (u0,u1), (u2,u3)
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-      for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+      for (int x = 0; x < 4; ++x) {
+        unsigned long long aa;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[x]));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[x][0]) : "l"(aa), "l"(b2.x));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[x][1]) : "l"(aa), "l"(b2.y));
+      }
     }
     __syncthreads();
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[x][0]), "=f"(acc[x][1]) : "l"(acc2[x][0]));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[x][2]), "=f"(acc[x][3]) : "l"(acc2[x][1]));
   }
   float lr_t = 0.f;
   if (m) {

@@ -22,6 +22,12 @@ def shard_samples(n_samples_total: int, world_size: int, rank: int):
     return first, count
 
 
+def shard_rows(n_rows_total: int, world_size: int, rank: int):
+    """Contiguous split of the rows of a dense operator / data set (config 5: A is row-sharded, SURVEY.md 8e);
+    returns (first_row, count).  Same rule as shard_samples."""
+    return shard_samples(n_rows_total, world_size, rank)
+
+
 def rank_philox_offset(step: int, first_sample: int, per_sample: int, total_samples: int) -> int:
     """Philox stream position of this rank's first draw at `step`: ranks read disjoint windows of ONE
     global stream, so the union over ranks equals the single-GPU draw of the same step."""

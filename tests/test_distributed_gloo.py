@@ -49,3 +49,57 @@ def test_philox_windows_are_disjoint_and_cover_the_stream():
         for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
             assert a1 <= b0
         assert spans[0][0] == 3 * S * per and spans[-1][1] == 4 * S * per
+
+
+# ---- config 5 (linear operator): row-sharded A, ONE all-reduce of [S*n + 4] floats -------------------
+def _linop_partial(A, y, p, U):
+    """What hb_linop_elbo_local computes on one rank's rows (oracle arithmetic, fp64): the partial
+    Zbar = R A with R = (1/S) d loglik / d F, and {loglik, sum E^2}."""
+    from oracle import henbun_oracle as O
+    S = U.shape[0]
+    Z = p["q_mu"] + U @ torch.tril(p["q_sqrt"]).T
+    F = Z @ A.T
+    var = O.log1pe_forward(p["var"])
+    E = F - y
+    ll = torch.sum(O.gaussian(y, F, var))
+    R = -(E / var) / S
+    return torch.cat([(R @ A).reshape(-1), torch.stack([ll, torch.sum(E * E), torch.zeros(()), torch.zeros(())]).to(A.dtype)])
+
+
+def _linop_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(0)                       # every rank builds the same problem, keeps its rows
+    M, n, S = 37, 6, 3
+    A = torch.tensor(rng.randn(M, n)); y = torch.tensor(rng.randn(M))
+    p = {"q_mu": torch.tensor(rng.randn(n)), "q_sqrt": torch.tensor(np.eye(n) + 0.1 * rng.randn(n, n)), "var": torch.tensor([0.2], dtype=torch.float64)}
+    U = torch.tensor(rng.randn(S, n))
+    first, cnt = parallel.shard_rows(M, world, rank)
+    buf = _linop_partial(A[first:first + cnt], y[first:first + cnt], p, U)
+    parallel.allreduce_sum_(buf)
+    out[rank] = (first, cnt, buf.numpy().copy())
+    dist.destroy_process_group()
+
+
+def test_linop_row_shards_sum_to_the_whole_operator():
+    from oracle import henbun_oracle as O
+    world = 2
+    mgr = mp.Manager(); out = mgr.dict()
+    mp.spawn(_linop_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    (f0, c0, b0), (f1, c1, b1) = out[0], out[1]
+    assert (f0, c0, f1, c1) == (0, 19, 19, 18)
+    assert np.array_equal(b0, b1)
+    rng = np.random.RandomState(0)
+    M, n, S = 37, 6, 3
+    A = rng.randn(M, n); y = rng.randn(M)
+    p = {"q_mu": rng.randn(n), "q_sqrt": np.eye(n) + 0.1 * rng.randn(n, n), "var": np.array([0.2])}
+    U = rng.randn(S, n)
+    whole = _linop_partial(torch.tensor(A), torch.tensor(y), {k: torch.tensor(v) for k, v in p.items()}, torch.tensor(U)).numpy()
+    assert np.allclose(b0, whole, rtol=1e-12, atol=1e-12)
+    # and the update stage's algebra: mu-bar = colsum(Zbar - Z/S) reproduces the oracle's autograd gradient
+    ref, g = O.value_and_grads(O.linear_operator_elbo, p, A, y, U)
+    Z = p["q_mu"] + U @ np.tril(p["q_sqrt"]).T
+    Zt = b0[:S * n].reshape(S, n) - Z / S
+    assert np.allclose(Zt.sum(0), g["q_mu"], rtol=1e-10)
+    gL = np.tril(Zt.T @ U) + np.diag(1.0 / np.diag(p["q_sqrt"]))
+    assert np.allclose(gL, g["q_sqrt"], rtol=1e-10, atol=1e-12)

@@ -75,37 +75,65 @@ if which in ("1", "2"):
 elif which == "5f":
     # config 5 through the fused C entry points (hb_linop_elbo_local / _update): per-phase CUDA-event times and the
     # HBM roofline of the step (algorithmic bytes: SURVEY.md 8d / csrc/linop.cu header)
+    # Under torchrun (N ranks) the operator is row-sharded: rank r streams M/N rows, one NCCL all-reduce of [S*n + 4]
+    # floats per step (strong scaling in M: the operator is fixed).
     from henbun_b200.fused import LinearOperatorStep
+    from henbun_b200 import parallel
+    import torch.distributed as dist
+    world, rank = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0))
+    if world > 1:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("nccl")
     M, n, S = 65536, 16384, 64
+    first, rows = parallel.shard_rows(M, world, rank)
     gen = torch.Generator(device="cuda").manual_seed(0)
-    A = torch.randn(M, n, device="cuda", generator=gen) / np.sqrt(n)
-    y = A[:, :256] @ torch.randn(256, device="cuda", generator=gen) + 0.1 * torch.randn(M, device="cuda", generator=gen)
-    st = LinearOperatorStep(A, y, S, lr=1e-3)
+    w_true = torch.randn(256, device="cuda", generator=gen)
+    gen_r = torch.Generator(device="cuda").manual_seed(100 + rank)
+    A = torch.randn(rows, n, device="cuda", generator=gen_r) / np.sqrt(n)
+    y = A[:, :256] @ w_true + 0.1 * torch.randn(rows, device="cuda", generator=gen_r)
+    st = LinearOperatorStep(A, y, S, m_total=M, lr=1e-3)
     st.q_sqrt.copy_(0.1 * torch.eye(n, device="cuda") + 1e-3 * torch.tril(torch.randn(n, n, device="cuda", generator=gen)))
     for i in range(3):
         st.step(None, i)
     steps = 10
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * steps + 1)]
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     ev[0].record()
     for i in range(steps):
-        st.local(None, 3 + i); ev[2 * i + 1].record()
-        st.update(); ev[2 * i + 2].record()
+        st.local(None, 3 + i); ev[3 * i + 1].record()
+        parallel.allreduce_sum_(st.zbar_stats); ev[3 * i + 2].record()
+        st.update(); ev[3 * i + 3].record()
     torch.cuda.synchronize()
-    t_local = np.median([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)])
-    t_upd = np.median([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps)])
-    ms = ev[0].elapsed_time(ev[-1]) / steps
+    t_local = np.median([ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(steps)])
+    t_coll = np.median([ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(steps)])
+    t_upd = np.median([ev[3 * i + 2].elapsed_time(ev[3 * i + 3]) for i in range(steps)])
+    tt = torch.tensor([ev[0].elapsed_time(ev[-1]) / steps], device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt)
     tri = n * (n + 1) / 2
-    bytes_local = 2 * 4.0 * M * n + 4 * tri + 4.0 * S * (3 * M + 4 * n)
+    bytes_local = 2 * 4.0 * rows * n + 4 * tri + 4.0 * S * (3 * rows + 4 * n)
     bytes_upd = 6 * 4 * tri + 4.0 * S * n * 4
     peak = 6550.1e9
-    print(f"config 5 fused (n={n}, A {M}x{n}, S={S}): {ms:.3f} ms/step = {S * M / ms * 1e3:.3e} evals/s; ELBO {float(st.out4[0]):.1f}")
-    print(f"  local  (sampler + F=ZA^T + loglik + Zbar=RA): {t_local:.3f} ms, {bytes_local / 1e9:.2f} GB algorithmic -> "
-          f"{bytes_local / t_local / 1e6:.0f} GB/s = {bytes_local / t_local / 1e-3 / peak:.2f} of HBM peak")
-    print(f"  update (mu-bar, var-bar, fused Lbar+Adam on tril): {t_upd:.3f} ms, {bytes_upd / 1e9:.2f} GB algorithmic -> "
-          f"{bytes_upd / t_upd / 1e6:.0f} GB/s = {bytes_upd / t_upd / 1e-3 / peak:.2f} of HBM peak")
-    print(f"  step: {(bytes_local + bytes_upd) / 1e9:.2f} GB algorithmic -> {(bytes_local + bytes_upd) / ms / 1e6:.0f} GB/s = "
-          f"{(bytes_local + bytes_upd) / ms / 1e-3 / peak:.2f} of HBM peak (6550 GB/s measured copy)", flush=True)
+    if rank == 0:
+        print(f"config 5 fused (n={n}, A {M}x{n} over {world} GPU(s), S={S}): {ms:.3f} ms/step = {S * M / ms * 1e3:.3e} evals/s; ELBO {float(st.out4[0]):.1f}")
+        print(f"  local  (sampler + F=ZA^T + loglik + Zbar=RA, {rows} rows): {t_local:.3f} ms, {bytes_local / 1e9:.2f} GB algorithmic -> "
+              f"{bytes_local / t_local / 1e6:.0f} GB/s = {bytes_local / t_local / 1e-3 / peak:.2f} of HBM peak")
+        print(f"  all-reduce of {st.zbar_stats.numel() * 4 / 1e6:.1f} MB: {t_coll:.3f} ms")
+        print(f"  update (mu-bar, var-bar, fused Lbar+Adam on tril): {t_upd:.3f} ms, {bytes_upd / 1e9:.2f} GB algorithmic -> "
+              f"{bytes_upd / t_upd / 1e6:.0f} GB/s = {bytes_upd / t_upd / 1e-3 / peak:.2f} of HBM peak")
+        print(f"  step/GPU: {(bytes_local + bytes_upd) / 1e9:.2f} GB algorithmic -> {(bytes_local + bytes_upd) / ms / 1e6:.0f} GB/s = "
+              f"{(bytes_local + bytes_upd) / ms / 1e-3 / peak:.2f} of HBM peak (6550 GB/s measured copy)", flush=True)
+    if world > 1:
+        # every rank must hold bit-identical parameters after the replicated update
+        chk = torch.stack([st.params.double().sum(), st.params.double().abs().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print("  replicas identical after", 3 + steps, "steps:", bool(torch.equal(lo, hi)), flush=True)
+        dist.destroy_process_group()
     m = None
 elif which == "4":
     class Amortised(hb.model.Model):
