@@ -42,6 +42,7 @@ static int tc_run(const GemmParams& p, cudaStream_t st, bool force) {
 static int gemm_dispatch(const GemmParams& p, cudaStream_t st) {
   if (p.C == p.A && p.N > 128) return HB_ERR_ARG;      // in-place needs one column tile per row block
   if (g_engine == 3) return gemm_simt(p, st);
+  if (p.force_simt) return gemm_small_eligible(p) ? gemm_small(p, st) : gemm_simt(p, st);
   if (g_engine == 2) { const int rc = tc_run(p, st, true); return rc < 0 ? HB_ERR_ARG : rc; }
   if (g_engine == 1 ? gemm_small_eligible(p) : prefer_small(p)) return gemm_small(p, st);
   if (g_engine == 0) { const int rc = tc_run(p, st, false); if (rc >= 0) return rc; }
@@ -86,7 +87,7 @@ int gemm(const GemmParams& p, cudaStream_t st) {
   const size_t i = g_prof.used++;
   g_prof.flops[i] = gemm_useful_flops(p);
   g_prof.shape[4 * i] = p.M; g_prof.shape[4 * i + 1] = p.N; g_prof.shape[4 * i + 2] = p.K;
-  g_prof.shape[4 * i + 3] = (g_engine == 2 || (g_engine == 0 && !prefer_small(p) && ((gemm_tc2_eligible(p) && tc_worth(p)) || gemm_tc_eligible(p)))) ? 1 : 0;
+  g_prof.shape[4 * i + 3] = p.force_simt ? 0 : (g_engine == 2 || (g_engine == 0 && !prefer_small(p) && ((gemm_tc2_eligible(p) && tc_worth(p)) || gemm_tc_eligible(p)))) ? 1 : 0;
   if (g_prof.shape[4 * i + 3] && !(get_tc_option() & 2) && gemm_tc2_eligible(p) && gemm_tc2_uses_pair(p)) g_prof.shape[4 * i + 3] = 2;
   cudaEventRecord(g_prof.ev0[i], st);
   const int rc = gemm_dispatch(p, st);
@@ -377,6 +378,8 @@ int hb_rbf_gram_bwd_x2(const float* G, long long ldg, long long strideG, const f
                          sym_lower, scale, dX2, S(stream));
 }
 
+int hb_set_exact_below(int n) { set_exact_below(n); return get_exact_below(); }
+int hb_set_panel_refinement(int mode) { set_panel_refinement(mode); return get_panel_refinement(); }
 size_t hb_potrf_workspace_bytes(int n) { return potrf_workspace_bytes(n); }
 int hb_potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
                    size_t ws_bytes, int* err_flag, void* stream) {

@@ -390,7 +390,8 @@ inline int split_point(int n) {
 struct Ctx {
   cudaStream_t st;
   float* dinv;        // [nblk][NB][NB]
-  float* tmp;         // [n][NB] scratch for leaf triangular solves
+  float* tmp;         // [rows][NB] scratch of the refined panel solves
+  int n_total = 0;    // order of the matrix being factored (selects the refinement mode)
   long long ldt;      // = NB
   int* err;
   void* tcws;         // scratch of the tensor-core GEMM engine (split-K partial tiles)
@@ -435,22 +436,57 @@ static inline void join_side(const Ctx& c) {
   c.side_pending = false;
 }
 
+// Factorisations of order <= 2048 are latency-bound (2048^3 flop = 0.2 ms even on the fp32 SIMT kernels), so their
+// products run in exact fp32: on the ill-conditioned notebook-size problems (config 1 / 2, cond 1e6) the split product's
+// 1.5e-6 per-product error was visible next to LAPACK's (tools/c2_err_probe.py).
+// Price at n = 2000: 3 factorisations + reverse modes 17.6 -> 29.5 ms (the SIMT kernels fill 10-30 of 148 SMs on these
+// shapes); gain: gradient error vs fp64 3-5x LAPACK's -> 1-3x.  hb_set_exact_below(0) turns it off.
+static int g_exact_below = 2048;
 inline int gemm_ws(const Ctx& c, GemmParams& g) {
+  g.force_simt = (c.n_total > 0 && c.n_total <= g_exact_below) ? 1 : 0;
   g.ws = c.tcws; g.ws_bytes = c.tcws_bytes;
   return gemm(g, c.st);
 }
 
 inline float* dinv_slot(const Ctx& c, int off) { return c.dinv + (long long)(off / NB) * NB * NB; }
 
+// Panel solves multiply by the explicit inverse of the 128 x 128 diagonal block (one in-place GEMM on the tensor-core
+// engine).  That is not backward stable: on ill-conditioned matrices (the 1-D notebook inputs, cond 1e6) the factor is
+// 2-3x further from the fp64 one than LAPACK's substitution-based spotrf (measured).  One step of
+// iterative refinement against the triangular block itself recovers it:
+//     T = B Dinv';  B <- B - T D';  T <- T + B Dinv';  B <- alpha T        (D' = D^T or D)
+// at the price of two more short-K products and a copy per panel.  Mode 0 = off, 1 = on, 2 = on for n <= 8192 (where the
+// panels are a negligible share of the work; default).
+static int g_panel_refine = 2;
+static inline bool refine_on(int n) { return g_panel_refine == 1 || (g_panel_refine == 2 && n <= 8192); }
+
+// Bp (m x w, in place) <- alpha * Bp * D^{-T} (trans) or alpha * Bp * D^{-1}, D = w x w lower block at global offset `off`
+// of the factor (its strict upper triangle in memory is NOT assumed zero).
+static int panel_solve(const Ctx& c, const float* D, long long ldd, int off, float* Bp, long long ldb, int m, int w,
+                       bool trans, float alpha, bool refine) {
+  GemmParams g;
+  g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = trans ? 1 : 0;
+  g.M = m; g.N = w; g.K = w;
+  if (!refine || !c.tmp) {
+    g.C = Bp; g.ldc = ldb; g.alpha = alpha; g.beta = 0.f;                  // in place
+    return gemm_ws(c, g);
+  }
+  float* T = c.tmp;
+  g.C = T; g.ldc = NB; g.alpha = 1.f; g.beta = 0.f;
+  HB_TRY(gemm_ws(c, g));                                                   // T = B Dinv'
+  GemmParams r;
+  r.A = T; r.lda = NB; r.B = D; r.ldb = ldd; r.transB = trans ? 1 : 0; r.b_tri = trans ? 2 : 1;
+  r.C = Bp; r.ldc = ldb; r.M = m; r.N = w; r.K = w; r.alpha = -1.f; r.beta = 1.f;
+  HB_TRY(gemm_ws(c, r));                                                   // B <- B - T D'   (the residual)
+  g.beta = 1.f;
+  HB_TRY(gemm_ws(c, g));                                                   // T <- T + R Dinv'
+  return copy2d(Bp, ldb, T, NB, m, w, alpha, c.st);
+}
+
 // B (m x k at Bp) <- B * L^{-T},  L = k x k lower block whose diagonal starts at global offset `off`
 int trsm_rlt(const Ctx& c, const float* L, long long ldl, int off, float* Bp, long long ldb, int m, int k) {
   if (m <= 0 || k <= 0) return HB_OK;
-  if (k <= NB) {
-    GemmParams g;
-    g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = 1;   // B <- B Dinv^T, in place
-    g.C = Bp; g.ldc = ldb; g.M = m; g.N = k; g.K = k; g.alpha = 1.f; g.beta = 0.f;
-    return gemm_ws(c, g);
-  }
+  if (k <= NB) return panel_solve(c, L, ldl, off, Bp, ldb, m, k, true, 1.f, refine_on(c.n_total));
   const int k1 = split_point(k), k2 = k - k1;
   HB_TRY(trsm_rlt(c, L, ldl, off, Bp, ldb, m, k1));
   GemmParams g;   // B2 -= B1 * L21^T
@@ -463,12 +499,7 @@ int trsm_rlt(const Ctx& c, const float* L, long long ldl, int off, float* Bp, lo
 // B <- B * L^{-1}
 int trsm_rln(const Ctx& c, const float* L, long long ldl, int off, float* Bp, long long ldb, int m, int k) {
   if (m <= 0 || k <= 0) return HB_OK;
-  if (k <= NB) {
-    GemmParams g;
-    g.A = Bp; g.lda = ldb; g.B = dinv_slot(c, off); g.ldb = NB; g.transB = 0;   // B <- B Dinv, in place
-    g.C = Bp; g.ldc = ldb; g.M = m; g.N = k; g.K = k; g.alpha = 1.f; g.beta = 0.f;
-    return gemm_ws(c, g);
-  }
+  if (k <= NB) return panel_solve(c, L, ldl, off, Bp, ldb, m, k, false, 1.f, refine_on(c.n_total));
   const int k1 = split_point(k), k2 = k - k1;
   HB_TRY(trsm_rln(c, L + (long long)k1 * ldl + k1, ldl, off + k1, Bp + k1, ldb, m, k2));
   GemmParams g;   // B1 -= B2 * L21
@@ -492,11 +523,8 @@ int potrf_cols(const Ctx& c, float* A, long long lda, int c0, int w, int n, bool
     join_side(c);                                      // the look-ahead leaf (if any) must be done before the solve
     const int below = n - (c0 + w);
     if (below <= 0) return HB_OK;
-    GemmParams g;                                      // panel <- panel * Dinv^T, in place
-    float* Pn = D + (long long)w * lda;
-    g.A = Pn; g.lda = lda; g.B = dinv_slot(c, c0); g.ldb = NB; g.transB = 1;
-    g.C = Pn; g.ldc = lda; g.M = below; g.N = w; g.K = w; g.alpha = 1.f; g.beta = 0.f;
-    return gemm_ws(c, g);
+    // panel <- panel * D^{-T} (in place; refined against D itself when the mode says so)
+    return panel_solve(c, D, lda, c0, D + (long long)w * lda, lda, below, w, true, 1.f, refine_on(n));
   }
   const int w1 = split_point(w), w2 = w - w1;
   HB_TRY(potrf_cols(c, A, lda, c0, w1, n, leaf_done));
@@ -559,10 +587,7 @@ int chol_rev_cols(const Ctx& c, const float* L, long long ldl, float* G, long lo
     if (below > 0) {
       float* Gp = GD + (long long)w * ldg;
       const float* Lp = LD + (long long)w * ldl;
-      GemmParams g;
-      g.A = Gp; g.lda = ldg; g.B = dinv_slot(c, c0); g.ldb = NB; g.transB = 0;
-      g.C = Gp; g.ldc = ldg; g.M = below; g.N = w; g.K = w; g.alpha = 0.5f; g.beta = 0.f;
-      HB_TRY(gemm_ws(c, g));
+      HB_TRY(panel_solve(c, LD, ldl, c0, Gp, ldg, below, w, false, 0.5f, refine_on(n)));
       GemmParams h;
       h.A = Gp; h.lda = ldg; h.transA = 1; h.B = Lp; h.ldb = ldl; h.transB = 0;
       h.C = GD; h.ldc = ldg; h.M = w; h.N = w; h.K = below; h.alpha = -2.f; h.beta = 1.f; h.c_tri = 1;
@@ -632,6 +657,11 @@ static size_t base_bytes(long long rows, int n) {
 
 size_t potrf_workspace_bytes(int n) { return base_bytes(n, n) + tc_bytes_for(-1, n); }
 
+void set_exact_below(int n) { g_exact_below = n < 0 ? 0 : n; }
+int get_exact_below() { return g_exact_below; }
+void set_panel_refinement(int mode) { g_panel_refine = (mode < 0 || mode > 2) ? 2 : mode; }
+int get_panel_refinement() { return g_panel_refine; }
+
 static int make_ctx(Ctx& c, int n, void* ws, size_t ws_bytes, int* err, cudaStream_t st) {
   if (ws_bytes < potrf_workspace_bytes(n) || !ws) return HB_ERR_WORKSPACE;
   const long long nblk = (n + NB - 1) / NB;
@@ -642,6 +672,7 @@ static int make_ctx(Ctx& c, int n, void* ws, size_t ws_bytes, int* err, cudaStre
   c.err = err;
   c.tcws = reinterpret_cast<char*>(c.dinv) + base_bytes(n, n) - 256;
   c.tcws_bytes = tc_bytes_for(-1, n);
+  c.n_total = n;
   return HB_OK;
 }
 
@@ -710,6 +741,7 @@ int trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int
   c.err = nullptr;
   c.tcws = reinterpret_cast<char*>(c.dinv) + base_bytes(m, n) - 256;
   c.tcws_bytes = tc_bytes_for(m, n);
+  c.n_total = n;
   trinv_blocks_kernel<<<(int)nblk, LEAF_THREADS, kLeafSmem3, st>>>(L, ldl, n, c.dinv);
   HB_CHECK_LAUNCH();
   return trans ? trsm_rlt(c, L, ldl, 0, X, ldx, m, n) : trsm_rln(c, L, ldl, 0, X, ldx, m, n);

@@ -92,11 +92,15 @@ __global__ void linop_scalars_kernel(const float* __restrict__ stats4, const flo
 //   Adam on loss = -ELBO:  gl = -g;  m = b1 m + (1-b1) gl;  v = b2 v + (1-b2) gl^2;  L -= lr_t m / (sqrt(v) + eps)
 // m == NULL: no update (gradient only).  gout != NULL: also store g (tiles that touch the lower triangle; entries with
 // j > i inside them are written as 0).
-template <bool PREFETCH>
-__global__ void __launch_bounds__(256) tril_rank_adam_kernel(float* __restrict__ Lq, float* __restrict__ m, float* __restrict__ v,
-                                                             float* __restrict__ gout, const float* __restrict__ Zt,
-                                                             const float* __restrict__ U, int n, int S, float lr, float b1,
-                                                             float b2, float eps, const int* step_dev, int step_host) {
+// What the first ncu capture said (profiles/r1_ncu_prof_tril_rank_adam_r1.csv): DRAM traffic = the algorithmic 3.2 GB,
+// DRAM 38 % busy, top stall long_scoreboard -- 35 % of the samples waiting for the operand staging (16 scalar loads
+// per thread in 4 dependent batches), 43 % in the epilogue (the loads of the four rows were serialised behind the
+// stores of the previous row: same base pointers).  Hence: float4 staging issued in one batch, the epilogue loads two
+// rows (6 x 16 B per thread) before it touches them, at most 85 registers (3 CTAs / SM).
+__global__ void __launch_bounds__(256, 3) tril_rank_adam_kernel(float* __restrict__ Lq, float* __restrict__ m, float* __restrict__ v,
+                                                                float* __restrict__ gout, const float* __restrict__ Zt,
+                                                                const float* __restrict__ U, int n, int S, float lr, float b1,
+                                                                float b2, float eps, const int* step_dev, int step_host) {
   // one CTA per lower-triangle tile: linear index k -> (ti, tj), tj <= ti, rows of tiles consecutive
   const long long kblk = blockIdx.x;
   int ti = (int)((sqrt(8.0 * (double)kblk + 1.0) - 1.0) * 0.5);
@@ -107,20 +111,8 @@ __global__ void __launch_bounds__(256) tril_rank_adam_kernel(float* __restrict__
   __shared__ __align__(16) float Us[64][64];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int i0 = ti * 64, j0 = tj * 64;
-  // The parameter / moment tiles are requested BEFORE the rank-S product so that their HBM latency hides under the
-  // 1024 FMAs per thread (the product reads only the L2-resident Zt and U).
   const bool vec = ((n & 3) == 0);
-  float4 pl[4], pm[4], pv[4];
-#pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    pl[x] = pm[x] = pv[x] = make_float4(1.f, 1.f, 1.f, 1.f);
-    const int i = i0 + ty * 4 + x, jb = j0 + tx * 4;
-    if (PREFETCH && vec && i < n && jb < n && jb <= i) {
-      const long long off = (long long)i * n + jb;
-      pl[x] = __ldcs(reinterpret_cast<const float4*>(Lq + off));
-      if (m) { pm[x] = __ldcs(reinterpret_cast<const float4*>(m + off)); pv[x] = __ldcs(reinterpret_cast<const float4*>(v + off)); }
-    }
-  }
+  const bool interior = vec && (i0 + 64 <= n);          // j0 <= i0, so the U columns are in range as well
   // rank-S product on packed fp32 FMAs (FFMA2: two lanes of one 64-bit register pair per instruction): the kernel is
   // issue-bound, not FMA-pipe-bound, so halving the FMA instruction count is what matters
   unsigned long long acc2[4][2];
@@ -128,25 +120,41 @@ __global__ void __launch_bounds__(256) tril_rank_adam_kernel(float* __restrict__
   for (int a = 0; a < 4; ++a) { acc2[a][0] = 0ull; acc2[a][1] = 0ull; }
   for (int s0 = 0; s0 < S; s0 += 64) {
     // stage Zt[s0..s0+63, i0..i0+63] and U[s0..s0+63, j0..j0+63] (zero-padded)
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-      const int s = idx >> 6, c = idx & 63;
-      const bool sv = (s0 + s) < S;
-      Zs[s][c] = (sv && (i0 + c) < n) ? __ldg(Zt + (long long)(s0 + s) * n + i0 + c) : 0.f;
-      Us[s][c] = (sv && (j0 + c) < n) ? __ldg(U + (long long)(s0 + s) * n + j0 + c) : 0.f;
+    if (interior && s0 + 64 <= S) {
+      float4 qz[4], qu[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int idx = tid + 256 * r, sr = idx >> 4, c4 = (idx & 15) * 4;
+        qz[r] = __ldg(reinterpret_cast<const float4*>(Zt + (long long)(s0 + sr) * n + i0 + c4));
+        qu[r] = __ldg(reinterpret_cast<const float4*>(U + (long long)(s0 + sr) * n + j0 + c4));
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int idx = tid + 256 * r, sr = idx >> 4, c4 = (idx & 15) * 4;
+        *reinterpret_cast<float4*>(&Zs[sr][c4]) = qz[r];
+        *reinterpret_cast<float4*>(&Us[sr][c4]) = qu[r];
+      }
+    } else {
+      for (int idx = tid; idx < 64 * 64; idx += 256) {
+        const int sr = idx >> 6, c = idx & 63;
+        const bool sv = (s0 + sr) < S;
+        Zs[sr][c] = (sv && (i0 + c) < n) ? __ldg(Zt + (long long)(s0 + sr) * n + i0 + c) : 0.f;
+        Us[sr][c] = (sv && (j0 + c) < n) ? __ldg(U + (long long)(s0 + sr) * n + j0 + c) : 0.f;
+      }
     }
     __syncthreads();
     const int sl = min(64, S - s0);
 #pragma unroll 4
-    for (int s = 0; s < sl; ++s) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&Zs[s][ty * 4]);
-      const ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(&Us[s][tx * 4]);    // (u0,u1), (u2,u3)
+    for (int sr = 0; sr < sl; ++sr) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&Zs[sr][ty * 4]);
+      const ulonglong2 b2v = *reinterpret_cast<const ulonglong2*>(&Us[sr][tx * 4]);    // (u0,u1), (u2,u3)
       const float a[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
       for (int x = 0; x < 4; ++x) {
         unsigned long long aa;
         asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[x]));
-        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[x][0]) : "l"(aa), "l"(b2.x));
-        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[x][1]) : "l"(aa), "l"(b2.y));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[x][0]) : "l"(aa), "l"(b2v.x));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[x][1]) : "l"(aa), "l"(b2v.y));
       }
     }
     __syncthreads();
@@ -162,55 +170,70 @@ __global__ void __launch_bounds__(256) tril_rank_adam_kernel(float* __restrict__
     const int t = step_dev ? *step_dev : step_host;
     lr_t = lr * sqrtf(1.f - powf(b2, (float)t)) / (1.f - powf(b1, (float)t));
   }
+  const int jb = j0 + tx * 4;
 #pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    const int i = i0 + ty * 4 + x;
-    if (i >= n) continue;
-    const int jb = j0 + tx * 4;
-    if (jb >= n || jb > i) continue;
-    const long long off = (long long)i * n + jb;
-    float l[4], mm[4], vv[4], g[4];
-    if (vec) {
-      if (!PREFETCH) {
-        pl[x] = __ldcs(reinterpret_cast<const float4*>(Lq + off));
-        if (m) { pm[x] = __ldcs(reinterpret_cast<const float4*>(m + off)); pv[x] = __ldcs(reinterpret_cast<const float4*>(v + off)); }
-      }
-      l[0] = pl[x].x; l[1] = pl[x].y; l[2] = pl[x].z; l[3] = pl[x].w;
-      mm[0] = pm[x].x; mm[1] = pm[x].y; mm[2] = pm[x].z; mm[3] = pm[x].w;
-      vv[0] = pv[x].x; vv[1] = pv[x].y; vv[2] = pv[x].z; vv[3] = pv[x].w;
-    } else {
+  for (int xp = 0; xp < 4; xp += 2) {
+    // two rows at a time: all their loads first
+    float l[2][4], mm[2][4], vv[2][4];
+    bool rowok[2];
 #pragma unroll
-      for (int y = 0; y < 4; ++y) {
-        const bool ok = (jb + y) < n;
-        l[y] = ok ? Lq[off + y] : 1.f;
-        if (m) { mm[y] = ok ? m[off + y] : 0.f; vv[y] = ok ? v[off + y] : 0.f; }
-      }
-    }
+    for (int h = 0; h < 2; ++h) {
+      const int i = i0 + ty * 4 + xp + h;
+      rowok[h] = (i < n) && (jb < n) && (jb <= i);
+      const long long off = (long long)i * n + jb;
 #pragma unroll
-    for (int y = 0; y < 4; ++y) {
-      const int j = jb + y;
-      const bool live = (j <= i) && (j < n);
-      g[y] = live ? acc[x][y] + ((j == i) ? 1.f / l[y] : 0.f) : 0.f;
-      if (m && live) {
-        const float gl = -g[y];
-        mm[y] = b1 * mm[y] + (1.f - b1) * gl;
-        vv[y] = b2 * vv[y] + (1.f - b2) * gl * gl;
-        l[y] -= lr_t * mm[y] / (sqrtf(vv[y]) + eps);
+      for (int y = 0; y < 4; ++y) { l[h][y] = 1.f; mm[h][y] = 0.f; vv[h][y] = 0.f; }
+      if (!rowok[h]) continue;
+      if (vec) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(Lq + off));
+        l[h][0] = q.x; l[h][1] = q.y; l[h][2] = q.z; l[h][3] = q.w;
+        if (m) {
+          const float4 qm = __ldcs(reinterpret_cast<const float4*>(m + off)), qv = __ldcs(reinterpret_cast<const float4*>(v + off));
+          mm[h][0] = qm.x; mm[h][1] = qm.y; mm[h][2] = qm.z; mm[h][3] = qm.w;
+          vv[h][0] = qv.x; vv[h][1] = qv.y; vv[h][2] = qv.z; vv[h][3] = qv.w;
+        }
+      } else {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          if ((jb + y) >= n) continue;
+          l[h][y] = Lq[off + y];
+          if (m) { mm[h][y] = m[off + y]; vv[h][y] = v[off + y]; }
+        }
       }
     }
-    if (vec) {
-      if (m) {
-        __stcs(reinterpret_cast<float4*>(Lq + off), make_float4(l[0], l[1], l[2], l[3]));
-        __stcs(reinterpret_cast<float4*>(m + off), make_float4(mm[0], mm[1], mm[2], mm[3]));
-        __stcs(reinterpret_cast<float4*>(v + off), make_float4(vv[0], vv[1], vv[2], vv[3]));
-      }
-      if (gout) *reinterpret_cast<float4*>(gout + off) = make_float4(g[0], g[1], g[2], g[3]);
-    } else {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (!rowok[h]) continue;
+      const int x = xp + h;
+      const int i = i0 + ty * 4 + x;
+      const long long off = (long long)i * n + jb;
+      float g[4];
 #pragma unroll
       for (int y = 0; y < 4; ++y) {
-        if ((jb + y) >= n) continue;
-        if (m && (jb + y) <= i) { Lq[off + y] = l[y]; m[off + y] = mm[y]; v[off + y] = vv[y]; }
-        if (gout) gout[off + y] = g[y];
+        const int j = jb + y;
+        const bool live = (j <= i) && (j < n);
+        g[y] = live ? acc[x][y] + ((j == i) ? 1.f / l[h][y] : 0.f) : 0.f;
+        if (m && live) {
+          const float gl = -g[y];
+          mm[h][y] = b1 * mm[h][y] + (1.f - b1) * gl;
+          vv[h][y] = b2 * vv[h][y] + (1.f - b2) * gl * gl;
+          l[h][y] -= lr_t * mm[h][y] / (sqrtf(vv[h][y]) + eps);
+        }
+      }
+      if (vec) {
+        if (m) {
+          __stcs(reinterpret_cast<float4*>(Lq + off), make_float4(l[h][0], l[h][1], l[h][2], l[h][3]));
+          __stcs(reinterpret_cast<float4*>(m + off), make_float4(mm[h][0], mm[h][1], mm[h][2], mm[h][3]));
+          __stcs(reinterpret_cast<float4*>(v + off), make_float4(vv[h][0], vv[h][1], vv[h][2], vv[h][3]));
+        }
+        if (gout) *reinterpret_cast<float4*>(gout + off) = make_float4(g[0], g[1], g[2], g[3]);
+      } else {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          if ((jb + y) >= n) continue;
+          if (m && (jb + y) <= i) { Lq[off + y] = l[h][y]; m[off + y] = mm[h][y]; v[off + y] = vv[h][y]; }
+          if (gout) gout[off + y] = g[y];
+        }
       }
     }
   }
@@ -230,11 +253,8 @@ int tril_rank_adam(float* Lq, float* m, float* v, float* gout, const float* Zt, 
   if (!Lq || !Zt || !U || ((m == nullptr) != (v == nullptr))) return HB_ERR_ARG;
   const long long t = cdiv(n, 64);
   const unsigned blocks = (unsigned)(t * (t + 1) / 2);
-  // HB_LINOP_PREFETCH=1: request the L/m/v tiles before the rank-S product (128 registers, 2 CTAs/SM) -- measured
-  // slower than relying on 4 resident CTAs/SM for the overlap (1.26 vs 1.02 ms at n=16384), kept for A/B runs.
-  static const bool prefetch = [] { const char* e = getenv("HB_LINOP_PREFETCH"); return e && e[0] == '1'; }();
-  if (prefetch) tril_rank_adam_kernel<true><<<blocks, 256, 0, st>>>(Lq, m, v, gout, Zt, U, n, S, lr, b1, b2, eps, step_dev, step_host);
-  else tril_rank_adam_kernel<false><<<blocks, 256, 0, st>>>(Lq, m, v, gout, Zt, U, n, S, lr, b1, b2, eps, step_dev, step_host);
+  // (Requesting all of L/m/v before the rank-S product needs 125 registers = 2 CTAs/SM: measured 1.26 ms against 1.02 ms.)
+  tril_rank_adam_kernel<<<blocks, 256, 0, st>>>(Lq, m, v, gout, Zt, U, n, S, lr, b1, b2, eps, step_dev, step_host);
   HB_CHECK_LAUNCH();
   return HB_OK;
 }

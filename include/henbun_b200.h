@@ -154,6 +154,14 @@ int hb_rbf_gram_bwd(const float* G, long long ldg, long long strideG, const floa
                     float* g_ell, void* ws, size_t ws_bytes, void* stream);
 
 /* tf.cholesky (gp/kernels.py:101; gp/gp.py:135), batched, in place, lower. */
+/* Panel solves of potrf / potrf_bwd / trsm multiply by explicit inverses of the 128 x 128 diagonal blocks; one step of
+ * iterative refinement against the triangular block restores LAPACK-grade accuracy on ill-conditioned matrices at the
+ * price of two more short-K products per panel.  mode: 0 off, 1 on, 2 (default) on for n <= 8192.  Returns the mode set. */
+int hb_set_panel_refinement(int mode);
+/* Factorisations (potrf / potrf_bwd / trsm) of order <= n run their products on the exact-fp32 SIMT kernels instead of
+ * the tensor-core split product (default n = 2048: latency-bound sizes, where the notebook models live and where the
+ * split product's 1.5e-6 error shows on ill-conditioned inputs).  0 disables.  Returns the value set. */
+int hb_set_exact_below(int n);
 size_t hb_potrf_workspace_bytes(int n);
 int hb_potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
                    size_t ws_bytes, int* err_flag, void* stream);

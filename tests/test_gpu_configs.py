@@ -5,7 +5,7 @@ at the named size (N=2000, 3 experts, full-covariance q_s / q_l + mean-field q_r
 Tolerances.  The well-conditioned golden case (N=30) is held to 1e-5 relative on the ELBO and 3e-5 norm-wise
 on every gradient.  The N=2000 1-D notebook input has cond(K + 3e-4 I) ~ 3e6, where fp32 itself (the
 reference's default precision, henbunrc:7) is 1e-4...9e-3 away from fp64 (SURVEY.md 8c "Tolerances"): the bar
-there is condition-scaled (0.5 * cond * 2^-24) with the fp32-CPU restatement's error printed next to ours.
+there is condition-scaled (0.15 * cond * 2^-24) with the fp32-CPU restatement's error printed next to ours.
 """
 import os
 
@@ -142,13 +142,13 @@ def test_expert_gpr_config2_full_size(n, S):
     ref32, gref32 = O.value_and_grads(fn32, p, X, Y[:, 0], U, dtype=torch.float32)
     # Bar at this size: cond(K + 3e-4 I) = 2.5e6 for the l = 1 kernels, so fp32 (the reference's default precision)
     # only promises cond * 2^-24 = 0.15 forward error.  Measured on these inputs: the fp32 CPU restatement (LAPACK
-    # spotrf) is 1e-4...9e-3 away from fp64 on the gradients, this library 6e-5...3.8e-2 (the panel solves multiply by
-    # explicit inverses of the 128x128 diagonal blocks, which costs 2-5x in forward error on such matrices --
-    # DESIGN.md 4.2; identical for the SIMT and tensor-core engines).  Asserted: 0.5 * cond * 2^-24 (= 0.075) on every
-    # gradient, 1e-4 on the ELBO; the ratio to the fp32-CPU error is printed for the record.
+    # spotrf) is 1e-4...9e-3 away from fp64 on the gradients, this library 2e-5...9e-3 (factorisations of order <= 2048
+    # run exact-fp32 products and refine the explicit-inverse panel solves; without both it was up to
+    # 3.8e-2).  Asserted: 0.15 * cond * 2^-24 (= 0.023) on every gradient, 1e-4 on the ELBO; the fp32-CPU error is
+    # printed next to ours for the record.
     Kc = O.rbf_K(torch.tensor(X), torch.tensor([1.0], dtype=torch.float64)).numpy() + jitter * np.eye(n)
     ev = np.linalg.eigvalsh(Kc)
-    tol_g = 0.5 * (ev[-1] / ev[0]) * 2.0 ** -24
+    tol_g = 0.15 * (ev[-1] / ev[0]) * 2.0 ** -24
     names = {"q_s.q_mu": "model.q_s.q_mu", "q_s.q_sqrt": "model.q_s.q_sqrt", "q_s.scale": "model.q_s.scale",
              "q_l.q_mu": "model.q_l.q_mu", "q_l.q_sqrt": "model.q_l.q_sqrt", "q_l.scale": "model.q_l.scale",
              "q_r.q_mu": "model.q_r.q_mu", "q_r.q_sqrt": "model.q_r.q_sqrt", "q_r.scale": "model.q_r.scale",

@@ -29,9 +29,22 @@ ref32, gref32 = O.value_and_grads(fn32, p, X, Y[:, 0], U, dtype=torch.float32)
 keys = list(gref)
 print("fp32-CPU   ELBO rel %.1e  grads %s" % (abs(ref32 - ref) / abs(ref), " ".join("%.0e" % T.rel_err(gref32[k], gref[k]) for k in keys)))
 lib = _lib.load()
-for label, eng, opt_bits in (("auto", 0, 0), ("simt", 1, 0), ("all-tf32", 0, 8), ("kloop", 3, 0)):
-    lib.hb_set_gemm_engine(eng); lib.hb_set_tc_option(opt_bits)
+# n <= 2048: the factorisation's products are exact fp32 whatever the engine (linalg.cu kExactBelow); larger n (argv[1])
+# shows the tensor-core engine.  refine: hb_set_panel_refinement mode (2 = default: on for n <= 8192).
+for label, eng, opt_bits, refine in (("default", 0, 0, 2), ("no-refine", 0, 0, 0), ("simt", 1, 0, 2), ("all-tf32", 0, 8, 2)):
+    lib.hb_set_gemm_engine(eng); lib.hb_set_tc_option(opt_bits); lib.hb_set_panel_refinement(refine)
     val, grads = T._value_and_grads(m, opt, eps)
     errs = [T.rel_err(grads["model." + k].reshape(gref[k].shape), gref[k]) for k in keys]
     print("%-10s ELBO rel %.1e  grads %s" % (label, abs(val - ref) / abs(ref), " ".join("%.0e" % e for e in errs)))
 print(keys)
+import time
+lib.hb_set_gemm_engine(0); lib.hb_set_tc_option(0)
+for refine in (0, 2):
+    lib.hb_set_panel_refinement(refine)
+    for _ in range(3):
+        T._value_and_grads(m, opt, eps)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(10):
+        T._value_and_grads(m, opt, eps)
+    torch.cuda.synchronize()
+    print("refine", refine, "ms per ELBO+grad", (time.perf_counter() - t0) * 100)
