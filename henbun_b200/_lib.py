@@ -56,6 +56,10 @@ SIGNATURES = {
     "hb_sample_tril_bwd": (_i, [_c_f, _i, _i, _c_f, _c_f, _i, _c_f, _fl, _c_f, _c_f, _c_f, _c_f]),
     "hb_gaussian_logpdf": (_i, [_c_f, _ll, _c_f, _ll, _c_f, _ll, _ll, _c_f, _c_f]),
     "hb_gaussian_logpdf_bwd": (_i, [_c_f, _ll, _c_f, _ll, _c_f, _ll, _ll, _c_f, _c_f, _c_f, _c_f]),
+    "hb_transform_fwd": (_i, [_i, _c_f, _ll, _fl, _fl, _c_f, _c_f]),
+    "hb_transform_bwd": (_i, [_i, _c_f, _ll, _fl, _fl, _c_f, _c_f, _c_f]),
+    "hb_transform_logjac": (_i, [_i, _c_f, _ll, _fl, _fl, _c_f, _c_f, _sz, _c_f]),
+    "hb_transform_logjac_bwd": (_i, [_i, _c_f, _ll, _fl, _fl, _c_f, _c_f, _c_f]),
     "hb_density_nargs": (_i, [_i]),
     "hb_density_logpdf": (_i, [_i, _c_f, _c_f, _ll, _c_f, _c_f]),
     "hb_density_logpdf_bwd": (_i, [_i, _c_f, _c_f, _ll, _c_f, _ll, _c_f, _c_f, _sz, _c_f]),

@@ -336,6 +336,21 @@ int hb_gaussian_logpdf_bwd(const float* x, long long x_period, const float* mu, 
                            void* stream) {
   return gaussian_logpdf_bwd(x, x_period, mu, mu_period, var, var_period, total, g, dmu, dvar, S(stream));
 }
+int hb_transform_fwd(int kind, const float* x, long long total, float p0, float p1, float* y, void* stream) {
+  return transform_fwd(kind, x, total, p0, p1, y, S(stream));
+}
+int hb_transform_bwd(int kind, const float* x, long long total, float p0, float p1, const float* gy, float* gx, void* stream) {
+  return transform_bwd(kind, x, total, p0, p1, gy, gx, S(stream));
+}
+int hb_transform_logjac(int kind, const float* x, long long total, float p0, float p1, float* out1, void* ws, size_t ws_bytes,
+                        void* stream) {
+  return transform_logjac(kind, x, total, p0, p1, out1, ws, ws_bytes, S(stream));
+}
+int hb_transform_logjac_bwd(int kind, const float* x, long long total, float p0, float p1, const float* g1, float* gx,
+                            void* stream) {
+  return transform_logjac_bwd(kind, x, total, p0, p1, g1, gx, S(stream));
+}
+
 int hb_density_nargs(int kind) { return density_nargs_host(kind); }
 
 int hb_density_logpdf(int kind, const float* const* args, const long long* periods, long long total, float* out,

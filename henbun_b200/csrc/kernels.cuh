@@ -47,6 +47,13 @@ int density_logpdf(int kind, const float* const* args, const long long* periods,
                    cudaStream_t st);
 int density_logpdf_bwd(int kind, const float* const* args, const long long* periods, long long total, const float* g,
                        long long g_period, float* const* dargs, void* ws, size_t ws_bytes, cudaStream_t st);
+// ---- transforms.py as kernels (transforms.cu) ----
+int transform_fwd(int kind, const float* x, long long total, float p0, float p1, float* y, cudaStream_t st);
+int transform_bwd(int kind, const float* x, long long total, float p0, float p1, const float* gy, float* gx, cudaStream_t st);
+int transform_logjac(int kind, const float* x, long long total, float p0, float p1, float* out1, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+int transform_logjac_bwd(int kind, const float* x, long long total, float p0, float p1, const float* g1, float* gx,
+                         cudaStream_t st);
 int gather_rows(float* dst, const float* src, const long long* index, long long n_index, long long row_elems,
                 cudaStream_t st);
 

@@ -438,7 +438,7 @@ static inline void join_side(const Ctx& c) {
 
 // Factorisations of order <= 2048 are latency-bound (2048^3 flop = 0.2 ms even on the fp32 SIMT kernels), so their
 // products run in exact fp32: on the ill-conditioned notebook-size problems (config 1 / 2, cond 1e6) the split product's
-// 1.5e-6 per-product error was visible next to LAPACK's (tools/c2_err_probe.py).
+// 1.5e-6 per-product error was visible next to LAPACK's (tests/probe_config2_errors.py).
 // Price at n = 2000: 3 factorisations + reverse modes 17.6 -> 29.5 ms (the SIMT kernels fill 10-30 of 148 SMs on these
 // shapes); gain: gradient error vs fp64 3-5x LAPACK's -> 1-3x.  hb_set_exact_below(0) turns it off.
 static int g_exact_below = 2048;

@@ -599,6 +599,62 @@ def gaussian_logpdf(x, mu, var):
 
 
 # --------------------------------------------------------------------------------------------
+# transforms.py: y = T(x) and sum log|T'(x)|
+# --------------------------------------------------------------------------------------------
+TRANSFORM_KINDS = {"exp": 1, "log1pe": 2, "logistic": 3}
+
+
+class _TransformFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kind, p0, p1):
+        xc = _c(_lib.f32(x))
+        y = torch.empty_like(xc)
+        check(_L().hb_transform_fwd(kind, ptr(xc), xc.numel(), p0, p1, ptr(y), stream()), "hb_transform_fwd")
+        ctx.save_for_backward(xc)
+        ctx.meta = (kind, p0, p1)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (xc,) = ctx.saved_tensors
+        kind, p0, p1 = ctx.meta
+        gx = torch.empty_like(xc)
+        check(_L().hb_transform_bwd(kind, ptr(xc), xc.numel(), p0, p1, ptr(_c(gy)), ptr(gx), stream()), "hb_transform_bwd")
+        return gx, None, None, None
+
+
+class _TransformLogJac(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kind, p0, p1):
+        xc = _c(_lib.f32(x))
+        out = torch.empty(1, device=xc.device)
+        ws = reduce_ws(xc.device)
+        check(_L().hb_transform_logjac(kind, ptr(xc), xc.numel(), p0, p1, ptr(out), ptr(ws), ws.numel(), stream()),
+              "hb_transform_logjac")
+        ctx.save_for_backward(xc)
+        ctx.meta = (kind, p0, p1)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        kind, p0, p1 = ctx.meta
+        gx = torch.empty_like(xc)
+        g1 = _c(g.reshape(1))
+        check(_L().hb_transform_logjac_bwd(kind, ptr(xc), xc.numel(), p0, p1, ptr(g1), ptr(gx), stream()),
+              "hb_transform_logjac_bwd")
+        return gx, None, None, None
+
+
+def transform_forward(name, x, p0=0.0, p1=1.0):
+    return _TransformFwd.apply(x, TRANSFORM_KINDS[name], float(p0), float(p1))
+
+
+def transform_log_jacobian(name, x, p0=0.0, p1=1.0):
+    return _TransformLogJac.apply(x, TRANSFORM_KINDS[name], float(p0), float(p1))
+
+
+# --------------------------------------------------------------------------------------------
 # MatBias: act(clip(x w + b))   (nn.py:31-32, 80-84)
 # --------------------------------------------------------------------------------------------
 class _MatBias(torch.autograd.Function):

@@ -1,14 +1,17 @@
 """Constrained-parameter transforms, mirror of Henbun/transforms.py:73-180,271.
 
 Each transform has numpy ``forward``/``backward`` (host side, used by assignment and ``.value``) and
-``tf_forward``/``tf_log_jacobian`` acting on device tensors inside ``tf_mode``.  These are O(#hyper-
-parameters) scalar glue (K13 in SURVEY.md): evaluated with torch elementwise ops so autograd supplies
-the sigmoid chain factor.
+``tf_forward``/``tf_log_jacobian`` acting on device tensors inside ``tf_mode``: one CUDA kernel each, forward
+and backward (csrc/transforms.cu, C ABI hb_transform_fwd / _bwd / _logjac / _logjac_bwd) -- the same code
+serves a one-element hyper-parameter and the [S, n] sample tensor of a transformed variational
+(variationals.py:110,129,204-208).
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
+
+from . import ops
 
 
 class Transform(object):
@@ -59,7 +62,7 @@ class Exp(Transform):
         self._lower = lower
 
     def tf_forward(self, x):
-        return torch.exp(x) + self._lower
+        return ops.transform_forward("exp", x, self._lower)
 
     def forward(self, x):
         return np.exp(x) + self._lower
@@ -68,7 +71,7 @@ class Exp(Transform):
         return np.log(y - self._lower)
 
     def tf_log_jacobian(self, x):
-        return torch.sum(x)
+        return ops.transform_log_jacobian("exp", x, self._lower)
 
     def __str__(self):
         return '+ve'
@@ -84,10 +87,10 @@ class Log1pe(Transform):
         return np.logaddexp(0.0, x) + self._lower
 
     def tf_forward(self, x):
-        return torch.nn.functional.softplus(x, beta=1.0, threshold=1e9) + self._lower
+        return ops.transform_forward("log1pe", x, self._lower)
 
     def tf_log_jacobian(self, x):
-        return -torch.sum(torch.log(1. + torch.exp(-x)))
+        return ops.transform_log_jacobian("log1pe", x, self._lower)
 
     def backward(self, y):
         y = np.asarray(y)
@@ -103,7 +106,7 @@ class Logistic(Transform):
         self.a, self.b = a, b
 
     def tf_forward(self, x):
-        return self.a + (self.b - self.a) / (1. + torch.exp(-x))
+        return ops.transform_forward("logistic", x, self.a, self.b)
 
     def forward(self, x):
         return self.a + (self.b - self.a) / (1. + np.exp(-x))
@@ -112,7 +115,7 @@ class Logistic(Transform):
         return -np.log((self.b - self.a) / (y - self.a) - 1.)
 
     def tf_log_jacobian(self, x):
-        return torch.sum(x - 2. * torch.log(torch.exp(x) + 1.) + float(np.log(self.b - self.a)))
+        return ops.transform_log_jacobian("logistic", x, self.a, self.b)
 
     def __str__(self):
         return '[' + str(self.a) + ', ' + str(self.b) + ']'

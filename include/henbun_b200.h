@@ -95,6 +95,22 @@ int hb_gaussian_logpdf(const float* x, long long x_period, const float* mu, long
 int hb_gaussian_logpdf_bwd(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
                            long long var_period, long long total, const float* g, float* dmu, float* dvar,
                            void* stream);
+/* Constrained-parameter transforms (Henbun/transforms.py) on device tensors: y = T(x), the log-Jacobian sum that the
+ * generic Variational._KL subtracts (variationals.py:204-208), and their backward passes.
+ *   HB_TRANSFORM_EXP 1      (transforms.py:90-107)   y = exp(x) + p0
+ *   HB_TRANSFORM_LOG1PE 2   (transforms.py:110-143)  y = log(1 + exp(x)) + p0        (transforms.positive, p0 = 1e-6)
+ *   HB_TRANSFORM_LOGISTIC 3 (transforms.py:146-180)  y = p0 + (p1 - p0) / (1 + exp(-x))
+ * bwd: gx = gy * T'(x).  logjac: *out1 = sum_e log|T'(x_e)| (deterministic; ws of hb_reduce_workspace_bytes()).
+ * logjac_bwd: gx = *g1 * d logjac / dx (g1 a device scalar). */
+#define HB_TRANSFORM_EXP 1
+#define HB_TRANSFORM_LOG1PE 2
+#define HB_TRANSFORM_LOGISTIC 3
+int hb_transform_fwd(int kind, const float* x, long long total, float p0, float p1, float* y, void* stream);
+int hb_transform_bwd(int kind, const float* x, long long total, float p0, float p1, const float* gy, float* gx, void* stream);
+int hb_transform_logjac(int kind, const float* x, long long total, float p0, float p1, float* out1, void* ws, size_t ws_bytes,
+                        void* stream);
+int hb_transform_logjac_bwd(int kind, const float* x, long long total, float p0, float p1, const float* g1, float* gx,
+                            void* stream);
 /* The log-densities of Henbun/densities.py as one elementwise family (csrc/density_family.cu).
  * kind (operands in the reference function's argument order, file:line in densities.py):
  *   HB_DENSITY_GAUSSIAN 0 (x, mu, var) :25-27      HB_DENSITY_GAMMA 5 (shape, scale, x) :49-51

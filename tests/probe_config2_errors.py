@@ -1,8 +1,10 @@
 """Config 2 (Expert GPR, N=2000, jitter 3e-4, cond ~3e6) gradient error vs the fp64 oracle under each GEMM engine
-setting, next to the fp32-CPU restatement's error.  Evidence for the accuracy discussion in DESIGN.md."""
+setting, next to the fp32-CPU restatement's error.  Evidence for the accuracy discussion in DESIGN.md 4.2.
+Lives under tests/ (not collected by pytest) because it uses the oracle as its checker.
+    python tests/probe_config2_errors.py [n] [jitter]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np, torch
 import henbun_b200 as hb
 from henbun_b200 import _lib
