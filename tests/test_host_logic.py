@@ -99,9 +99,12 @@ def test_transforms_numpy_roundtrip():               # test_transforms.py:49-53
     x = np.random.RandomState(0).randn(10)
     for t in (hb.transforms.Identity(), hb.transforms.Exp(), hb.transforms.Log1pe(), hb.transforms.Logistic(7.3, 19.4)):
         assert np.allclose(t.backward(t.forward(x)), x, atol=1e-4)
-        xt = torch.tensor(x)
-        assert np.allclose(t.tf_forward(xt).numpy(), t.forward(x), atol=1e-12)      # test_transforms.py:39-47
     assert hb.transforms.positive.__class__ is hb.transforms.Log1pe
+    # the device side (tf_forward / tf_log_jacobian, test_transforms.py:39-47) is a CUDA kernel: tests/test_gpu_transforms.py.
+    # On a CPU tensor it must raise, not fall back.
+    with pytest.raises(Exception):
+        hb.transforms.Log1pe().tf_forward(torch.tensor(x, dtype=torch.float32))
+    assert hb.transforms.Identity().tf_forward(torch.tensor(x)) is not None
 
 
 def test_paramlist_and_aliases():
