@@ -289,7 +289,9 @@ int gemm_simt(const GemmParams& p, cudaStream_t st) {
   kp.vecA = aligned16(p.A) && (p.lda % 4 == 0) && (p.sA % 4 == 0);
   kp.vecB = aligned16(p.B) && (p.ldb % 4 == 0) && (p.sB % 4 == 0);
   kp.vecC = aligned16(p.C) && (p.ldc % 4 == 0) && (p.sC % 4 == 0);
-  const bool small_m = p.M <= 64;
+  // 64-row tiles when the row count is small or when 128-row tiles would leave most of the 148 SMs idle (the exact-fp32
+  // factorisations of order <= 2048 live on such shapes)
+  const bool small_m = p.M <= 64 || (long long)cdiv(p.M, 128) * cdiv(p.N, 128) * p.batch < 148;
   const int BM = small_m ? 64 : 128;
   kp.tiles_m = cdiv(p.M, BM);
   kp.tiles_n = cdiv(p.N, 128);
