@@ -72,6 +72,61 @@ if which in ("1", "2"):
     ms = timed(m.ELBO(), 20)
     print(f"config {which} (N={n}, S={S}, jitter {jitter:g}): {ms:.3f} ms/step = {S * n / ms * 1e3:.3e} evals/s; "
           f"ELBO {float(m.ELBO().run()):.4f}", flush=True)
+elif which == "1f":
+    # config 1 through the fused C entry point (hb_gp_elbo_step + hb_adam_tf1, full-covariance q): eager launches and
+    # replay of the same launches captured in a CUDA graph.  SURVEY.md 8d: this config is launch-latency-bound; the
+    # floor is one kernel (~5-10 us).  (A captured graph replays the SAME Philox offset -- timing only.)
+    import ctypes as C
+    from henbun_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(0)
+    n, D, S, jitter = 100, 1, 10, 1e-3
+    X = np.linspace(0, 6, n).reshape(-1, 1).astype(np.float32); Y = (np.sin(X[:, 0]) + 0.3 * rng.randn(n)).astype(np.float32)
+    cfg = _lib.GpConfig(n, D, S, 1, 1, jitter, 0, 0)
+    npar = lib.hb_gp_param_count(C.byref(cfg))
+    q_sqrt = (0.3 * np.eye(n) + 0.02 * np.tril(rng.randn(n, n))).astype(np.float32)
+    params = torch.tensor(np.concatenate([0.1 * rng.randn(n), q_sqrt.ravel(), [0.54], [0.54], [0.54], [-0.5]]).astype(np.float32), device="cuda")
+    assert params.numel() == npar
+    grads = torch.zeros(npar, device="cuda"); am = torch.zeros(npar, device="cuda"); av = torch.zeros(npar, device="cuda")
+    ctr = torch.zeros(1, dtype=torch.int32, device="cuda"); out4 = torch.zeros(4, device="cuda"); err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    wsb = lib.hb_gp_elbo_workspace_bytes(C.byref(cfg)); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    Xd, Yd = torch.tensor(X, device="cuda"), torch.tensor(Y, device="cuda")
+
+    def step(it):
+        cfg.offset = C.c_ulonglong(it * ((S * n + 3) // 4 * 4))
+        _lib.check(lib.hb_gp_elbo_step(C.byref(cfg), _lib.ptr(Xd), _lib.ptr(Yd), _lib.ptr(params), None, _lib.ptr(grads), _lib.ptr(out4),
+                                       _lib.ptr(ws), wsb, _lib.ptr(err), _lib.stream()), "hb_gp_elbo_step")
+        _lib.check(lib.hb_increment_i32(_lib.ptr(ctr), _lib.stream()), "inc")
+        _lib.check(lib.hb_adam_tf1(_lib.ptr(params), _lib.ptr(grads), _lib.ptr(am), _lib.ptr(av), npar, -1.0, 1e-3, 0.9, 0.999, 1e-8,
+                                   _lib.ptr(ctr), 0, _lib.stream()), "adam")
+    for i in range(20):
+        step(i)
+    l0 = lib.hb_launch_count(); step(20); per_step = lib.hb_launch_count() - l0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); ev0.record()
+    for i in range(200):
+        step(21 + i)
+    ev1.record(); torch.cuda.synchronize()
+    eager = ev0.elapsed_time(ev1) / 200 * 1e3
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step(300)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            step(301)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(20):
+        g.replay()
+    torch.cuda.synchronize(); ev0.record()
+    for _ in range(500):
+        g.replay()
+    ev1.record(); torch.cuda.synchronize()
+    graph = ev0.elapsed_time(ev1) / 500 * 1e3
+    print(f"config 1 fused C entry (N={n}, full-covariance q, S={S}, {per_step} kernels/step): eager {eager:.1f} us/step = "
+          f"{S * n / eager * 1e6:.3e} evals/s; CUDA-graph replay {graph:.1f} us/step = {S * n / graph * 1e6:.3e} evals/s; "
+          f"ELBO {float(out4[0]):.3f}, err flag {int(err.item())}", flush=True)
+    m = None
 elif which == "5f":
     # config 5 through the fused C entry points (hb_linop_elbo_local / _update): per-phase CUDA-event times and the
     # HBM roofline of the step (algorithmic bytes: SURVEY.md 8d / csrc/linop.cu header)
