@@ -172,7 +172,9 @@ int hb_rbf_gram_bwd(const float* G, long long ldg, long long strideG, const floa
 /* tf.cholesky (gp/kernels.py:101; gp/gp.py:135), batched, in place, lower. */
 /* Panel solves of potrf / potrf_bwd / trsm multiply by explicit inverses of the 128 x 128 diagonal blocks; one step of
  * iterative refinement against the triangular block restores LAPACK-grade accuracy on ill-conditioned matrices at the
- * price of two more short-K products per panel.  mode: 0 off, 1 on, 2 (default) on for n <= 8192.  Returns the mode set. */
+ * price of two more short-K products per panel.  mode: 0 explicit inverse only, 1 refined, 2 (default) refined for n <= 8192, 3 no inverse: the panel is solved by
+ * substitution against the triangular block (panel_trsm_kernel; as accurate as mode 1, slower at large n).  Returns
+ * the mode set. */
 int hb_set_panel_refinement(int mode);
 /* Factorisations (potrf / potrf_bwd / trsm) of order <= n run their products on the exact-fp32 SIMT kernels instead of
  * the tensor-core split product (default n = 2048: latency-bound sizes, where the notebook models live and where the

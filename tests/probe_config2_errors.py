@@ -32,8 +32,8 @@ keys = list(gref)
 print("fp32-CPU   ELBO rel %.1e  grads %s" % (abs(ref32 - ref) / abs(ref), " ".join("%.0e" % T.rel_err(gref32[k], gref[k]) for k in keys)))
 lib = _lib.load()
 # n <= 2048: the factorisation's products are exact fp32 whatever the engine (linalg.cu kExactBelow); larger n (argv[1])
-# shows the tensor-core engine.  refine: hb_set_panel_refinement mode (2 = default: on for n <= 8192).
-for label, eng, opt_bits, refine in (("default", 0, 0, 2), ("no-refine", 0, 0, 0), ("simt", 1, 0, 2), ("all-tf32", 0, 8, 2)):
+# shows the tensor-core engine.  refine: hb_set_panel_refinement mode (2 = default: refined for n <= 8192; 3 = substitution kernel).
+for label, eng, opt_bits, refine in (("default", 0, 0, 2), ("inverse", 0, 0, 0), ("subst", 0, 0, 3), ("simt+subst", 1, 0, 3)):
     lib.hb_set_gemm_engine(eng); lib.hb_set_tc_option(opt_bits); lib.hb_set_panel_refinement(refine)
     val, grads = T._value_and_grads(m, opt, eps)
     errs = [T.rel_err(grads["model." + k].reshape(gref[k].shape), gref[k]) for k in keys]
@@ -41,7 +41,7 @@ for label, eng, opt_bits, refine in (("default", 0, 0, 2), ("no-refine", 0, 0, 0
 print(keys)
 import time
 lib.hb_set_gemm_engine(0); lib.hb_set_tc_option(0)
-for refine in (0, 2):
+for refine in (0, 1, 3):
     lib.hb_set_panel_refinement(refine)
     for _ in range(3):
         T._value_and_grads(m, opt, eps)
@@ -50,3 +50,4 @@ for refine in (0, 2):
         T._value_and_grads(m, opt, eps)
     torch.cuda.synchronize()
     print("refine", refine, "ms per ELBO+grad", (time.perf_counter() - t0) * 100)
+lib.hb_set_panel_refinement(2)

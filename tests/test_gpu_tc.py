@@ -179,6 +179,49 @@ def test_potrf_and_reverse_mode_on_tensor_cores(lib, n):
     assert eG < 5e-6, eG                                    # measured 2e-7 .. 1e-6
 
 
+@pytest.mark.parametrize("mode", [0, 1, 3])
+@pytest.mark.parametrize("n", [300, 1000, 2500])
+def test_panel_solve_modes(lib, n, mode):
+    """hb_set_panel_refinement: explicit-inverse panels (0), refined (1) and the substitution kernel (3) all reproduce the
+    fp64 factor, its reverse mode and the right-sided triangular solves (n not a multiple of the 128-wide leaf)."""
+    g = torch.Generator("cuda").manual_seed(n + mode)
+    X = torch.randn(n, 8, device="cuda", generator=g, dtype=torch.float64)
+    K64 = torch.exp(-0.5 * torch.cdist(X, X) ** 2 / 0.25) + 1e-3 * torch.eye(n, device="cuda", dtype=torch.float64)
+    Lbar = torch.tril(torch.randn(n, n, device="cuda", generator=g, dtype=torch.float64))
+    Kr = K64.clone().requires_grad_(True)
+    Lref = torch.linalg.cholesky(Kr)
+    (Lref * Lbar).sum().backward()
+    Gref = torch.tril(0.5 * (Kr.grad + Kr.grad.T))
+    A = K64.float().contiguous(); G = Lbar.float().contiguous()
+    wsb = lib.hb_potrf_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    try:
+        assert lib.hb_set_panel_refinement(mode) == mode
+        assert lib.hb_potrf_lower(P(A), n, 0, n, 1, 1, P(ws), wsb, P(err), ST()) == 0
+        assert lib.hb_potrf_lower_bwd(P(A), n, 0, P(G), n, 0, n, 1, P(ws), wsb, ST()) == 0
+        m = 77
+        B = torch.randn(m, n, device="cuda", generator=g, dtype=torch.float64)
+        tws = lib.hb_trsm_workspace_bytes(m, n)
+        tw = torch.empty(tws, dtype=torch.uint8, device="cuda")
+        sols = []
+        for trans in (1, 0):
+            Xs = B.float().contiguous()
+            assert lib.hb_trsm_right_lower(P(A), n, P(Xs), n, m, n, trans, P(tw), tws, ST()) == 0
+            sols.append(Xs)
+        torch.cuda.synchronize()
+    finally:
+        lib.hb_set_panel_refinement(2)
+    assert err.item() == 0
+    L = Lref.detach()
+    assert (torch.linalg.norm(A.double() - L) / torch.linalg.norm(L)).item() < 2e-6
+    assert (torch.linalg.norm(torch.tril(G.double()) - Gref) / torch.linalg.norm(Gref)).item() < 5e-6
+    ref_t = torch.linalg.solve_triangular(L, B.T, upper=False).T            # B L^{-T}
+    ref_n = torch.linalg.solve_triangular(L.T, B.T, upper=True).T           # B L^{-1}
+    assert (torch.linalg.norm(sols[0].double() - ref_t) / torch.linalg.norm(ref_t)).item() < 5e-6
+    assert (torch.linalg.norm(sols[1].double() - ref_n) / torch.linalg.norm(ref_n)).item() < 5e-6
+
+
 def test_gp_step_tensor_cores_match_simt(lib):
     """Fused ELBO + gradient step at a size where the tensor-core engine takes the large products, against the same
     step on the fp32 SIMT kernels (same eps stream): ELBO to 1e-5 relative (north-star tolerance), gradients normwise."""
