@@ -122,6 +122,11 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    # A/B switches from the environment (accuracy vs speed of the factorisations, include/henbun_b200.h)
+    if os.environ.get("HB_EXACT_BELOW") is not None:
+        lib.hb_set_exact_below(int(os.environ["HB_EXACT_BELOW"]))
+    if os.environ.get("HB_PANEL_REFINEMENT") is not None:
+        lib.hb_set_panel_refinement(int(os.environ["HB_PANEL_REFINEMENT"]))
     _lib = lib
     return lib
 

@@ -8,6 +8,22 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+@pytest.fixture(autouse=True)
+def _seed_global_rngs():
+    """Variables initialise from numpy's global RNG (tf.truncated_normal in the reference, param.py:206-208) and the
+    Indexer draws minibatches from it (model.py:147-149): seed it per test so that every test sees the same model whatever
+    the order / selection of tests in the process (unseeded, borderline tolerances on the ill-conditioned notebook
+    inputs flaked from run to run)."""
+    import numpy as np
+    np.random.seed(1234)
+    try:
+        import torch
+        torch.manual_seed(1234)
+    except Exception:  # pragma: no cover
+        pass
+    yield
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
 
