@@ -12,12 +12,14 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-f
 fi
 # 2. config 5 fused step: the fused Lbar + Adam kernel and the three GEMM shapes
 python tools/configs_probe.py 5f > gpurun_out/plain_5f.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:tril_rank_adam -s 3 -c 1 -o gpurun_out/prof_tril_rank_adam_r1 \
+ncu --set full --clock-control none --import-source on -k regex:tril_rank_adam -s 3 -c 1 -o gpurun_out/prof_tril_rank_adam_r1${SUFFIX} \
     python tools/configs_probe.py 5f > gpurun_out/ncu_5f_a.log 2>&1
+if [ -z "$SKIP_GEMMS" ]; then
 ncu --set full --clock-control none --import-source on -k regex:gemm_tc2_kernel -s 9 -c 3 -o gpurun_out/prof_linop_gemms_r1 \
     python tools/configs_probe.py 5f > gpurun_out/ncu_5f_b.log 2>&1
+fi
 # 3. config 4: the density family kernels at [32*4096, 784]
 python tools/configs_probe.py 4 > gpurun_out/plain_4.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:density_ -s 6 -c 2 -o gpurun_out/prof_density_r1 \
+ncu --set full --clock-control none --import-source on -k regex:density_ -s 6 -c 2 -o gpurun_out/prof_density_r1${SUFFIX} \
     python tools/configs_probe.py 4 > gpurun_out/ncu_4.log 2>&1
-tail -2 gpurun_out/plain_5f.log gpurun_out/plain_4.log; tail -c 300 gpurun_out/plain_n65536.log; ls -la gpurun_out | tail -12
+tail -n 3 gpurun_out/plain_5f.log; tail -n 1 gpurun_out/plain_4.log
