@@ -56,14 +56,22 @@ def extrapolation_factor(n_full, n_sample, S):
     return (1.0 - q) * r ** 3 + q * r ** 2
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1 to every rank: override it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(n_full, D, S, n_sample, steps=2, warmup=1):
-    """Oracle (torch-CPU fp32) ELBO+grad+Adam step on a bounded sample, extrapolated ~N^3."""
+    """Oracle (torch-CPU fp32) ELBO+grad+Adam step on a bounded sample, extrapolated by flop count."""
     import torch
     from oracle import cpu_baseline as cb
     n_sample = min(n_sample, n_full)
     if n_sample >= 8192:
         steps = 1
-    t, _, threads = cb.time_gpr_steps(n_sample, D, S, steps=steps, warmup=warmup)
+    t, _, threads = cb.time_gpr_steps(n_sample, D, S, steps=steps, warmup=warmup, threads=host_threads())
     scale = extrapolation_factor(n_full, n_sample, S)
     t_full = t * scale
     return {
@@ -130,7 +138,8 @@ def run_reference(a):
     n_s = min(a.cpu_n, a.n)
     # same job as our arm at --gpus N: weak scaling in S, i.e. S * N samples per step on the one host
     S_tot = a.samples * max(1, a.gpus)
-    t, _, threads = cb.time_gpr_steps(n_s, a.dim, S_tot, steps=max(1, min(a.steps, 5)), warmup=max(1, min(a.warmup, 1)))
+    t, _, threads = cb.time_gpr_steps(n_s, a.dim, S_tot, steps=max(1, min(a.steps, 5)), warmup=max(1, min(a.warmup, 1)),
+                                      threads=host_threads())
     scale = extrapolation_factor(a.n, n_s, S_tot)
     val = S_tot * a.n / (t * scale)
     sample = (f"torch-CPU fp32 restatement of the reference graph (TensorFlow is not installable here), "
