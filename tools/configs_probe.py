@@ -139,7 +139,7 @@ elif which == "5f":
     if world > 1:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         dist.init_process_group("nccl")
-    M, n, S = 65536, 16384, 64
+    M, n, S = 65536, 16384, int(sys.argv[2]) if len(sys.argv) > 2 else 64       # S sweep: SURVEY.md 8d ({1, 8, 64}, headline 64)
     first, rows = parallel.shard_rows(M, world, rank)
     gen = torch.Generator(device="cuda").manual_seed(0)
     w_true = torch.randn(256, device="cuda", generator=gen)
