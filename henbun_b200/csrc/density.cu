@@ -13,22 +13,26 @@ namespace {
 
 __global__ void __launch_bounds__(256) gauss_fwd_kernel(const float* __restrict__ f, const float* __restrict__ f_scale,
                                                         const float* __restrict__ y,
-                                                        long long total, long long yp, const float* __restrict__ var,
+                                                        long long total, long long yp, long long ydiv,
+                                                        const float* __restrict__ var,
                                                         float rcoef, float* __restrict__ resid, double* partials) {
   __shared__ double red[64];
   double acc[2] = {0.0, 0.0};
   const float iv = 1.f / __ldg(var);
   const float rs = -rcoef * iv;
   const float fs = f_scale ? __ldg(f_scale) : 1.f;
-  const bool vec = ((total & 3) == 0) && ((yp & 3) == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && (!resid || (reinterpret_cast<uintptr_t>(resid) & 15) == 0);
+  // ydiv > 0: sample-minor layout f[r * ydiv + s], y read at e / ydiv (one y per row of ydiv samples)
+  const bool vec = ((total & 3) == 0) && (ydiv > 0 ? ((ydiv & 3) == 0) : (((yp & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0))) &&
+                   ((reinterpret_cast<uintptr_t>(f) & 15) == 0) && (!resid || (reinterpret_cast<uintptr_t>(resid) & 15) == 0);
   const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
   if (vec) {
     for (long long g = gid; g < total / 4; g += gsz) {
       const long long e0 = 4 * g;
       float4 ff = __ldg(reinterpret_cast<const float4*>(f + e0));
       ff.x *= fs; ff.y *= fs; ff.z *= fs; ff.w *= fs;
-      const float4 yy = __ldg(reinterpret_cast<const float4*>(y + (e0 % yp)));
+      float4 yy;
+      if (ydiv > 0) { const float y1 = __ldg(y + e0 / ydiv); yy = make_float4(y1, y1, y1, y1); }
+      else yy = __ldg(reinterpret_cast<const float4*>(y + (e0 % yp)));
       const float e[4] = {ff.x - yy.x, ff.y - yy.y, ff.z - yy.z, ff.w - yy.w};
       const float fv[4] = {ff.x, ff.y, ff.z, ff.w};
 #pragma unroll
@@ -41,7 +45,7 @@ __global__ void __launch_bounds__(256) gauss_fwd_kernel(const float* __restrict_
   } else {
     for (long long e0 = gid; e0 < total; e0 += gsz) {
       const float ff = fs * f[e0];
-      const float e = ff - y[e0 % yp];
+      const float e = ff - (ydiv > 0 ? y[e0 / ydiv] : y[e0 % yp]);
       acc[0] += (double)(e * e);
       acc[1] += (double)(e * ff);
       if (resid) resid[e0] = rs * e;
@@ -112,14 +116,21 @@ int gaussian_logpdf_bwd(const float* x, long long x_period, const float* mu, lon
 
 int gauss_loglik_fwd(const float* f, const float* f_scale, const float* y, long long total, long long y_period,
                      const float* var, float rcoef, float* resid, float* out3, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (total < 0 || y_period <= 0 || !var || !out3) return HB_ERR_ARG;
+  return gauss_loglik_fwd_ex(f, f_scale, y, total, y_period, 0, var, rcoef, resid, out3, ws, ws_bytes, st);
+}
+
+// y_div > 0: f is [rows, y_div] (sample-minor) and y has one entry per row; otherwise y is read at e % y_period.
+int gauss_loglik_fwd_ex(const float* f, const float* f_scale, const float* y, long long total, long long y_period,
+                        long long y_div, const float* var, float rcoef, float* resid, float* out3, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
+  if (total < 0 || y_period <= 0 || y_div < 0 || !var || !out3) return HB_ERR_ARG;
   if (total > 0 && (!f || !y)) return HB_ERR_ARG;
   if (!ws || ws_bytes < kReduceWsBytes) return HB_ERR_WORKSPACE;
   long long nb = (total / 4 + 255) / 256;
   if (nb < 1) nb = 1;
   if (nb > kReduceBlocks) nb = kReduceBlocks;
   double* partials = reinterpret_cast<double*>(ws);
-  gauss_fwd_kernel<<<(int)nb, 256, 0, st>>>(f, f_scale, y, total, y_period, var, rcoef, resid, partials);
+  gauss_fwd_kernel<<<(int)nb, 256, 0, st>>>(f, f_scale, y, total, y_period, y_div, var, rcoef, resid, partials);
   HB_CHECK_LAUNCH();
   gauss_finalize_kernel<<<1, 32, 0, st>>>(partials, (int)nb, total, var, out3);
   HB_CHECK_LAUNCH();

@@ -28,6 +28,7 @@ struct GemmParams {
   int clip = 0;
   float clip_lo = -50.f, clip_hi = 50.f;
   int force_simt = 0;      // exact fp32 products (SIMT kernels) whatever the global engine mode says
+  int hint_split_waves = 0;  // tcgen05 engine: consider split-K up to 147 tiles (default: < 74), split count by wave efficiency
   int hint_bn128 = 0;      // tcgen05 engine: 128-wide output tiles even when N > 128 (more CTAs for short-M products
                            // that cannot use split-K: triangular masks / bias epilogue)
   void* ws = nullptr;      // optional scratch for the tcgen05 engine (hi/lo operand copies)

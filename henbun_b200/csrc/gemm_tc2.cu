@@ -179,7 +179,7 @@ __device__ __forceinline__ void store_tile(const float (&acc)[BN / 2], const Tc2
   const bool post = (p.bias != nullptr) || p.act != ACT_NONE || p.clip;
   // rows ew, ew+8, ...: RB rows per trip so that RB * (BN/128) reads of the old C are in flight per lane (one read per
   // trip made the beta = 1 epilogue latency-bound: 16 dependent DRAM round trips per warp)
-  constexpr int RB = 4, SEGS = BN / 128;
+  constexpr int RB = 4, SEGS = (BN + 127) / 128;       // BN = 64: one segment, lanes 16..31 idle
 #pragma unroll 1
   for (int r0 = ew; r0 < BM; r0 += 8 * RB) {
     float4 oldv[RB][SEGS];
@@ -191,7 +191,7 @@ __device__ __forceinline__ void store_tile(const float (&acc)[BN / 2], const Tc2
       for (int seg = 0; seg < SEGS; ++seg) {
         const int gj = n0 + seg * 128 + lane * 4;
         oldv[b][seg] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fastC && r0 + 8 * b < BM && gi < p.M && gj + 3 < p.N && !(p.c_tri == 1 && gj + 3 > gi))
+        if (fastC && seg * 128 + lane * 4 < BN && r0 + 8 * b < BM && gi < p.M && gj + 3 < p.N && !(p.c_tri == 1 && gj + 3 > gi))
           oldv[b][seg] = *reinterpret_cast<const float4*>(Cbase + (long long)gi * p.ldc + gj);
       }
     }
@@ -205,7 +205,7 @@ __device__ __forceinline__ void store_tile(const float (&acc)[BN / 2], const Tc2
       for (int seg = 0; seg < SEGS; ++seg) {
         const int cj = seg * 128 + lane * 4;
         const int gj = n0 + cj;
-        if (gj >= p.N) continue;
+        if (cj >= BN || gj >= p.N) continue;
         float o[4];
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
                      : "r"(sm_tile + (uint32_t)(r * LDT + cj) * 4u));
@@ -267,8 +267,8 @@ template <int ROWS, bool KMAJOR, bool MASK, bool BFX>
 __device__ __forceinline__ void convert_tile(uint32_t raw, uint32_t lo, int ct, int mode, int r0, int k0) {
   constexpr int CHUNKS = ROWS * BK * 4 / 16;
   constexpr int PER = CHUNKS / 128;
-  constexpr int BATCH = 4;
-  static_assert(PER % BATCH == 0, "tile size");
+  constexpr int BATCH = (PER % 4 == 0) ? 4 : PER;     // 64-row tiles: 2 chunks per thread
+  static_assert(PER >= 1 && PER % BATCH == 0, "tile size");
 #pragma unroll 1
   for (int b = 0; b < PER; b += BATCH) {
     float4 v[BATCH];
@@ -859,7 +859,9 @@ bool gemm_tc2_uses_pair(const GemmParams& p) {
 int gemm_tc2(const GemmParams& p, cudaStream_t st) {
   static const int b2rk[5] = {0, 2, 1, 4, 3};      // mask of op(B)[k][n] expressed in (n, k) space
   const bool akm = (p.transA == 0), bkm = (p.transB == 1);
-  const int BN = (p.N <= 128 || p.hint_bn128) ? 128 : 256;
+  // 64-wide tiles for N <= 64: a [rows, S <= 64] product (config 5 with the operator as the M operand) would waste
+  // half of every MMA on a 128-wide tile
+  const int BN = (p.N <= 64) ? 64 : (p.N <= 128 || p.hint_bn128) ? 128 : 256;
   // CTA pairs (256 x 256 tiles) once there are enough of them to fill the GPU; bit 2 of the option word disables them
   const bool pair = gemm_tc2_uses_pair(p);
   CUtensorMap ta, tb;
@@ -875,7 +877,7 @@ int gemm_tc2(const GemmParams& p, cudaStream_t st) {
   // split-K for "tall reductions" (small output, long K): partial tiles into the caller's scratch, then one
   // deterministic reduction pass.  Used when the output has too few tiles to occupy the GPU.
   const long long tiles = (long long)cdiv(p.M, BM) * cdiv(p.N, BN);
-  if (p.ws && tiles < 74 && p.K >= 512 && !p.a_tri && !p.b_tri && !p.bias && p.act == ACT_NONE && !p.clip) {
+  if (p.ws && tiles < (p.hint_split_waves ? 148 : 74) && p.K >= 512 && !p.a_tri && !p.b_tri && !p.bias && p.act == ACT_NONE && !p.clip) {
     int want = (int)((148 + tiles - 1) / tiles);
     const int kblocks = cdiv(p.K, BK);
     if (tiles >= 32) {
@@ -899,7 +901,8 @@ int gemm_tc2(const GemmParams& p, cudaStream_t st) {
       Tc2Params sp = tp;
       sp.C = part; sp.ldc = p.N; sp.beta = 0.f; sp.c_tri = p.c_tri; sp.ksplit = per; sp.csplit = (long long)p.M * p.N;
       sp.vecC = (p.N % 4 == 0);
-      int rc = (BN == 128) ? launch2<128>(akm, bkm, ta, tb, sp, st) : launch2<256>(akm, bkm, ta, tb, sp, st);
+      int rc = (BN == 64) ? launch2<64>(akm, bkm, ta, tb, sp, st)
+               : (BN == 128) ? launch2<128>(akm, bkm, ta, tb, sp, st) : launch2<256>(akm, bkm, ta, tb, sp, st);
       if (rc != HB_OK) return rc;
       const long long tot = (long long)p.M * p.N;
       int nb = (int)((tot + 255) / 256); if (nb > 148 * 8) nb = 148 * 8;
@@ -908,6 +911,7 @@ int gemm_tc2(const GemmParams& p, cudaStream_t st) {
       return HB_OK;
     }
   }
+  if (BN == 64) return launch2<64>(akm, bkm, ta, tb, tp, st);
   if (BN == 128) return launch2<128>(akm, bkm, ta, tb, tp, st);
   return launch2<256>(akm, bkm, ta, tb, tp, st);
 }

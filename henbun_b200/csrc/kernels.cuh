@@ -35,6 +35,9 @@ int axpby(float* y, const float* x, long long n, float a, float b, cudaStream_t 
 // ---- densities.gaussian (density.cu) ----
 int gauss_loglik_fwd(const float* f, const float* f_scale, const float* y, long long total, long long y_period,
                      const float* var, float rcoef, float* resid, float* out3, void* ws, size_t ws_bytes, cudaStream_t st);
+int gauss_loglik_fwd_ex(const float* f, const float* f_scale, const float* y, long long total, long long y_period,
+                        long long y_div, const float* var, float rcoef, float* resid, float* out3, void* ws, size_t ws_bytes,
+                        cudaStream_t st);
 int gaussian_logpdf(const float* x, long long x_period, const float* mu, long long mu_period, const float* var,
                     long long var_period, long long total, float* out, cudaStream_t st);
 

@@ -42,7 +42,7 @@ def build(A, y, p, S, m_total=None, **kw):
     return st
 
 
-@pytest.mark.parametrize("M,n,S", [(300, 70, 5), (512, 128, 64), (1000, 257, 3), (64, 64, 1), (2048, 512, 96)])
+@pytest.mark.parametrize("M,n,S", [(300, 70, 5), (512, 128, 64), (1000, 257, 3), (64, 64, 1), (2048, 512, 96), (4096, 1024, 64)])
 def test_value_and_gradients_vs_oracle(M, n, S):
     A, y, p, U = make_problem(M, n, S)
     st = build(A, y, p, S)

@@ -82,6 +82,20 @@ def test_tc_single_cta_layouts(lib, M, N, K, tA, tB):
 
 
 @pytest.mark.parametrize("tA,tB", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", [(4096, 64, 512), (300, 64, 100), (1000, 48, 336), (128, 16, 64)])
+def test_tc_64_wide_tiles(lib, M, N, K, tA, tB):
+    """N <= 64 runs the 128 x 64 tile instantiation (config 5 with the operator as the M operand)."""
+    assert run(lib, M, N, K, tA, tB, alpha=-1.0, beta=1.0) < 3e-6
+
+
+def test_tc_64_wide_tiles_split_k_and_masks(lib):
+    assert run(lib, 256, 64, 8192, 1, 0, alpha=0.5, beta=0.0, with_ws=True) < 3e-6      # long K, split through the scratch
+    assert run(lib, 16384, 64, 4096, 1, 0, with_ws=True) < 3e-6                         # the Zbar^T = A^T R^T shape class
+    assert run(lib, 512, 64, 512, 0, 0, a_tri=1) < 3e-6
+    assert run(lib, 512, 64, 512, 0, 1, b_tri=2) < 3e-6
+
+
+@pytest.mark.parametrize("tA,tB", LAYOUTS)
 def test_tc_cta_pair_layouts(lib, tA, tB):
     # >= 64 tiles of 256 x 256 -> cta_group::2 kernel; ragged edges in M, N and K
     assert run(lib, 2100, 2180, 520, tA, tB, alpha=-1.0, beta=1.0) < 3e-6
