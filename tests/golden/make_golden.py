@@ -52,7 +52,7 @@ def save(name, **arrays):
                 flat[k + "/" + kk] = np.asarray(vv)
         else:
             flat[k] = np.asarray(v)
-    path = os.path.join(HERE, name + ".npz")
+    path = os.path.join(os.environ.get("HB_GOLDEN_OUT", HERE), name + ".npz")
     np.savez_compressed(path, **flat)
     print("wrote", path, {k: np.shape(v) for k, v in flat.items()})
 

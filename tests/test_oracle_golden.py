@@ -205,3 +205,24 @@ def test_expert_gpr_model():
     assert np.allclose(v, g["elbo"], rtol=1e-10)
     for k in p:
         assert np.allclose(gr[k].ravel(), g["grad"]["model." + k].ravel(), rtol=1e-6, atol=1e-9), k
+
+
+def test_golden_vectors_regenerate_from_the_reference(tmp_path):
+    """The committed vectors are exactly what the UNMODIFIED reference (/root/reference, on the TF-1 shim) produces:
+    re-run the generator into a scratch directory and compare array by array.  Skipped where the reference tree is
+    absent (the GPU box)."""
+    import subprocess
+    import sys
+    import pytest
+    if not os.path.isdir("/root/reference/Henbun"):
+        pytest.skip("reference tree not present")
+    env = dict(os.environ, HB_GOLDEN_OUT=str(tmp_path))
+    subprocess.run([sys.executable, os.path.join(G, "make_golden.py")], check=True, env=env, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, timeout=600)
+    names = sorted(f for f in os.listdir(G) if f.endswith(".npz"))
+    assert names and sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz")) == names
+    for f in names:
+        a, b = np.load(os.path.join(G, f)), np.load(os.path.join(tmp_path, f))
+        assert set(a.files) == set(b.files), f
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (f, k)
