@@ -41,52 +41,57 @@ def _act_name(fn):
     return getattr(fn, '_hb_act', None)
 
 
+def _per_layer(spec, count):
+    """A single value (repeated) or an explicit per-layer list."""
+    return list(spec) if isinstance(spec, list) else [spec] * count
+
+
 class MatBias(Parameterized):
+    """One dense layer: parameters w [*n_layers, fan_in, fan_out] and b [*n_layers, 1, fan_out] (nn.py:23-29); calling
+    it evaluates activation(clip(x w + b)) as ONE kernel (GEMM with the bias / clip / activation epilogue)."""
+
     def __init__(self, nodes, n_layers=[], mean=0.0, stddev=1.0, variable=Variable,
                  collections=[graph_key.VARIABLES]):
-        """w: [*n_layers, in, out], b: [*n_layers, 1, out] (nn.py:23-29)."""
-        assert (len(nodes) == 2)
+        assert len(nodes) == 2                                    # [fan_in, fan_out] (nn.py:23)
+        fan_in, fan_out = nodes
         Parameterized.__init__(self)
-        self.w = variable(shape=[nodes[0], nodes[1]], n_layers=n_layers, mean=mean, stddev=stddev,
-                          collections=collections)
-        self.b = variable(shape=[1, nodes[1]], n_layers=n_layers, mean=mean, stddev=stddev,
-                          collections=collections)
+        common = dict(n_layers=n_layers, mean=mean, stddev=stddev, collections=collections)
+        self.w = variable(shape=[fan_in, fan_out], **common)
+        self.b = variable(shape=[1, fan_out], **common)
 
     def __call__(self, x, activation=None):
-        num = settings.numerics
-        return ops.matbias(x, self.w, self.b, act=activation or 'none', clip=bool(num.clip_by_value),
-                           lo=num.clip_value_min, hi=num.clip_value_max)
+        numerics = settings.numerics
+        return ops.matbias(x, self.w, self.b, act=activation if activation else 'none',
+                           clip=bool(numerics.clip_by_value), lo=numerics.clip_value_min, hi=numerics.clip_value_max)
 
 
 class NeuralNet(Parameterized):
+    """Chain of MatBias layers over the widths in ``nodes``; hidden layers use ``neuron_types`` (one callable or a list),
+    the output layer is linear (nn.py:34-87).  Layers are reachable as ``net[i]`` and as attributes ``matbias<i>``
+    (the names the reference's parameter tree / checkpoints use)."""
+
     def __init__(self, nodes, n_layers=[], mean=0.0, stddev=1.0, variable_types=Variable,
                  neuron_types=sigmoid, collections=[graph_key.VARIABLES]):
         Parameterized.__init__(self)
         self.nodes = nodes
-        if not isinstance(variable_types, list):
-            variable_types = [variable_types for _ in range(len(nodes) - 1)]
-        if not isinstance(neuron_types, list):
-            self.neuron_types = [neuron_types for _ in range(len(nodes) - 2)]
-        else:
-            self.neuron_types = neuron_types
+        n_dense = len(nodes) - 1
+        self.neuron_types = _per_layer(neuron_types, n_dense - 1)
         self._matbias_list = []
-        for i in range(len(nodes) - 1):
-            matbias = MatBias(nodes=[nodes[i], nodes[i + 1]], n_layers=n_layers, mean=mean, stddev=stddev,
-                              variable=variable_types[i], collections=collections)
-            self._matbias_list.append(matbias)
-            setattr(self, 'matbias' + str(i), matbias)
+        for i, (width_in, width_out, vtype) in enumerate(zip(nodes[:-1], nodes[1:], _per_layer(variable_types, n_dense))):
+            layer = MatBias([width_in, width_out], n_layers=n_layers, mean=mean, stddev=stddev, variable=vtype,
+                            collections=collections)
+            self._matbias_list.append(layer)
+            setattr(self, 'matbias%d' % i, layer)
 
     def __call__(self, x):
-        """y_{l+1} = act_l(matbias_l(y_l)), last layer linear (nn.py:73-84); must run in tf_mode."""
+        """Must run in tf_mode.  A named activation (tf.sigmoid / tf.nn.relu / tf.tanh or its string) goes into the
+        GEMM epilogue; any other callable is applied to the layer's linear output."""
+        *hidden, last = self._matbias_list
         y = x
-        for i in range(len(self.nodes) - 2):
-            typ = self.neuron_types[i]
-            name = _act_name(typ)
-            if name is not None:
-                y = self._matbias_list[i](y, activation=name)          # fused epilogue
-            else:
-                y = typ(self._matbias_list[i](y))                       # arbitrary user callable
-        return self._matbias_list[-1](y)
+        for layer, act in zip(hidden, self.neuron_types):
+            fused = _act_name(act)
+            y = layer(y, activation=fused) if fused is not None else act(layer(y))
+        return last(y)
 
     def __getitem__(self, i):
         return self._matbias_list[i]

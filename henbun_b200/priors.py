@@ -1,95 +1,118 @@
-"""Priors, mirror of Henbun/priors.py.  ``Normal`` (:44-52) is the one on the hot path (its log-density
-is folded into the sampler kernel's KL reduction for variationals.Normal); the rest (:55-116) are
-elementwise variants."""
+"""Priors over (transformed) parameters -- the public surface of Henbun/priors.py (Normal :44-52, Gaussian :55-65,
+LogNormal :68-78, Gamma :81-91, Laplace :94-104, Uniform :107-116) on top of this package's density kernels.
+
+Design: a prior is (a member of the densities.py kernel family, where the random variable sits among that member's
+operands, its hyper-parameters).  ``logp`` is one elementwise kernel launch of that member plus the sum the reference
+applies (priors are univariate, so an array argument means the sum of the element log-densities); the backward is the
+member's backward kernel.  Hyper-parameters are kept as float32 host arrays (attributes named as in the reference,
+``mu``/``var``/``shape``/``scale``/``sigma``) and travel to the device once per call.
+"""
 from __future__ import annotations
 
 import numpy as np
 import torch
 
 from .param import Parameterized
-from . import densities
+from . import ops
 
 np_float_type = np.float32
+_LOG_2PI = float(np.log(2.0 * np.pi))
+
+
+def _hyper(value):
+    return np.atleast_1d(np.asarray(value, dtype=np_float_type))
 
 
 class Prior(Parameterized):
+    """Base class.  Subclasses either fill in the three class attributes below or override ``logp``.
+
+    _family : name of the densities.py member evaluated by the kernel family (ops.DENSITY_KINDS)
+    _fields : attribute names of the hyper-parameters, in the order given to ``__init__``
+    _x_slot : index of the random variable among the member's operands (hyper-parameters fill the other slots in order)
+    _tag    : prefix used by ``__str__``
+    """
+    _family = None
+    _fields = ()
+    _x_slot = 0
+    _tag = "prior"
+
+    def __init__(self, *hyper):
+        Parameterized.__init__(self)
+        if len(hyper) != len(self._fields):
+            raise TypeError("%s takes %d hyper-parameter(s)" % (type(self).__name__, len(self._fields)))
+        for name, value in zip(self._fields, hyper):
+            setattr(self, name, _hyper(value))
+
+    def _operands(self, x):
+        hyper = [torch.as_tensor(getattr(self, name), device=x.device) for name in self._fields]
+        hyper.insert(self._x_slot, x if x.dtype == torch.float32 else x.to(torch.float32))
+        return hyper
+
     def logp(self, x):
-        raise NotImplementedError
+        """Sum of the element log-densities at x."""
+        if self._family is None:
+            raise NotImplementedError
+        return torch.sum(ops.density(self._family, *self._operands(x)))
 
     def __str__(self):
-        raise NotImplementedError
+        if self._family is None:
+            raise NotImplementedError
+        return self._tag + "(" + ",".join(str(getattr(self, name)) for name in self._fields) + ")"
 
 
 class Normal(Prior):
-    """Zero-mean unit-variance Gaussian prior."""
+    """Standard normal prior; this is the prior of variationals.Normal / Gaussian, whose KL never calls it because the
+    sampler kernel already reduces -1/2 sum(logdet + u^2 - z^2) (variationals.py:225-230).  Used by the generic
+    Variational._KL only."""
+
+    def __init__(self):
+        Prior.__init__(self)
 
     def logp(self, x):
-        return -0.5 * torch.sum(float(np.log(2 * np.pi)) + torch.square(x))
+        return -0.5 * (_LOG_2PI * x.numel() + torch.sum(torch.square(x)))
 
     def __str__(self):
-        return "N(" + str(0) + "," + str(1) + ")"
+        return "N(0,1)"
 
 
 class Gaussian(Prior):
+    _family, _fields, _x_slot, _tag = "gaussian", ("mu", "var"), 0, "N"
+
     def __init__(self, mu, var):
-        Prior.__init__(self)
-        self.mu = np.atleast_1d(np.array(mu, np_float_type))
-        self.var = np.atleast_1d(np.array(var, np_float_type))
-
-    def logp(self, x):
-        return torch.sum(densities.gaussian(x, self.mu, self.var))
-
-    def __str__(self):
-        return "N(" + str(self.mu) + "," + str(self.var) + ")"
+        Prior.__init__(self, mu, var)
 
 
 class LogNormal(Prior):
+    _family, _fields, _x_slot, _tag = "lognormal", ("mu", "var"), 0, "logN"
+
     def __init__(self, mu, var):
-        Prior.__init__(self)
-        self.mu = np.atleast_1d(np.array(mu, np_float_type))
-        self.var = np.atleast_1d(np.array(var, np_float_type))
-
-    def logp(self, x):
-        return torch.sum(densities.lognormal(x, self.mu, self.var))
-
-    def __str__(self):
-        return "logN(" + str(self.mu) + "," + str(self.var) + ")"
+        Prior.__init__(self, mu, var)
 
 
 class Gamma(Prior):
+    _family, _fields, _x_slot, _tag = "gamma", ("shape", "scale"), 2, "Ga"
+
     def __init__(self, shape, scale):
-        Prior.__init__(self)
-        self.shape = np.atleast_1d(np.array(shape, np_float_type))
-        self.scale = np.atleast_1d(np.array(scale, np_float_type))
-
-    def logp(self, x):
-        return torch.sum(densities.gamma(self.shape, self.scale, x))
-
-    def __str__(self):
-        return "Ga(" + str(self.shape) + "," + str(self.scale) + ")"
+        Prior.__init__(self, shape, scale)
 
 
 class Laplace(Prior):
+    _family, _fields, _x_slot, _tag = "laplace", ("mu", "sigma"), 2, "Lap."
+
     def __init__(self, mu, sigma):
-        Prior.__init__(self)
-        self.mu = np.atleast_1d(np.array(mu, np_float_type))
-        self.sigma = np.atleast_1d(np.array(sigma, np_float_type))
-
-    def logp(self, x):
-        return torch.sum(densities.laplace(self.mu, self.sigma, x))
-
-    def __str__(self):
-        return "Lap.(" + str(self.mu) + "," + str(self.sigma) + ")"
+        Prior.__init__(self, mu, sigma)
 
 
 class Uniform(Prior):
+    """Flat density on [lower, upper]: logp is a constant per element, no kernel involved."""
+
     def __init__(self, lower=0, upper=1):
         Prior.__init__(self)
-        self.log_height = - np.log(upper - lower)
         self.lower, self.upper = lower, upper
+        self.log_height = -float(np.log(upper - lower))
 
     def logp(self, x):
         return self.log_height * float(x.numel())
 
     def __str__(self):
-        return "U(" + str(self.lower) + "," + str(self.upper) + ")"
+        return "U(%s,%s)" % (self.lower, self.upper)
