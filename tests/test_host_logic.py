@@ -129,3 +129,43 @@ def test_no_silent_cpu_fallback():
     from henbun_b200 import _lib
     with pytest.raises(_lib.HenbunB200Error):
         _lib.ptr(torch.zeros(3))
+
+
+def test_priors_host_side():                         # priors.py:44-116 (strings, hyper-parameter storage)
+    g = hb.priors.Gaussian(0.5, [1.0, 2.0])
+    assert g.mu.dtype == np.float32 and g.mu.shape == (1,) and g.var.shape == (2,)
+    assert str(g) == "N(" + str(g.mu) + "," + str(g.var) + ")"
+    assert str(hb.priors.LogNormal(0.0, 1.0)).startswith("logN(") and str(hb.priors.Gamma(2.0, 1.5)).startswith("Ga(")
+    assert str(hb.priors.Laplace(0.0, 1.0)).startswith("Lap.(") and str(hb.priors.Normal()) == "N(0,1)"
+    u = hb.priors.Uniform(1.0, 3.0)
+    assert str(u) == "U(1.0,3.0)" and np.isclose(u.log_height, -np.log(2.0))
+    assert np.isclose(u.logp(torch.zeros(5, 2)), 10 * -np.log(2.0))                  # constant: no kernel involved
+    with pytest.raises(NotImplementedError):
+        hb.priors.Prior().logp(torch.zeros(1))
+    with pytest.raises(TypeError):
+        hb.priors.Gaussian.__mro__[1].__init__(hb.priors.Gaussian.__new__(hb.priors.Gaussian), 1.0)   # wrong hyper count
+
+
+def test_neural_net_structure():                     # nn.py:34-87, test_nn.py shapes
+    net = hb.nn.NeuralNet([6, 5, 4, 3], n_layers=[2], stddev=0.3)
+    assert [net[i].w.shape for i in range(3)] == [[6, 5], [5, 4], [4, 3]]
+    assert [net[i].b.shape for i in range(3)] == [[1, 5], [1, 4], [1, 3]]
+    assert net.matbias1 is net[1] and len(net.neuron_types) == 2
+    assert net[0].w._host.shape == (2, 6, 5)                                         # [*n_layers, in, out]
+    names = [v.long_name for v in net.get_variables()]
+    assert names == sorted(names) and len(names) == 6
+    with pytest.raises(AssertionError):
+        hb.nn.MatBias([3, 4, 5])
+    mixed = hb.nn.NeuralNet([3, 3, 3, 2], neuron_types=[hb.nn.tanh, hb.nn.relu])
+    assert mixed.neuron_types == [hb.nn.tanh, hb.nn.relu]
+
+
+def test_bench_cpu_extrapolation_rule():
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    assert bench.extrapolation_factor(4096, 4096, 64) == 1.0
+    f = bench.extrapolation_factor(65536, 16384, 64)
+    assert 16.0 < f < 64.0 and abs(f - 62.9) < 0.1                                   # cubic term dominates at S = 64
+    assert bench.extrapolation_factor(65536, 16384, 512) < f                          # more samples -> larger quadratic share
+    assert bench.host_threads() >= 1
