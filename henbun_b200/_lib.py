@@ -49,6 +49,7 @@ SIGNATURES = {
     "hb_phase_begin": (_i, []),
     "hb_phase_end": (_i, [C.POINTER(C.c_double), _i]),
     "hb_randn_philox": (_i, [_c_f, _ll, _ull, _ull, _c_f]),
+    "hb_philox4x32_10": (_i, [_c_f, _ll, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _c_f]),
     "hb_sample_diag_fwd": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _c_f, _ull, _ull, _i, _c_f, _c_f, _c_f, _sz, _c_f]),
     "hb_sample_diag_bwd": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _c_f, _ull, _ull, _i, _c_f, _c_f, _fl, _c_f, _c_f, _ll,
                                 _c_f, _ll, _fl, _c_f]),

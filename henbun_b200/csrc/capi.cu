@@ -12,9 +12,7 @@ static int g_engine = 0;
 void set_gemm_engine(int mode) { g_engine = mode; }
 int get_gemm_engine() { return g_engine; }
 
-int gemm_tc(const GemmParams& p, cudaStream_t stream);   // gemm_tc.cu  (generation 1: operand-preparation pass + workspace)
-bool gemm_tc_eligible(const GemmParams& p);
-int gemm_tc2(const GemmParams& p, cudaStream_t stream);  // gemm_tc2.cu (generation 2: in-kernel split, no workspace)
+int gemm_tc2(const GemmParams& p, cudaStream_t stream);  // gemm_tc2.cu (in-kernel hi/lo split, no workspace)
 bool gemm_tc2_eligible(const GemmParams& p);
 bool gemm_tc2_uses_pair(const GemmParams& p);
 int get_tc_option();
@@ -32,9 +30,7 @@ static bool prefer_small(const GemmParams& p) {
   return !(tiles >= 24 && gemm_tc2_eligible(p) && tc_worth(p));
 }
 static int tc_run(const GemmParams& p, cudaStream_t st, bool force) {
-  const bool v1 = (get_tc_option() & 2) != 0;
-  if (!v1 && gemm_tc2_eligible(p) && (force || tc_worth(p))) return gemm_tc2(p, st);
-  if (gemm_tc_eligible(p)) return gemm_tc(p, st);
+  if (gemm_tc2_eligible(p) && (force || tc_worth(p))) return gemm_tc2(p, st);
   return -1;
 }
 
@@ -87,8 +83,8 @@ int gemm(const GemmParams& p, cudaStream_t st) {
   const size_t i = g_prof.used++;
   g_prof.flops[i] = gemm_useful_flops(p);
   g_prof.shape[4 * i] = p.M; g_prof.shape[4 * i + 1] = p.N; g_prof.shape[4 * i + 2] = p.K;
-  g_prof.shape[4 * i + 3] = p.force_simt ? 0 : (g_engine == 2 || (g_engine == 0 && !prefer_small(p) && ((gemm_tc2_eligible(p) && tc_worth(p)) || gemm_tc_eligible(p)))) ? 1 : 0;
-  if (g_prof.shape[4 * i + 3] && !(get_tc_option() & 2) && gemm_tc2_eligible(p) && gemm_tc2_uses_pair(p)) g_prof.shape[4 * i + 3] = 2;
+  g_prof.shape[4 * i + 3] = p.force_simt ? 0 : (g_engine == 2 || (g_engine == 0 && !prefer_small(p) && (gemm_tc2_eligible(p) && tc_worth(p)))) ? 1 : 0;
+  if (g_prof.shape[4 * i + 3] && gemm_tc2_eligible(p) && gemm_tc2_uses_pair(p)) g_prof.shape[4 * i + 3] = 2;
   cudaEventRecord(g_prof.ev0[i], st);
   const int rc = gemm_dispatch(p, st);
   cudaEventRecord(g_prof.ev1[i], st);
@@ -267,6 +263,11 @@ int hb_randn_philox(float* out, long long count, unsigned long long seed, unsign
   return randn_philox(out, count, seed, offset, S(stream));
 }
 
+int hb_philox4x32_10(unsigned int* out, long long n_blocks, const unsigned int* ctr4_host, const unsigned int* key2_host,
+                     void* stream) {
+  return philox_raw(out, n_blocks, ctr4_host, key2_host, S(stream));
+}
+
 int hb_sample_diag_fwd(const float* mu, long long ld_mu, const float* omega, long long ld_omega, int rows, int cols,
                        const float* eps, unsigned long long seed, unsigned long long offset, int Sn, float* z,
                        float* kl_out, void* ws, size_t ws_bytes, void* stream) {
@@ -436,7 +437,7 @@ int hb_gemm_ws(const float* A, long long lda, long long strideA, int transA, int
   return gemm(g, S(stream));
 }
 
-size_t hb_gemm_tc_workspace_bytes(int M, int N, int K) { return gemm_tc_workspace_bytes(M, N, K); }
+size_t hb_gemm_tc_workspace_bytes(int, int, int) { return 0; }   // the engine consumes operands in place
 int hb_set_tc_option(int v) { set_tc_option(v); return HB_OK; }
 int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int c_tri, int M,
                   int N, int K, float alpha, float beta, void* ws, size_t ws_bytes, void* stream) {

@@ -72,14 +72,19 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
   c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
 }
 
-__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t ctr, uint32_t (&out)[4]) {
-  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+// Philox-4x32-10 of Salmon et al. (Random123): 128-bit counter c, 64-bit key (k0, k1); c is replaced by the output.
+__device__ __forceinline__ void philox4x32_10_core(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     philox_round(c, k0, k1);
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
+}
+
+// The library's streams use counter = (ctr, 0, 0) and key = seed.
+__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t ctr, uint32_t (&out)[4]) {
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+  philox4x32_10_core(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
 

@@ -259,6 +259,23 @@ int fill_f32(float* a, long long n, float v, cudaStream_t st) {
   HB_CHECK_LAUNCH();
   return HB_OK;
 }
+// Raw Philox-4x32-10 blocks (known-answer tests): block b = core(counter = ctr4 + b on the low 64 bits, key).
+__global__ void philox_raw_kernel(uint32_t* out, long long n_blocks, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                  uint32_t k0, uint32_t k1) {
+  for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < n_blocks; b += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long lo = (((unsigned long long)c1 << 32) | c0) + (unsigned long long)b;
+    uint32_t c[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), c2, c3};
+    philox4x32_10_core(c, k0, k1);
+    out[4 * b] = c[0]; out[4 * b + 1] = c[1]; out[4 * b + 2] = c[2]; out[4 * b + 3] = c[3];
+  }
+}
+int philox_raw(uint32_t* out, long long n_blocks, const uint32_t* ctr4, const uint32_t* key2, cudaStream_t st) {
+  if (n_blocks <= 0) return HB_OK;
+  if (!out || !ctr4 || !key2) return HB_ERR_ARG;
+  philox_raw_kernel<<<grid_for(n_blocks, 256), 256, 0, st>>>(out, n_blocks, ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1]);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
 int randn_philox(float* out, long long count, unsigned long long seed, unsigned long long offset, cudaStream_t st) {
   if (count <= 0) return HB_OK;
   if (!out || (offset & 3ull)) return HB_ERR_ARG;

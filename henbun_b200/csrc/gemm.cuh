@@ -41,8 +41,8 @@ int gemm(const GemmParams& p, cudaStream_t stream);
 int gemm_simt(const GemmParams& p, cudaStream_t stream);
 int gemm_small(const GemmParams& p, cudaStream_t stream);      // K <= 256, whole-K staging (latency-oriented); C may alias A if N <= 128
 bool gemm_small_eligible(const GemmParams& p);
-size_t gemm_tc_workspace_bytes(int M, int N, int K);
-void set_tc_option(int v);   // bit0: gen-1 explicit hi copies | bit1: use generation 1 | bit2: no CTA pairs in generation 2 | bit3: three TF32 passes instead of TF32 + bf16 cross terms
+void set_tc_option(int v);   // bit2: no CTA pairs | bit3: three TF32 passes instead of TF32 + bf16 cross terms
+int get_tc_option();
 void set_gemm_engine(int mode);
 int get_gemm_engine();
 

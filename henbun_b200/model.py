@@ -94,12 +94,14 @@ class Model(Parameterized):
         self._new_run(self._run_ctx)
         return out
 
-    def _begin_run(self, n_samples=1, eps=None, seed=None):
+    def _begin_run(self, n_samples=1, eps=None, seed=None, shard=None):
         ctx = self._run_ctx
         ctx.n_samples = int(n_samples)
         ctx.eps = eps or {}
         if seed is not None:
             ctx.seed = int(seed)
+        # (first sample of this rank, samples over all ranks): ranks read disjoint windows of one Philox stream
+        ctx.first_sample, ctx.total_samples = shard if shard is not None else (0, int(n_samples))
         self._new_run(ctx)
 
     def validate(self):
@@ -178,13 +180,22 @@ class Optimizer(object):
 
     # ---- compile: bind parameters to flat buffers, create Adam slots ----
     def compile(self, optimizer=None, collection=graph_key.VARIABLES, global_step=None, n_samples=1, seed=0,
-                verbose=True):
+                verbose=True, shard=None, fused=True):
+        """``shard`` (multi-GPU, one process per GPU): 'samples' splits the n_samples draws over the ranks
+        (contiguous windows of ONE Philox stream, so the union over ranks is the single-GPU draw), 'batch' keeps
+        n_samples per rank and splits the minibatch (each rank draws its own indices and its own Philox window).
+        Default: 'batch' when the model holds MinibatchData, else 'samples'.  ``fused=True`` lets compile bind a
+        recognised objective to one of the fused C entry points (henbun_b200/fused.py)."""
         if verbose:
             print('compiling...')
         m = self.model
         self.optimizer = optimizer if optimizer is not None else _default_adam
         self.n_samples = int(n_samples)
         self.global_step = global_step
+        self._seed = int(seed)
+        self._shard_mode = shard
+        self._want_fused = bool(fused)
+        self._fused = None
         m.initialize()
         variables = [v for v in m.get_variables(collection) if isinstance(v, Variable) and v.is_parameter]
         # de-duplicate while keeping the reference's name-sorted order (param.py:467-475)
@@ -199,8 +210,8 @@ class Optimizer(object):
         total = int(offs[-1])
         self._flat = torch.zeros(max(total, 4), device=dev)
         self._flat_grad = torch.zeros(max(total, 4), device=dev)
-        for v, o, s in zip(var_list, offs[:-1], sizes):
-            v._rebind(self._flat[o:o + s], self._flat_grad[o:o + s])
+        self._slices = [(int(o), int(s)) for o, s in zip(offs[:-1], sizes)]
+        self._bind_all()
         # Adam slots are (re)created at every compile, parameter values are kept (test_model.py:61-74)
         self._m = torch.zeros_like(self._flat)
         self._v = torch.zeros_like(self._flat)
@@ -214,6 +225,33 @@ class Optimizer(object):
         self._evaluate(self.feed_dict(None) if self._no_minibatch() else None, dry=True)
         if verbose:
             print('finished.')
+
+    def _bind_all(self):
+        for v, (o, s) in zip(self.var_list, self._slices):
+            v._rebind(self._flat[o:o + s], self._flat_grad[o:o + s])
+
+    def _ensure_bound(self):
+        """Another Optimizer compiled over some of the same variables re-binds them to ITS flat buffers (TF minimize
+        ops share tf.Variables: testing/test_gp.py compiles likelihood_ana then likelihood_var).  Take the
+        variables back -- current values are copied into this optimizer's buffer, Adam slots are kept."""
+        for v, (o, s) in zip(self.var_list, self._slices):
+            t = v._tensor
+            if t is None or t.data_ptr() != self._flat.data_ptr() + 4 * o or t.grad is None or \
+                    t.grad.data_ptr() != self._flat_grad.data_ptr() + 4 * o:
+                v._rebind(self._flat[o:o + s], self._flat_grad[o:o + s])
+
+    def _shard(self):
+        """(first_sample, local_count, total_count, world) of this rank for the compiled n_samples."""
+        from . import parallel
+        world, rank = parallel.world()
+        S = self.n_samples
+        if world == 1:
+            return 0, S, S, 1
+        mode = self._shard_mode or ('samples' if self._no_minibatch() else 'batch')
+        if mode == 'samples' and S % world == 0:
+            first, count = parallel.shard_samples(S, world, rank)
+            return first, count, S, world
+        return rank * S, S, S * world, world        # every rank draws S samples of its own window
 
     def _no_minibatch(self):
         return not any(isinstance(d, MinibatchData) for d in self.model.get_variables(graph_key.DATA))
@@ -231,14 +269,16 @@ class Optimizer(object):
         if feed_dict is None and dry:
             return None
         m._feed(feed_dict or {})
+        self._ensure_bound()
+        first, count, total, _ = self._shard()
         with settings.temp_settings(self._compiled_settings):
-            m._begin_run(self.n_samples, eps)
+            m._begin_run(count, eps, shard=(first, total))
             with torch.set_grad_enabled(grad):
                 with m.tf_mode():
                     obj = self.likelihood_method(m)
         if not isinstance(obj, torch.Tensor):
             obj = torch.as_tensor(obj, dtype=torch.float32, device=_device())
-        return obj.reshape(()) / float(self.n_samples)
+        return obj.reshape(()) / float(count)
 
     def run(self, minibatch_size=None, training=True, eps=None):
         """Objective value with the current parameters (mean over the compiled n_samples)."""
@@ -274,6 +314,11 @@ class Optimizer(object):
         self._require_compiled()
         iteration = 0
         last = None
+        if minibatch_size is not None:
+            # batch-sharded multi-GPU run: each rank draws minibatch_size / world rows of its own
+            world = self._shard()[3]
+            if world > 1 and (self._shard_mode or 'batch') == 'batch':
+                minibatch_size = max(1, int(minibatch_size) // world)
         while iteration < maxiter:
             try:
                 last = self._step_once(self.feed_dict(minibatch_size), eps=eps)
@@ -282,5 +327,8 @@ class Optimizer(object):
                     ops.check_numerics()
             except KeyboardInterrupt:
                 raise KeyboardInterrupt
+        # a failed factorisation must not go unnoticed whatever maxiter is (tf.cholesky raises immediately upstream):
+        # one flag read per optimize() call
+        ops.check_numerics()
         self.last_objective = last
         return last

@@ -224,6 +224,35 @@ def check_numerics(device=None):
             raise FloatingPointError(f"Cholesky decomposition was not successful: non-positive pivot at row {v - 1}")
 
 
+_INPLACE_BYTES = 256 << 20
+
+
+def _own_grad(g):
+    """Buffer the in-place reverse-mode factorisation may overwrite.  Small gradients are cloned; from 256 MB on
+    the incoming gradient itself is used (it is the fresh output of the consumer's backward -- a second n x n copy
+    costs 17 GB at N = 65536)."""
+    g = g if g.is_contiguous() else g.contiguous()
+    if g.numel() * 4 < _INPLACE_BYTES or g._base is not None:
+        return g.clone()
+    return g
+
+
+def _mirror_lower_(G):
+    """G <- tril(G) + tril(G, -1)^T block by block (bounded temporaries)."""
+    n = G.shape[-1]
+    step = 4096
+    for i0 in range(0, n, step):
+        i1 = min(n, i0 + step)
+        for j0 in range(0, i0 + 1, step):
+            j1 = min(n, j0 + step)
+            if j0 == i0:
+                blk = G[..., i0:i1, j0:j1]
+                blk.copy_(blk.tril() + blk.tril(-1).transpose(-1, -2))
+            else:
+                G[..., j0:j1, i0:i1].copy_(G[..., i0:i1, j0:j1].transpose(-1, -2))
+    return G
+
+
 class _Cholesky(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A):
@@ -242,12 +271,14 @@ class _Cholesky(torch.autograd.Function):
         (Lw,) = ctx.saved_tensors
         n = Lw.shape[-1]
         batch = int(Lw.numel() // (n * n)) if n else 0
-        G = g.contiguous().clone()
+        G = _own_grad(g)
         ws, nb = _potrf_ws(n, Lw.device)
         check(_L().hb_potrf_lower_bwd(ptr(Lw), n, n * n, ptr(G), n, n * n, n, batch, ptr(ws), nb, stream()),
               "hb_potrf_lower_bwd")
-        Gl = torch.tril(G)
-        return Gl + torch.tril(G, -1).transpose(-1, -2)       # full symmetric gradient, like TF
+        # full symmetric gradient, like TF: mirror the lower triangle in place (no n x n temporaries)
+        G.tril_()
+        G.add_(G.transpose(-1, -2).triu(1)) if G.numel() * 4 < _INPLACE_BYTES else _mirror_lower_(G)
+        return G
 
 
 def cholesky(A):
@@ -265,6 +296,14 @@ def _kern_shapes(X, X2):
     return batch, n, n2, D
 
 
+def _check_grad_dims(ctx, D):
+    """The Gram backward kernels hold one input row in registers (D <= 32); say so at forward time instead of
+    failing in backward with a bare 'invalid argument'."""
+    if D > 32 and any(ctx.needs_input_grad):
+        raise ValueError(f"stationary kernels with more than 32 input dimensions (got {D}) can be evaluated but not "
+                         "differentiated by this library")
+
+
 class _RbfK(torch.autograd.Function):
     """UnitRBF.K / UnitCsymRBF.K (gp/kernels.py:110-111,122-126)."""
 
@@ -272,6 +311,7 @@ class _RbfK(torch.autograd.Function):
     def forward(ctx, X, X2, ell, csym):
         X = _c(X); X2c = None if X2 is None else _c(X2); ell = _c(ell).reshape(-1)
         batch, n, n2, D = _kern_shapes(X, X2c)
+        _check_grad_dims(ctx, D)
         K = torch.empty((batch, n, n2) if X.dim() == 3 else (n, n2), device=X.device)
         check(_L().hb_rbf_gram_fwd(ptr(X), ptr(X2c), n, n2, D, batch, ptr(ell), ell.numel(), ptr(K), n2, n * n2, 0.0,
                                    0, int(csym), stream()), "hb_rbf_gram_fwd")
@@ -326,6 +366,7 @@ class _KernCholesky(torch.autograd.Function):
     def forward(ctx, X, ell, jitter, csym):
         X = _c(X); ell = _c(ell).reshape(-1)
         batch, n, _, D = _kern_shapes(X, None)
+        _check_grad_dims(ctx, D)
         Lw = torch.empty((batch, n, n) if X.dim() == 3 else (n, n), device=X.device)
         lib = _L()
         check(lib.hb_rbf_gram_fwd(ptr(X), None, n, n, D, batch, ptr(ell), ell.numel(), ptr(Lw), n, n * n, float(jitter),
@@ -343,15 +384,17 @@ class _KernCholesky(torch.autograd.Function):
         if ctx.needs_input_grad[0] and ctx.csym:
             raise NotImplementedError("gradient w.r.t. the inputs of UnitCsymRBF is not implemented")
         batch, n, _, D = _kern_shapes(X, None)
-        G = g.contiguous().clone()
+        G = _own_grad(g)
         lib = _L()
         ws, nb = _potrf_ws(n, X.device)
         check(lib.hb_potrf_lower_bwd(ptr(Lw), n, n * n, ptr(G), n, n * n, n, batch, ptr(ws), nb, stream()),
               "hb_potrf_lower_bwd")
-        rws = reduce_ws(X.device)
-        gl = torch.empty(ell.numel(), device=X.device)
-        check(lib.hb_rbf_gram_bwd(ptr(G), n, n * n, ptr(X), None, n, n, D, batch, ptr(ell), ell.numel(), 1, ctx.csym,
-                                  None, ptr(gl), ptr(rws), rws.numel(), stream()), "hb_rbf_gram_bwd")
+        gl = None
+        if ctx.needs_input_grad[1]:
+            rws = reduce_ws(X.device)
+            gl = torch.empty(ell.numel(), device=X.device)
+            check(lib.hb_rbf_gram_bwd(ptr(G), n, n * n, ptr(X), None, n, n, D, batch, ptr(ell), ell.numel(), 1, ctx.csym,
+                                      None, ptr(gl), ptr(rws), rws.numel(), stream()), "hb_rbf_gram_bwd")
         gX = None
         if ctx.needs_input_grad[0]:
             # K-bar is symmetric (lower triangle stored): both kernel arguments are X -> twice the second-argument part

@@ -461,15 +461,21 @@ class Data(Variable):
         t = torch.as_tensor(np.ascontiguousarray(array)).to(self._dtype)
         if self._pinned is None or self._pinned.shape != t.shape:
             self._pinned = torch.empty(t.shape, dtype=self._dtype).pin_memory()
+            self._h2d_done = None
+        if self._tensor is None or self._tensor.shape != t.shape:
             self._tensor = torch.empty(t.shape, dtype=self._dtype, device=_device())
+        if getattr(self, '_h2d_done', None) is not None:
+            self._h2d_done.synchronize()      # the previous async copy out of the staging buffer must have drained
         self._pinned.copy_(t)
         self._tensor.copy_(self._pinned, non_blocking=True)
+        self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record()
 
     def get_feed_dict(self, minibatch_index=None):
         return {self: self.data}
 
     def tensor(self):
-        if self._tensor is None:
+        if self._tensor is None or getattr(self, '_resident_src', None) is None:
             self._upload(self.data)
         return self._tensor
 
@@ -477,8 +483,7 @@ class Data(Variable):
         if not np.all(value.shape == self.data.shape):
             raise ValueError('The shape of data must be the same.')
         self.data = value
-        self._tensor = None
-        self._resident_src = None
+        self._resident_src = None          # next feed copies the new array (device buffer and staging are kept)
 
     @property
     def value(self):

@@ -32,12 +32,21 @@ class RunContext(object):
         self.seed = int(seed)
         self.offset = int(offset)
         self.eps = eps or {}
+        self.first_sample = 0                 # multi-GPU: this rank's first sample ...
+        self.total_samples = self.n_samples   # ... of the samples drawn over all ranks
 
     def take(self, count):
         """Reserve `count` Philox stream positions (rounded up to a multiple of 4)."""
         off = self.offset
         self.offset += (int(count) + 3) // 4 * 4
         return off
+
+    def take_sharded(self, per_sample):
+        """Stream position of this rank's first draw of a [n_samples, per_sample] block: the block of ALL ranks'
+        samples is reserved, this rank reads its contiguous window of it (parallel.rank_philox_offset)."""
+        total = max(int(self.total_samples), int(self.n_samples))
+        off = self.take(total * int(per_sample))
+        return off + (int(self.first_sample) * int(per_sample)) // 4 * 4
 
 
 _default_ctx = RunContext()
@@ -118,14 +127,14 @@ class Variational(Parameterized):
         lead = tuple(q_mu.shape)
         if self.q_shape == 'diagonal':
             ue = None if u is None else u.reshape((S,) + lead)
-            off = self._ctx.take(S * q_mu.numel()) if u is None else 0
+            off = self._ctx.take_sharded(q_mu.numel()) if u is None else 0
             z, kl = ops.sample_diag(q_mu, q_sqrt, ue, self._ctx.seed, off, S)
             self.u = ue
         else:
             n = self.size
             B = int(q_mu.numel() // n)
             if u is None:
-                off = self._ctx.take(B * S * n)
+                off = self._ctx.take_sharded(B * n)
                 ue = ops.randn_philox((S, B, n), self._ctx.seed, off, q_mu.device)
             else:
                 ue = u.reshape(S, B, n)

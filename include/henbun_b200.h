@@ -60,6 +60,11 @@ int hb_phase_end(double* out_ms_host, int capacity);
  * Element i of the stream (seed, offset) is identical whether it is materialised here or
  * regenerated inside hb_sample_diag_{fwd,bwd}.  offset must be a multiple of 4. */
 int hb_randn_philox(float* out, long long count, unsigned long long seed, unsigned long long offset, void* stream);
+/* The raw generator underneath (known-answer tests against the Random123 vectors): out[4b .. 4b+3] =
+ * Philox-4x32-10(counter = ctr4 + b on its low 64 bits, key = key2).  ctr4_host / key2_host are HOST arrays of 4 / 2
+ * words.  The library's own streams use counter = (offset/4 + block, 0, 0), key = seed. */
+int hb_philox4x32_10(unsigned int* out, long long n_blocks, const unsigned int* ctr4_host, const unsigned int* key2_host,
+                     void* stream);
 
 /* Variational._sample 'diagonal' (variationals.py:138-142) fused with Normal._KL (:225-230) and
  * logdet (:183-184).  mu/omega: [rows, cols] with row strides (LOCAL variationals read the two halves

@@ -18,23 +18,7 @@ import torch
 from . import henbun_oracle as O
 
 
-def make_gp_problem(n, D, S, seed=0, dtype=np.float32):
-    """Synthetic config-3 inputs: X~N(0,I_D), Y=sin(sum x/sqrt(D))+0.1 eps,
-    UnitRBF lengthscale 0.5, Gaussian([n,1],'diagonal') with mu~0.1 randn, omega=-1, k_var=var=1.
-    Lengthscale 0.5 instead of SURVEY's 1.0: at N=65536, D=8, ell=1 the Gram matrix has
-    lambda_max ~ N/81 ~ 800 and a numerically zero lambda_min, so K + 1e-5 I is not positive definite
-    in fp32 (cond ~ 8e7 > 2^24) -- the reference's own fp32 tf.cholesky would raise
-    InvalidArgumentError there (our kernel reports the failing pivot through err_flag).  ell=0.5
-    keeps the full-size problem well posed in the reference's default float_type (henbunrc:7)."""
-    rng = np.random.RandomState(seed)
-    X = rng.randn(n, D).astype(dtype)
-    Y = (np.sin(X.sum(1) / math.sqrt(D)) + 0.1 * rng.randn(n)).astype(dtype)
-    one = float(O.log1pe_backward(1.0))
-    half = float(O.log1pe_backward(0.5))
-    p = dict(q_mu=(0.1 * rng.randn(n)).astype(dtype), q_sqrt=np.full(n, -1.0, dtype),
-             scale=np.array([one], dtype), lengthscales=np.array([half], dtype),
-             k_var=np.array([one], dtype), var=np.array([one], dtype))
-    return X, Y, p
+from henbun_b200.synthetic import make_gp_problem   # noqa: F401  (the generator lives with the product; re-exported)
 
 
 def time_gpr_steps(n, D, S, steps=2, warmup=1, threads=None, seed=0):

@@ -270,14 +270,14 @@ def csym_rbf_K(X, lengthscales, X2=None):
 
 def Kdiag(X):
     """UnitStationary.Kdiag (gp/kernels.py:90-91)."""
-    return torch.ones(X.shape[:-1], dtype=X.dtype)
+    return torch.ones(X.shape[:-1], dtype=X.dtype, device=X.device)
 
 
 def kern_cholesky(X, lengthscales, jitter=1e-5, K_fn=rbf_K):
     """UnitStationary.Cholesky (gp/kernels.py:93-101) + tf_wraps.eye (tf_wraps.py:26-30)."""
     n = X.shape[-2]
     K = K_fn(X, lengthscales)
-    return torch.linalg.cholesky(K + jitter * torch.eye(n, dtype=X.dtype))
+    return torch.linalg.cholesky(K + jitter * torch.eye(n, dtype=X.dtype, device=X.device))
 
 
 def gp_samples(L, u):
@@ -563,13 +563,21 @@ def linear_operator_elbo(p, A, y, U):
     return (ll - kl) / U.shape[0]
 
 
-def value_and_grads(fn, p: Dict[str, np.ndarray], *args, dtype=torch.float64, **kw):
-    """Evaluate fn(p, ...) and d fn / d p by torch autograd on the CPU."""
-    tp = {k: torch.tensor(np.asarray(v), dtype=dtype, requires_grad=True) for k, v in p.items()}
-    targs = [(_t(a, dtype) if isinstance(a, (np.ndarray, torch.Tensor)) else
-              ({k: _t(v, dtype) for k, v in a.items()} if isinstance(a, dict) else a)) for a in args]
+def value_and_grads(fn, p: Dict[str, np.ndarray], *args, dtype=torch.float64, device="cpu", **kw):
+    """Evaluate fn(p, ...) and d fn / d p by torch autograd (fp64).  device="cuda" runs the SAME restatement through
+    torch's fp64 library kernels on the GPU -- used by the parity tests at the named sizes (N >= 16384), where the CPU
+    would need minutes; it is still only the checker."""
+    tp = {k: torch.tensor(np.asarray(v), dtype=dtype, device=device, requires_grad=True) for k, v in p.items()}
+
+    def conv(a):
+        if isinstance(a, (np.ndarray, torch.Tensor)):
+            return _t(a, dtype).to(device)
+        if isinstance(a, dict):
+            return {k: _t(v, dtype).to(device) for k, v in a.items()}
+        return a
+    targs = [conv(a) for a in args]
     val = fn(tp, *targs, **kw)
     val.backward()
-    grads = {k: (v.grad.numpy().copy() if v.grad is not None else np.zeros_like(np.asarray(p[k], dtype=np.float64)))
-             for k, v in tp.items()}
+    grads = {k: (v.grad.detach().cpu().numpy().copy() if v.grad is not None else
+                 np.zeros_like(np.asarray(p[k], dtype=np.float64))) for k, v in tp.items()}
     return float(val.detach()), grads

@@ -169,3 +169,24 @@ def test_bench_cpu_extrapolation_rule():
     assert 16.0 < f < 64.0 and abs(f - 62.9) < 0.1                                   # cubic term dominates at S = 64
     assert bench.extrapolation_factor(65536, 16384, 512) < f                          # more samples -> larger quadratic share
     assert bench.host_threads() >= 1
+
+
+def test_philox4x32_10_published_algorithm_reproduces_the_kat_vectors():
+    """Independent restatement of Philox-4x32-10 (Salmon et al. 2011: multipliers 0xD2511F53 / 0xCD9E8D57, Weyl key
+    increments 0x9E3779B9 / 0xBB67AE85) against the three Random123 known-answer vectors that the GPU test
+    (tests/test_gpu_parity_named.py) pins the device generator to."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+
+    def philox(c, k):
+        c = list(c); k = list(k)
+        for _ in range(10):
+            p0 = M0 * c[0]; p1 = M1 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xffffffff, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xffffffff]
+            k = [(k[0] + W0) & 0xffffffff, (k[1] + W1) & 0xffffffff]
+        return tuple(c)
+    kat = [((0,) * 4, (0,) * 2, (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for c, k, want in kat:
+        assert philox(c, k) == want
