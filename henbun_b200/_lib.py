@@ -84,6 +84,8 @@ SIGNATURES = {
     "hb_gemm_tc_workspace_bytes": (_sz, [_i, _i, _i]),
     "hb_set_tc_option": (_i, [_i]),
     "hb_gemm_tn_tc": (_i, [_c_f, _ll, _c_f, _ll, _c_f, _ll, _i, _i, _i, _i, _fl, _fl, _c_f, _sz, _c_f]),
+    "hb_gemm_presplit_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "hb_gemm_presplit": (_i, [_c_f, _ll, _i, _c_f, _ll, _i, _c_f, _ll, _i, _i, _i, _i, _fl, _fl, _i, _i, _i, _c_f, _sz, _c_f]),
     "hb_act_bwd_colsum_workspace_bytes": (_sz, [_i, _i]),
     "hb_act_bwd_colsum_ws": (_i, [_c_f, _c_f, _c_f, _i, _i, _ll, _i, _i, _fl, _fl, _c_f, _c_f, _sz, _c_f]),
     "hb_act_bwd_colsum": (_i, [_c_f, _c_f, _c_f, _i, _i, _ll, _i, _i, _fl, _fl, _c_f, _c_f]),

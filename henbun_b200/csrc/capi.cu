@@ -2,6 +2,7 @@
 #include "../../include/henbun_b200.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "gemm_h2.cuh"
 #include <vector>
 #include <cstdio>
 #include <cstdlib>
@@ -446,6 +447,70 @@ int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, 
   g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.ws = ws; g.ws_bytes = ws_bytes;
   const int rc = tc_run(g, S(stream), true);   // bypasses the size heuristic: always a tensor-core engine
   return rc < 0 ? HB_ERR_ARG : rc;
+}
+
+// ---- pre-split fp16 hi/lo engine (gemm_h2.cu), standalone: split both operands, then multiply --------------------
+static size_t h2_probe_layout(int M, int N, int K, int transA, int transB, size_t off[6]) {
+  const long long ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
+  const long long lda = (ca + 63) / 64 * 64, ldb = (cb + 63) / 64 * 64;
+  size_t o = 0;
+  off[0] = o; o += align_up((size_t)ra * lda * 2);
+  off[1] = o; o += align_up((size_t)ra * lda * 2);
+  off[2] = o; o += align_up((size_t)rb * ldb * 2);
+  off[3] = o; o += align_up((size_t)rb * ldb * 2);
+  off[4] = o; o += align_up((size_t)(2 * ((ca + 127) / 128) + 16) * sizeof(float));   // max bits | inverse scales of A's column blocks
+  off[5] = o; o += align_up(16 * sizeof(float));                                       // B: max bits, {s, 1/s}
+  return o + 256;
+}
+size_t hb_gemm_presplit_workspace_bytes(int M, int N, int K, int transA, int transB) {
+  size_t off[6];
+  return h2_probe_layout(M, N, K, transA, transB, off);
+}
+int hb_gemm_presplit(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                     long long ldc, int c_tri, int M, int N, int K, float alpha, float beta, int a_bmode, int a_blockscale,
+                     int skip_split, void* ws, size_t ws_bytes, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return HB_OK;
+  if (!A || !B || !C) return HB_ERR_ARG;
+  size_t off[6];
+  if (!ws || ws_bytes < h2_probe_layout(M, N, K, transA, transB, off)) return HB_ERR_WORKSPACE;
+  cudaStream_t st = S(stream);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  const long long ra = transA ? K : M, ca = transA ? M : K, rb = transB ? N : K, cb = transB ? K : N;
+  const long long ldah = (ca + 63) / 64 * 64, ldbh = (cb + 63) / 64 * 64;
+  __half* ah = reinterpret_cast<__half*>(base + off[0]); __half* al = reinterpret_cast<__half*>(base + off[1]);
+  __half* bh = reinterpret_cast<__half*>(base + off[2]); __half* bl = reinterpret_cast<__half*>(base + off[3]);
+  const int nblk = (int)((ca + 127) / 128);
+  unsigned* amax = reinterpret_cast<unsigned*>(base + off[4]);
+  float* ainv = reinterpret_cast<float*>(base + off[4]) + nblk + 8;
+  unsigned* bmax = reinterpret_cast<unsigned*>(base + off[5]);
+  float* bsc = reinterpret_cast<float*>(base + off[5]) + 4;
+  if (!skip_split) {
+    if (cudaMemsetAsync(base + off[4], 0, (size_t)(nblk + 8) * 4, st) != cudaSuccess) return HB_ERR_CUDA;
+    if (cudaMemsetAsync(base + off[5], 0, 16, st) != cudaSuccess) return HB_ERR_CUDA;
+    if (a_blockscale) {       // one scale per 128-column block of the stored A
+      if (ca % 128) return HB_ERR_ARG;
+      for (int b = 0; b < nblk; ++b) {
+        HB_TRY(h2_absmax(A + 128 * b, lda, ra, 128, 0, 0, amax + b, st));
+        HB_TRY(h2_split(A + 128 * b, lda, ra, 128, nullptr, amax + b, ainv + b, 0, 0, ah + 128 * b, al + 128 * b, ldah, st));
+      }
+    } else {
+      if (ca % 8) return HB_ERR_ARG;
+      HB_TRY(h2_absmax(A, lda, ra, (int)ca, 0, 0, amax, st));
+      HB_TRY(h2_split(A, lda, ra, (int)ca, nullptr, amax, ainv, 0, 0, ah, al, ldah, st));
+    }
+    if (cb % 8) return HB_ERR_ARG;
+    HB_TRY(h2_absmax(B, ldb, rb, (int)cb, 0, 0, bmax, st));
+    HB_TRY(h2_scale_from_max(bmax, 0, bsc, st));
+    HB_TRY(h2_split(B, ldb, rb, (int)cb, bsc, nullptr, nullptr, 0, 0, bh, bl, ldbh, st));
+  }
+  H2Gemm g;
+  g.a_hi = ah; g.a_lo = al; g.lda = ldah; g.a_kmajor = transA ? 0 : 1;
+  g.b_hi = bh; g.b_lo = bl; g.ldb = ldbh; g.b_kmajor = transB ? 1 : 0;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.c_tri = c_tri; g.a_bmode = a_bmode;
+  if (a_blockscale) { if (transA) g.a_minv = ainv; else g.a_kinv = ainv; }
+  else g.a_inv = ainv;
+  g.b_inv = bsc + 1;
+  return gemm_h2(g, st);
 }
 
 size_t hb_act_bwd_colsum_workspace_bytes(int rows, int cols) { return act_bwd_colsum_workspace_bytes(rows, cols); }

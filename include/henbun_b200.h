@@ -228,6 +228,17 @@ size_t hb_gemm_tc_workspace_bytes(int M, int N, int K);
 int hb_set_tc_option(int v);
 int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int c_tri, int M,
                   int N, int K, float alpha, float beta, void* ws, size_t ws_bytes, void* stream);
+/* The engine behind the big products of hb_potrf_lower / hb_potrf_lower_bwd at n >= 4096 (csrc/gemm_h2.cu), standalone:
+ * both fp32 operands are split once into fp16 hi/lo pairs scaled by a power of two taken from their absolute maximum
+ * (22 mantissa bits; a_blockscale = 1: one scale per 128-column block of the stored A), then multiplied by three
+ * kind::f16 tcgen05 MMAs per k-step with two-level fp32 accumulation.  C = alpha op(A) op(B) + beta C, layouts as
+ * hb_gemm (transA = 0: A stored [M, K]; transB = 0: B stored [K, N]).  a_bmode (square op(A), 128-blocks): 1 keeps
+ * k-block < row-block, 2 keeps k-block > row-block.  skip_split = 1 reuses the shadows a previous call left in ws
+ * (timing the product alone).  M, N > 128; K, lda, ldb multiples of 8. */
+size_t hb_gemm_presplit_workspace_bytes(int M, int N, int K, int transA, int transB);
+int hb_gemm_presplit(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
+                     long long ldc, int c_tri, int M, int N, int K, float alpha, float beta, int a_bmode, int a_blockscale,
+                     int skip_split, void* ws, size_t ws_bytes, void* stream);
 /* Backward helper of MatBias: dz = dy * act'(y) (through the output y), dbias[c] = sum_r dz[r,c]. */
 /* Same with a scratch buffer of hb_act_bwd_colsum_workspace_bytes(rows, cols): full-grid kernel + deterministic partial
  * reduction (the scratch-free entry point uses one block per 32 columns).  Falls back to it when ws is NULL / too small. */
