@@ -458,7 +458,7 @@ static size_t h2_probe_layout(int M, int N, int K, int transA, int transB, size_
   off[1] = o; o += align_up((size_t)ra * lda * 2);
   off[2] = o; o += align_up((size_t)rb * ldb * 2);
   off[3] = o; o += align_up((size_t)rb * ldb * 2);
-  off[4] = o; o += align_up((size_t)(2 * ((ca + 127) / 128) + 16) * sizeof(float));   // max bits | inverse scales of A's column blocks
+  off[4] = o; o += align_up((size_t)(4 * ((ca + 127) / 128) + 32) * sizeof(float));   // max bits | inverse scales of A's column blocks (+ diagonal blocks)
   off[5] = o; o += align_up(16 * sizeof(float));                                       // B: max bits, {s, 1/s}
   return o + 256;
 }
@@ -481,17 +481,25 @@ int hb_gemm_presplit(const float* A, long long lda, int transA, const float* B, 
   __half* bh = reinterpret_cast<__half*>(base + off[2]); __half* bl = reinterpret_cast<__half*>(base + off[3]);
   const int nblk = (int)((ca + 127) / 128);
   unsigned* amax = reinterpret_cast<unsigned*>(base + off[4]);
-  float* ainv = reinterpret_cast<float*>(base + off[4]) + nblk + 8;
+  float* ainv = reinterpret_cast<float*>(base + off[4]) + 2 * nblk + 8;
+  unsigned* dmax = amax + nblk + 4;
+  float* dinv = ainv + nblk + 4;
   unsigned* bmax = reinterpret_cast<unsigned*>(base + off[5]);
   float* bsc = reinterpret_cast<float*>(base + off[5]) + 4;
   if (!skip_split) {
-    if (cudaMemsetAsync(base + off[4], 0, (size_t)(nblk + 8) * 4, st) != cudaSuccess) return HB_ERR_CUDA;
+    if (cudaMemsetAsync(base + off[4], 0, (size_t)(2 * nblk + 8) * 4, st) != cudaSuccess) return HB_ERR_CUDA;
     if (cudaMemsetAsync(base + off[5], 0, 16, st) != cudaSuccess) return HB_ERR_CUDA;
     if (a_blockscale) {       // one scale per 128-column block of the stored A
       if (ca % 128) return HB_ERR_ARG;
       for (int b = 0; b < nblk; ++b) {
         HB_TRY(h2_absmax(A + 128 * b, lda, ra, 128, 0, 0, amax + b, st));
         HB_TRY(h2_split(A + 128 * b, lda, ra, 128, nullptr, amax + b, ainv + b, 0, 0, ah + 128 * b, al + 128 * b, ldah, st));
+        if (a_bmode == 1 && !transA) {   // the diagonal block of a K-major square A gets its own scale (as the reverse-mode leaves do)
+          const float* D = A + (long long)128 * b * lda + 128 * b;
+          HB_TRY(h2_absmax(D, lda, 128, 128, 0, 0, dmax + b, st));
+          HB_TRY(h2_split(D, lda, 128, 128, nullptr, dmax + b, dinv + b, 0, 0, ah + (long long)128 * b * ldah + 128 * b,
+                          al + (long long)128 * b * ldah + 128 * b, ldah, st));
+        }
       }
     } else {
       if (ca % 8) return HB_ERR_ARG;
@@ -507,7 +515,7 @@ int hb_gemm_presplit(const float* A, long long lda, int transA, const float* B, 
   g.a_hi = ah; g.a_lo = al; g.lda = ldah; g.a_kmajor = transA ? 0 : 1;
   g.b_hi = bh; g.b_lo = bl; g.ldb = ldbh; g.b_kmajor = transB ? 1 : 0;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = beta; g.c_tri = c_tri; g.a_bmode = a_bmode;
-  if (a_blockscale) { if (transA) g.a_minv = ainv; else g.a_kinv = ainv; }
+  if (a_blockscale) { if (transA) g.a_minv = ainv; else { g.a_kinv = ainv; if (a_bmode == 1) g.a_dinv = dinv; } }
   else g.a_inv = ainv;
   g.b_inv = bsc + 1;
   return gemm_h2(g, st);

@@ -68,6 +68,7 @@ struct H2Params {
   int a_bmode;
   const float* a_inv;
   const float* a_kinv;
+  const float* a_dinv;
   const float* a_minv;
   const float* b_inv;
 };
@@ -103,8 +104,8 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int kb_lo = 0, kb_hi = (p.K + H_BK - 1) / H_BK;
   const int t0 = pm0 >> 7;                            // first 128-row block of the pair tile
-  if (hp.a_bmode == 1) kb_hi = min(kb_hi, H_CHS * (t0 + 1));
-  else if (hp.a_bmode == 2) kb_lo = min(kb_hi, H_CHS * (t0 + 1));
+  if (hp.a_bmode == 1) kb_hi = min(kb_hi, H_CHS * (t0 + 2));          // k-blocks <= the pair tile's second row block
+  else if (hp.a_bmode == 2) kb_lo = min(kb_hi, H_CHS * (t0 + 1));     // k-blocks > the pair tile's first row block
   const int num_k = max(kb_hi - kb_lo, 0);
   const int num_c = (num_k + H_CHS - 1) / H_CHS;
 
@@ -136,7 +137,7 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         if (rank == 0) mbar_expect_tx(full_bar(s), 2 * H_STAGE);
         const int k0 = (kb_lo + kb) * H_BK;
         const int kc = k0 >> 7;
-        const bool zeroA = (hp.a_bmode == 1 && !(kc < rb)) || (hp.a_bmode == 2 && !(kc > rb));
+        const bool zeroA = (hp.a_bmode == 1 && kc > rb) || (hp.a_bmode == 2 && !(kc > rb));
         if (AKM) {
           const int r = zeroA ? H_OOB : m0;
           tma_load_2d_pair(st, &tmAh, fb, k0, r);
@@ -203,9 +204,11 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
 #pragma unroll
     for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
     const int c_first = kb_lo / H_CHS;                 // 128-chunk index of the first chunk (kb_lo is chunk aligned)
+    const int rbk = m0 >> 7;
     for (int c = 0; c < num_c; ++c) {
       const int buf = c & 1;
-      const float cs = hp.a_kinv ? __ldg(hp.a_kinv + c_first + c) : 1.f;
+      float cs = 1.f;
+      if (hp.a_kinv) cs = __ldg(((hp.a_bmode == 1 && c_first + c == rbk) ? hp.a_dinv : hp.a_kinv) + c_first + c);
       mbar_wait(tfull_bar(buf), (uint32_t)((c >> 1) & 1));
       tc_fence_after();
 #pragma unroll
@@ -308,6 +311,14 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ A
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
 }
 
+__global__ void diag_absmax_kernel(const float* __restrict__ A, long long ld, int n, unsigned* out_bits) {
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(A[(long long)i * ld + i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+
 // power-of-two scale that brings `maxv` to [2^(H2_TARGET_EXP-1), 2^H2_TARGET_EXP]
 __device__ __forceinline__ float scale_for(float maxv) {
   if (!(maxv > 0.f) || !isfinite(maxv)) return 1.f;
@@ -398,7 +409,8 @@ int gemm_h2(const H2Gemm& g, cudaStream_t st) {
   tp.c_tri = g.c_tri; tp.a_mode = 0; tp.b_mode = 0; tp.tiles_m = 0; tp.tiles_n = 0;
   tp.vecC = aligned16(g.C) && (g.ldc % 4 == 0);
   tp.ksplit = 0; tp.csplit = 0; tp.bias = nullptr; tp.act = ACT_NONE; tp.clip = 0; tp.clip_lo = 0.f; tp.clip_hi = 0.f;
-  hp.a_bmode = g.a_bmode; hp.a_inv = g.a_inv; hp.a_kinv = g.a_kinv; hp.a_minv = g.a_minv; hp.b_inv = g.b_inv;
+  hp.a_bmode = g.a_bmode; hp.a_inv = g.a_inv; hp.a_kinv = g.a_kinv; hp.a_dinv = g.a_dinv ? g.a_dinv : g.a_kinv;
+  hp.a_minv = g.a_minv; hp.b_inv = g.b_inv;
   if (g.a_kmajor) return g.b_kmajor ? launch_h2<true, true>(m, hp, st) : launch_h2<true, false>(m, hp, st);
   return g.b_kmajor ? launch_h2<false, true>(m, hp, st) : launch_h2<false, false>(m, hp, st);
 }
@@ -408,6 +420,13 @@ int h2_absmax(const float* A, long long ld, long long rows, int cols, int lower_
   if (rows <= 0 || cols <= 0) return HB_OK;
   if ((cols & 3) || (ld & 3) || !aligned16(A)) return HB_ERR_ARG;
   absmax_kernel<<<grid_rows(rows * (cols >> 2), 256), 256, 0, st>>>(A, ld, rows, cols, lower_only, diag_off, out_bits);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+int h2_diag_absmax(const float* A, long long ld, int n, unsigned* out_bits, cudaStream_t st) {
+  if (n <= 0) return HB_OK;
+  diag_absmax_kernel<<<cdiv(n, 256) > 148 ? 148 : cdiv(n, 256), 256, 0, st>>>(A, ld, n, out_bits);
   HB_CHECK_LAUNCH();
   return HB_OK;
 }

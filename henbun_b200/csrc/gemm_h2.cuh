@@ -11,7 +11,8 @@ constexpr int H2_TARGET_EXP = 7;     // operands are scaled so that their absolu
 // hi/lo shadow pairs holding x * s (s a power of two), either K-major (stored [rows x K]) or MN-major (stored [K x rows]).
 // Inverse scales (device memory): a_inv / b_inv scalars; a_kinv[k / 128] per 128-block along K; a_minv[m / 128] per
 // 128-row block of M (each may be null = 1).
-// a_bmode (square op(A), 128-blocks): 0 all | 1 keep k-block < row-block | 2 keep k-block > row-block.
+// a_bmode (square op(A), 128-blocks): 0 all | 1 keep k-block <= row-block, the diagonal blocks carrying their own
+// inverse scales a_dinv[k / 128] (null: a_kinv) | 2 keep k-block > row-block.
 struct H2Gemm {
   const __half *a_hi = nullptr, *a_lo = nullptr; long long lda = 0; int a_kmajor = 1;
   const __half *b_hi = nullptr, *b_lo = nullptr; long long ldb = 0; int b_kmajor = 1;
@@ -19,7 +20,7 @@ struct H2Gemm {
   int M = 0, N = 0, K = 0;
   float alpha = 1.f, beta = 0.f;
   int c_tri = 0, a_bmode = 0;
-  const float *a_inv = nullptr, *a_kinv = nullptr, *a_minv = nullptr, *b_inv = nullptr;
+  const float *a_inv = nullptr, *a_kinv = nullptr, *a_dinv = nullptr, *a_minv = nullptr, *b_inv = nullptr;
 };
 bool gemm_h2_eligible(int M, int N, int K);
 int gemm_h2(const H2Gemm& g, cudaStream_t st);
@@ -27,6 +28,7 @@ int gemm_h2(const H2Gemm& g, cudaStream_t st);
 // atomicMax of |A| over a [rows x cols] block into *out_bits (bit pattern of a non-negative float; zero it first)
 int h2_absmax(const float* A, long long ld, long long rows, int cols, int lower_only, long long diag_off, unsigned* out_bits,
               cudaStream_t st);
+int h2_diag_absmax(const float* A, long long ld, int n, unsigned* out_bits, cudaStream_t st);
 // scale2 = {s, 1/s}, s the power of two that brings max (or sqrt(max)) to 2^H2_TARGET_EXP
 int h2_scale_from_max(const unsigned* max_bits, int sqrt_of_max, float* scale2, cudaStream_t st);
 // hi/lo fp16 split of A * s into the shadows (same indices, leading dimension ldh).  s = scale2[0], or derived from

@@ -233,7 +233,7 @@ int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, 
  * (22 mantissa bits; a_blockscale = 1: one scale per 128-column block of the stored A), then multiplied by three
  * kind::f16 tcgen05 MMAs per k-step with two-level fp32 accumulation.  C = alpha op(A) op(B) + beta C, layouts as
  * hb_gemm (transA = 0: A stored [M, K]; transB = 0: B stored [K, N]).  a_bmode (square op(A), 128-blocks): 1 keeps
- * k-block < row-block, 2 keeps k-block > row-block.  skip_split = 1 reuses the shadows a previous call left in ws
+ * k-block <= row-block, 2 keeps k-block > row-block.  skip_split = 1 reuses the shadows a previous call left in ws
  * (timing the product alone).  M, N > 128; K, lda, ldb multiples of 8. */
 size_t hb_gemm_presplit_workspace_bytes(int M, int N, int K, int transA, int transB);
 int hb_gemm_presplit(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,

@@ -26,7 +26,7 @@ def run(M, N, K, tA, tB, c_tri=0, bmode=0, blockscale=0, alpha=1.0, beta=0.0, wi
     opA = (A.T if tA else A).double(); opB = (B.T if tB else B).double()
     if bmode:
         rb = torch.arange(M, device="cuda") // 128; kb = torch.arange(K, device="cuda") // 128
-        keep = (kb[None, :] < rb[:, None]) if bmode == 1 else (kb[None, :] > rb[:, None])
+        keep = (kb[None, :] <= rb[:, None]) if bmode == 1 else (kb[None, :] > rb[:, None])
         opA = opA * keep
     ref = alpha * opA @ opB + beta * C0.double()
     got = C.double()
