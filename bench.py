@@ -279,7 +279,7 @@ def main():
         peak_src = "measured bf16 dense sustained (MEASURED_PEAKS.json)"
         if peak is None:
             peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained)"
-        n_gemm, gemm_ms, gemm_flop, n_pair, pair_ms, pair_flop = prof[:6]
+        n_gemm, gemm_ms, gemm_flop, n_pair, pair_ms, pair_flop, h2_ms, h2_flop = prof[:8]
         traffic = None
         try:    # DRAM bytes of one captured launch of the dominant kernel (ncu --set full, summary committed in profiles/)
             tr = {}
@@ -294,6 +294,7 @@ def main():
             traffic = None
         achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         pair_achieved = pair_flop / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0
+        h2_achieved = h2_flop / (h2_ms * 1e-3) / 1e12 if h2_ms > 0 else 0.0
         eng = lib.hb_get_gemm_engine()
         line = {
             "metric": METRIC, "value": evals * a.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
@@ -324,6 +325,10 @@ def main():
                                 "ms_per_step": pair_ms, "useful_flop_per_step": pair_flop, "achieved": pair_achieved,
                                 "frac": pair_achieved / peak if peak else None,
                                 "share_of_step": pair_ms / ms_prof if ms_prof > 0 else None},
+                "presplit_kernel": {"kernel": "gemm_h2_pair_kernel (tcgen05 cta_group::2, fp16 hi/lo shadows, 3 MMAs per k-step)",
+                                    "ms_per_step": h2_ms, "useful_flop_per_step": h2_flop, "achieved": h2_achieved,
+                                    "frac": h2_achieved / peak if peak else None,
+                                    "share_of_step": h2_ms / ms_prof if ms_prof > 0 else None},
                 "note": ("fp32 parity (1e-5) needs a split product: hi*hi in TF32 (two K=8 MMAs per 16-wide k-block) + lo*hi and hi*lo "
                          "in bf16 (one K=16 MMA each) = 4 tensor-pipe slots where a bf16 GEMM needs 1, i.e. frac <= 0.25 against the "
                          "bf16 peak for this formulation"),

@@ -72,6 +72,7 @@ SIGNATURES = {
     "hb_rbf_gram_bwd_x2": (_i, [_c_f, _ll, _ll, _c_f, _c_f, _i, _i, _i, _i, _c_f, _i, _i, _fl, _c_f, _c_f]),
     "hb_set_panel_refinement": (_i, [_i]),
     "hb_set_exact_below": (_i, [_i]),
+    "hb_set_presplit_engine": (_i, [_i]),
     "hb_potrf_workspace_bytes": (_sz, [_i]),
     "hb_potrf_lower": (_i, [_c_f, _ll, _ll, _i, _i, _i, _c_f, _sz, _c_f, _c_f]),
     "hb_potrf_lower_bwd": (_i, [_c_f, _ll, _ll, _c_f, _ll, _ll, _i, _i, _c_f, _sz, _c_f]),

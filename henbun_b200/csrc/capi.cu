@@ -78,6 +78,18 @@ static double gemm_useful_flops(const GemmParams& p) {
   return f;
 }
 
+int gemm_prof_begin(double useful_flops, int M, int N, int K, int kind, cudaStream_t st) {
+  if (!g_prof.on || g_prof.used >= g_prof.ev0.size()) return -1;
+  const size_t i = g_prof.used++;
+  g_prof.flops[i] = useful_flops;
+  g_prof.shape[4 * i] = M; g_prof.shape[4 * i + 1] = N; g_prof.shape[4 * i + 2] = K; g_prof.shape[4 * i + 3] = kind;
+  cudaEventRecord(g_prof.ev0[i], st);
+  return (int)i;
+}
+void gemm_prof_end(int slot, cudaStream_t st) {
+  if (slot >= 0) cudaEventRecord(g_prof.ev1[slot], st);
+}
+
 int gemm(const GemmParams& p, cudaStream_t st) {
   if (!g_prof.on || g_prof.used >= g_prof.ev0.size() || p.M <= 0 || p.N <= 0 || p.batch <= 0)
     return gemm_dispatch(p, st);
@@ -226,14 +238,16 @@ int hb_profile_end_ex(double* out8_host) {
   const size_t used = g_prof.used;
   const int rc = hb_profile_end(out8_host);
   if (rc != HB_OK) return rc;
-  double pn = 0.0, pms = 0.0, pfl = 0.0;
+  double pn = 0.0, pms = 0.0, pfl = 0.0, hms = 0.0, hfl = 0.0;
   for (size_t i = 0; i < used; ++i) {
-    if (g_prof.shape[4 * i + 3] != 2) continue;
+    const long long kind = g_prof.shape[4 * i + 3];
+    if (kind != 2 && kind != 3) continue;
     float t = 0.f;
     if (cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]) != cudaSuccess) return HB_ERR_CUDA;
-    pn += 1.0; pms += t; pfl += g_prof.flops[i];
+    if (kind == 2) { pn += 1.0; pms += t; pfl += g_prof.flops[i]; }
+    else { hms += t; hfl += g_prof.flops[i]; }
   }
-  out8_host[3] = pn; out8_host[4] = pms; out8_host[5] = pfl; out8_host[6] = 0.0; out8_host[7] = 0.0;
+  out8_host[3] = pn; out8_host[4] = pms; out8_host[5] = pfl; out8_host[6] = hms; out8_host[7] = hfl;
   return HB_OK;
 }
 
@@ -396,6 +410,7 @@ int hb_rbf_gram_bwd_x2(const float* G, long long ldg, long long strideG, const f
 }
 
 int hb_set_exact_below(int n) { set_exact_below(n); return get_exact_below(); }
+int hb_set_presplit_engine(int on) { set_presplit_engine(on); return get_presplit_engine(); }
 int hb_set_panel_refinement(int mode) { set_panel_refinement(mode); return get_panel_refinement(); }
 size_t hb_potrf_workspace_bytes(int n) { return potrf_workspace_bytes(n); }
 int hb_potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
@@ -660,7 +675,7 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
     HB_TRY(gemm(g, st));
   }
   phase_mark(st);
-  HB_TRY(potrf_lower_bwd(K, n, 0, G, n, 0, n, 1, pws, L.potrf_bytes, st));
+  HB_TRY(potrf_lower_bwd(K, n, 0, G, n, 0, n, 1, pws, L.potrf_bytes, st, /*l_shadow_valid=*/1));
   phase_mark(st);
   HB_TRY(rbf_gram_bwd(G, n, 0, X, nullptr, n, n, c.D, 0, 0, d_ell, c.n_ell, 1, 1, 0, d_a, g_ell, red, kReduceWsBytes, st));
   gp_scalar_bwd_kernel<<<1, 32, 0, st>>>(sc, ll3, kl, (long long)Sn * n, Sn, p_scale, p_ell, c.n_ell, p_kvar, p_var,

@@ -43,6 +43,9 @@ int gemm_small(const GemmParams& p, cudaStream_t stream);      // K <= 256, whol
 bool gemm_small_eligible(const GemmParams& p);
 void set_tc_option(int v);   // bit2: no CTA pairs | bit3: three TF32 passes instead of TF32 + bf16 cross terms
 int get_tc_option();
+// per-launch timing hooks for launches that bypass hb::gemm (the pre-split engine): slot = prof_begin(...); launch; prof_end(slot)
+int gemm_prof_begin(double useful_flops, int M, int N, int K, int kind, cudaStream_t st);   // -1 when profiling is off
+void gemm_prof_end(int slot, cudaStream_t st);
 void set_gemm_engine(int mode);
 int get_gemm_engine();
 

@@ -88,6 +88,8 @@ int increment_i32(int* p, cudaStream_t st);
 // ---- linalg.cu ----
 void set_panel_refinement(int mode);   // 0 explicit inverse, 1 refined, 2 refined for n <= 8192, 2 is the default, 3 substitution kernel
 int get_panel_refinement();
+void set_presplit_engine(int on);
+int get_presplit_engine();
 void set_exact_below(int n);           // factorisations of order <= n use exact fp32 products (default 2048)
 int get_exact_below();
 size_t potrf_workspace_bytes(int n);
@@ -95,7 +97,7 @@ size_t trsm_workspace_bytes(int m, int n);
 int potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
                 size_t ws_bytes, int* err_flag, cudaStream_t st);
 int potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, long long ldg, long long strideG,
-                    int n, int batch, void* ws, size_t ws_bytes, cudaStream_t st);
+                    int n, int batch, void* ws, size_t ws_bytes, cudaStream_t st, int l_shadow_valid = 0);
 int trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int m, int n, int trans, void* ws,
                      size_t ws_bytes, cudaStream_t st);
 

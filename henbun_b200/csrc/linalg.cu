@@ -8,6 +8,7 @@
 // The recursion splits on multiples of NB; leaves (<= NB) run in one CTA out of shared memory and
 // also emit the inverse of the diagonal block, so every triangular solve above the leaves is a GEMM.
 #include "gemm.cuh"
+#include "gemm_h2.cuh"
 #include "kernels.cuh"
 #include <cstdlib>
 
@@ -507,7 +508,43 @@ struct Ctx {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_main = nullptr, ev_side = nullptr;
   mutable bool side_pending = false;     // a leaf is in flight on the side stream and the main stream has not joined it
+  // fp16 hi/lo shadows of the finished panels (gemm_h2.cu): L in both directions, K-bar in the reverse mode; null = off
+  __half *lh = nullptr, *ll = nullptr, *gh = nullptr, *gl = nullptr;
+  long long ldh = 0;
+  unsigned* lmax = nullptr;   // bit pattern of max |diag K| (forward) / max |L| (stand-alone reverse)
+  float* lscale = nullptr;    // {s_L, 1 / s_L}
+  unsigned* gmax = nullptr;   // [2 nblk]: panel maxima, then diagonal-block maxima
+  float* ginv = nullptr;      // [2 nblk]: inverse scales of the K-bar panels, then of its diagonal blocks
+  int nblk = 0;
 };
+
+// Orders from which the big products run on the pre-split engine.  Below, no product has enough 256 x 256 tiles.
+constexpr int H2_MIN_N = 4096;
+static int g_use_h2 = 1;
+inline bool h2_on(int n) { return g_use_h2 && n >= H2_MIN_N && (n % 8) == 0; }
+inline long long h2_ld(int n) { return ((long long)n + 63) / 64 * 64; }
+
+static double h2_flops(const H2Gemm& h) {
+  double f = 2.0 * (double)h.M * (double)h.N * (double)h.K;
+  if (h.c_tri) {
+    const double M = h.M, N = h.N;
+    f *= ((M >= N) ? M * N - 0.5 * N * (N - 1.0) : 0.5 * M * (M + 1.0)) / (M * N);
+  }
+  if (h.a_bmode) f *= 0.5;
+  return f;
+}
+static int run_h2(const Ctx& c, const H2Gemm& h) {
+  const int slot = gemm_prof_begin(h2_flops(h), h.M, h.N, h.K, 3, c.st);
+  const int rc = gemm_h2(h, c.st);
+  gemm_prof_end(slot, c.st);
+  return rc;
+}
+// split the finished panel L[r0 .. r0+rows, c0 .. c0+w) into the L shadow
+static int split_L(const Ctx& c, const float* L, long long ldl, int r0, int c0, int rows, int w) {
+  if (!c.lh || rows <= 0 || (w & 7)) return HB_OK;
+  return h2_split(L + (long long)r0 * ldl + c0, ldl, rows, w, c.lscale, nullptr, nullptr, 0, 0,
+                  c.lh + (long long)r0 * c.ldh + c0, c.ll + (long long)r0 * c.ldh + c0, c.ldh, c.st);
+}
 
 // Side stream and its two events, created once per device (the only state this library keeps besides cuFuncAttributes;
 // HB_LOOKAHEAD=0 in the environment disables the look-ahead).
@@ -641,7 +678,8 @@ int potrf_cols(const Ctx& c, float* A, long long lda, int c0, int w, int n, bool
     const int below = n - (c0 + w);
     if (below <= 0) return HB_OK;
     // panel <- panel * D^{-T} (in place; refined against D itself when the mode says so)
-    return panel_solve(c, D, lda, c0, D + (long long)w * lda, lda, below, w, true, 1.f, refine_on(n));
+    HB_TRY(panel_solve(c, D, lda, c0, D + (long long)w * lda, lda, below, w, true, 1.f, refine_on(n)));
+    return split_L(c, A, lda, c0 + w, c0, below, w);      // the panel is final: its fp16 hi/lo shadow feeds every later update
   }
   const int w1 = split_point(w), w2 = w - w1;
   HB_TRY(potrf_cols(c, A, lda, c0, w1, n, leaf_done));
@@ -651,8 +689,22 @@ int potrf_cols(const Ctx& c, float* A, long long lda, int c0, int w, int n, bool
   GemmParams g;
   g.A = P; g.lda = lda; g.B = P; g.ldb = lda; g.transB = 1;
   g.C = P + w1; g.ldc = lda; g.M = M; g.N = w2; g.K = w1; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
+  auto update = [&](const GemmParams& q, int row_off, int col_off) -> int {
+    // q updates C = P[row_off.., w1 + col_off ..] with A = P[row_off.., 0 .. w1), B = P[col_off .., 0 .. w1)
+    if (c.lh && gemm_h2_eligible(q.M, q.N, q.K)) {
+      H2Gemm h;
+      const long long ra = c0 + w1 + row_off, rb = c0 + w1 + col_off;
+      h.a_hi = c.lh + ra * c.ldh + c0; h.a_lo = c.ll + ra * c.ldh + c0; h.lda = c.ldh; h.a_kmajor = 1;
+      h.b_hi = c.lh + rb * c.ldh + c0; h.b_lo = c.ll + rb * c.ldh + c0; h.ldb = c.ldh; h.b_kmajor = 1;
+      h.C = q.C; h.ldc = q.ldc; h.M = q.M; h.N = q.N; h.K = q.K; h.alpha = q.alpha; h.beta = q.beta; h.c_tri = q.c_tri;
+      h.a_inv = c.lscale + 1; h.b_inv = c.lscale + 1;
+      return run_h2(c, h);
+    }
+    GemmParams qq = q;
+    return gemm_ws(c, qq);
+  };
   if (!c.side || w1 > 1024) {   // splitting a long-K update costs more than hiding one 76 us leaf behind it
-    HB_TRY(gemm_ws(c, g));
+    HB_TRY(update(g, 0, 0));
     return potrf_cols(c, A, lda, c0 + w1, w2, n);
   }
   // look-ahead: update the next diagonal block first, factor it on the side stream, update the rest meanwhile
@@ -673,7 +725,7 @@ int potrf_cols(const Ctx& c, float* A, long long lda, int c0, int w, int n, bool
       GemmParams t = g;                                // rows [nb, M) x cols [nb, w2): lower trapezoid of its own
       t.A = P + (long long)nb * lda; t.B = P + (long long)nb * lda;
       t.C = P + w1 + (long long)nb * lda + nb; t.M = M - nb; t.N = w2 - nb; t.c_tri = 1;
-      HB_TRY(gemm_ws(c, t));
+      HB_TRY(update(t, nb, nb));
     }
   }
   return potrf_cols(c, A, lda, c0 + w1, w2, n, /*leaf_done=*/true);
@@ -696,6 +748,17 @@ int potrf_rec(const Ctx& c, float* A, long long lda, int off, int n) {
 //              G[T, left] -= 2 sym(G[T, right]) L[T, left]
 //              rev_cols(left half)
 // Launch count ~ 4 n/NB (the square recursion needed ~ 3 (n/NB) log2(n/NB)) and every GEMM spans all rows below.
+// the (full, symmetric) diagonal block of K-bar the leaf just wrote gets its own scale: its entries can be orders of
+// magnitude above the panel below it (short lengthscales: K ~ I)
+static int split_G_diag(const Ctx& c, const float* G, long long ldg, int c0, int w, cudaStream_t st) {
+  if (!c.gh || (w & 7)) return HB_OK;
+  const int b = c0 / NB;
+  const float* GD = G + (long long)c0 * ldg + c0;
+  const long long o = (long long)c0 * c.ldh + c0;
+  HB_TRY(h2_absmax(GD, ldg, w, w, 0, 0, c.gmax + c.nblk + b, st));
+  return h2_split(GD, ldg, w, w, nullptr, c.gmax + c.nblk + b, c.ginv + c.nblk + b, 0, 0, c.gh + o, c.gl + o, c.ldh, st);
+}
+
 int chol_rev_cols(const Ctx& c, const float* L, long long ldl, float* G, long long ldg, int c0, int w, int n) {
   float* GD = G + (long long)c0 * ldg + c0;
   const float* LD = L + (long long)c0 * ldl + c0;
@@ -705,6 +768,12 @@ int chol_rev_cols(const Ctx& c, const float* L, long long ldl, float* G, long lo
       float* Gp = GD + (long long)w * ldg;
       const float* Lp = LD + (long long)w * ldl;
       HB_TRY(panel_solve(c, LD, ldl, c0, Gp, ldg, below, w, false, 0.5f, refine_on(n)));
+      if (c.gh && !(w & 7)) {      // the panel of K-bar is final: scale by its own maximum, split into the shadow
+        const int b = c0 / NB;
+        HB_TRY(h2_absmax(Gp, ldg, below, w, 0, 0, c.gmax + b, c.st));
+        const long long o = (long long)(c0 + w) * c.ldh + c0;
+        HB_TRY(h2_split(Gp, ldg, below, w, nullptr, c.gmax + b, c.ginv + b, 0, 0, c.gh + o, c.gl + o, c.ldh, c.st));
+      }
       GemmParams h;
       h.A = Gp; h.lda = ldg; h.transA = 1; h.B = Lp; h.ldb = ldl; h.transB = 0;
       h.C = GD; h.ldc = ldg; h.M = w; h.N = w; h.K = below; h.alpha = -2.f; h.beta = 1.f; h.c_tri = 1;
@@ -717,13 +786,14 @@ int chol_rev_cols(const Ctx& c, const float* L, long long ldl, float* G, long lo
       fork_side(c);
       chol_rev_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.side>>>(LD, ldl, 0, GD, ldg, 0, w, dinv_slot(c, c0), 0);
       HB_CHECK_LAUNCH();
+      HB_TRY(split_G_diag(c, G, ldg, c0, w, c.side));
       cudaEventRecord(c.ev_side, c.side);
       c.side_pending = true;
       return HB_OK;
     }
     chol_rev_leaf_kernel<<<1, LEAF_THREADS, kLeafSmem3, c.st>>>(LD, ldl, 0, GD, ldg, 0, w, dinv_slot(c, c0), 0);
     HB_CHECK_LAUNCH();
-    return HB_OK;
+    return split_G_diag(c, G, ldg, c0, w, c.st);
   }
   const int w1 = split_point(w), w2 = w - w1;
   const int r1 = c0 + w1, rb = c0 + w, nb = n - rb;
@@ -734,17 +804,48 @@ int chol_rev_cols(const Ctx& c, const float* L, long long ldl, float* G, long lo
     float* G_R_right = G + (long long)rb * ldg + r1;        // [nb x w2]
     float* G_R_left = G + (long long)rb * ldg + c0;         // [nb x w1]
     const float* L_R_left = L + (long long)rb * ldl + c0;   // [nb x w1]
-    GemmParams a;
-    a.A = G_R_right; a.lda = ldg; a.B = L_T_left; a.ldb = ldl; a.transB = 0;
-    a.C = G_R_left; a.ldc = ldg; a.M = nb; a.N = w1; a.K = w2; a.alpha = -2.f; a.beta = 1.f;
-    HB_TRY(gemm_ws(c, a));
-    GemmParams b;
-    b.A = G_R_right; b.lda = ldg; b.transA = 1; b.B = L_R_left; b.ldb = ldl; b.transB = 0;
-    b.C = G_T_left; b.ldc = ldg; b.M = w2; b.N = w1; b.K = nb; b.alpha = -2.f; b.beta = 1.f;
-    HB_TRY(gemm_ws(c, b));
+    const bool h2 = c.gh && c.lh && !(w2 % NB);     // column blocks of G[., right] are whole 128-blocks
+    if (h2 && gemm_h2_eligible(nb, w1, w2)) {
+      H2Gemm h;   // G[R, left] -= 2 G[R, right] L[T, left]: A K-major with one scale per 128 columns, B = L MN-major
+      const long long oa = (long long)rb * c.ldh + r1, ob = (long long)r1 * c.ldh + c0;
+      h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 1; h.a_kinv = c.ginv + r1 / NB;
+      h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
+      h.C = G_R_left; h.ldc = ldg; h.M = nb; h.N = w1; h.K = w2; h.alpha = -2.f; h.beta = 1.f;
+      HB_TRY(run_h2(c, h));
+    } else {
+      GemmParams a;
+      a.A = G_R_right; a.lda = ldg; a.B = L_T_left; a.ldb = ldl; a.transB = 0;
+      a.C = G_R_left; a.ldc = ldg; a.M = nb; a.N = w1; a.K = w2; a.alpha = -2.f; a.beta = 1.f;
+      HB_TRY(gemm_ws(c, a));
+    }
+    if (h2 && gemm_h2_eligible(w2, w1, nb)) {
+      H2Gemm h;   // G[T, left] -= 2 G[R, right]^T L[R, left]: A MN-major (scales along M), B = L MN-major
+      const long long oa = (long long)rb * c.ldh + r1, ob = (long long)rb * c.ldh + c0;
+      h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 0; h.a_minv = c.ginv + r1 / NB;
+      h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
+      h.C = G_T_left; h.ldc = ldg; h.M = w2; h.N = w1; h.K = nb; h.alpha = -2.f; h.beta = 1.f;
+      HB_TRY(run_h2(c, h));
+    } else {
+      GemmParams b;
+      b.A = G_R_right; b.lda = ldg; b.transA = 1; b.B = L_R_left; b.ldb = ldl; b.transB = 0;
+      b.C = G_T_left; b.ldc = ldg; b.M = w2; b.N = w1; b.K = nb; b.alpha = -2.f; b.beta = 1.f;
+      HB_TRY(gemm_ws(c, b));
+    }
   }
   join_side(c);     // the next products read the diagonal blocks of G[T, right]
-  {
+  if (c.gh && c.lh && !(w2 % NB) && gemm_h2_eligible(w2, w1, w2)) {
+    // G[T, left] -= 2 sym(G[T, right]) L[T, left] from the shadows: block-lower part (diagonal blocks included, they are
+    // stored full and carry their own scales) + transpose of the strictly block-lower part
+    H2Gemm h;
+    const long long oa = (long long)r1 * c.ldh + r1, ob = (long long)r1 * c.ldh + c0;
+    h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 1; h.a_bmode = 1;
+    h.a_kinv = c.ginv + r1 / NB; h.a_dinv = c.ginv + c.nblk + r1 / NB;
+    h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
+    h.C = G_T_left; h.ldc = ldg; h.M = w2; h.N = w1; h.K = w2; h.alpha = -2.f; h.beta = 1.f;
+    HB_TRY(run_h2(c, h));
+    h.a_kmajor = 0; h.a_bmode = 2; h.a_kinv = nullptr; h.a_dinv = nullptr; h.a_minv = c.ginv + r1 / NB;
+    HB_TRY(run_h2(c, h));
+  } else {
     GemmParams g;   // G[T, left] -= 2 sym(G[T, right]) L[T, left], sym from the lower triangle
     g.A = G + (long long)r1 * ldg + r1; g.lda = ldg; g.a_tri = 1; g.B = L_T_left; g.ldb = ldl; g.transB = 0;
     g.C = G_T_left; g.ldc = ldg; g.M = w2; g.N = w1; g.K = w2; g.alpha = -2.f; g.beta = 1.f;
@@ -772,7 +873,14 @@ static size_t base_bytes(long long rows, int n) {
   return ((size_t)(nblk * NB * NB + rows * NB) * sizeof(float) + 256 + 255) / 256 * 256;
 }
 
-size_t potrf_workspace_bytes(int n) { return base_bytes(n, n) + tc_bytes_for(-1, n); }
+// fp16 hi/lo shadows of L and K-bar + their scales (orders >= H2_MIN_N only)
+static size_t h2_scale_bytes(int n) { return ((size_t)(16 + 4 * ((n + NB - 1) / NB)) * 4 + 255) / 256 * 256; }
+static size_t h2_shadow_bytes(int n) { return ((size_t)n * h2_ld(n) * 2 + 255) / 256 * 256; }
+static size_t h2_bytes_for(int n) { return (n >= H2_MIN_N && n % 8 == 0) ? h2_scale_bytes(n) + 4 * h2_shadow_bytes(n) : 0; }
+
+size_t potrf_workspace_bytes(int n) { return base_bytes(n, n) + tc_bytes_for(-1, n) + h2_bytes_for(n); }
+void set_presplit_engine(int on) { g_use_h2 = on ? 1 : 0; }
+int get_presplit_engine() { return g_use_h2; }
 
 void set_exact_below(int n) { g_exact_below = n < 0 ? 0 : n; }
 int get_exact_below() { return g_exact_below; }
@@ -790,6 +898,19 @@ static int make_ctx(Ctx& c, int n, void* ws, size_t ws_bytes, int* err, cudaStre
   c.tcws = reinterpret_cast<char*>(c.dinv) + base_bytes(n, n) - 256;
   c.tcws_bytes = tc_bytes_for(-1, n);
   c.n_total = n;
+  if (h2_on(n) && h2_bytes_for(n)) {
+    char* hb = reinterpret_cast<char*>(c.tcws) + c.tcws_bytes;
+    c.nblk = (int)nblk;
+    c.lmax = reinterpret_cast<unsigned*>(hb);
+    c.lscale = reinterpret_cast<float*>(hb) + 4;
+    c.gmax = reinterpret_cast<unsigned*>(hb) + 8;
+    c.ginv = reinterpret_cast<float*>(hb) + 8 + 2 * nblk;
+    hb += h2_scale_bytes(n);
+    const size_t sb = h2_shadow_bytes(n);
+    c.lh = reinterpret_cast<__half*>(hb); c.ll = reinterpret_cast<__half*>(hb + sb);
+    c.gh = reinterpret_cast<__half*>(hb + 2 * sb); c.gl = reinterpret_cast<__half*>(hb + 3 * sb);
+    c.ldh = h2_ld(n);
+  }
   return HB_OK;
 }
 
@@ -809,6 +930,11 @@ int potrf_lower(float* A, long long lda, long long strideA, int n, int batch, in
   attach_side(c);
   for (int b = 0; b < batch; ++b) {
     float* Ab = A + (long long)b * strideA;
+    if (c.lh) {     // |L_ij| <= sqrt(max_i K_ii): the scale of L's shadow is known before the first panel exists
+      if (cudaMemsetAsync(c.lmax, 0, 16, st) != cudaSuccess) return HB_ERR_CUDA;
+      HB_TRY(h2_diag_absmax(Ab, lda, n, c.lmax, st));
+      HB_TRY(h2_scale_from_max(c.lmax, 1, c.lscale, st));
+    }
     HB_TRY(potrf_rec(c, Ab, lda, 0, n));
     join_side(c);
     if (zero_upper) HB_TRY(zero_strict_upper(Ab, lda, n, st));
@@ -819,7 +945,7 @@ int potrf_lower(float* A, long long lda, long long strideA, int n, int batch, in
 // Reverse mode: on entry G's lower triangle holds dObj/dL, on exit dObj/dK (full-symmetric
 // convention, lower triangle valid).  L is the factor from potrf_lower (lower triangle read).
 int potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, long long ldg, long long strideG,
-                    int n, int batch, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    int n, int batch, void* ws, size_t ws_bytes, cudaStream_t st, int l_shadow_valid) {
   if (n < 0 || batch < 0 || (n > 0 && (!L || !G || ldl < n || ldg < n))) return HB_ERR_ARG;
   if (n == 0 || batch == 0) return HB_OK;
   HB_TRY(ensure_attrs());
@@ -834,6 +960,15 @@ int potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, 
   const int nblk = (n + NB - 1) / NB;
   for (int b = 0; b < batch; ++b) {
     const float* Lb = L + (long long)b * strideL;
+    if (c.gh) {
+      if (cudaMemsetAsync(c.gmax, 0, (size_t)2 * c.nblk * 4, st) != cudaSuccess) return HB_ERR_CUDA;
+      if (!(l_shadow_valid && batch == 1)) {     // stand-alone call: L's shadow has to be built from L itself
+        if (cudaMemsetAsync(c.lmax, 0, 16, st) != cudaSuccess) return HB_ERR_CUDA;
+        HB_TRY(h2_absmax(Lb, ldl, n, n, 1, 0, c.lmax, st));
+        HB_TRY(h2_scale_from_max(c.lmax, 0, c.lscale, st));
+        HB_TRY(h2_split(Lb, ldl, n, n, c.lscale, nullptr, nullptr, 1, 0, c.lh, c.ll, c.ldh, st));
+      }
+    }
     trinv_blocks_kernel<<<nblk, LEAF_THREADS, kLeafSmem3, st>>>(Lb, ldl, n, c.dinv);
     HB_CHECK_LAUNCH();
     HB_TRY(chol_rev_rec(c, Lb, ldl, G + (long long)b * strideG, ldg, 0, n));

@@ -48,8 +48,8 @@ int hb_get_gemm_engine(void);
  * hb_profile_end synchronises and fills a HOST array {launches, total ms, useful FLOP, 0}. */
 int hb_profile_begin(int max_gemm_launches);
 int hb_profile_end(double* out4_host);
-/* As hb_profile_end, plus the share of the CTA-pair tcgen05 kernel: out8 = {launches, ms, useful FLOP, pair launches,
- * pair ms, pair useful FLOP, 0, 0}. */
+/* As hb_profile_end, plus the shares of the two CTA-pair tcgen05 kernels: out8 = {launches, ms, useful FLOP,
+ * in-kernel-split pair kernel launches, ms, useful FLOP, pre-split (fp16 hi/lo) pair kernel ms, useful FLOP}. */
 int hb_profile_end_ex(double* out8_host);
 /* Phase timing of one hb_gp_elbo_step: hb_phase_begin(); step; n = hb_phase_end(ms, cap) fills ms[0..n) with
  * {scalars + Gram fwd, potrf, sampler + F + log-lik + W, sampler bwd + Lbar, potrf_bwd, Gram bwd + scalar grads}. */
@@ -185,6 +185,10 @@ int hb_set_panel_refinement(int mode);
  * the tensor-core split product (default n = 2048: latency-bound sizes, where the notebook models live and where the
  * split product's 1.5e-6 error shows on ill-conditioned inputs).  0 disables.  Returns the value set. */
 int hb_set_exact_below(int n);
+/* Factorisations of order >= 4096 (n % 8 == 0) keep fp16 hi/lo "shadow" copies of every finished panel of L and of K-bar
+ * in their workspace and run their big products on the pre-split tcgen05 engine (csrc/gemm_h2.cu, see hb_gemm_presplit).
+ * 0 turns that off (all products on the in-kernel-split engine, as in round 1).  Returns the value set. */
+int hb_set_presplit_engine(int on);
 size_t hb_potrf_workspace_bytes(int n);
 int hb_potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
                    size_t ws_bytes, int* err_flag, void* stream);

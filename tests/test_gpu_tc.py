@@ -165,10 +165,11 @@ def test_short_k_kernel_masks(lib, tri):
     assert run(lib, 256, 256, 200, 1, 0, c_tri=1, alpha=-1.0, beta=1.0, engine=1) < 2e-6
 
 
-@pytest.mark.parametrize("n", [1000, 2176, 3000])
+@pytest.mark.parametrize("n", [1000, 2176, 3000, 4224, 8200, 12288])
 def test_potrf_and_reverse_mode_on_tensor_cores(lib, n):
     """Column-recursive Cholesky + reverse mode with the automatic engine choice (tensor cores for the large
-    products) against fp64 LAPACK / torch autograd on the GPU."""
+    products; from n = 4096 the big ones on the pre-split fp16 hi/lo engine, 8200 = ragged last block) against fp64
+    LAPACK / torch autograd on the GPU."""
     g = torch.Generator("cuda").manual_seed(n)
     X = torch.randn(n, 8, device="cuda", generator=g, dtype=torch.float64)
     K64 = torch.exp(-0.5 * torch.cdist(X, X) ** 2 / 0.25) + 1e-3 * torch.eye(n, device="cuda", dtype=torch.float64)
