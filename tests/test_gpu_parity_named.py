@@ -88,6 +88,7 @@ def test_fused_gp_step_matches_fp64_oracle_at_named_sizes(lib, n):
     from henbun_b200 import _lib
     from henbun_b200.synthetic import make_gp_problem, pack_gp_params, GP_PARAM_ORDER
     D, S = 8, 64
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < (14 * n * n * 8):
         pytest.skip("not enough free HBM for the fp64 checker")
@@ -129,6 +130,7 @@ def test_full_size_adjoint_identity_and_round_trip(lib, refine):
     library's own level-3 path at full size.  Kbar comes back in the full-symmetric convention (an off-diagonal entry
     counts twice in the inner product)."""
     n, D, R = 65536, 8, 64
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < 150 * (1 << 30):
         pytest.skip("needs ~140 GB of free HBM")
