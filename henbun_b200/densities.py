@@ -23,11 +23,17 @@ def _like(*xs):
 
 
 def _call(name, *args):
+    from . import trace as _trace
+    if _trace.is_sym(*args):
+        raise _trace.TraceError(f"densities.{name} is not traced")
     like = _like(*args)
     return ops.density(name, *[_t(a, like) for a in args])
 
 
 def gaussian(x, mu, var):
+    from . import trace as _trace
+    if _trace.is_sym(x, mu, var):
+        return _trace.Sym('gaussian', x, mu, var)
     return _call("gaussian", x, mu, var)
 
 

@@ -98,3 +98,244 @@ class LinearOperatorStep(object):
         parallel.allreduce_sum_(self.zbar_stats)
         out = self.update(grads=g, apply_adam=False)
         return out, g
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Binding of traced objectives (trace.py) to the whole-step entry points: what Optimizer.compile does with the tree
+# ------------------------------------------------------------------------------------------------------------------
+def _is_positive_scalar(v):
+    from . import transforms
+    from .param import Variable
+    return isinstance(v, Variable) and v.is_parameter and isinstance(v.transform, transforms.Log1pe) and \
+        int(np.prod(v._host.shape)) == 1 and abs(float(getattr(v.transform, '_lower', 1e-6)) - 1e-6) < 1e-12
+
+
+def _leaf(node, op):
+    from .trace import Sym
+    return node.args[0] if isinstance(node, Sym) and node.op == op else None
+
+
+def _variationals_of(model):
+    from .variationals import Variational
+    from .param import Parameterized
+    out = []
+
+    def walk(p):
+        for c in p.sorted_variables:
+            if isinstance(c, Variational):
+                out.append(c)
+            if isinstance(c, Parameterized):
+                walk(c)
+    walk(model)
+    return out
+
+
+def _split_elbo(tree, model):
+    """tree = reduce_sum(gaussian(data, f, var)) - KL(model)  ->  (data variable, f, var variable) or None."""
+    from .trace import Sym
+    from .param import graph_key
+    if not (isinstance(tree, Sym) and tree.op == 'sub' and len(tree.args) == 2):
+        return None
+    ll, kl = tree.args
+    if not (isinstance(kl, Sym) and kl.op == 'KL' and kl.args[0] is model):
+        return None
+    if not (isinstance(ll, Sym) and ll.op == 'reduce_sum' and ll.kw.get('axis') is None):
+        return None
+    g = ll.args[0]
+    if not (isinstance(g, Sym) and g.op == 'gaussian'):
+        return None
+    y, f, var = g.args
+    yv, vv = _leaf(y, 'data'), _leaf(var, 'param')
+    if yv is None or vv is None or not _is_positive_scalar(vv):
+        return None
+    return yv, f, vv, kl.args[1]
+
+
+class GpElboBinding(object):
+    """notebooks/GaussianProcess.ipynb:109-148 recognised in a traced objective:
+        y_fit = matmul(kern.Cholesky(X), q) * sqrt(k_var);  ELBO = reduce_sum(gaussian(Y, y_fit, var)) - KL()
+    with q = variationals.Gaussian([n, 1]) (diagonal or fullrank), kern = UnitRBF.  One call of hb_gp_elbo_step writes the
+    ELBO and d ELBO / d (free parameters) straight into the Optimizer's flat gradient buffer, which is laid out in the
+    entry point's packing [q_mu | q_sqrt | scale | lengthscales | k_var | var]."""
+
+    def __init__(self, model, q, kern, k_var, var, X, Y):
+        self.model, self.q, self.kern, self.k_var, self.var, self.X, self.Y = model, q, kern, k_var, var, X, Y
+        g = object.__getattribute__
+        self.var_order = [g(q, 'q_mu'), g(q, 'q_sqrt'), g(q, 'scale'), g(kern, 'lengthscales'), k_var, var]
+        self.lib = _lib.load()
+        self._ws = None
+        self._key = None
+
+    @staticmethod
+    def match(tree, model):
+        from .trace import Sym
+        from .variationals import Gaussian, OffsetGaussian
+        from .gp.kernels import UnitRBF
+        from .param import Data, MinibatchData, graph_key, _is
+        from . import transforms
+        parts = _split_elbo(tree, model)
+        if parts is None:
+            return None
+        Y, f, var, kl_coll = parts
+        if kl_coll not in (None, graph_key.VARIABLES):
+            return None
+        if not (isinstance(f, Sym) and f.op == 'mul'):
+            return None
+        a, b = f.args
+        if isinstance(a, Sym) and a.op == 'sqrt':
+            a, b = b, a
+        if not (isinstance(b, Sym) and b.op == 'sqrt'):
+            return None
+        k_var = _leaf(b.args[0], 'param')
+        if k_var is None or not _is_positive_scalar(k_var):
+            return None
+        mm = a
+        if not (isinstance(mm, Sym) and mm.op == 'matmul' and not mm.kw['ta'] and not mm.kw['tb']):
+            return None
+        ch, smp = mm.args
+        if not (isinstance(ch, Sym) and ch.op == 'cholesky' and isinstance(smp, Sym) and smp.op == 'sample'):
+            return None
+        kern, Xs = ch.args
+        X = _leaf(Xs, 'data')
+        q = smp.args[0]
+        if X is None or isinstance(X, MinibatchData) or isinstance(Y, MinibatchData):
+            return None
+        if type(kern) is not UnitRBF or type(q) is not Gaussian or smp.args[1] is not None:
+            return None
+        ell = object.__getattribute__(kern, 'lengthscales')
+        from .param import Variable
+        if not (isinstance(ell, Variable) and ell.is_parameter and isinstance(ell.transform, transforms.Log1pe)
+                and abs(float(ell.transform._lower) - 1e-6) < 1e-12):
+            return None
+        if X.data.ndim != 2 or Y.data.shape != (X.data.shape[0], 1):
+            return None
+        n, D = X.data.shape
+        if list(q._shape) != [n, 1] or q.n_layers or q.n_batch is not None or q.is_local or D > 32:
+            return None
+        if int(np.prod(ell._host.shape)) not in (1, D):
+            return None
+        scale = object.__getattribute__(q, 'scale')
+        if not _is_positive_scalar(scale) or not isinstance(q.transform, transforms.Identity):
+            return None
+        if _variationals_of(model) != [q]:           # KL() must be exactly this variational's
+            return None
+        return GpElboBinding(model, q, kern, k_var, var, X, Y)
+
+    def step(self, opt, count, eps, seed, offset):
+        """Forward + backward into opt._flat_grad; returns the ELBO (mean over the `count` samples) as a 0-d tensor."""
+        from . import ops
+        X, Y = self.X.tensor(), self.Y.tensor()
+        n, D = X.shape
+        n_ell = int(np.prod(object.__getattribute__(self.kern, 'lengthscales')._host.shape))
+        full = 1 if self.q.q_shape == 'fullrank' else 0
+        cfg = _lib.GpConfig(int(n), int(D), int(count), n_ell, full, float(opt._compiled_settings.numerics.jitter_level),
+                            int(seed), int(offset))
+        key = (n, D, count, n_ell, full)
+        if self._key != key:
+            self._wsb = int(self.lib.hb_gp_elbo_workspace_bytes(C.byref(cfg)))
+            self._ws = torch.empty(self._wsb, dtype=torch.uint8, device=X.device)
+            self._out4 = torch.zeros(4, device=X.device)
+            self._key = key
+        e = None
+        if eps is not None:
+            e = torch.as_tensor(np.asarray(eps), dtype=torch.float32) if not isinstance(eps, torch.Tensor) else eps
+            e = e.to(X.device, torch.float32).reshape(count, n).contiguous()
+        check(self.lib.hb_gp_elbo_step(C.byref(cfg), ptr(X), ptr(Y), ptr(opt._flat), ptr(e), ptr(opt._flat_grad), ptr(self._out4),
+                                       ptr(self._ws), self._wsb, ptr(ops.err_flag(X.device)), stream()), "hb_gp_elbo_step")
+        return self._out4[0]
+
+
+class LinopElboBinding(object):
+    """BASELINE config 5 recognised in a traced objective:
+        f = matmul(q, A, transpose_b=True);  ELBO = reduce_sum(gaussian(y, f, var)) - KL()
+    with q = variationals.Normal([n], 'fullrank').  The step runs hb_linop_elbo_local / _update on the Optimizer's flat
+    buffers (packing [q_sqrt | q_mu | var]); the q_sqrt gradient is formed and consumed by Adam in one pass."""
+
+    def __init__(self, model, q, var, A, y):
+        self.model, self.q, self.var, self.A, self.y = model, q, var, A, y
+        g = object.__getattribute__
+        self.var_order = [g(q, 'q_sqrt'), g(q, 'q_mu'), var]
+        self.fused_adam = True
+        self._st = None
+
+    @staticmethod
+    def match(tree, model):
+        from .trace import Sym
+        from .variationals import Normal
+        from .param import MinibatchData, graph_key
+        from . import transforms
+        parts = _split_elbo(tree, model)
+        if parts is None:
+            return None
+        y, f, var, kl_coll = parts
+        if kl_coll not in (None, graph_key.VARIABLES):
+            return None
+        if not (isinstance(f, Sym) and f.op == 'matmul' and not f.kw['ta'] and f.kw['tb']):
+            return None
+        smp, As = f.args
+        A = _leaf(As, 'data')
+        if not (isinstance(smp, Sym) and smp.op == 'sample') or A is None:
+            return None
+        q = smp.args[0]
+        if type(q) is not Normal or q.q_shape != 'fullrank' or q.n_layers or q.n_batch is not None or q.is_local:
+            return None
+        if isinstance(A, MinibatchData) or isinstance(y, MinibatchData) or A.data.ndim != 2:
+            return None
+        M, n = A.data.shape
+        if list(q._shape) != [n] or int(np.prod(y.data.shape)) != M:
+            return None
+        if _variationals_of(model) != [q]:
+            return None
+        return LinopElboBinding(model, q, var, A, y)
+
+    def step(self, opt, count, eps, seed, offset, world):
+        A, y = self.A.tensor(), self.y.tensor()
+        if self._st is None or self._st.S != count:
+            st = LinearOperatorStep.__new__(LinearOperatorStep)
+            st.lib = _lib.load()
+            st.A, st.y = A, y.reshape(-1)
+            M, n = A.shape
+            st.n, st.S = int(n), int(count)
+            st.cfg = _lib.LinopConfig(int(M), int(M), st.n, st.S, int(seed), 0)
+            st.count = int(st.lib.hb_linop_param_count(C.byref(st.cfg)))
+            st.params, st.m, st.v = opt._flat[:st.count], opt._m[:st.count], opt._v[:st.count]
+            st.zbar_stats = torch.empty(st.S * st.n + 4, device=A.device)
+            st.out4 = torch.zeros(4, device=A.device)
+            st.ws_bytes = int(st.lib.hb_linop_workspace_bytes(C.byref(st.cfg)))
+            st.ws = torch.empty(st.ws_bytes, dtype=torch.uint8, device=A.device)
+            st.step_dev = opt._step
+            self._st = st
+        st = self._st
+        st.A, st.y = A, y.reshape(-1)
+        o = opt.optimizer
+        st.hyper = (float(o.learning_rate), float(o.beta1), float(o.beta2), float(o.epsilon))
+        st.cfg.seed = int(seed)
+        st.cfg.offset = int(offset)
+        e = None
+        if eps is not None:
+            e = torch.as_tensor(np.asarray(eps), dtype=torch.float32) if not isinstance(eps, torch.Tensor) else eps
+            e = e.to(A.device, torch.float32).reshape(count, st.n).contiguous()
+        check(st.lib.hb_linop_elbo_local(C.byref(st.cfg), ptr(st.A), ptr(st.y), ptr(st.params), ptr(e), ptr(st.zbar_stats),
+                                         ptr(st.ws), st.ws_bytes, stream()), "hb_linop_elbo_local")
+        # Adam's t: the Optimizer's counter holds the number of finished steps; the kernel wants the 1-based step
+        check(st.lib.hb_increment_i32(ptr(opt._step), stream()), "hb_increment_i32")
+        lr, b1, b2, ep = st.hyper
+        check(st.lib.hb_linop_elbo_update(C.byref(st.cfg), ptr(st.params), ptr(st.zbar_stats), None, ptr(st.m), ptr(st.v),
+                                          lr, b1, b2, ep, ptr(opt._step), 0, ptr(st.out4), ptr(st.ws), st.ws_bytes, stream()),
+              "hb_linop_elbo_update")
+        return st.out4[0]
+
+
+BINDINGS = (GpElboBinding, LinopElboBinding)
+
+
+def bind(tree, model):
+    """First whole-step entry point whose graph equals the traced objective, or None."""
+    for cls in BINDINGS:
+        try:
+            b = cls.match(tree, model)
+        except Exception:       # a shape the matcher did not foresee: keep the eager path
+            b = None
+        if b is not None:
+            return b
+    return None

@@ -56,11 +56,17 @@ class UnitStationary(Kern):
 
     def Cholesky(self, X):
         """Cholesky factor of K(X) + jitter*I; [n,d] -> [n,n], [N,n,d] -> [N,n,n] (gp/kernels.py:93-101)."""
+        from .. import trace as _trace
+        if isinstance(X, _trace.Sym):
+            return _trace.Sym('cholesky', self, X)
         X = _dev(X)
         return ops.kern_cholesky(X, self.lengthscales, settings.numerics.jitter_level, self._csym)
 
 
 def _dev(x):
+    from .. import trace as _trace
+    if isinstance(x, _trace.Sym):
+        raise _trace.TraceError("this kernel method is not traced")
     if isinstance(x, torch.Tensor):
         return x
     return torch.as_tensor(np.asarray(x, dtype=np_float_type)).cuda()

@@ -203,10 +203,17 @@ class Optimizer(object):
         for v in variables:
             if id(v) not in seen:
                 seen.add(id(v)); var_list.append(v)
+        # graph building: trace the objective once; a recognised graph is bound to its whole-step C entry point and
+        # the flat buffer takes that entry point's parameter packing
+        binding = self._trace_and_bind() if fused else None
+        if binding is not None and {id(v) for v in binding.var_order} == {id(v) for v in var_list}:
+            var_list = list(binding.var_order)
+            self._fused = binding
         self.var_list = var_list
         dev = _device()
         sizes = [int(np.prod(v._host.shape)) for v in var_list]
-        offs = np.concatenate([[0], np.cumsum([(s + 3) // 4 * 4 for s in sizes])]).astype(np.int64)
+        pad = (lambda s: s) if self._fused is not None else (lambda s: (s + 3) // 4 * 4)
+        offs = np.concatenate([[0], np.cumsum([pad(s) for s in sizes])]).astype(np.int64)
         total = int(offs[-1])
         self._flat = torch.zeros(max(total, 4), device=dev)
         self._flat_grad = torch.zeros(max(total, 4), device=dev)
@@ -225,6 +232,31 @@ class Optimizer(object):
         self._evaluate(self.feed_dict(None) if self._no_minibatch() else None, dry=True)
         if verbose:
             print('finished.')
+
+    def _trace_and_bind(self):
+        from . import trace, fused
+        m = self.model
+        if bool(settings.numerics.clip_by_value):
+            return None                       # the whole-step entry points implement the default (clip off) graph
+        tree = None
+        try:
+            with trace.tracing():
+                with m.tf_mode():
+                    tree = self.likelihood_method(m)
+        except Exception:
+            tree = None
+        finally:
+            for v in fused._variationals_of(m):
+                if '_sym_feed' in v.__dict__:
+                    del v.__dict__['_sym_feed']
+        if not isinstance(tree, trace.Sym):
+            return None
+        return fused.bind(tree, m)
+
+    @property
+    def fused_entry(self):
+        """Name of the whole-step C entry point this objective was bound to at compile time (None: eager tape)."""
+        return type(self._fused).__name__ if self._fused is not None else None
 
     def _bind_all(self):
         for v, (o, s) in zip(self.var_list, self._slices):
@@ -294,7 +326,35 @@ class Optimizer(object):
         if self._flat is None:
             raise RuntimeError('call .compile() first')
 
+    def _fused_step(self, feed_dict, eps):
+        """One step through the bound whole-step entry point: same Philox windows, same Adam rule as the tape path."""
+        m, b = self.model, self._fused
+        m._feed(feed_dict or {})
+        self._ensure_bound()
+        first, count, total, world = self._shard()
+        with settings.temp_settings(self._compiled_settings):
+            m._begin_run(count, eps, shard=(first, total))
+        ctx = m._run_ctx
+        q = b.q
+        e = None if not eps else eps.get(q, None)
+        q_mu = object.__getattribute__(q, 'q_mu')
+        offset = ctx.take_sharded(int(np.prod(q_mu._host.shape))) if e is None else 0
+        o = self.optimizer
+        if getattr(b, 'fused_adam', False):
+            return b.step(self, count, e, ctx.seed, offset, world)
+        obj = b.step(self, count, e, ctx.seed, offset)
+        if world > 1:
+            torch.distributed.all_reduce(self._flat_grad)
+        ops._lib.check(ops._L().hb_increment_i32(ops.ptr(self._step), ops.stream()), "hb_increment_i32")
+        ops.adam_tf1_(self._flat, self._flat_grad, self._m, self._v, self._step, o.learning_rate, o.beta1, o.beta2,
+                      o.epsilon, grad_scale=-1.0 / world)
+        return obj
+
     def _step_once(self, feed_dict, eps=None):
+        if self._fused is not None:
+            world = self._shard()[3]
+            if world == 1 or not getattr(self._fused, 'fused_adam', False):
+                return self._fused_step(feed_dict, eps)
         self._flat_grad.zero_()
         obj = self._evaluate(feed_dict, eps=eps, grad=True)
         obj.backward()

@@ -60,6 +60,9 @@ class MatBias(Parameterized):
         self.b = variable(shape=[1, fan_out], **common)
 
     def __call__(self, x, activation=None):
+        from . import trace as _trace
+        if isinstance(x, _trace.Sym):
+            raise _trace.TraceError("a bare MatBias call is not traced")
         numerics = settings.numerics
         return ops.matbias(x, self.w, self.b, act=activation if activation else 'none',
                            clip=bool(numerics.clip_by_value), lo=numerics.clip_value_min, hi=numerics.clip_value_max)
@@ -86,6 +89,9 @@ class NeuralNet(Parameterized):
     def __call__(self, x):
         """Must run in tf_mode.  A named activation (tf.sigmoid / tf.nn.relu / tf.tanh or its string) goes into the
         GEMM epilogue; any other callable is applied to the layer's linear output."""
+        from . import trace as _trace
+        if isinstance(x, _trace.Sym):
+            return _trace.Sym('nn', self, x)
         *hidden, last = self._matbias_list
         y = x
         for layer, act in zip(hidden, self.neuron_types):

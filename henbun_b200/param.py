@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import transforms
+from . import trace as _trace
 from ._lib import HenbunB200Error
 
 np_float_type = np.float32
@@ -151,6 +152,8 @@ class Variable(Parentable):
 
     def tensor(self):
         """In tf_mode this object is seen as transform(free value) (param.py:211-218)."""
+        if _trace.active():
+            return _trace.Sym('param' if self.is_parameter else 'local', self)
         if not self.is_parameter:
             return self._tensor
         return self.transform.tf_forward(self._ensure_device())
@@ -335,6 +338,9 @@ class Parameterized(Parentable):
 
     def feed(self, x):
         """Split the last axis of x over the LOCAL children in name-sorted order (param.py:516-537)."""
+        if _trace.active():
+            object.__setattr__(self, '_sym_feed', x)
+            return
         local = self.get_variables(graph_key.LOCAL)
         if len(local) == 0:
             return
@@ -357,6 +363,8 @@ class Parameterized(Parentable):
 
     def KL(self, collection=None):
         """Sum of the children's KL (param.py:549-560)."""
+        if _trace.active():
+            return _trace.Sym('KL', self, collection)
         KL_list = [p.KL(collection) for p in self.sorted_variables if hasattr(p, 'KL')]
         KL_list = [k for k in KL_list if isinstance(k, torch.Tensor)]      # drop the numpy zeros of KL-less children
         if len(KL_list) == 0:
@@ -475,6 +483,8 @@ class Data(Variable):
         return {self: self.data}
 
     def tensor(self):
+        if _trace.active():
+            return _trace.Sym('data', self)
         if self._tensor is None or getattr(self, '_resident_src', None) is None:
             self._upload(self.data)
         return self._tensor
@@ -521,6 +531,8 @@ class MinibatchData(Data):
             self._tensor = self._resident[idx.to(self._resident.device)]
 
     def tensor(self):
+        if _trace.active():
+            return _trace.Sym('mbdata', self)
         return self._tensor
 
     def assign(self, value):

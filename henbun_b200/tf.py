@@ -10,6 +10,7 @@ import torch
 from . import ops as _ops
 from . import nn as _nn
 from . import train  # noqa: F401  (tf.train.AdamOptimizer)
+from . import trace as _trace
 
 float32 = torch.float32
 float64 = torch.float64
@@ -17,6 +18,8 @@ int32 = torch.int32
 
 
 def _t(x):
+    if isinstance(x, _trace.Sym):
+        raise _trace.TraceError("this tf op is not traced")
     if isinstance(x, torch.Tensor):
         return x
     return torch.as_tensor(np.asarray(x, dtype=np.float32)).cuda()
@@ -30,6 +33,8 @@ convert_to_tensor = constant
 
 
 def matmul(a, b, transpose_a=False, transpose_b=False):
+    if _trace.is_sym(a, b):
+        return _trace.Sym('matmul', a, b, ta=bool(transpose_a), tb=bool(transpose_b))
     return _ops.matmul(_t(a), _t(b), transpose_a, transpose_b)
 
 
@@ -45,6 +50,8 @@ def matrix_triangular_solve(matrix, rhs, lower=True, adjoint=False):
 
 
 def reduce_sum(x, axis=None, keep_dims=False):
+    if isinstance(x, _trace.Sym):
+        return _trace.Sym('reduce_sum', x, axis=axis, keep_dims=keep_dims)
     x = _t(x)
     return torch.sum(x) if axis is None else torch.sum(x, dim=axis, keepdim=keep_dims)
 
@@ -59,7 +66,7 @@ def reduce_max(x, axis=None, keep_dims=False):
     return torch.max(x) if axis is None else torch.amax(x, dim=axis, keepdim=keep_dims)
 
 
-def sqrt(x): return torch.sqrt(_t(x))
+def sqrt(x): return _trace.Sym('sqrt', x) if isinstance(x, _trace.Sym) else torch.sqrt(_t(x))
 def square(x): return torch.square(_t(x))
 def exp(x): return torch.exp(_t(x))
 def log(x): return torch.log(_t(x))

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import transforms, priors, densities, ops
+from . import trace as _trace
 from .tf_wraps import clip
 from .param import Variable, graph_key, Parameterized, _is, _in_collection
 
@@ -148,6 +149,8 @@ class Variational(Parameterized):
     def tensor(self):
         """In tf_mode this object is seen as a sample from the variational distribution
         (variationals.py:112-119)."""
+        if _trace.active():
+            return _trace.Sym('sample', self, getattr(self, '_sym_feed', None))
         if self._tensor is None:
             if self.is_local:
                 return None
@@ -160,6 +163,9 @@ class Variational(Parameterized):
 
     def feed(self, x):
         """LOCAL: route the encoder output into q_mu / q_sqrt and sample (variationals.py:121-129)."""
+        if _trace.active():
+            object.__setattr__(self, '_sym_feed', x)
+            return
         Parameterized.feed(self, x)
         if self.is_local:
             self._draw()
@@ -181,6 +187,8 @@ class Variational(Parameterized):
         return torch.log(torch.square(torch.diagonal(q_sqrt, dim1=-2, dim2=-1)))
 
     def KL(self, collection=None):
+        if _trace.active():
+            return _trace.Sym('KL', self, collection)
         if collection is None or _in_collection(collection, self.collections):
             return self._KL()
         return np.zeros([], dtype=np_float_type)
@@ -244,6 +252,8 @@ class Gaussian(Normal):
                               stddev=0.1 * scale_mean, transform=transforms.positive, collections=collections)
 
     def tensor(self):
+        if _trace.active():
+            return _trace.Sym('sample', self, getattr(self, '_sym_feed', None))
         t = Normal.tensor(self)
         if t is None:
             return None
@@ -264,6 +274,8 @@ class OffsetGaussian(Gaussian):
                                collections=collections)
 
     def tensor(self):
+        if _trace.active():
+            return _trace.Sym('sample', self, getattr(self, '_sym_feed', None))
         t = Gaussian.tensor(self)
         if t is None:
             return None

@@ -21,8 +21,8 @@ from . import henbun_oracle as O
 from henbun_b200.synthetic import make_gp_problem   # noqa: F401  (the generator lives with the product; re-exported)
 
 
-def time_gpr_steps(n, D, S, steps=2, warmup=1, threads=None, seed=0):
-    """Median seconds per (ELBO + gradient + TF-1 Adam) step of the oracle in torch-CPU fp32."""
+def time_gpr_steps(n, D, S, steps=2, warmup=1, threads=None, seed=0, reduce="median"):
+    """Median (or mean) seconds per (ELBO + gradient + TF-1 Adam) step of the oracle in torch-CPU fp32."""
     if threads:
         torch.set_num_threads(int(threads))
     X, Y, p = make_gp_problem(n, D, S, seed)
@@ -47,4 +47,5 @@ def time_gpr_steps(n, D, S, steps=2, warmup=1, threads=None, seed=0):
         last = float(elbo.detach())
         if it >= warmup:
             times.append(dt)
-    return float(np.median(times)), last, torch.get_num_threads()
+    t = float(np.mean(times)) if reduce == "mean" else float(np.median(times))
+    return t, last, torch.get_num_threads()

@@ -408,3 +408,96 @@ def test_linear_operator_model_matches_oracle():
     assert abs(float(val) - ref) <= 1e-5 * abs(ref)
     for name, var in (('q_mu', m.q.q_mu), ('q_sqrt', m.q.q_sqrt), ('var', m.var)):
         assert rel_err(var._tensor.grad.detach().cpu().numpy(), gref[name]) < 2e-5, name
+
+
+# ------------------------------------------------------------------ compile() binds recognised graphs to the fused entry points
+@pytest.mark.parametrize("q_shape,n", [('diagonal', 260), ('fullrank', 130)])
+def test_fused_binding_matches_the_eager_tape(q_shape, n):
+    """The same notebook objective compiled with and without the whole-step binding: identical Philox windows, so five
+    Adam steps must land on the same parameters (and on the oracle's, through the injected-eps trajectory test above)."""
+    rng = np.random.RandomState(5)
+    D, S = 4, 6
+    X = rng.randn(n, D); Y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.randn(n, 1)
+    ms = []
+    for fused in (True, False):
+        np.random.seed(77)
+        m = GPR(X=X, Y=Y, q_shape=q_shape)
+        m.ELBO_gaussian().compile(optimizer=tf.train.AdamOptimizer(0.01), n_samples=S, seed=11, verbose=False, fused=fused)
+        assert (m.ELBO_gaussian().fused_entry == 'GpElboBinding') == fused
+        objs = [float(m.ELBO_gaussian().optimize(maxiter=1)) for _ in range(5)]
+        ms.append((_gpr_free_params(m, q_shape), objs))
+    (pf, of), (pt, ot) = ms
+    assert np.allclose(of, ot, rtol=2e-5)
+    for k in pf:
+        assert np.allclose(pf[k], pt[k], rtol=1e-4, atol=2e-6), k
+
+
+def test_fused_linear_operator_binding_matches_the_eager_tape():
+    rng = np.random.RandomState(2)
+    M, n, S = 300, 64, 8
+    A = (rng.randn(M, n) / np.sqrt(n)).astype(np.float32); y = (A @ rng.randn(n) + 0.1 * rng.randn(M)).astype(np.float32)
+    out = []
+    for fused in (True, False):
+        np.random.seed(3)
+        m = LinearOperator(A=A, y=y)
+        m.q.q_sqrt = 0.1 * np.eye(n) + 1e-3 * np.tril(rng.randn(n, n)) if False else 0.1 * np.eye(n)
+        m.ELBO().compile(optimizer=tf.train.AdamOptimizer(0.01), n_samples=S, seed=5, verbose=False, fused=fused)
+        assert (m.ELBO().fused_entry == 'LinopElboBinding') == fused
+        objs = [float(m.ELBO().optimize(maxiter=1)) for _ in range(4)]
+        g = lambda v: v._free_numpy().astype(np.float64)
+        out.append((np.tril(g(m.q.q_sqrt)), g(m.q.q_mu), g(m.var), objs))
+    for a, b in zip(out[0][:3], out[1][:3]):
+        assert np.allclose(a, b, rtol=1e-4, atol=2e-6)
+    assert np.allclose(out[0][3], out[1][3], rtol=2e-5)
+
+
+class TwoObjectives(hb.model.Model):              # testing/test_gp.py compiles two objectives over the same variables
+    def setUp(self):
+        self.p = hb.param.Variable([4])
+
+    @hb.model.AutoOptimize()
+    def first(self):
+        return -tf.reduce_sum(tf.square(self.p - 1.0))
+
+    @hb.model.AutoOptimize()
+    def second(self):
+        return -tf.reduce_sum(tf.square(self.p + 1.0))
+
+
+def test_two_optimizers_over_the_same_variables_alternate():
+    m = TwoObjectives()
+    m.first().compile(optimizer=tf.train.AdamOptimizer(0.05), verbose=False)
+    m.second().compile(optimizer=tf.train.AdamOptimizer(0.05), verbose=False)     # re-binds p to the second optimizer's buffers
+    p0 = m.p.value.copy()
+    m.first().optimize(maxiter=200)                                               # ... the first must take it back and train
+    assert np.all(np.abs(m.p.value - 1.0) < np.abs(p0 - 1.0))
+    assert np.allclose(m.p.value, 1.0, atol=0.05)
+    m.second().optimize(maxiter=400)
+    assert np.allclose(m.p.value, -1.0, atol=0.05)
+    m.first().optimize(maxiter=400)
+    assert np.allclose(m.p.value, 1.0, atol=0.05)
+
+
+def test_data_can_be_replaced_between_runs():
+    """testing/test_data.py test_replacement: assigning a new array to a Data object takes effect at the next run."""
+    class M(hb.model.Model):
+        def setUp(self):
+            self.d = hb.param.Data(np.ones((3, 2)))
+            self.p = hb.param.Variable([1])
+
+        @hb.model.AutoOptimize()
+        def obj(self):
+            return -tf.reduce_sum(tf.square(self.d * self.p))
+    m = M()
+    m.obj().compile(verbose=False)
+    m.p = np.ones(1) * 2.0
+    v1 = float(m.obj().run())
+    m.d = np.full((3, 2), 3.0)
+    v2 = float(m.obj().run())
+    m.obj().optimize(maxiter=2)
+    m.d = np.full((3, 2), 1.0)
+    v3 = float(m.obj().run())
+    assert np.isclose(v1, -24.0) and np.isclose(v2, -216.0)
+    assert abs(v3) < 24.0 + 1e-3
+    with pytest.raises(ValueError):
+        m.d = np.ones((4, 2))

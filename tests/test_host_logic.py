@@ -190,3 +190,121 @@ def test_philox4x32_10_published_algorithm_reproduces_the_kat_vectors():
             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
     for c, k, want in kat:
         assert philox(c, k) == want
+
+
+# ------------------------------------------------------------------ graph tracing / binding (no kernels are launched)
+def _trace(model, method):
+    from henbun_b200 import trace
+    with trace.tracing():
+        with model.tf_mode():
+            return method.__wrapped__(model)
+
+
+def test_tracer_recognises_the_gp_and_linear_operator_objectives():
+    import henbun_b200 as hb
+    import henbun_b200.tf as tf
+    from henbun_b200 import fused
+    rng = np.random.RandomState(0)
+    X = rng.randn(20, 3); Y = rng.randn(20, 1)
+
+    class GPR(hb.model.Model):
+        def setUp(self, q_shape='diagonal'):
+            self.X = hb.param.Data(X); self.Y = hb.param.Data(Y)
+            self.q = hb.variationals.Gaussian(shape=[20, 1], q_shape=q_shape)
+            self.kern = hb.gp.kernels.UnitRBF()
+            self.k_var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+            self.var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+
+        @hb.model.AutoOptimize()
+        def ELBO(self):
+            y_fit = tf.matmul(self.kern.Cholesky(self.X), self.q) * tf.sqrt(self.k_var)
+            return tf.reduce_sum(hb.densities.gaussian(self.Y, y_fit, self.var)) - self.KL()
+
+        @hb.model.AutoOptimize()
+        def ELBO_student(self):          # a graph with no whole-step entry point
+            y_fit = tf.matmul(self.kern.Cholesky(self.X), self.q) * tf.sqrt(self.k_var)
+            return tf.reduce_sum(hb.densities.student_t(self.Y, y_fit, self.var, 3.0)) - self.KL()
+
+    for q_shape in ('diagonal', 'fullrank'):
+        m = GPR(q_shape=q_shape)
+        b = fused.bind(_trace(m, GPR.ELBO), m)
+        assert type(b).__name__ == 'GpElboBinding'
+        assert [v.long_name for v in b.var_order] == ['model.q.q_mu', 'model.q.q_sqrt', 'model.q.scale', 'model.kern.lengthscales',
+                                                      'model.k_var', 'model.var']
+    m = GPR()
+    with pytest.raises(Exception):
+        _trace(m, GPR.ELBO_student)                      # untraced op: compile() falls back to the eager tape
+    assert m._tf_mode is False                           # tf_mode was left cleanly
+
+    A = rng.randn(30, 8).astype(np.float32); y = rng.randn(30).astype(np.float32)
+
+    class LO(hb.model.Model):
+        def setUp(self):
+            self.A = hb.param.Data(A); self.y = hb.param.Data(y)
+            self.q = hb.variationals.Normal([8], q_shape='fullrank', stddev=0.1)
+            self.var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+
+        @hb.model.AutoOptimize()
+        def ELBO(self):
+            f = tf.matmul(self.q, self.A, transpose_b=True)
+            return tf.reduce_sum(hb.densities.gaussian(self.y, f, self.var)) - self.KL()
+
+    m2 = LO()
+    b2 = fused.bind(_trace(m2, LO.ELBO), m2)
+    assert type(b2).__name__ == 'LinopElboBinding'
+    assert [v.long_name for v in b2.var_order] == ['model.q.q_sqrt', 'model.q.q_mu', 'model.var']
+
+
+def test_tracer_rejects_graphs_that_only_look_similar():
+    import henbun_b200 as hb
+    import henbun_b200.tf as tf
+    from henbun_b200 import fused
+    rng = np.random.RandomState(0)
+    X = rng.randn(20, 3); Y = rng.randn(20, 1)
+
+    class TwoQ(hb.model.Model):                          # a second variational contributes to KL(): not the fused graph
+        def setUp(self):
+            self.X = hb.param.Data(X); self.Y = hb.param.Data(Y)
+            self.q = hb.variationals.Gaussian(shape=[20, 1])
+            self.q2 = hb.variationals.Normal([3])
+            self.kern = hb.gp.kernels.UnitRBF()
+            self.k_var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+            self.var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+
+        @hb.model.AutoOptimize()
+        def ELBO(self):
+            y_fit = tf.matmul(self.kern.Cholesky(self.X), self.q) * tf.sqrt(self.k_var)
+            return tf.reduce_sum(hb.densities.gaussian(self.Y, y_fit, self.var)) - self.KL()
+
+    m = TwoQ()
+    assert fused.bind(_trace(m, TwoQ.ELBO), m) is None
+
+    class NoSqrt(hb.model.Model):                        # k_var instead of sqrt(k_var)
+        def setUp(self):
+            self.X = hb.param.Data(X); self.Y = hb.param.Data(Y)
+            self.q = hb.variationals.Gaussian(shape=[20, 1])
+            self.kern = hb.gp.kernels.UnitRBF()
+            self.k_var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+            self.var = hb.param.Variable(shape=[1], transform=hb.transforms.positive)
+
+        @hb.model.AutoOptimize()
+        def ELBO(self):
+            y_fit = tf.matmul(self.kern.Cholesky(self.X), self.q) * self.k_var
+            return tf.reduce_sum(hb.densities.gaussian(self.Y, y_fit, self.var)) - self.KL()
+
+    m = NoSqrt()
+    assert fused.bind(_trace(m, NoSqrt.ELBO), m) is None
+
+
+def test_run_context_windows_of_one_philox_stream():
+    """Ranks of a sample-sharded run read disjoint, contiguous windows whose union is the single-GPU draw."""
+    from henbun_b200.variationals import RunContext
+    per_sample, S, world = 1000, 8, 4
+    single = RunContext(n_samples=S); single.total_samples = S
+    o0 = single.take_sharded(per_sample)
+    offs = []
+    for r in range(world):
+        c = RunContext(n_samples=S // world); c.first_sample, c.total_samples = r * (S // world), S
+        offs.append(c.take_sharded(per_sample))
+        assert c.offset == single.offset                  # every rank reserves the block of ALL samples
+    assert offs == [o0 + r * (S // world) * per_sample for r in range(world)]
