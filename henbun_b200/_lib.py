@@ -65,6 +65,7 @@ SIGNATURES = {
     "hb_density_logpdf": (_i, [_i, _c_f, _c_f, _ll, _c_f, _c_f]),
     "hb_density_logpdf_bwd": (_i, [_i, _c_f, _c_f, _ll, _c_f, _ll, _c_f, _c_f, _sz, _c_f]),
     "hb_gather_rows": (_i, [_c_f, _c_f, _c_f, _ll, _ll, _c_f]),
+    "hb_random_index": (_i, [_c_f, _ll, _c_f, _ll, _ull, _ull, _c_f]),
     "hb_gauss_loglik_fwd": (_i, [_c_f, _c_f, _c_f, _ll, _ll, _c_f, _fl, _c_f, _c_f, _c_f, _sz, _c_f]),
     "hb_rbf_gram_fwd": (_i, [_c_f, _c_f, _i, _i, _i, _i, _c_f, _i, _c_f, _ll, _ll, _fl, _i, _i, _c_f]),
     "hb_rbf_gram_bwd": (_i, [_c_f, _ll, _ll, _c_f, _c_f, _i, _i, _i, _i, _c_f, _i, _i, _i, _c_f, _c_f, _c_f, _sz,

@@ -384,6 +384,11 @@ int hb_gather_rows(float* dst, const float* src, const long long* index, long lo
   return gather_rows(dst, src, index, n_index, row_elems, S(stream));
 }
 
+int hb_random_index(long long* out, long long n_index, const long long* pool, long long pool_size, unsigned long long seed,
+                    unsigned long long offset, void* stream) {
+  return random_index(out, n_index, pool, pool_size, seed, offset, S(stream));
+}
+
 int hb_gauss_loglik_fwd(const float* f, const float* f_scale, const float* y, long long total, long long y_period,
                         const float* var, float rcoef, float* resid, float* out3, void* ws, size_t ws_bytes,
                         void* stream) {

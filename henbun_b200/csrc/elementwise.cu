@@ -259,6 +259,33 @@ int fill_f32(float* a, long long n, float v, cudaStream_t st) {
   HB_CHECK_LAUNCH();
   return HB_OK;
 }
+// Indexer.train_index on the device (Henbun/model.py:147-149: pool[np.random.randint(0, len(pool), B)], with replacement):
+// out[i] = pool[floor(u_i * pool_size)], u_i from two Philox words (64-bit multiply-shift), pool == nullptr -> identity.
+__global__ void random_index_kernel(long long* out, long long n_index, const long long* __restrict__ pool, unsigned long long pool_size,
+                                    unsigned long long seed, unsigned long long offset) {
+  const long long ngroups = (n_index + 1) / 2;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < ngroups; g += (long long)gridDim.x * blockDim.x) {
+    uint32_t r[4];
+    philox4x32_10(seed, (offset >> 2) + (unsigned long long)g, r);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const long long i = 2 * g + c;
+      if (i >= n_index) break;
+      const unsigned long long w = ((unsigned long long)r[2 * c + 1] << 32) | r[2 * c];
+      const unsigned long long j = __umul64hi(w, pool_size);
+      out[i] = pool ? pool[j] : (long long)j;
+    }
+  }
+}
+int random_index(long long* out, long long n_index, const long long* pool, long long pool_size, unsigned long long seed,
+                 unsigned long long offset, cudaStream_t st) {
+  if (n_index <= 0) return HB_OK;
+  if (!out || pool_size <= 0 || (offset & 3ull)) return HB_ERR_ARG;
+  random_index_kernel<<<grid_for((n_index + 1) / 2, 256), 256, 0, st>>>(out, n_index, pool, (unsigned long long)pool_size, seed, offset);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
 // Raw Philox-4x32-10 blocks (known-answer tests): block b = core(counter = ctr4 + b on the low 64 bits, key).
 __global__ void philox_raw_kernel(uint32_t* out, long long n_blocks, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                   uint32_t k0, uint32_t k1) {

@@ -14,6 +14,8 @@ int transpose2d(float* dst, long long ldd, const float* src, long long lds, int 
 int zero_strict_upper(float* a, long long lda, int n, cudaStream_t st);
 int fill_f32(float* a, long long n, float v, cudaStream_t st);
 int randn_philox(float* out, long long count, unsigned long long seed, unsigned long long offset, cudaStream_t st);
+int random_index(long long* out, long long n_index, const long long* pool, long long pool_size, unsigned long long seed,
+                 unsigned long long offset, cudaStream_t st);
 int philox_raw(uint32_t* out, long long n_blocks, const uint32_t* ctr4_host, const uint32_t* key2_host, cudaStream_t st);
 
 // ---- Variational sampler + one-sample KL (sampler.cu) ----

@@ -142,6 +142,24 @@ class Indexer(object):
     def test_index(self, minibatch_size):
         return self._test_index[np.random.randint(0, self.test_size, minibatch_size)]
 
+    # ---- the same draws on the device: no host RNG, no host gather, no H2D copy per step ----
+    def _device_pool(self, which):
+        key = '_dev_' + which
+        if getattr(self, key, None) is None or getattr(self, key + '_src', None) is not getattr(self, '_' + which + '_index'):
+            host = getattr(self, '_' + which + '_index')
+            setattr(self, key, torch.as_tensor(np.asarray(host, dtype=np.int64)).to(_device()))
+            setattr(self, key + '_src', host)
+        return getattr(self, key)
+
+    def device_index(self, minibatch_size, seed, offset, training=True):
+        """int64 device tensor of `minibatch_size` indices drawn with replacement from the train (test) split by the
+        Philox stream (seed, offset) -- hb_random_index."""
+        pool = self._device_pool('train' if training else 'test')
+        out = torch.empty(int(minibatch_size), dtype=torch.int64, device=pool.device)
+        ops._lib.check(ops._L().hb_random_index(ops.ptr(out), int(minibatch_size), ops.ptr(pool), pool.numel(), int(seed),
+                                                int(offset), ops.stream()), "hb_random_index")
+        return out
+
 
 class AutoOptimize(object):
     """Decorator turning a model method into an Optimizer factory (Henbun/model.py:155-188)."""
@@ -180,7 +198,7 @@ class Optimizer(object):
 
     # ---- compile: bind parameters to flat buffers, create Adam slots ----
     def compile(self, optimizer=None, collection=graph_key.VARIABLES, global_step=None, n_samples=1, seed=0,
-                verbose=True, shard=None, fused=True):
+                verbose=True, shard=None, fused=True, device_index=True):
         """``shard`` (multi-GPU, one process per GPU): 'samples' splits the n_samples draws over the ranks
         (contiguous windows of ONE Philox stream, so the union over ranks is the single-GPU draw), 'batch' keeps
         n_samples per rank and splits the minibatch (each rank draws its own indices and its own Philox window).
@@ -196,6 +214,8 @@ class Optimizer(object):
         self._shard_mode = shard
         self._want_fused = bool(fused)
         self._fused = None
+        self._device_index = bool(device_index)    # minibatch indices drawn on the device (False: numpy's global RNG, as upstream)
+        self._index_draws = 0
         m.initialize()
         variables = [v for v in m.get_variables(collection) if isinstance(v, Variable) and v.is_parameter]
         # de-duplicate while keeping the reference's name-sorted order (param.py:467-475)
@@ -229,7 +249,9 @@ class Optimizer(object):
         self.optimize_op = self._step_once
         m.validate()
         # one evaluation now: shape errors and unfed LOCAL variables surface here, like graph building
-        self._evaluate(self.feed_dict(None) if self._no_minibatch() else None, dry=True)
+        # (a traced-and-bound graph has been validated already: no need to allocate the eager path's buffers)
+        if self._fused is None:
+            self._evaluate(self.feed_dict(None) if self._no_minibatch() else None, dry=True)
         if verbose:
             print('finished.')
 
@@ -291,6 +313,15 @@ class Optimizer(object):
     def feed_dict(self, minibatch_size=None, training=True):
         if minibatch_size is None:
             return self.model.get_feed_dict(None)
+        if getattr(self, '_device_index', False) and self.model._index.data_size is not None:
+            # a Philox stream of its own (key = seed + 1): index draws never collide with the eps windows
+            from . import parallel
+            _, rank = parallel.world()
+            per = (int(minibatch_size) + 1) // 2 * 4
+            off = self._index_draws * per
+            self._index_draws += 1
+            idx = self.model._index.device_index(minibatch_size, self._seed + 1 + 7919 * rank, off, training)
+            return self.model.get_feed_dict(idx)
         elif training:
             return self.model.get_feed_dict(self.model._index.train_index(minibatch_size))
         return self.model.get_feed_dict(self.model._index.test_index(minibatch_size))
@@ -300,6 +331,7 @@ class Optimizer(object):
         m = self.model
         if feed_dict is None and dry:
             return None
+        m.initialize()                           # pending assignments apply at the next run (Henbun/model.py:84-96)
         m._feed(feed_dict or {})
         self._ensure_bound()
         first, count, total, _ = self._shard()
@@ -329,6 +361,7 @@ class Optimizer(object):
     def _fused_step(self, feed_dict, eps):
         """One step through the bound whole-step entry point: same Philox windows, same Adam rule as the tape path."""
         m, b = self.model, self._fused
+        m.initialize()
         m._feed(feed_dict or {})
         self._ensure_bound()
         first, count, total, world = self._shard()

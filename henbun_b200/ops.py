@@ -330,20 +330,33 @@ class _RbfK(torch.autograd.Function):
         want_x = ctx.needs_input_grad[0]
         want_x2 = ctx.has_x2 and ctx.needs_input_grad[1]
         if want_x or want_x2:
-            if ctx.csym:
-                raise NotImplementedError("gradient w.r.t. the inputs of UnitCsymRBF is not implemented")
             gT = g.transpose(-1, -2).contiguous()
-            if want_x2 or not ctx.has_x2:       # second-argument part: dX2_j = sum_i G_ij K_ij (x_i - x2_j)/ell^2
-                d2 = torch.empty_like(X2)
-                check(lib.hb_rbf_gram_bwd_x2(ptr(g), n2, n * n2, ptr(X), ptr(X2), n, n2, D, batch, ptr(ell), ell.numel(), 0,
-                                             1.0, ptr(d2), stream()), "hb_rbf_gram_bwd_x2")
-                if ctx.has_x2:
-                    gX2 = d2
-            if want_x:                          # first-argument part: the same contraction on G^T with swapped roles
-                d1 = torch.empty_like(X)
-                check(lib.hb_rbf_gram_bwd_x2(ptr(gT), n, n * n2, ptr(X2), ptr(X), n2, n, D, batch, ptr(ell), ell.numel(), 0,
-                                             1.0, ptr(d1), stream()), "hb_rbf_gram_bwd_x2")
-                gX = d1 if ctx.has_x2 else d1 + d2      # K(X, X): both arguments are X
+
+            def second_arg(Xa, Xb, sign):       # sign * sum_i G_ij K_rbf(xa_i, xb_j) (xa_i - xb_j)/ell^2
+                d = torch.empty_like(Xb)
+                check(lib.hb_rbf_gram_bwd_x2(ptr(g), n2, n * n2, ptr(Xa), ptr(Xb), n, n2, D, batch, ptr(ell), ell.numel(), 0,
+                                             float(sign), ptr(d), stream()), "hb_rbf_gram_bwd_x2")
+                return d
+
+            def first_arg(Xa, Xb):              # the same contraction on G^T with swapped roles
+                d = torch.empty_like(Xa)
+                check(lib.hb_rbf_gram_bwd_x2(ptr(gT), n, n * n2, ptr(Xb), ptr(Xa), n2, n, D, batch, ptr(ell), ell.numel(), 0,
+                                             1.0, ptr(d), stream()), "hb_rbf_gram_bwd_x2")
+                return d
+            d2 = second_arg(X, X2, 1.0) if (want_x2 or not ctx.has_x2) else None
+            d1 = first_arg(X, X2) if want_x else None
+            if ctx.csym:
+                # UnitCsymRBF (gp/kernels.py:122-126) adds K_rbf(x, -x2): its first-argument gradient is that of K_rbf at
+                # (x, -x2), its second-argument gradient the NEGATIVE of K_rbf's second-argument gradient at (x, -x2)
+                nX2 = (-X2).contiguous()
+                if d2 is not None:
+                    d2 = d2 + second_arg(X, nX2, -1.0)
+                if d1 is not None:
+                    d1 = d1 + first_arg(X, nX2)
+            if ctx.has_x2:
+                gX, gX2 = d1, (d2 if want_x2 else None)
+            elif want_x:
+                gX = d1 + d2                    # K(X, X): both arguments are X
         if ctx.needs_input_grad[2]:
             ws = reduce_ws(X.device)
             gl = torch.empty(ell.numel(), device=X.device)
@@ -381,8 +394,6 @@ class _KernCholesky(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         X, ell, Lw = ctx.saved_tensors
-        if ctx.needs_input_grad[0] and ctx.csym:
-            raise NotImplementedError("gradient w.r.t. the inputs of UnitCsymRBF is not implemented")
         batch, n, _, D = _kern_shapes(X, None)
         G = _own_grad(g)
         lib = _L()
@@ -401,6 +412,12 @@ class _KernCholesky(torch.autograd.Function):
             gX = torch.empty_like(X)
             check(lib.hb_rbf_gram_bwd_x2(ptr(G), n, n * n, ptr(X), None, n, n, D, batch, ptr(ell), ell.numel(), 1, 2.0,
                                          ptr(gX), stream()), "hb_rbf_gram_bwd_x2")
+            if ctx.csym:    # + the mirrored term K_rbf(x, -x'), symmetric as well: -2 x its second-argument gradient at (X, -X)
+                nX = (-X).contiguous()
+                gc = torch.empty_like(X)
+                check(lib.hb_rbf_gram_bwd_x2(ptr(G), n, n * n, ptr(X), ptr(nX), n, n, D, batch, ptr(ell), ell.numel(), 1, -2.0,
+                                             ptr(gc), stream()), "hb_rbf_gram_bwd_x2")
+                gX = gX + gc
         return gX, gl, None, None
 
 

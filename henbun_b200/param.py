@@ -524,7 +524,7 @@ class MinibatchData(Data):
         from . import ops
         if self._resident is None:
             self._resident = torch.as_tensor(np.ascontiguousarray(self.data)).to(self._dtype).to(_device())
-        idx = torch.as_tensor(np.asarray(index, dtype=np.int64))
+        idx = index if isinstance(index, torch.Tensor) else torch.as_tensor(np.asarray(index, dtype=np.int64))
         if self._dtype == torch.float32:
             self._tensor = ops.gather_rows(self._resident, idx.to(self._resident.device))
         else:

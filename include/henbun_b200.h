@@ -148,6 +148,11 @@ int hb_density_logpdf_bwd(int kind, const float* const* args, const long long* p
 /* MinibatchData.get_feed_dict (param.py:733-739) on device: dst[i,:] = src[index[i],:], index int64. */
 int hb_gather_rows(float* dst, const float* src, const long long* index, long long n_index, long long row_elems,
                    void* stream);
+/* Indexer.train_index (model.py:147-149) on device: out[i] = pool[j_i], j_i uniform in [0, pool_size) with replacement,
+ * drawn from Philox(seed, offset) (two 32-bit words per index; 2 * ceil(n_index / 2) stream positions).  pool == NULL:
+ * out[i] = j_i.  Feeds hb_gather_rows without any host work or host->device copy per step. */
+int hb_random_index(long long* out, long long n_index, const long long* pool, long long pool_size, unsigned long long seed,
+                    unsigned long long offset, void* stream);
 /* reduce_sum(densities.gaussian(y, f_scale*f, var)) fused with the residual for the backward.
  * f: [total]; y: [y_period] broadcast; var, f_scale: device scalars (f_scale may be NULL = 1).
  * resid (may be NULL) = -rcoef*(f_scale*f - y)/var.  out3 = {loglik, sum E^2, sum E*(f_scale*f)}. */

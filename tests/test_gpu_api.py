@@ -501,3 +501,39 @@ def test_data_can_be_replaced_between_runs():
     assert abs(v3) < 24.0 + 1e-3
     with pytest.raises(ValueError):
         m.d = np.ones((4, 2))
+
+
+def test_device_minibatch_index_matches_its_definition():
+    """hb_random_index: out[i] = pool[(w_i * pool_size) >> 64], w_i = two consecutive Philox words -- checked against the
+    raw generator; draws stay inside the train split and are reproducible per (seed, offset)."""
+    import ctypes as C
+    from henbun_b200 import _lib
+    lib = _lib.load()
+    ix = hb.model.Indexer()
+    ix.setUp(1000)
+    a = ix.device_index(257, seed=5, offset=8).cpu().numpy()
+    b = ix.device_index(257, seed=5, offset=8).cpu().numpy()
+    c = ix.device_index(257, seed=6, offset=8).cpu().numpy()
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert set(a.tolist()) <= set(ix._train_index.tolist())
+    raw = torch.zeros(4 * 129, dtype=torch.int32, device="cuda")
+    ctr = (C.c_uint32 * 4)(2, 0, 0, 0); key = (C.c_uint32 * 2)(5, 0)
+    assert lib.hb_philox4x32_10(_lib.ptr(raw), 129, ctr, key, _lib.stream()) == 0
+    w = raw.cpu().numpy().view(np.uint32).astype(np.uint64)
+    w64 = (w[1::2] << np.uint64(32)) | w[0::2]
+    j = np.array([(int(x) * ix.train_size) >> 64 for x in w64[:257]])
+    assert np.array_equal(a, ix._train_index[j])
+    t = ix.device_index(64, seed=1, offset=0, training=False).cpu().numpy()
+    assert set(t.tolist()) <= set(ix._test_index.tolist())
+
+
+def test_minibatch_training_runs_on_device_indices():
+    rng = np.random.RandomState(0)
+    Xall = rng.randn(400, 12).astype(np.float32)
+    m = Amortised(X=Xall)
+    m.ELBO().compile(n_samples=3, verbose=False)                      # device_index=True is the default
+    v = [float(m.ELBO().optimize(maxiter=1, minibatch_size=32)) for _ in range(3)]
+    assert all(np.isfinite(v))
+    m2 = Amortised(X=Xall)
+    m2.ELBO().compile(n_samples=3, verbose=False, device_index=False)  # numpy's global RNG, as upstream
+    assert np.isfinite(float(m2.ELBO().optimize(maxiter=2, minibatch_size=32)))

@@ -76,3 +76,32 @@ def test_sparse_gp_trains_inducing_points():
     free = [p for p in model.get_tf_variables() if p.grad is not None and tuple(p.shape) == tuple(z.shape)]
     assert free, "no gradient reached the inducing points"
     assert rel_err(free[0].grad.cpu(), tz.grad) < 2e-4
+
+
+@pytest.mark.parametrize("n,m,D", [(37, 21, 2), (64, 64, 1), (50, 90, 5)])
+def test_csym_rbf_input_gradients(n, m, D):
+    """UnitCsymRBF (gp/kernels.py:113-131): K(x, x2) + K(x, -x2).  Gradients w.r.t. both arguments, w.r.t. X when both
+    arguments are X, and through the kernel Cholesky -- all vs the oracle's csym_rbf_K under autograd."""
+    from henbun_b200 import ops
+    rng = np.random.RandomState(7 * n + m)
+    X = 0.6 * rng.randn(n, D); Z = 0.6 * rng.randn(m, D); ell = np.array([0.9]); W = rng.randn(n, m)
+    tX, tZ = (torch.tensor(a, requires_grad=True) for a in (X, Z))
+    (O.csym_rbf_K(tX, torch.tensor(ell), tZ) * torch.tensor(W)).sum().backward()
+    c = lambda a, g=False: torch.tensor(a, dtype=torch.float32, device="cuda", requires_grad=g)
+    dX, dZ = c(X, True), c(Z, True)
+    (ops.rbf_K(dX, dZ, c(ell), True) * c(W)).sum().backward()
+    assert rel_err(dX.grad.cpu(), tX.grad) < 1e-4
+    assert rel_err(dZ.grad.cpu(), tZ.grad) < 1e-4
+    W2 = rng.randn(n, n)
+    tX2 = torch.tensor(X, requires_grad=True)
+    (O.csym_rbf_K(tX2, torch.tensor(ell)) * torch.tensor(W2)).sum().backward()
+    dX2 = c(X, True)
+    (ops.rbf_K(dX2, None, c(ell), True) * c(W2)).sum().backward()
+    assert rel_err(dX2.grad.cpu(), tX2.grad) < 1e-4
+    # through the fused kernel-Cholesky (K-bar symmetric, lower storage)
+    Wl = np.tril(rng.randn(n, n))
+    tX3 = torch.tensor(X, requires_grad=True)
+    (O.kern_cholesky(tX3, torch.tensor(ell), 1e-2, K_fn=O.csym_rbf_K) * torch.tensor(Wl)).sum().backward()
+    dX3 = c(X, True)
+    (ops.kern_cholesky(dX3, c(ell), 1e-2, True) * c(Wl)).sum().backward()
+    assert rel_err(dX3.grad.cpu(), tX3.grad) < 5e-4
