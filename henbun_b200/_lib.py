@@ -31,6 +31,11 @@ class GpConfig(C.Structure):
                 ("seed", _ull), ("offset", _ull)]
 
 
+class AdamConfig(C.Structure):
+    _fields_ = [("lr", _fl), ("b1", _fl), ("b2", _fl), ("eps", _fl), ("grad_scale", _fl), ("step_dev", C.c_void_p),
+                ("step_host", _i)]
+
+
 class LinopConfig(C.Structure):
     _fields_ = [("M", _i), ("M_total", _ll), ("n", _i), ("S", _i), ("seed", _ull), ("offset", _ull)]
 
@@ -101,6 +106,13 @@ SIGNATURES = {
     "hb_linop_elbo_local": (_i, [C.POINTER(LinopConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f]),
     "hb_linop_elbo_update": (_i, [C.POINTER(LinopConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _fl, _fl, _fl, _fl, _c_f, _i,
                                   _c_f, _c_f, _sz, _c_f]),
+    "hb_gp_small_max_n": (_i, [_i]),
+    "hb_set_small_gp_kernel": (_i, [_i]),
+    "hb_gp_small_workspace_bytes": (_sz, [C.POINTER(GpConfig), _i]),
+    "hb_gp_small_step": (_i, [C.POINTER(GpConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, C.POINTER(AdamConfig), _c_f, _sz,
+                              _c_f, _c_f]),
+    "hb_gp_small_step_f64": (_i, [C.POINTER(GpConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, C.POINTER(AdamConfig), _c_f,
+                                  _sz, _c_f, _c_f]),
     "hb_gp_param_count": (_sz, [C.POINTER(GpConfig)]),
     "hb_gp_elbo_workspace_bytes": (_sz, [C.POINTER(GpConfig)]),
     "hb_gp_elbo_step": (_i, [C.POINTER(GpConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f, _c_f]),

@@ -568,6 +568,38 @@ int hb_zero_strict_upper(float* a, long long lda, int n, void* stream) { return 
 // ---------------------------------------------------------------------------------------------
 // fused variational-GP ELBO + gradient
 // ---------------------------------------------------------------------------------------------
+static int g_small_gp = 1;
+int hb_set_small_gp_kernel(int on) { g_small_gp = on ? 1 : 0; return g_small_gp; }
+int hb_gp_small_max_n(int f64) { return gp_small_max_n(f64); }
+size_t hb_gp_small_workspace_bytes(const hb_gp_config* c, int f64) {
+  if (!c) return 0;
+  return gp_small_workspace_elems(c->n, c->S) * (f64 ? 8 : 4) + 256;
+}
+int hb_gp_small_step(const hb_gp_config* cfg, const float* X, const float* Y, float* params, const float* eps, float* grads,
+                     float* out4, float* adam_m, float* adam_v, const hb_adam_config* adam, void* ws, size_t ws_bytes,
+                     int* err_flag, void* stream) {
+  if (!cfg) return HB_ERR_ARG;
+  if (!ws || ws_bytes < hb_gp_small_workspace_bytes(cfg, 0)) return HB_ERR_WORKSPACE;
+  if ((adam_m || adam_v) && (!adam || !adam_m || !adam_v)) return HB_ERR_ARG;
+  float* w = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  return gp_small_step_f32(cfg->n, cfg->D, cfg->S, cfg->n_ell, cfg->q_fullrank, cfg->jitter, cfg->seed, cfg->offset, X, Y, params, eps,
+                           grads, out4, w, err_flag, adam_m, adam_v, adam ? adam->step_dev : nullptr, adam ? adam->step_host : 0,
+                           adam ? adam->lr : 0.f, adam ? adam->b1 : 0.f, adam ? adam->b2 : 0.f, adam ? adam->eps : 0.f,
+                           adam ? adam->grad_scale : 0.f, S(stream));
+}
+int hb_gp_small_step_f64(const hb_gp_config* cfg, const double* X, const double* Y, double* params, const double* eps, double* grads,
+                         double* out4, double* adam_m, double* adam_v, const hb_adam_config* adam, void* ws, size_t ws_bytes,
+                         int* err_flag, void* stream) {
+  if (!cfg) return HB_ERR_ARG;
+  if (!ws || ws_bytes < hb_gp_small_workspace_bytes(cfg, 1)) return HB_ERR_WORKSPACE;
+  if ((adam_m || adam_v) && (!adam || !adam_m || !adam_v)) return HB_ERR_ARG;
+  double* w = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  return gp_small_step_f64(cfg->n, cfg->D, cfg->S, cfg->n_ell, cfg->q_fullrank, (double)cfg->jitter, cfg->seed, cfg->offset, X, Y, params,
+                           eps, grads, out4, w, err_flag, adam_m, adam_v, adam ? adam->step_dev : nullptr, adam ? adam->step_host : 0,
+                           adam ? (double)adam->lr : 0.0, adam ? (double)adam->b1 : 0.0, adam ? (double)adam->b2 : 0.0,
+                           adam ? (double)adam->eps : 0.0, adam ? (double)adam->grad_scale : 0.0, S(stream));
+}
+
 size_t hb_gp_param_count(const hb_gp_config* c) {
   if (!c) return 0;
   return (size_t)c->n + (c->q_fullrank ? (size_t)c->n * c->n : (size_t)c->n) + 1 + c->n_ell + 2;
@@ -601,6 +633,11 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
   float* kl = ll3 + 3;                 // 1 float
 
   const int n = c.n, Sn = c.S;
+  if (n <= gp_small_max_n(0) && g_small_gp) {
+    // notebook-sized model: the whole step is ONE persistent CTA (gp_small.cu); Z | F | R | W are adjacent -> 4 S n floats
+    return gp_small_step_f32(n, c.D, Sn, c.n_ell, c.q_fullrank, c.jitter, c.seed, c.offset, X, Y, const_cast<float*>(params), eps,
+                             grads, out4, Z, err_flag, nullptr, nullptr, nullptr, 0, 0.f, 0.f, 0.f, 0.f, 0.f, st);
+  }
   const size_t nq = c.q_fullrank ? (size_t)n * n : (size_t)n;
   const float* p_mu = params;
   const float* p_sq = params + n;

@@ -1,0 +1,362 @@
+// One persistent CTA for the whole ELBO + gradient (+ TF-1 Adam) step of the variational GP regression graph when the
+// model is notebook sized (n <= 128 in fp32, n <= 112 in fp64):
+//     notebooks/GaussianProcess.ipynb:109-148   y_fit = matmul(kern.Cholesky(X), q) * sqrt(k_var)
+//                                                ELBO  = reduce_sum(gaussian(Y, y_fit, var)) - KL()
+// The reference launches ~60 TensorFlow ops per session.run for this graph; round 1 of this library needed 23 kernels
+// (0.24 ms per step, 60 % of it in two one-CTA leaf kernels that also computed block inverses nobody needs at this
+// size).  Here the Gram matrix, its Cholesky factor and the adjoint live in shared memory from the first to the last
+// instruction: Gram -> potrf (right-looking, one column per step) -> sampler + KL -> F = a L Z^T -> log-likelihood ->
+// z-bar, L-bar -> sampler backward -> reverse-mode Cholesky (level-2 form of Murray 2016, in place, no inverse) ->
+// Gram backward -> scalar chain rules -> optional Adam.  The arithmetic type is a template parameter: the fp64
+// instantiation is the float_type = float64 path of the reference (henbunrc:7) for the 1-D notebook inputs, whose Gram
+// matrices (cond 1e6) put an fp32 factorisation 3 orders of magnitude away from the 1e-5 parity bar.
+#include "kernels.cuh"
+
+namespace hb {
+
+namespace {
+
+constexpr int GS_THREADS = 512;
+
+template <typename T> struct SmallLimits;
+template <> struct SmallLimits<float> { static constexpr int max_n = 128; };
+template <> struct SmallLimits<double> { static constexpr int max_n = 112; };
+
+template <typename T> __device__ __forceinline__ T t_exp(T x);
+template <> __device__ __forceinline__ float t_exp<float>(float x) { return expf(x); }
+template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
+template <typename T> __device__ __forceinline__ T t_log(T x);
+template <> __device__ __forceinline__ float t_log<float>(float x) { return logf(x); }
+template <> __device__ __forceinline__ double t_log<double>(double x) { return log(x); }
+template <typename T> __device__ __forceinline__ T t_sqrt(T x);
+template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
+template <typename T> __device__ __forceinline__ T t_softplus(T x) {
+  const T ax = x < T(0) ? -x : x;
+  return (x > T(0) ? x : T(0)) + (T)log1p((double)t_exp<T>(-ax));
+}
+template <typename T> __device__ __forceinline__ T t_sigmoid(T x) { return T(1) / (T(1) + t_exp<T>(-x)); }
+
+template <typename T>
+struct SmallArgs {
+  int n, D, S, n_ell, q_fullrank;
+  T jitter;
+  unsigned long long seed, offset;
+  const T* X; const T* Y; T* params; const T* eps; T* grads; T* out4;
+  T* ws;                 // 4 * S * n elements: Z | U | R | Zbar
+  int* err_flag;
+  // optional fused Adam (m == nullptr: gradients only)
+  T* m; T* v; const int* step_dev; int step_host; T lr, b1, b2, eps_adam, grad_scale;
+};
+
+// block-wide sum of one double per thread; result broadcast to every thread
+__device__ __forceinline__ double block_sum_all(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < GS_THREADS / 32; ++i) t += red[i];
+  return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GS_THREADS, 1) gp_small_step_kernel(const SmallArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char gs_smem[];
+  const int n = a.n, S = a.S, D = a.D, tid = threadIdx.x;
+  const int LD = n | 1;                                  // odd leading dimension: conflict-free column walks
+  T* L = reinterpret_cast<T*>(gs_smem);                  // K, then its Cholesky factor (lower)
+  T* G = L + (size_t)n * LD;                             // L-bar, then K-bar (lower)
+  T* ell = G + (size_t)n * LD;                           // [n_ell]
+  T* colv = ell + 32;                                    // [n] scratch column
+  __shared__ double red[GS_THREADS / 32];
+  __shared__ T sh_piv;
+  __shared__ int sh_bad;
+
+  const size_t nq = a.q_fullrank ? (size_t)n * n : (size_t)n;
+  T* p_mu = a.params; T* p_sq = a.params + n; T* p_scale = p_sq + nq; T* p_ell = p_scale + 1;
+  T* p_kvar = p_ell + a.n_ell; T* p_var = p_kvar + 1;
+  T* g_mu = a.grads; T* g_sq = a.grads + n; T* g_scale = g_sq + nq; T* g_ell = g_scale + 1;
+  T* g_kvar = g_ell + a.n_ell; T* g_var = g_kvar + 1;
+  T* Z = a.ws; T* U = Z + (size_t)S * n; T* R = U + (size_t)S * n; T* Zb = R + (size_t)S * n;
+
+  // ---- positive hyper-parameters (transforms.positive: softplus + 1e-6, transforms.py:133-134) ----
+  const T s_q = t_softplus<T>(*p_scale) + T(1e-6);
+  const T kv = t_softplus<T>(*p_kvar) + T(1e-6);
+  const T var = t_softplus<T>(*p_var) + T(1e-6);
+  const T amp = t_sqrt<T>(kv) * s_q;
+  for (int d = tid; d < a.n_ell; d += GS_THREADS) ell[d] = t_softplus<T>(p_ell[d]) + T(1e-6);
+  if (tid == 0) sh_bad = 0;
+  __syncthreads();
+
+  // ---- K = rbf(X) + jitter I, lower triangle (gp/kernels.py:54-84, 100-101, 110-111) ----
+  for (int e = tid; e < n * n; e += GS_THREADS) {
+    const int i = e / n, j = e % n;
+    T val = T(0);
+    if (j <= i) {
+      T r2 = T(0);
+      for (int d = 0; d < D; ++d) {
+        const T df = (a.X[i * D + d] - a.X[j * D + d]) / ell[a.n_ell == 1 ? 0 : d];
+        r2 += df * df;
+      }
+      val = t_exp<T>(T(-0.5) * r2) + (i == j ? a.jitter : T(0));
+    }
+    L[i * LD + j] = val;
+  }
+  __syncthreads();
+
+  // ---- potrf, right-looking, one column per step (tf.cholesky) ----
+  for (int j = 0; j < n; ++j) {
+    if (tid == 0) {
+      const T d = L[j * LD + j];
+      if (!(d > T(0)) && sh_bad == 0) sh_bad = j + 1;
+      sh_piv = t_sqrt<T>(d > T(0) ? d : T(1));
+    }
+    __syncthreads();
+    const T piv = sh_piv, rp = T(1) / piv;
+    for (int i = j + tid; i < n; i += GS_THREADS) {
+      const T x = (i == j) ? piv : L[i * LD + j] * rp;
+      L[i * LD + j] = x;
+      colv[i] = x;
+    }
+    __syncthreads();
+    const int m = n - j - 1;                             // trailing order
+    for (int e = tid; e < m * m; e += GS_THREADS) {
+      const int r = j + 1 + e / m, c = j + 1 + e % m;
+      if (c <= r) L[r * LD + c] -= colv[r] * colv[c];
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && sh_bad != 0 && a.err_flag) atomicCAS(a.err_flag, 0, sh_bad);
+
+  // ---- sampler + one-sample KL (variationals.py:138-146, 183-186, 225-230) ----
+  double kl_part = 0.0;
+  for (int e = tid; e < S * n; e += GS_THREADS) {
+    const T u = a.eps ? a.eps[e] : (T)philox_normal_at(a.seed, a.offset, (unsigned long long)e);
+    U[e] = u;
+  }
+  __syncthreads();
+  for (int e = tid; e < S * n; e += GS_THREADS) {
+    const int s = e / n, i = e % n;
+    T z, logdet;
+    if (!a.q_fullrank) {
+      z = p_mu[i] + t_exp<T>(p_sq[i]) * U[e];
+      logdet = T(2) * p_sq[i];
+    } else {
+      T acc = p_mu[i];
+      const T* lq = p_sq + (size_t)i * n;
+      for (int k = 0; k <= i; ++k) acc += lq[k] * U[s * n + k];
+      z = acc;
+      logdet = t_log<T>(lq[i] * lq[i]);
+    }
+    Z[e] = z;
+    const T u = U[e];
+    kl_part += (double)(logdet + u * u - z * z);
+  }
+  const double kl = -0.5 * block_sum_all(kl_part, red);
+  __syncthreads();
+
+  // ---- F = amp * Z L^T, log-likelihood, residual R = dELBO/dF (densities.py:25-27) ----
+  double ll_part = 0.0, e2_part = 0.0, ef_part = 0.0;
+  const T inv_S = T(1) / (T)S;
+  for (int e = tid; e < S * n; e += GS_THREADS) {
+    const int s = e / n, i = e % n;
+    T acc = T(0);
+    const T* zr = Z + (size_t)s * n;
+    for (int k = 0; k <= i; ++k) acc += L[i * LD + k] * zr[k];
+    const T F = amp * acc;
+    const T E = a.Y[i] - F;
+    ll_part += (double)(T(-0.9189385332046727) - T(0.5) * t_log<T>(var) - T(0.5) * E * E / var);
+    e2_part += (double)(E * E);
+    ef_part += (double)(E * acc);                        // sum E * Fraw
+    R[e] = E / var * inv_S;
+  }
+  const double ll = block_sum_all(ll_part, red);
+  const double sumE2 = block_sum_all(e2_part, red);
+  const double sumEFraw = block_sum_all(ef_part, red);
+  __syncthreads();
+
+  // ---- z-bar = amp * R L  (+ the KL's -z/S), L-bar = amp * tril(R^T Z) ----
+  for (int e = tid; e < S * n; e += GS_THREADS) {
+    const int s = e / n, k = e % n;
+    T acc = T(0);
+    const T* rr = R + (size_t)s * n;
+    for (int i = k; i < n; ++i) acc += rr[i] * L[i * LD + k];
+    Zb[e] = amp * acc - Z[e] * inv_S;
+  }
+  for (int e = tid; e < n * n; e += GS_THREADS) {
+    const int i = e / n, k = e % n;
+    T acc = T(0);
+    if (k <= i) {
+      for (int s = 0; s < S; ++s) acc += R[s * n + i] * Z[s * n + k];
+      acc *= amp;
+    }
+    G[i * LD + k] = acc;
+  }
+  __syncthreads();
+
+  // ---- sampler backward ----
+  for (int k = tid; k < n; k += GS_THREADS) {
+    T gm = T(0), go = T(0);
+    for (int s = 0; s < S; ++s) {
+      const T zt = Zb[s * n + k];
+      gm += zt;
+      if (!a.q_fullrank) go += zt * U[s * n + k];
+    }
+    g_mu[k] = gm;
+    if (!a.q_fullrank) g_sq[k] = go * t_exp<T>(p_sq[k]) + T(1);
+  }
+  if (a.q_fullrank) {
+    for (int e = tid; e < n * n; e += GS_THREADS) {
+      const int i = e / n, k = e % n;
+      T acc = T(0);
+      if (k <= i) {
+        for (int s = 0; s < S; ++s) acc += Zb[s * n + i] * U[s * n + k];
+        if (k == i) acc += T(1) / p_sq[(size_t)i * n + i];
+      }
+      g_sq[(size_t)i * n + k] = acc;
+    }
+  }
+
+  // ---- reverse-mode Cholesky, level-2, in place: G (L-bar) -> dELBO / dK over the stored lower triangle ----
+  for (int j = n - 1; j >= 0; --j) {
+    // reverse of the trailing update of column j: Lbar[r, j] -= sum_c (Abar[r, c] + Abar[c, r]) L[c, j]  (r, c > j)
+    const int m = n - j - 1;
+    for (int r = j + 1 + tid; r < n; r += GS_THREADS) {
+      T acc = T(0);
+      for (int c = j + 1; c < n; ++c) {
+        const T ab = (c <= r) ? G[r * LD + c] : G[c * LD + r];
+        acc += ab * L[c * LD + j] * ((c == r) ? T(2) : T(1));
+      }
+      colv[r] = acc;
+    }
+    __syncthreads();
+    double dot = 0.0;
+    const T ljj = L[j * LD + j];
+    for (int r = j + 1 + tid; r < n; r += GS_THREADS) {
+      const T lb = G[r * LD + j] - colv[r];              // adjoint of L[r, j]
+      G[r * LD + j] = lb / ljj;                          // reverse of the column scaling: adjoint of A[r, j]
+      dot += (double)(lb * L[r * LD + j]);
+    }
+    (void)m;
+    const double tot = block_sum_all(dot, red);
+    if (tid == 0) {
+      const T lbjj = G[j * LD + j] - (T)tot / ljj;       // adjoint of L[j, j]
+      G[j * LD + j] = lbjj / (T(2) * ljj);               // reverse of the square root
+    }
+    __syncthreads();
+  }
+
+  // ---- Gram backward: dELBO / d ell (K recomputed from X; the diagonal does not depend on ell) ----
+  {
+    double acc_e[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int d0 = 0; d0 < a.n_ell; d0 += 4) {
+      for (int q = 0; q < 4; ++q) acc_e[q] = 0.0;
+      for (int e = tid; e < n * n; e += GS_THREADS) {
+        const int i = e / n, j = e % n;
+        if (j >= i) continue;
+        T r2 = T(0);
+        for (int d = 0; d < D; ++d) {
+          const T df = (a.X[i * D + d] - a.X[j * D + d]) / ell[a.n_ell == 1 ? 0 : d];
+          r2 += df * df;
+        }
+        const T gk = G[i * LD + j] * t_exp<T>(T(-0.5) * r2);
+        if (a.n_ell == 1) {
+          acc_e[0] += (double)(gk * r2 / ell[0]);          // dK/d ell = K r2 / ell
+        } else {
+          for (int q = 0; q < 4 && d0 + q < a.n_ell; ++q) {
+            const T df = (a.X[i * D + d0 + q] - a.X[j * D + d0 + q]) / ell[d0 + q];
+            acc_e[q] += (double)(gk * df * df / ell[d0 + q]);
+          }
+        }
+      }
+      for (int q = 0; q < 4 && d0 + q < a.n_ell; ++q) {
+        const double t = block_sum_all(acc_e[q], red);
+        if (tid == 0) g_ell[d0 + q] = (T)t * t_sigmoid<T>(p_ell[d0 + q]);
+      }
+    }
+  }
+
+  // ---- scalar gradients and the ELBO ----
+  if (tid == 0) {
+    const double v = (double)var, am = (double)amp, sq = (double)s_q, kvd = (double)kv;
+    const double invS = 1.0 / (double)S;
+    const double ga = invS * sumEFraw / v;                         // dELBO / d amp = sum R * Fraw
+    const double gv = invS * (-0.5 * (double)S * n / v + 0.5 * sumE2 / (v * v));
+    *g_scale = (T)(ga * sqrt(kvd) * (double)t_sigmoid<T>(*p_scale));
+    *g_kvar = (T)(ga * sq / (2.0 * sqrt(kvd)) * (double)t_sigmoid<T>(*p_kvar));
+    *g_var = (T)(gv * (double)t_sigmoid<T>(*p_var));
+    (void)am;
+    a.out4[0] = (T)((ll - kl) * invS); a.out4[1] = (T)ll; a.out4[2] = (T)kl; a.out4[3] = T(0);
+  }
+
+  // ---- optional TF-1 Adam on -ELBO (model.py:206,220) ----
+  if (a.m) {
+    __threadfence_block();
+    __syncthreads();
+    const int t = a.step_dev ? *a.step_dev : a.step_host;
+    const double lr_t = (double)a.lr * sqrt(1.0 - pow((double)a.b2, (double)t)) / (1.0 - pow((double)a.b1, (double)t));
+    const size_t npar = (size_t)n + nq + 3 + a.n_ell;
+    for (size_t i = tid; i < npar; i += GS_THREADS) {
+      if (a.q_fullrank && i >= (size_t)n && i < (size_t)n + nq) {
+        const size_t q = i - n;
+        if (q % n > q / n) continue;                     // strict upper triangle of q_sqrt: zero gradient upstream, never moves
+      }
+      const T g = a.grad_scale * a.grads[i];
+      const T mm = a.b1 * a.m[i] + (T(1) - a.b1) * g;
+      const T vv = a.b2 * a.v[i] + (T(1) - a.b2) * g * g;
+      a.m[i] = mm; a.v[i] = vv;
+      a.params[i] -= (T)lr_t * mm / (t_sqrt<T>(vv) + a.eps_adam);
+    }
+  }
+}
+
+template <typename T>
+size_t small_smem_bytes(int n) {
+  const size_t LD = (size_t)(n | 1);
+  return (2 * (size_t)n * LD + 32 + (size_t)n + 8) * sizeof(T) + 64;
+}
+
+template <typename T>
+int launch_small(const SmallArgs<T>& a, cudaStream_t st) {
+  if (a.n <= 0 || a.n > SmallLimits<T>::max_n || a.D <= 0 || a.D > 32 || a.S <= 0 || (a.n_ell != 1 && a.n_ell != a.D))
+    return HB_ERR_ARG;
+  if (!a.X || !a.Y || !a.params || !a.grads || !a.out4 || !a.ws) return HB_ERR_ARG;
+  if (!a.eps && (a.offset & 3ull)) return HB_ERR_ARG;
+  const size_t smem = small_smem_bytes<T>(a.n);
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
+    if (cudaFuncSetAttribute(gp_small_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess)
+      return HB_ERR_CUDA;
+    attr_set = 227 * 1024;
+  }
+  gp_small_step_kernel<T><<<1, GS_THREADS, smem, st>>>(a);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+}  // namespace
+
+int gp_small_max_n(int f64) { return f64 ? SmallLimits<double>::max_n : SmallLimits<float>::max_n; }
+size_t gp_small_workspace_elems(int n, int S) { return 4 * (size_t)S * n + 16; }
+
+int gp_small_step_f32(int n, int D, int S, int n_ell, int q_fullrank, float jitter, unsigned long long seed, unsigned long long offset,
+                      const float* X, const float* Y, float* params, const float* eps, float* grads, float* out4, float* ws,
+                      int* err_flag, float* m, float* v, const int* step_dev, int step_host, float lr, float b1, float b2,
+                      float eps_adam, float grad_scale, cudaStream_t st) {
+  SmallArgs<float> a{n, D, S, n_ell, q_fullrank, jitter, seed, offset, X, Y, params, eps, grads, out4, ws, err_flag,
+                     m, v, step_dev, step_host, lr, b1, b2, eps_adam, grad_scale};
+  return launch_small<float>(a, st);
+}
+
+int gp_small_step_f64(int n, int D, int S, int n_ell, int q_fullrank, double jitter, unsigned long long seed, unsigned long long offset,
+                      const double* X, const double* Y, double* params, const double* eps, double* grads, double* out4, double* ws,
+                      int* err_flag, double* m, double* v, const int* step_dev, int step_host, double lr, double b1, double b2,
+                      double eps_adam, double grad_scale, cudaStream_t st) {
+  SmallArgs<double> a{n, D, S, n_ell, q_fullrank, jitter, seed, offset, X, Y, params, eps, grads, out4, ws, err_flag,
+                      m, v, step_dev, step_host, lr, b1, b2, eps_adam, grad_scale};
+  return launch_small<double>(a, st);
+}
+
+}  // namespace hb

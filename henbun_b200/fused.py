@@ -165,6 +165,8 @@ class GpElboBinding(object):
         self.lib = _lib.load()
         self._ws = None
         self._key = None
+        self._p64 = None
+        self._src64 = None
 
     @staticmethod
     def match(tree, model):
@@ -221,27 +223,83 @@ class GpElboBinding(object):
             return None
         return GpElboBinding(model, q, kern, k_var, var, X, Y)
 
-    def step(self, opt, count, eps, seed, offset):
-        """Forward + backward into opt._flat_grad; returns the ELBO (mean over the `count` samples) as a 0-d tensor."""
+    # notebook-sized models: the whole step, Adam included, is one persistent CTA (csrc/gp_small.cu)
+    @property
+    def fused_adam(self):
+        n = self.X.data.shape[0]
+        return n <= int(self.lib.hb_gp_small_max_n(1 if self._f64() else 0)) and parallel.world()[0] == 1
+
+    @staticmethod
+    def _f64():
+        from ._settings import settings
+        return str(settings.dtypes.float_type) == 'float64'
+
+    def _cfg(self, opt, count, seed, offset):
+        n, D = self.X.data.shape
+        n_ell = int(np.prod(object.__getattribute__(self.kern, 'lengthscales')._host.shape))
+        full = 1 if self.q.q_shape == 'fullrank' else 0
+        return _lib.GpConfig(int(n), int(D), int(count), n_ell, full, float(opt._compiled_settings.numerics.jitter_level),
+                             int(seed), int(offset)), (n, D, count, n_ell, full)
+
+    def _eps(self, eps, count, n, device, dtype):
+        if eps is None:
+            return None
+        e = torch.as_tensor(np.asarray(eps), dtype=dtype) if not isinstance(eps, torch.Tensor) else eps
+        return e.to(device, dtype).reshape(count, n).contiguous()
+
+    def step(self, opt, count, eps, seed, offset, world=None):
+        """Forward + backward into opt._flat_grad; returns the ELBO (mean over the `count` samples) as a 0-d tensor.
+        Called with `world` (fused_adam): the Adam update happens inside the same kernel."""
         from . import ops
         X, Y = self.X.tensor(), self.Y.tensor()
         n, D = X.shape
-        n_ell = int(np.prod(object.__getattribute__(self.kern, 'lengthscales')._host.shape))
-        full = 1 if self.q.q_shape == 'fullrank' else 0
-        cfg = _lib.GpConfig(int(n), int(D), int(count), n_ell, full, float(opt._compiled_settings.numerics.jitter_level),
-                            int(seed), int(offset))
-        key = (n, D, count, n_ell, full)
+        cfg, key = self._cfg(opt, count, seed, offset)
+        with_adam = world is not None
+        f64 = with_adam and self._f64()
+        key = key + (with_adam, f64)
         if self._key != key:
-            self._wsb = int(self.lib.hb_gp_elbo_workspace_bytes(C.byref(cfg)))
+            if with_adam:
+                self._wsb = int(self.lib.hb_gp_small_workspace_bytes(C.byref(cfg), 1 if f64 else 0))
+            else:
+                self._wsb = int(self.lib.hb_gp_elbo_workspace_bytes(C.byref(cfg)))
             self._ws = torch.empty(self._wsb, dtype=torch.uint8, device=X.device)
-            self._out4 = torch.zeros(4, device=X.device)
+            self._out4 = torch.zeros(4, device=X.device, dtype=torch.float64 if f64 else torch.float32)
+            self._p64 = None
             self._key = key
-        e = None
-        if eps is not None:
-            e = torch.as_tensor(np.asarray(eps), dtype=torch.float32) if not isinstance(eps, torch.Tensor) else eps
-            e = e.to(X.device, torch.float32).reshape(count, n).contiguous()
-        check(self.lib.hb_gp_elbo_step(C.byref(cfg), ptr(X), ptr(Y), ptr(opt._flat), ptr(e), ptr(opt._flat_grad), ptr(self._out4),
-                                       ptr(self._ws), self._wsb, ptr(ops.err_flag(X.device)), stream()), "hb_gp_elbo_step")
+        err = ops.err_flag(X.device)
+        if not with_adam:
+            e = self._eps(eps, count, n, X.device, torch.float32)
+            check(self.lib.hb_gp_elbo_step(C.byref(cfg), ptr(X), ptr(Y), ptr(opt._flat), ptr(e), ptr(opt._flat_grad), ptr(self._out4),
+                                           ptr(self._ws), self._wsb, ptr(err), stream()), "hb_gp_elbo_step")
+            return self._out4[0]
+        o = opt.optimizer
+        check(self.lib.hb_increment_i32(ptr(opt._step), stream()), "hb_increment_i32")
+        adam = _lib.AdamConfig(float(o.learning_rate), float(o.beta1), float(o.beta2), float(o.epsilon), -1.0,
+                               C.c_void_p(opt._step.data_ptr()), 0)
+        npar = int(self.lib.hb_gp_param_count(C.byref(cfg)))
+        if not f64:
+            e = self._eps(eps, count, n, X.device, torch.float32)
+            check(self.lib.hb_gp_small_step(C.byref(cfg), ptr(X), ptr(Y), ptr(opt._flat), ptr(e), ptr(opt._flat_grad), ptr(self._out4),
+                                            ptr(opt._m), ptr(opt._v), C.byref(adam), ptr(self._ws), self._wsb, ptr(err), stream()),
+                  "hb_gp_small_step")
+            return self._out4[0]
+        # float_type = float64 (henbunrc:7): fp64 master copies of parameters / moments live here, the Optimizer's fp32 flat
+        # buffer mirrors them after every step (so .value, save() and the eager evaluation keep working)
+        if self._p64 is None or self._src64 is not (self.X.data, self.Y.data):
+            dev = X.device
+            self._X64 = torch.as_tensor(np.ascontiguousarray(self.X.data, dtype=np.float64)).to(dev)
+            self._Y64 = torch.as_tensor(np.ascontiguousarray(self.Y.data, dtype=np.float64)).to(dev).reshape(-1)
+            self._src64 = (self.X.data, self.Y.data)
+            if self._p64 is None:
+                self._p64 = opt._flat[:npar].double()
+                self._g64 = torch.zeros(npar, dtype=torch.float64, device=dev)
+                self._m64 = opt._m[:npar].double(); self._v64 = opt._v[:npar].double()
+        e = self._eps(eps, count, n, X.device, torch.float64)
+        check(self.lib.hb_gp_small_step_f64(C.byref(cfg), ptr(self._X64), ptr(self._Y64), ptr(self._p64), ptr(e), ptr(self._g64),
+                                            ptr(self._out4), ptr(self._m64), ptr(self._v64), C.byref(adam), ptr(self._ws), self._wsb,
+                                            ptr(err), stream()), "hb_gp_small_step_f64")
+        opt._flat[:npar].copy_(self._p64)
+        opt._flat_grad[:npar].copy_(self._g64)
         return self._out4[0]
 
 

@@ -252,6 +252,7 @@ class Optimizer(object):
         # (a traced-and-bound graph has been validated already: no need to allocate the eager path's buffers)
         if self._fused is None:
             self._evaluate(self.feed_dict(None) if self._no_minibatch() else None, dry=True)
+        m._run_ctx.offset = 0                     # the training stream starts at position 0 whichever executor was bound
         if verbose:
             print('finished.')
 

@@ -283,6 +283,26 @@ typedef struct {
   unsigned long long seed, offset;
 } hb_gp_config;
 size_t hb_gp_param_count(const hb_gp_config* cfg);
+/* Notebook-sized models (n <= hb_gp_small_max_n(0) = 128 in fp32, hb_gp_small_max_n(1) = 112 in fp64): the whole step --
+ * Gram, Cholesky, sampler + KL, projection, log-likelihood, the complete backward and, when adam_m / adam_v are given,
+ * the TF-1 Adam update -- is ONE persistent CTA with K / L / K-bar resident in shared memory (csrc/gp_small.cu).
+ * hb_gp_elbo_step takes this path by itself for n <= 128 (hb_set_small_gp_kernel(0) restores the multi-kernel path).
+ * The _f64 variant is the reference's float_type = float64 (henbunrc:7) for this graph: every pointer is double,
+ * same packing.  adam: grad_scale = -1 minimises -ELBO; step counter read from *step_dev when non-NULL. */
+typedef struct {
+  float lr, b1, b2, eps, grad_scale;
+  const int* step_dev;
+  int step_host;
+} hb_adam_config;
+int hb_gp_small_max_n(int f64);
+int hb_set_small_gp_kernel(int on);
+size_t hb_gp_small_workspace_bytes(const hb_gp_config* cfg, int f64);
+int hb_gp_small_step(const hb_gp_config* cfg, const float* X, const float* Y, float* params, const float* eps, float* grads,
+                     float* out4, float* adam_m, float* adam_v, const hb_adam_config* adam, void* ws, size_t ws_bytes,
+                     int* err_flag, void* stream);
+int hb_gp_small_step_f64(const hb_gp_config* cfg, const double* X, const double* Y, double* params, const double* eps,
+                         double* grads, double* out4, double* adam_m, double* adam_v, const hb_adam_config* adam, void* ws,
+                         size_t ws_bytes, int* err_flag, void* stream);
 size_t hb_gp_elbo_workspace_bytes(const hb_gp_config* cfg);
 int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, const float* params, const float* eps,
                     float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream);
