@@ -32,7 +32,8 @@ class GpConfig(C.Structure):
 
 
 class AdamConfig(C.Structure):
-    _fields_ = [("lr", _fl), ("b1", _fl), ("b2", _fl), ("eps", _fl), ("grad_scale", _fl), ("step_dev", C.c_void_p),
+    _fields_ = [("lr", C.c_double), ("b1", C.c_double), ("b2", C.c_double), ("eps", C.c_double), ("grad_scale", C.c_double),
+                ("step_dev", C.c_void_p),
                 ("step_host", _i)]
 
 

@@ -584,8 +584,8 @@ int hb_gp_small_step(const hb_gp_config* cfg, const float* X, const float* Y, fl
   float* w = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
   return gp_small_step_f32(cfg->n, cfg->D, cfg->S, cfg->n_ell, cfg->q_fullrank, cfg->jitter, cfg->seed, cfg->offset, X, Y, params, eps,
                            grads, out4, w, err_flag, adam_m, adam_v, adam ? adam->step_dev : nullptr, adam ? adam->step_host : 0,
-                           adam ? adam->lr : 0.f, adam ? adam->b1 : 0.f, adam ? adam->b2 : 0.f, adam ? adam->eps : 0.f,
-                           adam ? adam->grad_scale : 0.f, S(stream));
+                           adam ? adam->lr : 0.0, adam ? adam->b1 : 0.0, adam ? adam->b2 : 0.0, adam ? adam->eps : 0.0,
+                           adam ? adam->grad_scale : 0.0, S(stream));
 }
 int hb_gp_small_step_f64(const hb_gp_config* cfg, const double* X, const double* Y, double* params, const double* eps, double* grads,
                          double* out4, double* adam_m, double* adam_v, const hb_adam_config* adam, void* ws, size_t ws_bytes,
@@ -596,8 +596,8 @@ int hb_gp_small_step_f64(const hb_gp_config* cfg, const double* X, const double*
   double* w = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
   return gp_small_step_f64(cfg->n, cfg->D, cfg->S, cfg->n_ell, cfg->q_fullrank, (double)cfg->jitter, cfg->seed, cfg->offset, X, Y, params,
                            eps, grads, out4, w, err_flag, adam_m, adam_v, adam ? adam->step_dev : nullptr, adam ? adam->step_host : 0,
-                           adam ? (double)adam->lr : 0.0, adam ? (double)adam->b1 : 0.0, adam ? (double)adam->b2 : 0.0,
-                           adam ? (double)adam->eps : 0.0, adam ? (double)adam->grad_scale : 0.0, S(stream));
+                           adam ? adam->lr : 0.0, adam ? adam->b1 : 0.0, adam ? adam->b2 : 0.0, adam ? adam->eps : 0.0,
+                           adam ? adam->grad_scale : 0.0, S(stream));
 }
 
 size_t hb_gp_param_count(const hb_gp_config* c) {
@@ -636,7 +636,7 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
   if (n <= gp_small_max_n(0) && g_small_gp) {
     // notebook-sized model: the whole step is ONE persistent CTA (gp_small.cu); Z | F | R | W are adjacent -> 4 S n floats
     return gp_small_step_f32(n, c.D, Sn, c.n_ell, c.q_fullrank, c.jitter, c.seed, c.offset, X, Y, const_cast<float*>(params), eps,
-                             grads, out4, Z, err_flag, nullptr, nullptr, nullptr, 0, 0.f, 0.f, 0.f, 0.f, 0.f, st);
+                             grads, out4, Z, err_flag, nullptr, nullptr, nullptr, 0, 0.0, 0.0, 0.0, 0.0, 0.0, st);
   }
   const size_t nq = c.q_fullrank ? (size_t)n * n : (size_t)n;
   const float* p_mu = params;

@@ -46,7 +46,7 @@ struct SmallArgs {
   T* ws;                 // 4 * S * n elements: Z | U | R | Zbar
   int* err_flag;
   // optional fused Adam (m == nullptr: gradients only)
-  T* m; T* v; const int* step_dev; int step_host; T lr, b1, b2, eps_adam, grad_scale;
+  T* m; T* v; const int* step_dev; int step_host; double lr, b1, b2, eps_adam, grad_scale;
 };
 
 // block-wide sum of one double per thread; result broadcast to every thread
@@ -65,13 +65,13 @@ template <typename T>
 __global__ void __launch_bounds__(GS_THREADS, 1) gp_small_step_kernel(const SmallArgs<T> a) {
   extern __shared__ __align__(16) unsigned char gs_smem[];
   const int n = a.n, S = a.S, D = a.D, tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;
   const int LD = n | 1;                                  // odd leading dimension: conflict-free column walks
   T* L = reinterpret_cast<T*>(gs_smem);                  // K, then its Cholesky factor (lower)
   T* G = L + (size_t)n * LD;                             // L-bar, then K-bar (lower)
   T* ell = G + (size_t)n * LD;                           // [n_ell]
   T* colv = ell + 32;                                    // [n] scratch column
   __shared__ double red[GS_THREADS / 32];
-  __shared__ T sh_piv;
   __shared__ int sh_bad;
 
   const size_t nq = a.q_fullrank ? (size_t)n * n : (size_t)n;
@@ -108,23 +108,20 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_small_step_kernel(const Smal
 
   // ---- potrf, right-looking, one column per step (tf.cholesky) ----
   for (int j = 0; j < n; ++j) {
-    if (tid == 0) {
-      const T d = L[j * LD + j];
-      if (!(d > T(0)) && sh_bad == 0) sh_bad = j + 1;
-      sh_piv = t_sqrt<T>(d > T(0) ? d : T(1));
-    }
-    __syncthreads();
-    const T piv = sh_piv, rp = T(1) / piv;
-    for (int i = j + tid; i < n; i += GS_THREADS) {
-      const T x = (i == j) ? piv : L[i * LD + j] * rp;
+    const T d = L[j * LD + j];                           // every thread takes the pivot itself: two barriers per column
+    if (tid == 0 && !(d > T(0)) && sh_bad == 0) sh_bad = j + 1;
+    const T piv = t_sqrt<T>(d > T(0) ? d : T(1)), rp = T(1) / piv;
+    for (int i = j + 1 + tid; i < n; i += GS_THREADS) {
+      const T x = L[i * LD + j] * rp;
       L[i * LD + j] = x;
       colv[i] = x;
     }
     __syncthreads();
-    const int m = n - j - 1;                             // trailing order
-    for (int e = tid; e < m * m; e += GS_THREADS) {
-      const int r = j + 1 + e / m, c = j + 1 + e % m;
-      if (c <= r) L[r * LD + c] -= colv[r] * colv[c];
+    if (tid == 0) L[j * LD + j] = piv;
+    // trailing update, 16 x 32 thread grid: rows ty + 16 i, columns tx + 32 k (c <= r)
+    for (int r = j + 1 + ty; r < n; r += 16) {
+      const T lr = colv[r];
+      for (int c = j + 1 + tx; c <= r; c += 32) L[r * LD + c] -= lr * colv[c];
     }
     __syncthreads();
   }
@@ -137,6 +134,10 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_small_step_kernel(const Smal
     U[e] = u;
   }
   __syncthreads();
+  if (a.q_fullrank) {       // stage q_sqrt in the adjoint's buffer (free until L-bar is formed): coalesced, read once
+    for (int e = tid; e < n * n; e += GS_THREADS) G[(e / n) * LD + (e % n)] = p_sq[e];
+    __syncthreads();
+  }
   for (int e = tid; e < S * n; e += GS_THREADS) {
     const int s = e / n, i = e % n;
     T z, logdet;
@@ -145,8 +146,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_small_step_kernel(const Smal
       logdet = T(2) * p_sq[i];
     } else {
       T acc = p_mu[i];
-      const T* lq = p_sq + (size_t)i * n;
-      for (int k = 0; k <= i; ++k) acc += lq[k] * U[s * n + k];
+      const T* lq = G + (size_t)i * LD;
+      const T* ur = U + (size_t)s * n;
+      for (int k = 0; k <= i; ++k) acc += lq[k] * ur[k];
       z = acc;
       logdet = t_log<T>(lq[i] * lq[i]);
     }
@@ -221,29 +223,33 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_small_step_kernel(const Smal
 
   // ---- reverse-mode Cholesky, level-2, in place: G (L-bar) -> dELBO / dK over the stored lower triangle ----
   for (int j = n - 1; j >= 0; --j) {
-    // reverse of the trailing update of column j: Lbar[r, j] -= sum_c (Abar[r, c] + Abar[c, r]) L[c, j]  (r, c > j)
-    const int m = n - j - 1;
-    for (int r = j + 1 + tid; r < n; r += GS_THREADS) {
+    // reverse of the trailing update of column j: Lbar[r, j] -= sum_c (Abar[r, c] + Abar[c, r]) L[c, j]  (r, c > j):
+    // warp ty owns rows ty + 16 i, its lanes split the columns, one shuffle reduction per row
+    for (int r = j + 1 + ty; r < n; r += 16) {
       T acc = T(0);
-      for (int c = j + 1; c < n; ++c) {
+      for (int c = j + 1 + tx; c < n; c += 32) {
         const T ab = (c <= r) ? G[r * LD + c] : G[c * LD + r];
         acc += ab * L[c * LD + j] * ((c == r) ? T(2) : T(1));
       }
-      colv[r] = acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (tx == 0) colv[r] = acc;
     }
     __syncthreads();
-    double dot = 0.0;
-    const T ljj = L[j * LD + j];
-    for (int r = j + 1 + tid; r < n; r += GS_THREADS) {
-      const T lb = G[r * LD + j] - colv[r];              // adjoint of L[r, j]
-      G[r * LD + j] = lb / ljj;                          // reverse of the column scaling: adjoint of A[r, j]
-      dot += (double)(lb * L[r * LD + j]);
-    }
-    (void)m;
-    const double tot = block_sum_all(dot, red);
-    if (tid == 0) {
-      const T lbjj = G[j * LD + j] - (T)tot / ljj;       // adjoint of L[j, j]
-      G[j * LD + j] = lbjj / (T(2) * ljj);               // reverse of the square root
+    if (ty == 0) {           // column phase in one warp: scale the column, dot product for the diagonal, no block-wide reduction
+      const T ljj = L[j * LD + j];
+      T dot = T(0);
+      for (int r = j + 1 + tx; r < n; r += 32) {
+        const T lb = G[r * LD + j] - colv[r];            // adjoint of L[r, j]
+        G[r * LD + j] = lb / ljj;                        // reverse of the column scaling: adjoint of A[r, j]
+        dot += lb * L[r * LD + j];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (tx == 0) {
+        const T lbjj = G[j * LD + j] - dot / ljj;        // adjoint of L[j, j]
+        G[j * LD + j] = lbjj / (T(2) * ljj);             // reverse of the square root
+      }
     }
     __syncthreads();
   }
@@ -296,18 +302,18 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_small_step_kernel(const Smal
     __threadfence_block();
     __syncthreads();
     const int t = a.step_dev ? *a.step_dev : a.step_host;
-    const double lr_t = (double)a.lr * sqrt(1.0 - pow((double)a.b2, (double)t)) / (1.0 - pow((double)a.b1, (double)t));
+    const double lr_t = a.lr * sqrt(1.0 - pow(a.b2, (double)t)) / (1.0 - pow(a.b1, (double)t));
     const size_t npar = (size_t)n + nq + 3 + a.n_ell;
     for (size_t i = tid; i < npar; i += GS_THREADS) {
       if (a.q_fullrank && i >= (size_t)n && i < (size_t)n + nq) {
         const size_t q = i - n;
         if (q % n > q / n) continue;                     // strict upper triangle of q_sqrt: zero gradient upstream, never moves
       }
-      const T g = a.grad_scale * a.grads[i];
-      const T mm = a.b1 * a.m[i] + (T(1) - a.b1) * g;
-      const T vv = a.b2 * a.v[i] + (T(1) - a.b2) * g * g;
+      const T g = (T)a.grad_scale * a.grads[i];
+      const T mm = (T)a.b1 * a.m[i] + (T)(1.0 - a.b1) * g;
+      const T vv = (T)a.b2 * a.v[i] + (T)(1.0 - a.b2) * g * g;
       a.m[i] = mm; a.v[i] = vv;
-      a.params[i] -= (T)lr_t * mm / (t_sqrt<T>(vv) + a.eps_adam);
+      a.params[i] -= (T)lr_t * mm / (t_sqrt<T>(vv) + (T)a.eps_adam);
     }
   }
 }
@@ -327,9 +333,10 @@ int launch_small(const SmallArgs<T>& a, cudaStream_t st) {
   const size_t smem = small_smem_bytes<T>(a.n);
   static size_t attr_set = 0;
   if (smem > attr_set) {
-    if (cudaFuncSetAttribute(gp_small_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess)
+    // 227 KB per CTA minus this kernel's static shared memory (reduction scratch)
+    if (cudaFuncSetAttribute(gp_small_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)) != cudaSuccess)
       return HB_ERR_CUDA;
-    attr_set = 227 * 1024;
+    attr_set = 226 * 1024;
   }
   gp_small_step_kernel<T><<<1, GS_THREADS, smem, st>>>(a);
   HB_CHECK_LAUNCH();
@@ -343,8 +350,8 @@ size_t gp_small_workspace_elems(int n, int S) { return 4 * (size_t)S * n + 16; }
 
 int gp_small_step_f32(int n, int D, int S, int n_ell, int q_fullrank, float jitter, unsigned long long seed, unsigned long long offset,
                       const float* X, const float* Y, float* params, const float* eps, float* grads, float* out4, float* ws,
-                      int* err_flag, float* m, float* v, const int* step_dev, int step_host, float lr, float b1, float b2,
-                      float eps_adam, float grad_scale, cudaStream_t st) {
+                      int* err_flag, float* m, float* v, const int* step_dev, int step_host, double lr, double b1, double b2,
+                      double eps_adam, double grad_scale, cudaStream_t st) {
   SmallArgs<float> a{n, D, S, n_ell, q_fullrank, jitter, seed, offset, X, Y, params, eps, grads, out4, ws, err_flag,
                      m, v, step_dev, step_host, lr, b1, b2, eps_adam, grad_scale};
   return launch_small<float>(a, st);

@@ -23,8 +23,8 @@ int gp_small_max_n(int f64);
 size_t gp_small_workspace_elems(int n, int S);
 int gp_small_step_f32(int n, int D, int S, int n_ell, int q_fullrank, float jitter, unsigned long long seed, unsigned long long offset,
                       const float* X, const float* Y, float* params, const float* eps, float* grads, float* out4, float* ws,
-                      int* err_flag, float* m, float* v, const int* step_dev, int step_host, float lr, float b1, float b2,
-                      float eps_adam, float grad_scale, cudaStream_t st);
+                      int* err_flag, float* m, float* v, const int* step_dev, int step_host, double lr, double b1, double b2,
+                      double eps_adam, double grad_scale, cudaStream_t st);
 int gp_small_step_f64(int n, int D, int S, int n_ell, int q_fullrank, double jitter, unsigned long long seed, unsigned long long offset,
                       const double* X, const double* Y, double* params, const double* eps, double* grads, double* out4, double* ws,
                       int* err_flag, double* m, double* v, const int* step_dev, int step_host, double lr, double b1, double b2,

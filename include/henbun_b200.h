@@ -290,7 +290,7 @@ size_t hb_gp_param_count(const hb_gp_config* cfg);
  * The _f64 variant is the reference's float_type = float64 (henbunrc:7) for this graph: every pointer is double,
  * same packing.  adam: grad_scale = -1 minimises -ELBO; step counter read from *step_dev when non-NULL. */
 typedef struct {
-  float lr, b1, b2, eps, grad_scale;
+  double lr, b1, b2, eps, grad_scale;
   const int* step_dev;
   int step_host;
 } hb_adam_config;

@@ -429,7 +429,7 @@ def test_fused_binding_matches_the_eager_tape(q_shape, n):
     (pf, of), (pt, ot) = ms
     assert np.allclose(of, ot, rtol=2e-5)
     for k in pf:
-        assert np.allclose(pf[k], pt[k], rtol=1e-4, atol=2e-6), k
+        assert np.allclose(pf[k], pt[k], rtol=1e-4, atol=2e-5), k      # two fp32 summation orders through 5 Adam steps
 
 
 def test_fused_linear_operator_binding_matches_the_eager_tape():
