@@ -511,8 +511,26 @@ def run_c1(d, steps=200):
         step(21 + i)
     ev1.record(); torch.cuda.synchronize()
     eager = ev0.elapsed_time(ev1) / steps * 1e3
+    # the same step as ONE persistent CTA with Adam inside (csrc/gp_small.cu; also the float64 route)
+    adam = _lib.AdamConfig(1e-3, 0.9, 0.999, 1e-8, -1.0, C.c_void_p(ctr.data_ptr()), 0)
+
+    def one(it):
+        cfg.offset = C.c_ulonglong(it * ((S * n + 3) // 4 * 4))
+        lib.hb_increment_i32(_lib.ptr(ctr), _lib.stream())
+        _lib.check(lib.hb_gp_small_step(C.byref(cfg), _lib.ptr(Xd), _lib.ptr(Yd), _lib.ptr(params), None, _lib.ptr(grads), _lib.ptr(out4),
+                                        _lib.ptr(am), _lib.ptr(av), C.byref(adam), _lib.ptr(ws), wsb, _lib.ptr(err), _lib.stream()),
+                   "hb_gp_small_step")
+    for i in range(10):
+        one(1000 + i)
+    torch.cuda.synchronize(); ev0.record()
+    for i in range(steps):
+        one(1100 + i)
+    ev1.record(); torch.cuda.synchronize()
+    single = ev0.elapsed_time(ev1) / steps * 1e3
     return {"workload": "BASELINE config 1: GP regression N=100 1-D, full-covariance q, S=10, fused C entry + Adam",
             "us_per_step": eager, "evals_per_sec": S * n / eager * 1e6, "kernels_per_step": int(per_step),
+            "single_cta_kernel_us_per_step": single,
+            "note": "default = multi-kernel path with blocked leaf factorisations; the one-CTA kernel (level-2 column steps) is the fp64 route",
             "elbo_last": float(out4[0]), "err_flag": int(err.item())}
 
 

@@ -226,8 +226,9 @@ class GpElboBinding(object):
     # notebook-sized models: the whole step, Adam included, is one persistent CTA (csrc/gp_small.cu)
     @property
     def fused_adam(self):
+        # the one-CTA kernel is the float64 route (henbunrc:7); in fp32 the multi-kernel path with blocked leaves is faster
         n = self.X.data.shape[0]
-        return n <= int(self.lib.hb_gp_small_max_n(1 if self._f64() else 0)) and parallel.world()[0] == 1
+        return self._f64() and n <= int(self.lib.hb_gp_small_max_n(1)) and parallel.world()[0] == 1
 
     @staticmethod
     def _f64():

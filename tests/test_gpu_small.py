@@ -65,7 +65,13 @@ def run_small(lib, X, Y, p, U, jitter, full, dtype, adam=None, via_elbo_step=Fal
     f64 = dtype == torch.float64
     if via_elbo_step:
         wsb = lib.hb_gp_elbo_workspace_bytes(C.byref(cfg)); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-        rc = lib.hb_gp_elbo_step(C.byref(cfg), P(Xd), P(Yd), P(params), P(Ud), P(grads), P(out4), P(ws), wsb, P(err), ST())
+        l0 = lib.hb_launch_count()
+        assert lib.hb_set_small_gp_kernel(1) == 1
+        try:
+            rc = lib.hb_gp_elbo_step(C.byref(cfg), P(Xd), P(Yd), P(params), P(Ud), P(grads), P(out4), P(ws), wsb, P(err), ST())
+        finally:
+            lib.hb_set_small_gp_kernel(0)
+        assert lib.hb_launch_count() - l0 == 1            # one kernel for the whole step
         m = v = None
     else:
         wsb = lib.hb_gp_small_workspace_bytes(C.byref(cfg), 1 if f64 else 0); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
