@@ -37,6 +37,16 @@ class AdamConfig(C.Structure):
                 ("step_host", _i)]
 
 
+HB_MAX_LAYERS = 8
+
+
+class AmortisedConfig(C.Structure):
+    _fields_ = [("B", _i), ("S", _i), ("latent", _i),
+                ("n_enc", _i), ("enc_nodes", _i * (HB_MAX_LAYERS + 1)), ("enc_act", _i * HB_MAX_LAYERS),
+                ("n_dec", _i), ("dec_nodes", _i * (HB_MAX_LAYERS + 1)), ("dec_act", _i * HB_MAX_LAYERS),
+                ("seed", _ull), ("offset", _ull)]
+
+
 class LinopConfig(C.Structure):
     _fields_ = [("M", _i), ("M_total", _ll), ("n", _i), ("S", _i), ("seed", _ull), ("offset", _ull)]
 
@@ -107,6 +117,9 @@ SIGNATURES = {
     "hb_linop_elbo_local": (_i, [C.POINTER(LinopConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f]),
     "hb_linop_elbo_update": (_i, [C.POINTER(LinopConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _fl, _fl, _fl, _fl, _c_f, _i,
                                   _c_f, _c_f, _sz, _c_f]),
+    "hb_amortised_param_count": (_sz, [C.POINTER(AmortisedConfig)]),
+    "hb_amortised_workspace_bytes": (_sz, [C.POINTER(AmortisedConfig)]),
+    "hb_amortised_elbo_step": (_i, [C.POINTER(AmortisedConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f]),
     "hb_gp_small_max_n": (_i, [_i]),
     "hb_set_small_gp_kernel": (_i, [_i]),
     "hb_gp_small_workspace_bytes": (_sz, [C.POINTER(GpConfig), _i]),

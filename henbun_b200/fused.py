@@ -223,6 +223,9 @@ class GpElboBinding(object):
             return None
         return GpElboBinding(model, q, kern, k_var, var, X, Y)
 
+    def per_sample(self):
+        return int(self.X.data.shape[0])
+
     # notebook-sized models: the whole step, Adam included, is one persistent CTA (csrc/gp_small.cu)
     @property
     def fused_adam(self):
@@ -347,6 +350,9 @@ class LinopElboBinding(object):
             return None
         return LinopElboBinding(model, q, var, A, y)
 
+    def per_sample(self):
+        return int(self.A.data.shape[1])
+
     def step(self, opt, count, eps, seed, offset, world):
         A, y = self.A.tensor(), self.y.tensor()
         if self._st is None or self._st.S != count:
@@ -385,7 +391,130 @@ class LinopElboBinding(object):
         return st.out4[0]
 
 
-BINDINGS = (GpElboBinding, LinopElboBinding)
+class AmortisedElboBinding(object):
+    """BASELINE config 4 recognised in a traced objective:
+        self.q_local = self.enc(self.X);  x_rec = self.dec(self.q_local)
+        ELBO = reduce_sum(gaussian(self.X, x_rec, self.var)) - self.KL(graph_key.LOCAL)
+    with enc / dec = nn.NeuralNet, q_local = LOCAL variationals.Normal([latent]) (diagonal), X = MinibatchData.
+    One call of hb_amortised_elbo_step (csrc/amortised.cu) on the gathered minibatch writes every gradient into the
+    Optimizer's flat buffer, laid out as [enc w0 | enc b0 | ... | dec w0 | dec b0 | ... | var]."""
+
+    def __init__(self, model, X, enc, dec, q, var):
+        self.model, self.X, self.enc, self.dec, self.q, self.var = model, X, enc, dec, q, var
+        g = object.__getattribute__
+        order = []
+        for net in (enc, dec):
+            for layer in net._matbias_list:
+                order += [g(layer, 'w'), g(layer, 'b')]
+        self.var_order = order + [var]
+        self.lib = _lib.load()
+        self._key = None
+
+    @staticmethod
+    def _net_ok(net):
+        from .nn import NeuralNet, _act_name
+        from .param import Variable
+        from . import transforms
+        if type(net) is not NeuralNet or len(net._matbias_list) > _lib.HB_MAX_LAYERS:
+            return False
+        g = object.__getattribute__
+        for layer in net._matbias_list:
+            for v in (g(layer, 'w'), g(layer, 'b')):
+                if type(v) is not Variable or not v.is_parameter or v.n_layers or not isinstance(v.transform, transforms.Identity):
+                    return False
+        return all(_act_name(a) in ('none', 'sigmoid', 'relu', 'tanh') for a in net.neuron_types)
+
+    @staticmethod
+    def match(tree, model):
+        from .trace import Sym
+        from .variationals import Normal
+        from .param import MinibatchData, graph_key
+        parts = _split_elbo_mb(tree, model)
+        if parts is None:
+            return None
+        X, f, var, kl_coll = parts
+        if kl_coll != graph_key.LOCAL or not isinstance(X, MinibatchData) or X.data.ndim != 2:
+            return None
+        if not (isinstance(f, Sym) and f.op == 'nn'):
+            return None
+        dec, smp = f.args
+        if not (isinstance(smp, Sym) and smp.op == 'sample'):
+            return None
+        q, fed = smp.args
+        if not (isinstance(fed, Sym) and fed.op == 'nn'):
+            return None
+        enc, xin = fed.args
+        if _leaf(xin, 'mbdata') is not X:
+            return None
+        if type(q) is not Normal or q.q_shape != 'diagonal' or not q.is_local or q.n_layers or len(q._shape) != 1:
+            return None
+        if not (AmortisedElboBinding._net_ok(enc) and AmortisedElboBinding._net_ok(dec)):
+            return None
+        lat, Dx = q._shape[0], X.data.shape[1]
+        if enc.nodes[0] != Dx or enc.nodes[-1] != 2 * lat or dec.nodes[0] != lat or dec.nodes[-1] != Dx:
+            return None
+        if _variationals_of(model) != [q]:
+            return None
+        return AmortisedElboBinding(model, X, enc, dec, q, var)
+
+    def per_sample(self):
+        return int(self.X.tensor().shape[0]) * int(self.q._shape[0])
+
+    def step(self, opt, count, eps, seed, offset):
+        from .nn import _act_name
+        X = self.X.tensor()
+        B = int(X.shape[0])
+        lat = int(self.q._shape[0])
+        key = (B, count)
+        if self._key != key:
+            cfg = _lib.AmortisedConfig()
+            cfg.B, cfg.S, cfg.latent = B, int(count), lat
+            for name, net in (('enc', self.enc), ('dec', self.dec)):
+                setattr(cfg, 'n_' + name, len(net._matbias_list))
+                nodes = getattr(cfg, name + '_nodes'); acts = getattr(cfg, name + '_act')
+                for i, w in enumerate(net.nodes):
+                    nodes[i] = int(w)
+                for i, a in enumerate(net.neuron_types):
+                    acts[i] = _lib.ACT[_act_name(a)]
+            self._cfg = cfg
+            self._wsb = int(self.lib.hb_amortised_workspace_bytes(C.byref(cfg)))
+            if self._wsb == 0:
+                raise _lib.HenbunB200Error("hb_amortised_elbo_step rejected the network shapes")
+            self._ws = torch.empty(self._wsb, dtype=torch.uint8, device=X.device)
+            self._out4 = torch.zeros(4, device=X.device)
+            self._key = key
+        cfg = self._cfg
+        cfg.seed, cfg.offset = int(seed), int(offset)
+        e = None
+        if eps is not None:
+            e = torch.as_tensor(np.asarray(eps), dtype=torch.float32) if not isinstance(eps, torch.Tensor) else eps
+            e = e.to(X.device, torch.float32).reshape(count, B, lat).contiguous()
+        check(self.lib.hb_amortised_elbo_step(C.byref(cfg), ptr(X), ptr(opt._flat), ptr(e), ptr(opt._flat_grad), ptr(self._out4),
+                                              ptr(self._ws), self._wsb, stream()), "hb_amortised_elbo_step")
+        return self._out4[0]
+
+
+def _split_elbo_mb(tree, model):
+    """As _split_elbo with a MinibatchData observation."""
+    from .trace import Sym
+    if not (isinstance(tree, Sym) and tree.op == 'sub' and len(tree.args) == 2):
+        return None
+    ll, kl = tree.args
+    if not (isinstance(kl, Sym) and kl.op == 'KL' and kl.args[0] is model):
+        return None
+    if not (isinstance(ll, Sym) and ll.op == 'reduce_sum' and ll.kw.get('axis') is None):
+        return None
+    g = ll.args[0]
+    if not (isinstance(g, Sym) and g.op == 'gaussian'):
+        return None
+    y, f, var = g.args
+    yv, vv = _leaf(y, 'mbdata'), _leaf(var, 'param')
+    if yv is None or vv is None or not _is_positive_scalar(vv):
+        return None
+    return yv, f, vv, kl.args[1]
+
+
+BINDINGS = (GpElboBinding, LinopElboBinding, AmortisedElboBinding)
 
 
 def bind(tree, model):

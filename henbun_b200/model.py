@@ -371,8 +371,7 @@ class Optimizer(object):
         ctx = m._run_ctx
         q = b.q
         e = None if not eps else eps.get(q, None)
-        q_mu = object.__getattribute__(q, 'q_mu')
-        offset = ctx.take_sharded(int(np.prod(q_mu._host.shape))) if e is None else 0
+        offset = ctx.take_sharded(b.per_sample()) if e is None else 0
         o = self.optimizer
         if getattr(b, 'fused_adam', False):
             return b.step(self, count, e, ctx.seed, offset, world)

@@ -308,6 +308,25 @@ size_t hb_gp_elbo_workspace_bytes(const hb_gp_config* cfg);
 int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, const float* params, const float* eps,
                     float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream);
 
+/* ---- fused ELBO + gradient of the amortised local-variable model (BASELINE config 4) ----------------------------
+ *   q_local = enc(X);  x_rec = dec(q_local);  ELBO = sum gaussian(X, x_rec, var) - KL(LOCAL),  S-sample mean
+ * enc / dec = nn.NeuralNet (nn.py:34-87: hidden layers act(x w + b), last layer linear), q_local = LOCAL
+ * variationals.Normal([latent]) fed with the encoder's output row [mu | log sigma] (param.py:516-537).
+ * X: this step's minibatch [B, enc_nodes[0]] (e.g. from hb_gather_rows).  eps: [S, B, latent] or NULL (Philox).
+ * params / grads packing (free space): enc w0 [in, out] | enc b0 [out] | enc w1 | ... | dec w0 | dec b0 | ... | var (1).
+ * out4 = {ELBO, loglik_sum, kl_sum, 0}.  *_act: HB_ACT_* of the hidden layers (n - 1 entries). */
+#define HB_MAX_LAYERS 8
+typedef struct {
+  int B, S, latent;
+  int n_enc, enc_nodes[HB_MAX_LAYERS + 1], enc_act[HB_MAX_LAYERS];
+  int n_dec, dec_nodes[HB_MAX_LAYERS + 1], dec_act[HB_MAX_LAYERS];
+  unsigned long long seed, offset;
+} hb_amortised_config;
+size_t hb_amortised_param_count(const hb_amortised_config* cfg);
+size_t hb_amortised_workspace_bytes(const hb_amortised_config* cfg);
+int hb_amortised_elbo_step(const hb_amortised_config* cfg, const float* X, const float* params, const float* eps, float* grads,
+                           float* out4, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- fused ELBO + gradient + Adam of the linear-operator model (BASELINE config 5) ---------------------
  * q = variationals.Normal([n], q_shape='fullrank') (variationals.py:94-96,144-146,185-186,225-230) observed through a
  * dense operator A [M, n]:  ELBO = sum gaussian(y, A z, var) - KL  (densities.py:25-27), S-sample mean.
