@@ -48,7 +48,7 @@ class AmortisedConfig(C.Structure):
 
 
 class LinopConfig(C.Structure):
-    _fields_ = [("M", _i), ("M_total", _ll), ("n", _i), ("S", _i), ("seed", _ull), ("offset", _ull)]
+    _fields_ = [("M", _i), ("M_total", _ll), ("n", _i), ("S", _i), ("seed", _ull), ("offset", _ull), ("presplit", _i)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check that every symbol the header
@@ -114,6 +114,7 @@ SIGNATURES = {
     "hb_zero_strict_upper": (_i, [_c_f, _ll, _i, _c_f]),
     "hb_linop_param_count": (_sz, [C.POINTER(LinopConfig)]),
     "hb_linop_workspace_bytes": (_sz, [C.POINTER(LinopConfig)]),
+    "hb_linop_prepare": (_i, [C.POINTER(LinopConfig), _c_f, _c_f, _sz, _c_f]),
     "hb_linop_elbo_local": (_i, [C.POINTER(LinopConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f]),
     "hb_linop_elbo_update": (_i, [C.POINTER(LinopConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _fl, _fl, _fl, _fl, _c_f, _i,
                                   _c_f, _c_f, _sz, _c_f]),

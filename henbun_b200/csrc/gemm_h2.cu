@@ -30,9 +30,14 @@ namespace hb {
 namespace {
 
 constexpr int H_BK = 64;
-constexpr int H_NSTAGE = 3;
 constexpr int H_TILE = 128 * H_BK * 2;          // 16 KB: 128 rows x 64 k of fp16
-constexpr int H_STAGE = 4 * H_TILE;             // A hi | A lo | B hi | B lo
+// per CTA and stage: A hi | A lo (128 rows each) | B hi | B lo (BN / 2 rows each).  BN = 256: 64 KB x 3 stages;
+// BN = 64 (few samples against a big operator: HBM-bound, deeper ring): 40 KB x 5 stages
+template <int BN> struct H2Geom {
+  static constexpr int B_TILE = (BN / 2) * H_BK * 2;
+  static constexpr int STAGE = 2 * H_TILE + 2 * B_TILE;
+  static constexpr int NSTAGE = (BN == 256) ? 3 : 5;
+};
 constexpr int H_CHS = 2;                        // stages per accumulation chunk (K = 128)
 constexpr int H_OOB = 1 << 30;                  // a coordinate outside every tensor: TMA fills the box with zeros
 
@@ -73,11 +78,13 @@ struct H2Params {
   const float* b_inv;
 };
 
-template <bool AKM, bool BKM>
+template <int BN, bool AKM, bool BKM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                     const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const H2Params hp) {
-  constexpr int BN = 256, PM = 256, HALF = BN / 2;
+  constexpr int PM = 256, HALF = BN / 2;
+  constexpr int H_NSTAGE = H2Geom<BN>::NSTAGE, H_STAGE = H2Geom<BN>::STAGE, B_TILE = H2Geom<BN>::B_TILE;
+  static_assert(BKM || BN == 256, "MN-major B operands need the 256-wide tile (64-element TMA boxes)");
   const Tc2Params& p = hp.t;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -99,7 +106,7 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   const int pm0 = tm * PM, n0 = tn * BN;
   if (p.c_tri == 1 && n0 > pm0 + PM - 1) return;      // same decision in both CTAs
   const int m0 = pm0 + 128 * (int)rank;
-  const int nb0 = n0 + 128 * (int)rank;
+  const int nb0 = n0 + (BN / 2) * (int)rank;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int kb_lo = 0, kb_hi = (p.K + H_BK - 1) / H_BK;
@@ -115,7 +122,7 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u));
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"((uint32_t)(2 * BN)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
   tc_fence_before();
@@ -153,12 +160,12 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
         const uint32_t sb = st + 2 * H_TILE;
         if (BKM) {
           tma_load_2d_pair(sb, &tmBh, fb, k0, nb0);
-          tma_load_2d_pair(sb + H_TILE, &tmBl, fb, k0, nb0);
+          tma_load_2d_pair(sb + B_TILE, &tmBl, fb, k0, nb0);
         } else {
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            tma_load_2d_pair(sb + i * (H_TILE / 2), &tmBh, fb, nb0 + 64 * i, k0);
-            tma_load_2d_pair(sb + H_TILE + i * (H_TILE / 2), &tmBl, fb, nb0 + 64 * i, k0);
+            tma_load_2d_pair(sb + i * (B_TILE / 2), &tmBh, fb, nb0 + 64 * i, k0);
+            tma_load_2d_pair(sb + B_TILE + i * (B_TILE / 2), &tmBl, fb, nb0 + 64 * i, k0);
           }
         }
         if (++s == H_NSTAGE) { s = 0; ph ^= 1u; }
@@ -181,7 +188,7 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
           tc_fence_after();
           const uint32_t st = base + s * H_STAGE;
           const uint64_t a_hi = make_desc_h<AKM>(st), a_lo = make_desc_h<AKM>(st + H_TILE);
-          const uint64_t b_hi = make_desc_h<BKM>(st + 2 * H_TILE), b_lo = make_desc_h<BKM>(st + 3 * H_TILE);
+          const uint64_t b_hi = make_desc_h<BKM>(st + 2 * H_TILE), b_lo = make_desc_h<BKM>(st + 2 * H_TILE + B_TILE);
 #pragma unroll
           for (int k2 = 0; k2 < H_BK / 16; ++k2) {
             const uint64_t da = (uint64_t)(ADV_A * k2), db = (uint64_t)(ADV_B * k2);
@@ -243,18 +250,18 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)));
   }
 }
 
 // Tensor map of one fp16 shadow operand.  K-major: stored [rows x K], box {64 k, 128 rows}; MN-major: stored [K x rows],
 // box {64 rows, 64 k}.  SWIZZLE_128B both ways.
-int make_map_h(CUtensorMap* map, const __half* ptr, long long rows, long long K, long long ld, bool kmajor) {
+int make_map_h(CUtensorMap* map, const __half* ptr, long long rows, long long K, long long ld, bool kmajor, int box_rows = 128) {
   auto enc = get_encode2();
   if (!enc) return HB_ERR_CUDA;
   cuuint64_t gdim[2], gstr[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2], estr[2] = {1, 1};
-  if (kmajor) { gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows; box[0] = H_BK; box[1] = 128; }
+  if (kmajor) { gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)rows; box[0] = H_BK; box[1] = (cuuint32_t)box_rows; }
   else { gdim[0] = (cuuint64_t)rows; gdim[1] = (cuuint64_t)K; box[0] = 64; box[1] = H_BK; }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -262,18 +269,18 @@ int make_map_h(CUtensorMap* map, const __half* ptr, long long rows, long long K,
   return r == CUDA_SUCCESS ? HB_OK : HB_ERR_CUDA;
 }
 
-template <bool AKM, bool BKM>
+template <int BN, bool AKM, bool BKM>
 int launch_h2(const CUtensorMap* m, H2Params hp, cudaStream_t st) {
-  constexpr int SMEM = H_NSTAGE * H_STAGE + 1024 + 256;
+  constexpr int SMEM = H2Geom<BN>::NSTAGE * H2Geom<BN>::STAGE + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(gemm_h2_pair_kernel<AKM, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_h2_pair_kernel<BN, AKM, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
       return HB_ERR_CUDA;
     attr_done = true;
   }
   hp.t.tiles_m = cdiv(hp.t.M, 256);
-  hp.t.tiles_n = cdiv(hp.t.N, 256);
-  gemm_h2_pair_kernel<AKM, BKM><<<2 * hp.t.tiles_m * hp.t.tiles_n, NTHREADS, SMEM, st>>>(m[0], m[1], m[2], m[3], hp);
+  hp.t.tiles_n = cdiv(hp.t.N, BN);
+  gemm_h2_pair_kernel<BN, AKM, BKM><<<2 * hp.t.tiles_m * hp.t.tiles_n, NTHREADS, SMEM, st>>>(m[0], m[1], m[2], m[3], hp);
   HB_CHECK_LAUNCH();
   return HB_OK;
 }
@@ -377,6 +384,33 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
   }
 }
 
+// hi/lo split of src [rows x cols] into TRANSPOSED shadows [cols x rows] (small operands only: the sample-minor
+// residual R^T [M, S] of the linear-operator step has to become the K-major operand R [S, M]).  32 x 32 tiles via smem.
+__global__ void __launch_bounds__(256) split_f16_transpose_kernel(const float* __restrict__ A, long long ld, int rows, int cols,
+                                                                  const unsigned* max_bits, float* inv_out, __half* hi, __half* lo,
+                                                                  long long ldh) {
+  __shared__ float tile[32][33];
+  const float s = scale_for(__uint_as_float(*max_bits));
+  if (inv_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *inv_out = 1.f / s;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? A[(long long)r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;                               // output row = source column
+    if (c < cols && r < rows) {
+      const float x = tile[tx][i] * s;
+      const unsigned short h = f2h_sat(x);
+      const unsigned short l = f2h_sat(x - h2f(h));
+      reinterpret_cast<unsigned short*>(hi)[(long long)c * ldh + r] = h;
+      reinterpret_cast<unsigned short*>(lo)[(long long)c * ldh + r] = l;
+    }
+  }
+}
+
 inline int grid_rows(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
   if (b > 148 * 16) b = 148 * 16;
@@ -398,11 +432,13 @@ int gemm_h2(const H2Gemm& g, cudaStream_t st) {
   if ((g.lda & 7) || (g.ldb & 7) || !aligned16(g.a_hi) || !aligned16(g.a_lo) || !aligned16(g.b_hi) || !aligned16(g.b_lo))
     return HB_ERR_ARG;
   if (g.a_bmode && (g.M != g.K)) return HB_ERR_ARG;             // block masks are defined on a square op(A)
+  const bool narrow = g.N <= 64;                 // 256 x 64 pair tiles: few samples against a big operator
+  if (narrow && !g.b_kmajor) return HB_ERR_ARG;
   CUtensorMap m[4];
   HB_TRY(make_map_h(&m[0], g.a_hi, g.M, g.K, g.lda, g.a_kmajor != 0));
   HB_TRY(make_map_h(&m[1], g.a_lo, g.M, g.K, g.lda, g.a_kmajor != 0));
-  HB_TRY(make_map_h(&m[2], g.b_hi, g.N, g.K, g.ldb, g.b_kmajor != 0));
-  HB_TRY(make_map_h(&m[3], g.b_lo, g.N, g.K, g.ldb, g.b_kmajor != 0));
+  HB_TRY(make_map_h(&m[2], g.b_hi, g.N, g.K, g.ldb, g.b_kmajor != 0, narrow ? 32 : 128));
+  HB_TRY(make_map_h(&m[3], g.b_lo, g.N, g.K, g.ldb, g.b_kmajor != 0, narrow ? 32 : 128));
   H2Params hp;
   Tc2Params& tp = hp.t;
   tp.C = g.C; tp.ldc = g.ldc; tp.M = g.M; tp.N = g.N; tp.K = g.K; tp.alpha = g.alpha; tp.beta = g.beta;
@@ -411,8 +447,9 @@ int gemm_h2(const H2Gemm& g, cudaStream_t st) {
   tp.ksplit = 0; tp.csplit = 0; tp.bias = nullptr; tp.act = ACT_NONE; tp.clip = 0; tp.clip_lo = 0.f; tp.clip_hi = 0.f;
   hp.a_bmode = g.a_bmode; hp.a_inv = g.a_inv; hp.a_kinv = g.a_kinv; hp.a_dinv = g.a_dinv ? g.a_dinv : g.a_kinv;
   hp.a_minv = g.a_minv; hp.b_inv = g.b_inv;
-  if (g.a_kmajor) return g.b_kmajor ? launch_h2<true, true>(m, hp, st) : launch_h2<true, false>(m, hp, st);
-  return g.b_kmajor ? launch_h2<false, true>(m, hp, st) : launch_h2<false, false>(m, hp, st);
+  if (narrow) return g.a_kmajor ? launch_h2<64, true, true>(m, hp, st) : launch_h2<64, false, true>(m, hp, st);
+  if (g.a_kmajor) return g.b_kmajor ? launch_h2<256, true, true>(m, hp, st) : launch_h2<256, true, false>(m, hp, st);
+  return g.b_kmajor ? launch_h2<256, false, true>(m, hp, st) : launch_h2<256, false, false>(m, hp, st);
 }
 
 int h2_absmax(const float* A, long long ld, long long rows, int cols, int lower_only, long long diag_off, unsigned* out_bits,
@@ -444,6 +481,17 @@ int h2_split(const float* A, long long ld, long long rows, int cols, const float
   if (!scale2 && !max_bits) return HB_ERR_ARG;
   split_f16_kernel<<<grid_rows(rows * (cols >> 3), 256), 256, 0, st>>>(A, ld, rows, cols, scale2, max_bits, inv_out, lower_only,
                                                                      diag_off, hi, lo, ldh);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
+int h2_split_transpose(const float* A, long long ld, int rows, int cols, const unsigned* max_bits, float* inv_out, __half* hi,
+                       __half* lo, long long ldh, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return HB_OK;
+  if (!max_bits || (ldh & 7) || !aligned16(hi) || !aligned16(lo)) return HB_ERR_ARG;
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+  if (grid.y > 65535) return HB_ERR_ARG;
+  split_f16_transpose_kernel<<<grid, 256, 0, st>>>(A, ld, rows, cols, max_bits, inv_out, hi, lo, ldh);
   HB_CHECK_LAUNCH();
   return HB_OK;
 }

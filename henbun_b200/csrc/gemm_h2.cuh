@@ -36,4 +36,8 @@ int h2_scale_from_max(const unsigned* max_bits, int sqrt_of_max, float* scale2, 
 int h2_split(const float* A, long long ld, long long rows, int cols, const float* scale2, const unsigned* max_bits,
              float* inv_out, int lower_only, long long diag_off, __half* hi, __half* lo, long long ldh, cudaStream_t st);
 
+// the same split into TRANSPOSED shadows [cols x rows] (scale from *max_bits; small operands)
+int h2_split_transpose(const float* A, long long ld, int rows, int cols, const unsigned* max_bits, float* inv_out, __half* hi,
+                       __half* lo, long long ldh, cudaStream_t st);
+
 }  // namespace hb

@@ -18,6 +18,7 @@
 //   hb_linop_elbo_update  : mu-bar, var-bar, fused Lbar + Adam                    (replicated on every rank)
 #include <stdlib.h>
 #include "kernels.cuh"
+#include "gemm_h2.cuh"
 #include "gemm.cuh"
 #include "../../include/henbun_b200.h"
 
@@ -27,6 +28,9 @@ namespace {
 
 struct LinopLayout {
   size_t off_U, off_Z, off_F, off_Zt, off_sc, off_gt, off_red, off_gemm, gemm_bytes, total;
+  // pre-split route (cfg.presplit): fp16 hi/lo shadows of the operator (written once by hb_linop_prepare), of Z and of R
+  size_t off_h2sc, off_Ah, off_Al, off_Zh, off_Zl, off_Rh, off_Rl;
+  long long ldA, ldZ, ldR;
 };
 
 inline size_t al256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -46,6 +50,15 @@ LinopLayout linop_layout(const hb_linop_config& c) {
   L.gemm_bytes = al256((size_t)10 * c.S * c.n * 4 + 256);
   if (L.gemm_bytes > ((size_t)40 << 20)) L.gemm_bytes = (size_t)40 << 20;
   L.off_gemm = o; o += L.gemm_bytes;
+  L.ldA = L.ldZ = ((long long)c.n + 63) / 64 * 64;
+  L.ldR = ((long long)(c.M > 0 ? c.M : 1) + 63) / 64 * 64;
+  if (c.presplit) {
+    L.off_h2sc = o; o += 256;
+    const size_t ab = al256((size_t)(c.M > 0 ? c.M : 1) * L.ldA * 2), zb = al256((size_t)c.S * L.ldZ * 2), rb = al256((size_t)c.S * L.ldR * 2);
+    L.off_Ah = o; o += ab; L.off_Al = o; o += ab;
+    L.off_Zh = o; o += zb; L.off_Zl = o; o += zb;
+    L.off_Rh = o; o += rb; L.off_Rl = o; o += rb;
+  }
   L.total = o;
   return L;
 }
@@ -242,6 +255,7 @@ __global__ void __launch_bounds__(256, 3) tril_rank_adam_kernel(float* __restric
 inline cudaStream_t ST(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline bool cfg_ok(const hb_linop_config& c) {
+  if (c.presplit && ((c.n & 7) || (c.M & 7) || (c.S & 7) || c.S > 256)) return false;      // TMA rows of 16-byte multiples
   return c.M >= 0 && c.n > 0 && c.S > 0 && c.M_total >= c.M;
 }
 
@@ -273,6 +287,24 @@ size_t hb_linop_param_count(const hb_linop_config* c) {
 size_t hb_linop_workspace_bytes(const hb_linop_config* c) {
   if (!c || !cfg_ok(*c)) return 0;
   return linop_layout(*c).total + 256;
+}
+
+int hb_linop_prepare(const hb_linop_config* cfg, const float* A, void* ws, size_t ws_bytes, void* stream) {
+  if (!cfg) return HB_ERR_ARG;
+  const hb_linop_config c = *cfg;
+  if (!cfg_ok(c) || !c.presplit) return HB_ERR_ARG;
+  if (c.M == 0) return HB_OK;
+  if (!A) return HB_ERR_ARG;
+  const LinopLayout L = linop_layout(c);
+  if (!ws || ws_bytes < L.total + 256) return HB_ERR_WORKSPACE;
+  cudaStream_t st = ST(stream);
+  char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  unsigned* mx = reinterpret_cast<unsigned*>(base + L.off_h2sc);       // [0] A max, [1] Z max, [2] R max
+  float* inv = reinterpret_cast<float*>(base + L.off_h2sc) + 8;        // [0] 1/sA, [1] 1/sZ, [2] 1/sR
+  if (cudaMemsetAsync(mx, 0, 32, st) != cudaSuccess) return HB_ERR_CUDA;
+  HB_TRY(h2_absmax(A, c.n, c.M, c.n, 0, 0, mx, st));
+  return h2_split(A, c.n, c.M, c.n, nullptr, mx, inv, 0, 0, reinterpret_cast<__half*>(base + L.off_Ah),
+                  reinterpret_cast<__half*>(base + L.off_Al), L.ldA, st);
 }
 
 int hb_linop_elbo_local(const hb_linop_config* cfg, const float* A, const float* y, const float* params, const float* eps,
@@ -317,7 +349,38 @@ int hb_linop_elbo_local(const hb_linop_config* cfg, const float* A, const float*
   // operand tile, not the MMA, and this orientation doubles the number of tiles that stage A (profiles/README.md).
   static const bool allow_swap = [] { const char* e = getenv("HB_LINOP_SWAP"); return e && e[0] == '1'; }();
   const bool swapped = allow_swap && Sn == 64;       // the engine takes N >= 64 only (smaller S: samples stay the M operand)
-  if (M > 0 && swapped) {
+  if (M > 0 && c.presplit) {
+    // Both passes over the operator on the pre-split engine (csrc/gemm_h2.cu, 256 x 64 pair tiles): the operator's fp16
+    // hi/lo shadow (hb_linop_prepare) is the M-side operand, K-major for F^T = A Z^T and MN-major for Zbar^T = A^T R^T, so
+    // no MMA row is padding and nothing but TMA touches shared memory -- the products are bound by streaming A from HBM.
+    unsigned* mx = reinterpret_cast<unsigned*>(base + L.off_h2sc);
+    float* inv = reinterpret_cast<float*>(base + L.off_h2sc) + 8;
+    __half* Ah = reinterpret_cast<__half*>(base + L.off_Ah); __half* Al = reinterpret_cast<__half*>(base + L.off_Al);
+    __half* Zh = reinterpret_cast<__half*>(base + L.off_Zh); __half* Zl = reinterpret_cast<__half*>(base + L.off_Zl);
+    __half* Rh = reinterpret_cast<__half*>(base + L.off_Rh); __half* Rl = reinterpret_cast<__half*>(base + L.off_Rl);
+    float* Zbt = reinterpret_cast<float*>(base + L.off_Zt);
+    if (cudaMemsetAsync(mx + 1, 0, 8, st) != cudaSuccess) return HB_ERR_CUDA;
+    HB_TRY(h2_absmax(Z, n, Sn, n, 0, 0, mx + 1, st));
+    HB_TRY(h2_split(Z, n, Sn, n, nullptr, mx + 1, inv + 1, 0, 0, Zh, Zl, L.ldZ, st));
+    {  // F^T [M, S] = A Z^T
+      H2Gemm h;
+      h.a_hi = Ah; h.a_lo = Al; h.lda = L.ldA; h.a_kmajor = 1; h.a_inv = inv;
+      h.b_hi = Zh; h.b_lo = Zl; h.ldb = L.ldZ; h.b_kmajor = 1; h.b_inv = inv + 1;
+      h.C = F; h.ldc = Sn; h.M = M; h.N = Sn; h.K = n;
+      HB_TRY(gemm_h2(h, st));
+    }
+    HB_TRY(gauss_loglik_fwd_ex(F, nullptr, y, (long long)Sn * M, M, Sn, sc, 1.f / (float)Sn, F, ll3, red, kReduceWsBytes, st));
+    HB_TRY(h2_absmax(F, Sn, M, Sn, 0, 0, mx + 2, st));
+    HB_TRY(h2_split_transpose(F, Sn, M, Sn, mx + 2, inv + 2, Rh, Rl, L.ldR, st));      // R^T [M, S] -> shadow of R [S, M]
+    {  // partial Zbar^T [n, S] = A^T R^T
+      H2Gemm h;
+      h.a_hi = Ah; h.a_lo = Al; h.lda = L.ldA; h.a_kmajor = 0; h.a_inv = inv;
+      h.b_hi = Rh; h.b_lo = Rl; h.ldb = L.ldR; h.b_kmajor = 1; h.b_inv = inv + 2;
+      h.C = Zbt; h.ldc = Sn; h.M = n; h.N = Sn; h.K = M;
+      HB_TRY(gemm_h2(h, st));
+    }
+    HB_TRY(transpose2d(zbar_stats, n, Zbt, Sn, n, Sn, 1.f, st));
+  } else if (M > 0 && swapped) {
     float* Zbt = reinterpret_cast<float*>(base + L.off_Zt);           // [n, S] scratch (free until the update call)
     {  // F^T [M, S] = A Z^T
       GemmParams g;

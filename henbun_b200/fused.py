@@ -24,7 +24,7 @@ class LinearOperatorStep(object):
     m_total: rows of the whole operator (defaults to this rank's count = single GPU)."""
 
     def __init__(self, A_rows: torch.Tensor, y_rows: torch.Tensor, n_samples: int, m_total: int = None, seed: int = 0,
-                 lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999, epsilon: float = 1e-8):
+                 lr: float = 1e-3, beta1: float = 0.9, beta2: float = 0.999, epsilon: float = 1e-8, presplit: bool = None):
         self.lib = _lib.load()
         self.A = _lib.f32(A_rows).contiguous()
         self.y = _lib.f32(y_rows).contiguous().reshape(-1)
@@ -32,7 +32,10 @@ class LinearOperatorStep(object):
         if self.y.numel() != M:
             raise ValueError("y must have one entry per row of A")
         self.n, self.S = int(n), int(n_samples)
-        self.cfg = _lib.LinopConfig(int(M), int(m_total if m_total is not None else M), self.n, self.S, int(seed), 0)
+        if presplit is None:
+            presplit = self.presplit_ok(M, n, self.S)
+        self.cfg = _lib.LinopConfig(int(M), int(m_total if m_total is not None else M), self.n, self.S, int(seed), 0,
+                                    1 if presplit else 0)
         dev = self.A.device
         self.count = int(self.lib.hb_linop_param_count(C.byref(self.cfg)))
         self.params = torch.zeros(self.count, device=dev)
@@ -45,6 +48,18 @@ class LinearOperatorStep(object):
         self.step_dev = torch.ones(1, dtype=torch.int32, device=dev)      # Adam's t (starts at 1)
         self.hyper = (float(lr), float(beta1), float(beta2), float(epsilon))
         self._stride = (self.S * self.n + 3) // 4 * 4
+        self.prepare()
+
+    @staticmethod
+    def presplit_ok(M, n, S):
+        """The pre-split engine (fp16 hi/lo shadow of the operator, + 4 bytes per element of A of workspace) streams A at
+        HBM speed from 64 MB on; TMA needs 16-byte rows."""
+        return M % 8 == 0 and n % 8 == 0 and S % 8 == 0 and S <= 256 and M * n >= (1 << 24)
+
+    def prepare(self):
+        """(Re)build the operator's shadow -- call again after changing A in place."""
+        if self.cfg.presplit:
+            check(self.lib.hb_linop_prepare(C.byref(self.cfg), ptr(self.A), ptr(self.ws), self.ws_bytes, stream()), "hb_linop_prepare")
 
     # ---- parameter access (free space) ----
     @property
@@ -361,7 +376,8 @@ class LinopElboBinding(object):
             st.A, st.y = A, y.reshape(-1)
             M, n = A.shape
             st.n, st.S = int(n), int(count)
-            st.cfg = _lib.LinopConfig(int(M), int(M), st.n, st.S, int(seed), 0)
+            st.cfg = _lib.LinopConfig(int(M), int(M), st.n, st.S, int(seed), 0,
+                                      1 if LinearOperatorStep.presplit_ok(int(M), int(n), int(count)) else 0)
             st.count = int(st.lib.hb_linop_param_count(C.byref(st.cfg)))
             st.params, st.m, st.v = opt._flat[:st.count], opt._m[:st.count], opt._v[:st.count]
             st.zbar_stats = torch.empty(st.S * st.n + 4, device=A.device)
@@ -370,6 +386,11 @@ class LinopElboBinding(object):
             st.ws = torch.empty(st.ws_bytes, dtype=torch.uint8, device=A.device)
             st.step_dev = opt._step
             self._st = st
+            self._prepared_src = None
+        if self._prepared_src is not getattr(self.A, '_resident_src', None):     # a new operator was fed: its shadow is stale
+            self._st.A = A
+            self._st.prepare()
+            self._prepared_src = getattr(self.A, '_resident_src', None)
         st = self._st
         st.A, st.y = A, y.reshape(-1)
         o = opt.optimizer

@@ -343,9 +343,14 @@ typedef struct {
   long long M_total;     /* rows of the whole operator (== M on one GPU) */
   int n, S;
   unsigned long long seed, offset;
+  int presplit;          /* 1: both passes over A run on the pre-split tcgen05 engine from an fp16 hi/lo shadow of A that
+                            hb_linop_prepare writes into the workspace once per operator (+ 4 bytes per element of A of
+                            workspace; n % 8 == 0, M % 8 == 0).  0: A is consumed as fp32 (in-kernel split). */
 } hb_linop_config;
 size_t hb_linop_param_count(const hb_linop_config* cfg);
 size_t hb_linop_workspace_bytes(const hb_linop_config* cfg);
+/* presplit = 1 only: split the operator into the workspace's shadow.  Call once, and again whenever A changes. */
+int hb_linop_prepare(const hb_linop_config* cfg, const float* A, void* ws, size_t ws_bytes, void* stream);
 int hb_linop_elbo_local(const hb_linop_config* cfg, const float* A, const float* y, const float* params, const float* eps,
                         float* zbar_stats, void* ws, size_t ws_bytes, void* stream);
 int hb_linop_elbo_update(const hb_linop_config* cfg, float* params, const float* zbar_stats, float* grads, float* m, float* v,

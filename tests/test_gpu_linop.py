@@ -59,6 +59,26 @@ def test_value_and_gradients_vs_oracle(M, n, S):
     assert np.array_equal(st.q_sqrt.cpu().numpy(), p["q_sqrt"].astype(np.float32))
 
 
+@pytest.mark.parametrize("M,n,S", [(2048, 512, 64), (4096, 1024, 64), (1024, 256, 8), (2048, 512, 128), (520, 264, 16)])
+def test_presplit_route_vs_oracle(M, n, S):
+    """Both passes over A on the pre-split fp16 hi/lo engine (hb_linop_prepare + cfg.presplit: 256 x 64 pair tiles, the
+    operator as the M-side operand): same bars as the fp32-operand route."""
+    A, y, p, U = make_problem(M, n, S, seed=3)
+    st = build(A, y, p, S, presplit=True)
+    assert st.cfg.presplit == 1
+    out, g = st.value_and_grads(torch.tensor(U, device="cuda"))
+    ref, gref = O.value_and_grads(O.linear_operator_elbo, p, A.astype(np.float64), y.astype(np.float64), U.astype(np.float64))
+    out = out.cpu().numpy(); g = g.cpu().numpy()
+    assert abs(out[0] - ref) <= 1e-5 * abs(ref)
+    assert rel_err(g[:n * n].reshape(n, n), gref["q_sqrt"]) < 1e-5
+    assert rel_err(g[n * n:n * n + n], gref["q_mu"]) < 1e-5
+    assert rel_err(g[n * n + n:], gref["var"]) < 1e-5
+    # and against the fp32-operand route of the same library
+    st0 = build(A, y, p, S, presplit=False)
+    out0, g0 = st0.value_and_grads(torch.tensor(U, device="cuda"))
+    assert rel_err(g, g0.cpu().numpy()) < 5e-6
+
+
 def test_adam_trajectory_vs_oracle():
     """5 fused steps == 5 x (fp64 oracle gradient + TF-1 Adam rule); the upper triangle never moves."""
     M, n, S = 400, 96, 8

@@ -64,9 +64,14 @@ e = run(2048, 1024, 2048, 0, 0, bmode=1, blockscale=1, alpha=-2.0, beta=1.0); pr
 e = run(2048, 1024, 2048, 1, 0, bmode=2, blockscale=1, alpha=-2.0, beta=1.0); print(f"bmode 2 (MN-major A): {e:.2e}"); ok &= e < 1e-6
 e = run(2304, 1024, 2304, 0, 0, bmode=1); print(f"bmode 1, 18 blocks: {e:.2e}"); ok &= e < 1e-6
 e = run(2304, 1024, 2304, 1, 0, bmode=2); print(f"bmode 2, 18 blocks: {e:.2e}"); ok &= e < 1e-6
+for (M, N, K) in ((4096, 64, 2048), (2048 + 128, 32, 1024), (8192, 64, 640)):       # 256 x 64 pair tiles (B K-major)
+    for tA in (0, 1):
+        e = run(M, N, K, tA, 1); print(f"narrow M={M} N={N} K={K} tA={tA} tB=1: {e:.2e}", flush=True); ok &= e < 1e-6
 print("PARITY", "OK" if ok else "FAILED", flush=True)
 
 # timing
+if len(sys.argv) > 1 and sys.argv[1] == "parity":
+    sys.exit(0 if ok else 1)
 for (M, N, K) in ((8192, 8192, 8192), (16384, 16384, 4096), (32768, 8192, 2048), (60000, 1024, 1024), (60000, 2048, 512)):
     for tA, tB in ((0, 1), (0, 0), (1, 0)):
         g = torch.Generator("cuda").manual_seed(1)
