@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true", help="skip the short config 1 / 4 / 5 measurements")
     ap.add_argument("--no-api-leg", action="store_true", help="e2e through the C ABI only (skips the Henbun-API leg)")
     ap.add_argument("--engine", type=int, default=0, help="GEMM engine: 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32")
+    ap.add_argument("--profile-csv", default=None, help="dump the per-launch GEMM events of the profiled step to this file")
     return ap.parse_args()
 
 
@@ -386,6 +387,8 @@ def run_c3(d, a):
     buf = (C.c_double * 8)()
     lib.hb_profile_end_ex(buf)
     prof = list(buf)
+    if a.profile_csv and d.rank == 0:
+        lib.hb_profile_dump_csv(a.profile_csv.encode())
     lib.hb_phase_begin()
     g.step()                                   # every rank steps (the step holds a collective); rank 0 reports
     pbuf = (C.c_double * 16)()
@@ -429,7 +432,7 @@ def run_c3(d, a):
             "l2": "inputs larger than L2 (K/L and Lbar/Kbar are N^2 fp32 = %.1f GB each)" % (4.0 * n * n / 1e9),
             "eps": "device Philox-4x32-10, regenerated in the backward; ranks read disjoint windows of one stream",
             "gemm_engine": {0: "auto", 1: "simt-fp32", 2: "tcgen05", 3: "simt-kloop"}.get(eng, str(eng)),
-            "presplit_engine": bool(lib.hb_set_presplit_engine(1)),
+            "presplit_engine": bool(_lib.OPTIONS.presplit_engine),
             "elbo_last": elbo,
         },
         "e2e": {"value": evals / (e2e_ms * 1e-3), "unit": UNIT,
@@ -622,8 +625,8 @@ def run_c4(d, steps, warmup, n_data=1000000, B=4096, S=32, latent=64):
     out = {"workload": f"BASELINE config 4: encoder 784-512-512-2x{latent} + mirrored decoder, {n_data} points resident, minibatch {B} "
                        f"over {d.world} rank(s), S={S}, Henbun API (" + str(opt.fused_entry or "eager tape over the CUDA operators") + ")",
            "metric": METRIC, "value": evals / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "scaling": "strong", "n_gpus": d.world,
-           "e2e": {"value": evals / (ms_e2e * 1e-3), "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(B // d.world * 8), "d2h_bytes_per_step": 8,
-                   "api": "model.ELBO().optimize(maxiter=1, minibatch_size=4096): minibatch indices drawn on the host every step, ELBO read back"},
+           "e2e": {"value": evals / (ms_e2e * 1e-3), "ms_per_step": ms_e2e, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                   "api": "model.ELBO().optimize(maxiter=1, minibatch_size=4096): data resident, minibatch indices drawn and rows gathered on the device, ELBO read back"},
            "roofline": {"bound": "tensor", "achieved": flop / d.world / (ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s",
                         "frac": flop / d.world / (ms * 1e-3) / 1e12 / tf_peak, "algorithmic_flop_per_step": flop, "peak_source": src},
            "elbo_last": last[0]}

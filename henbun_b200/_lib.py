@@ -26,9 +26,20 @@ _fl = C.c_float
 _sz = C.c_size_t
 
 
+class Options(C.Structure):
+    """hb_options (include/henbun_b200.h): behavioural switches that travel with every call."""
+    _fields_ = [("gemm_engine", _i), ("exact_below", _i), ("panel_refinement", _i), ("presplit_engine", _i),
+                ("small_gp_kernel", _i), ("tc_option", _i), ("lookahead", _i)]
+
+
+# The process-wide DEFAULT the Python layer passes when a caller gives no options of its own.  The C library itself keeps
+# no configuration; `lib.hb_set_*` below are Python-side conveniences that edit this object (tests, A/B runs).
+OPTIONS = Options(0, 2048, 2, 1, 0, 0, 1)
+
+
 class GpConfig(C.Structure):
     _fields_ = [("n", _i), ("D", _i), ("S", _i), ("n_ell", _i), ("q_fullrank", _i), ("jitter", _fl),
-                ("seed", _ull), ("offset", _ull)]
+                ("seed", _ull), ("offset", _ull), ("opt", C.POINTER(Options))]
 
 
 class AdamConfig(C.Structure):
@@ -44,11 +55,12 @@ class AmortisedConfig(C.Structure):
     _fields_ = [("B", _i), ("S", _i), ("latent", _i),
                 ("n_enc", _i), ("enc_nodes", _i * (HB_MAX_LAYERS + 1)), ("enc_act", _i * HB_MAX_LAYERS),
                 ("n_dec", _i), ("dec_nodes", _i * (HB_MAX_LAYERS + 1)), ("dec_act", _i * HB_MAX_LAYERS),
-                ("seed", _ull), ("offset", _ull)]
+                ("seed", _ull), ("offset", _ull), ("opt", C.POINTER(Options))]
 
 
 class LinopConfig(C.Structure):
-    _fields_ = [("M", _i), ("M_total", _ll), ("n", _i), ("S", _i), ("seed", _ull), ("offset", _ull), ("presplit", _i)]
+    _fields_ = [("M", _i), ("M_total", _ll), ("n", _i), ("S", _i), ("seed", _ull), ("offset", _ull), ("presplit", _i),
+                ("opt", C.POINTER(Options))]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check that every symbol the header
@@ -57,10 +69,10 @@ SIGNATURES = {
     "hb_version": (_i, []),
     "hb_launch_count": (_ull, []),
     "hb_reduce_workspace_bytes": (_sz, []),
-    "hb_set_gemm_engine": (_i, [_i]),
-    "hb_get_gemm_engine": (_i, []),
+    "hb_options_init": (None, [C.POINTER(Options)]),
     "hb_profile_begin": (_i, [_i]),
     "hb_profile_end": (_i, [C.POINTER(C.c_double)]),
+    "hb_profile_dump_csv": (_i, [C.c_char_p]),
     "hb_profile_end_ex": (_i, [C.POINTER(C.c_double)]),
     "hb_phase_begin": (_i, []),
     "hb_phase_end": (_i, [C.POINTER(C.c_double), _i]),
@@ -87,20 +99,16 @@ SIGNATURES = {
     "hb_rbf_gram_bwd": (_i, [_c_f, _ll, _ll, _c_f, _c_f, _i, _i, _i, _i, _c_f, _i, _i, _i, _c_f, _c_f, _c_f, _sz,
                              _c_f]),
     "hb_rbf_gram_bwd_x2": (_i, [_c_f, _ll, _ll, _c_f, _c_f, _i, _i, _i, _i, _c_f, _i, _i, _fl, _c_f, _c_f]),
-    "hb_set_panel_refinement": (_i, [_i]),
-    "hb_set_exact_below": (_i, [_i]),
-    "hb_set_presplit_engine": (_i, [_i]),
     "hb_potrf_workspace_bytes": (_sz, [_i]),
-    "hb_potrf_lower": (_i, [_c_f, _ll, _ll, _i, _i, _i, _c_f, _sz, _c_f, _c_f]),
-    "hb_potrf_lower_bwd": (_i, [_c_f, _ll, _ll, _c_f, _ll, _ll, _i, _i, _c_f, _sz, _c_f]),
+    "hb_potrf_lower": (_i, [_c_f, _ll, _ll, _i, _i, _i, _c_f, _sz, _c_f, _c_f, C.POINTER(Options)]),
+    "hb_potrf_lower_bwd": (_i, [_c_f, _ll, _ll, _c_f, _ll, _ll, _i, _i, _c_f, _sz, _c_f, C.POINTER(Options)]),
     "hb_trsm_workspace_bytes": (_sz, [_i, _i]),
-    "hb_trsm_right_lower": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _i, _c_f, _sz, _c_f]),
+    "hb_trsm_right_lower": (_i, [_c_f, _ll, _c_f, _ll, _i, _i, _i, _c_f, _sz, _c_f, C.POINTER(Options)]),
     "hb_gemm": (_i, [_c_f, _ll, _ll, _i, _i, _c_f, _ll, _ll, _i, _i, _c_f, _ll, _ll, _i, _i, _i, _i, _i, _fl, _fl,
                      _c_f, _ll, _i, _i, _fl, _fl, _c_f]),
     "hb_gemm_ws": (_i, [_c_f, _ll, _ll, _i, _i, _c_f, _ll, _ll, _i, _i, _c_f, _ll, _ll, _i, _i, _i, _i, _i, _fl, _fl,
-                        _c_f, _ll, _i, _i, _fl, _fl, _c_f, _sz, _c_f]),
+                        _c_f, _ll, _i, _i, _fl, _fl, _c_f, _sz, _c_f, C.POINTER(Options)]),
     "hb_gemm_tc_workspace_bytes": (_sz, [_i, _i, _i]),
-    "hb_set_tc_option": (_i, [_i]),
     "hb_gemm_tn_tc": (_i, [_c_f, _ll, _c_f, _ll, _c_f, _ll, _i, _i, _i, _i, _fl, _fl, _c_f, _sz, _c_f]),
     "hb_gemm_presplit_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "hb_gemm_presplit": (_i, [_c_f, _ll, _i, _c_f, _ll, _i, _c_f, _ll, _i, _i, _i, _i, _fl, _fl, _i, _i, _i, _c_f, _sz, _c_f]),
@@ -122,7 +130,6 @@ SIGNATURES = {
     "hb_amortised_workspace_bytes": (_sz, [C.POINTER(AmortisedConfig)]),
     "hb_amortised_elbo_step": (_i, [C.POINTER(AmortisedConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f]),
     "hb_gp_small_max_n": (_i, [_i]),
-    "hb_set_small_gp_kernel": (_i, [_i]),
     "hb_gp_small_workspace_bytes": (_sz, [C.POINTER(GpConfig), _i]),
     "hb_gp_small_step": (_i, [C.POINTER(GpConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, C.POINTER(AdamConfig), _c_f, _sz,
                               _c_f, _c_f]),
@@ -154,13 +161,67 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    # A/B switches from the environment (accuracy vs speed of the factorisations, include/henbun_b200.h)
+    _install_option_plumbing(lib)
+    # A/B switches from the environment (accuracy vs speed of the factorisations) edit the Python-side default
     if os.environ.get("HB_EXACT_BELOW") is not None:
         lib.hb_set_exact_below(int(os.environ["HB_EXACT_BELOW"]))
     if os.environ.get("HB_PANEL_REFINEMENT") is not None:
         lib.hb_set_panel_refinement(int(os.environ["HB_PANEL_REFINEMENT"]))
     _lib = lib
     return lib
+
+
+# entry points whose LAST argument is `const hb_options*`, and whole-step entry points whose config struct carries it
+_TRAILING_OPT = ("hb_gemm_ws", "hb_potrf_lower", "hb_potrf_lower_bwd", "hb_trsm_right_lower")
+_CFG_OPT = ("hb_gp_elbo_step", "hb_linop_prepare", "hb_linop_elbo_local", "hb_linop_elbo_update", "hb_amortised_elbo_step")
+
+
+def _install_option_plumbing(lib):
+    """Callers that do not pass options get the Python-side default OPTIONS; `lib.hb_set_*` edit that default.  (The C
+    functions of those names were removed in round 2: configuration travels with the call.)"""
+    def trailing(fn, nargs):
+        def call(*args):
+            if len(args) == nargs - 1:
+                args = args + (C.byref(OPTIONS),)
+            return fn(*args)
+        call.__name__ = fn.__name__
+        return call
+
+    def cfg_first(fn):
+        def call(cfg_ref, *args):
+            cfg = getattr(cfg_ref, "_obj", None)
+            if cfg is not None and not cfg.opt:
+                cfg.opt = C.pointer(OPTIONS)
+            return fn(cfg_ref, *args)
+        call.__name__ = fn.__name__
+        return call
+    for name in _TRAILING_OPT:
+        setattr(lib, name, trailing(getattr(lib, name), len(SIGNATURES[name][1])))
+    for name in _CFG_OPT:
+        setattr(lib, name, cfg_first(getattr(lib, name)))
+
+    def set_engine(mode):
+        if mode < 0 or mode > 3:
+            return HB_ERR_ARG
+        OPTIONS.gemm_engine = int(mode)
+        return HB_OK
+
+    def set_refinement(mode):
+        OPTIONS.panel_refinement = int(mode) if 0 <= mode <= 3 else 2
+        return OPTIONS.panel_refinement
+
+    def set_field(field, conv=int):
+        def f(v):
+            setattr(OPTIONS, field, conv(v))
+            return getattr(OPTIONS, field)
+        return f
+    lib.hb_set_gemm_engine = set_engine
+    lib.hb_get_gemm_engine = lambda: OPTIONS.gemm_engine
+    lib.hb_set_panel_refinement = set_refinement
+    lib.hb_set_exact_below = set_field("exact_below", lambda v: max(0, int(v)))
+    lib.hb_set_presplit_engine = set_field("presplit_engine", lambda v: 1 if v else 0)
+    lib.hb_set_small_gp_kernel = set_field("small_gp_kernel", lambda v: 1 if v else 0)
+    lib.hb_set_tc_option = lambda v: (setattr(OPTIONS, "tc_option", int(v)), HB_OK)[1]
 
 
 _ERR = {HB_ERR_ARG: "invalid argument", HB_ERR_CUDA: "CUDA launch/runtime failure",

@@ -142,6 +142,7 @@ size_t hb_amortised_workspace_bytes(const hb_amortised_config* c) {
 int hb_amortised_elbo_step(const hb_amortised_config* cfg, const float* X, const float* params, const float* eps, float* grads,
                            float* out4, void* ws, size_t ws_bytes, void* stream) {
   if (!cfg || !X || !params || !grads || !out4) return HB_ERR_ARG;
+  OptScope scope(cfg->opt);
   const hb_amortised_config c = *cfg;
   if (!valid(c)) return HB_ERR_ARG;
   if (!eps && (c.offset & 3ull)) return HB_ERR_ARG;

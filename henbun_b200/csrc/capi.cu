@@ -9,9 +9,23 @@
 
 namespace hb {
 
-static int g_engine = 0;
-void set_gemm_engine(int mode) { g_engine = mode; }
-int get_gemm_engine() { return g_engine; }
+// ---- options of the call in flight (include/henbun_b200.h: hb_options) ------------------------------------------------
+// The library keeps no mutable configuration.  Every extern "C" entry point that reaches the level-3 engine installs the
+// caller's hb_options for its own duration on the calling thread (OptScope) and the kernels' host code reads them through
+// the opt_*() accessors; outside any call, and for NULL, the defaults of hb_options_init apply.
+static const hb_options kDefaultOptions = {0, 2048, 2, 1, 0, 0, 1};
+static thread_local const hb_options* tl_options = nullptr;
+static inline const hb_options& cur_opt() { return tl_options ? *tl_options : kDefaultOptions; }
+int opt_gemm_engine() { const int e = cur_opt().gemm_engine; return (e < 0 || e > 3) ? 0 : e; }
+int opt_exact_below() { const int n = cur_opt().exact_below; return n < 0 ? 0 : n; }
+int opt_panel_refinement() { const int m = cur_opt().panel_refinement; return (m < 0 || m > 3) ? 2 : m; }
+int opt_presplit_engine() { return cur_opt().presplit_engine != 0; }
+int opt_small_gp_kernel() { return cur_opt().small_gp_kernel != 0; }
+int opt_tc_option() { return cur_opt().tc_option; }
+int opt_lookahead() { return cur_opt().lookahead != 0; }
+OptScope::OptScope(const ::hb_options* o) : prev(tl_options) { if (o) tl_options = o; }
+OptScope::~OptScope() { tl_options = prev; }
+#define g_engine (opt_gemm_engine())
 
 int gemm_tc2(const GemmParams& p, cudaStream_t stream);  // gemm_tc2.cu (in-kernel hi/lo split, no workspace)
 bool gemm_tc2_eligible(const GemmParams& p);
@@ -191,12 +205,7 @@ extern "C" {
 int hb_version(void) { return 100; }
 unsigned long long hb_launch_count(void) { return g_launches; }
 size_t hb_reduce_workspace_bytes(void) { return kReduceWsBytes; }
-int hb_set_gemm_engine(int mode) {
-  if (mode < 0 || mode > 3) return HB_ERR_ARG;
-  set_gemm_engine(mode);
-  return HB_OK;
-}
-int hb_get_gemm_engine(void) { return get_gemm_engine(); }
+void hb_options_init(hb_options* opt) { if (opt) *opt = kDefaultOptions; }
 
 int hb_profile_begin(int max_gemm_launches) {
   if (max_gemm_launches < 0) return HB_ERR_ARG;
@@ -217,18 +226,27 @@ int hb_profile_end(double* out4_host) {
   if (!out4_host) return HB_ERR_ARG;
   if (cudaDeviceSynchronize() != cudaSuccess) return HB_ERR_CUDA;
   double ms = 0.0, fl = 0.0;
-  const char* csv = getenv("HB_PROFILE_CSV");      // optional per-launch dump (debug aid for profiles/)
-  FILE* f = csv ? fopen(csv, "w") : nullptr;
-  if (f) fprintf(f, "M,N,K,tc,useful_flop,ms\n");
   for (size_t i = 0; i < g_prof.used; ++i) {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]) != cudaSuccess) { if (f) fclose(f); return HB_ERR_CUDA; }
+    if (cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]) != cudaSuccess) return HB_ERR_CUDA;
     ms += t; fl += g_prof.flops[i];
-    if (f) fprintf(f, "%lld,%lld,%lld,%lld,%.0f,%.6f\n", g_prof.shape[4 * i], g_prof.shape[4 * i + 1], g_prof.shape[4 * i + 2],
-                   g_prof.shape[4 * i + 3], g_prof.flops[i], t);
   }
-  if (f) fclose(f);
   out4_host[0] = (double)g_prof.used; out4_host[1] = ms; out4_host[2] = fl; out4_host[3] = 0.0;
+  return HB_OK;
+}
+// Per-launch dump of the last profiled region (call after hb_profile_end[_ex], before the next hb_profile_begin).
+int hb_profile_dump_csv(const char* path) {
+  if (!path) return HB_ERR_ARG;
+  FILE* f = fopen(path, "w");
+  if (!f) return HB_ERR_ARG;
+  fprintf(f, "M,N,K,tc,useful_flop,ms\n");
+  for (size_t i = 0; i < g_prof.used; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.ev0[i], g_prof.ev1[i]) != cudaSuccess) { fclose(f); return HB_ERR_CUDA; }
+    fprintf(f, "%lld,%lld,%lld,%lld,%.0f,%.6f\n", g_prof.shape[4 * i], g_prof.shape[4 * i + 1], g_prof.shape[4 * i + 2],
+            g_prof.shape[4 * i + 3], g_prof.flops[i], t);
+  }
+  fclose(f);
   return HB_OK;
 }
 // Same, but also splits out the launches that ran the CTA-pair tcgen05 kernel (the dominant kernel):
@@ -414,21 +432,21 @@ int hb_rbf_gram_bwd_x2(const float* G, long long ldg, long long strideG, const f
                          sym_lower, scale, dX2, S(stream));
 }
 
-int hb_set_exact_below(int n) { set_exact_below(n); return get_exact_below(); }
-int hb_set_presplit_engine(int on) { set_presplit_engine(on); return get_presplit_engine(); }
-int hb_set_panel_refinement(int mode) { set_panel_refinement(mode); return get_panel_refinement(); }
 size_t hb_potrf_workspace_bytes(int n) { return potrf_workspace_bytes(n); }
 int hb_potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
-                   size_t ws_bytes, int* err_flag, void* stream) {
+                   size_t ws_bytes, int* err_flag, void* stream, const hb_options* opt) {
+  OptScope scope(opt);
   return potrf_lower(A, lda, strideA, n, batch, zero_upper, ws, ws_bytes, err_flag, S(stream));
 }
 int hb_potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, long long ldg, long long strideG,
-                       int n, int batch, void* ws, size_t ws_bytes, void* stream) {
+                       int n, int batch, void* ws, size_t ws_bytes, void* stream, const hb_options* opt) {
+  OptScope scope(opt);
   return potrf_lower_bwd(L, ldl, strideL, G, ldg, strideG, n, batch, ws, ws_bytes, S(stream));
 }
 size_t hb_trsm_workspace_bytes(int m, int n) { return trsm_workspace_bytes(m, n); }
 int hb_trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int m, int n, int trans, void* ws,
-                        size_t ws_bytes, void* stream) {
+                        size_t ws_bytes, void* stream, const hb_options* opt) {
+  OptScope scope(opt);
   return trsm_right_lower(L, ldl, X, ldx, m, n, trans, ws, ws_bytes, S(stream));
 }
 
@@ -437,13 +455,14 @@ int hb_gemm(const float* A, long long lda, long long strideA, int transA, int a_
             int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
             int clip, float clip_lo, float clip_hi, void* stream) {
   return hb_gemm_ws(A, lda, strideA, transA, a_tri, B, ldb, strideB, transB, b_tri, C, ldc, strideC, c_tri, M, N, K,
-                    batch, alpha, beta, bias, strideBias, act, clip, clip_lo, clip_hi, nullptr, 0, stream);
+                    batch, alpha, beta, bias, strideBias, act, clip, clip_lo, clip_hi, nullptr, 0, stream, nullptr);
 }
 
 int hb_gemm_ws(const float* A, long long lda, long long strideA, int transA, int a_tri, const float* B, long long ldb,
                long long strideB, int transB, int b_tri, float* C, long long ldc, long long strideC, int c_tri, int M,
                int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
-               int clip, float clip_lo, float clip_hi, void* ws, size_t ws_bytes, void* stream) {
+               int clip, float clip_lo, float clip_hi, void* ws, size_t ws_bytes, void* stream, const hb_options* opt) {
+  OptScope scope(opt);
   GemmParams g;
   g.ws = ws; g.ws_bytes = ws_bytes;
   g.A = A; g.lda = lda; g.sA = strideA; g.transA = transA; g.a_tri = a_tri;
@@ -459,7 +478,6 @@ int hb_gemm_ws(const float* A, long long lda, long long strideA, int transA, int
 }
 
 size_t hb_gemm_tc_workspace_bytes(int, int, int) { return 0; }   // the engine consumes operands in place
-int hb_set_tc_option(int v) { set_tc_option(v); return HB_OK; }
 int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int c_tri, int M,
                   int N, int K, float alpha, float beta, void* ws, size_t ws_bytes, void* stream) {
   GemmParams g;
@@ -568,8 +586,6 @@ int hb_zero_strict_upper(float* a, long long lda, int n, void* stream) { return 
 // ---------------------------------------------------------------------------------------------
 // fused variational-GP ELBO + gradient
 // ---------------------------------------------------------------------------------------------
-static int g_small_gp = 0;   // measured: 280 us (one CTA, level-2 column steps) against 239 us for the 23-kernel path at N = 100
-int hb_set_small_gp_kernel(int on) { g_small_gp = on ? 1 : 0; return g_small_gp; }
 int hb_gp_small_max_n(int f64) { return gp_small_max_n(f64); }
 size_t hb_gp_small_workspace_bytes(const hb_gp_config* c, int f64) {
   if (!c) return 0;
@@ -612,6 +628,7 @@ size_t hb_gp_elbo_workspace_bytes(const hb_gp_config* c) {
 int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, const float* params, const float* eps,
                     float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream) {
   if (!cfg || !X || !Y || !params || !grads || !out4) return HB_ERR_ARG;
+  OptScope scope(cfg->opt);
   const hb_gp_config c = *cfg;
   if (c.n <= 0 || c.D <= 0 || c.D > 32 || c.S <= 0 || (c.n_ell != 1 && c.n_ell != c.D)) return HB_ERR_ARG;
   if (!eps && (c.offset & 3ull)) return HB_ERR_ARG;
@@ -633,7 +650,7 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
   float* kl = ll3 + 3;                 // 1 float
 
   const int n = c.n, Sn = c.S;
-  if (n <= gp_small_max_n(0) && g_small_gp) {
+  if (n <= gp_small_max_n(0) && opt_small_gp_kernel()) {
     // notebook-sized model: the whole step is ONE persistent CTA (gp_small.cu); Z | F | R | W are adjacent -> 4 S n floats
     return gp_small_step_f32(n, c.D, Sn, c.n_ell, c.q_fullrank, c.jitter, c.seed, c.offset, X, Y, const_cast<float*>(params), eps,
                              grads, out4, Z, err_flag, nullptr, nullptr, nullptr, 0, 0.0, 0.0, 0.0, 0.0, 0.0, st);

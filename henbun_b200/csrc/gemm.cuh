@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+struct hb_options;   // include/henbun_b200.h
+
 namespace hb {
 
 // Triangular masks are expressed in the index space of op(A) (m,k) and op(B) (k,n):
@@ -41,12 +43,24 @@ int gemm(const GemmParams& p, cudaStream_t stream);
 int gemm_simt(const GemmParams& p, cudaStream_t stream);
 int gemm_small(const GemmParams& p, cudaStream_t stream);      // K <= 256, whole-K staging (latency-oriented); C may alias A if N <= 128
 bool gemm_small_eligible(const GemmParams& p);
-void set_tc_option(int v);   // bit2: no CTA pairs | bit3: three TF32 passes instead of TF32 + bf16 cross terms
-int get_tc_option();
+// Options of the C call in flight on this thread (include/henbun_b200.h: hb_options; defaults outside any call).  The
+// extern "C" entry points install them for their own duration (capi.cu: OptScope); the library keeps no mutable configuration.
+int opt_gemm_engine();
+int opt_exact_below();
+int opt_panel_refinement();
+int opt_presplit_engine();
+int opt_small_gp_kernel();
+int opt_tc_option();
+int opt_lookahead();
+struct OptScope {     // installs the caller's options for the duration of one extern "C" call (capi.cu)
+  const ::hb_options* prev;
+  explicit OptScope(const ::hb_options* o);
+  ~OptScope();
+};
+inline int get_tc_option() { return opt_tc_option(); }
+inline int get_gemm_engine() { return opt_gemm_engine(); }
 // per-launch timing hooks for launches that bypass hb::gemm (the pre-split engine): slot = prof_begin(...); launch; prof_end(slot)
 int gemm_prof_begin(double useful_flops, int M, int N, int K, int kind, cudaStream_t st);   // -1 when profiling is off
 void gemm_prof_end(int slot, cudaStream_t st);
-void set_gemm_engine(int mode);
-int get_gemm_engine();
 
 }  // namespace hb

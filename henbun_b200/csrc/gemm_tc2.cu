@@ -19,10 +19,8 @@
 
 namespace hb {
 
-// A/B switches of the engine: bit 2 = no CTA pairs, bit 3 = three TF32 passes instead of TF32 + bf16 cross terms.
-static int g_tc_option = 0;
-void set_tc_option(int v) { g_tc_option = v; }
-int get_tc_option() { return g_tc_option; }
+// A/B switches of the engine (hb_options.tc_option): bit 2 = no CTA pairs, bit 3 = three TF32 passes instead of TF32 + bf16
+// cross terms.
 
 namespace {
 

@@ -100,12 +100,6 @@ int adam_tf1(float* theta, const float* grad, float* m, float* v, long long n, f
 int increment_i32(int* p, cudaStream_t st);
 
 // ---- linalg.cu ----
-void set_panel_refinement(int mode);   // 0 explicit inverse, 1 refined, 2 refined for n <= 8192, 2 is the default, 3 substitution kernel
-int get_panel_refinement();
-void set_presplit_engine(int on);
-int get_presplit_engine();
-void set_exact_below(int n);           // factorisations of order <= n use exact fp32 products (default 2048)
-int get_exact_below();
 size_t potrf_workspace_bytes(int n);
 size_t trsm_workspace_bytes(int m, int n);
 int potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,

@@ -520,8 +520,7 @@ struct Ctx {
 
 // Orders from which the big products run on the pre-split engine.  Below, no product has enough 256 x 256 tiles.
 constexpr int H2_MIN_N = 4096;
-static int g_use_h2 = 1;
-inline bool h2_on(int n) { return g_use_h2 && n >= H2_MIN_N && (n % 8) == 0; }
+inline bool h2_on(int n) { return opt_presplit_engine() && n >= H2_MIN_N && (n % 8) == 0; }
 inline long long h2_ld(int n) { return ((long long)n + 63) / 64 * 64; }
 
 static double h2_flops(const H2Gemm& h) {
@@ -546,8 +545,8 @@ static int split_L(const Ctx& c, const float* L, long long ldl, int r0, int c0, 
                   c.lh + (long long)r0 * c.ldh + c0, c.ll + (long long)r0 * c.ldh + c0, c.ldh, c.st);
 }
 
-// Side stream and its two events, created once per device (the only state this library keeps besides cuFuncAttributes;
-// HB_LOOKAHEAD=0 in the environment disables the look-ahead).
+// Side stream and its two events, created once per device: a resource cache, not configuration (hb_options.lookahead = 0
+// keeps a call off it).
 struct SideState { cudaStream_t st = nullptr; cudaEvent_t a = nullptr, b = nullptr; bool tried = false; };
 static SideState g_side[64];
 static void attach_side(Ctx& c) {
@@ -556,8 +555,7 @@ static void attach_side(Ctx& c) {
   SideState& s = g_side[dev];
   if (!s.tried) {
     s.tried = true;
-    const char* e = getenv("HB_LOOKAHEAD");
-    if (!(e && e[0] == '0')) {
+    {
       int lo = 0, hi = 0;
       cudaDeviceGetStreamPriorityRange(&lo, &hi);
       if (cudaStreamCreateWithPriority(&s.st, cudaStreamNonBlocking, hi) != cudaSuccess) s.st = nullptr;
@@ -565,6 +563,7 @@ static void attach_side(Ctx& c) {
                    cudaEventCreateWithFlags(&s.b, cudaEventDisableTiming) != cudaSuccess)) s.st = nullptr;
     }
   }
+  if (!opt_lookahead()) return;                 // hb_options.lookahead = 0: everything on the caller's stream
   c.side = s.st; c.ev_main = s.a; c.ev_side = s.b;
 }
 // side stream picks up everything issued on the main stream so far
@@ -584,9 +583,8 @@ static inline void join_side(const Ctx& c) {
 // 1.5e-6 per-product error was visible next to LAPACK's (tests/probe_config2_errors.py).
 // Price at n = 2000: 3 factorisations + reverse modes 17.6 -> 29.5 ms (the SIMT kernels fill 10-30 of 148 SMs on these
 // shapes); gain: gradient error vs fp64 3-5x LAPACK's -> 1-3x.  hb_set_exact_below(0) turns it off.
-static int g_exact_below = 2048;
 inline int gemm_ws(const Ctx& c, GemmParams& g) {
-  g.force_simt = (c.n_total > 0 && c.n_total <= g_exact_below) ? 1 : 0;
+  g.force_simt = (c.n_total > 0 && c.n_total <= opt_exact_below()) ? 1 : 0;
   g.ws = c.tcws; g.ws_bytes = c.tcws_bytes;
   return gemm(g, c.st);
 }
@@ -603,14 +601,13 @@ inline float* dinv_slot(const Ctx& c, int off) { return c.dinv + (long long)(off
 // panel_trsm_kernel solves the panel by substitution against the triangular block (backward stable, one pass over the
 // panel).  Mode 3 measured: same accuracy as mode 1, but +27 ms on the N=65536 step (1319 vs 1292 ms: 8 warps per SM
 // on a shared-memory-bound substitution lose to the tensor-core product with the inverse) -- opt-in only.
-static int g_panel_refine = 2;
-static inline bool refine_on(int n) { return g_panel_refine == 1 || (g_panel_refine == 2 && n <= 8192); }
+static inline bool refine_on(int n) { const int m = opt_panel_refinement(); return m == 1 || (m == 2 && n <= 8192); }
 
 // Bp (m x w, in place) <- alpha * Bp * D^{-T} (trans) or alpha * Bp * D^{-1}, D = w x w lower block at global offset `off`
 // of the factor (its strict upper triangle in memory is NOT assumed zero).
 static int panel_solve(const Ctx& c, const float* D, long long ldd, int off, float* Bp, long long ldb, int m, int w,
                        bool trans, float alpha, bool refine) {
-  if (g_panel_refine == 3) {
+  if (opt_panel_refinement() == 3) {
     if (m <= 0 || w <= 0) return HB_OK;
     const int nb = cdiv(m, PT_ROWS);
     if (trans) panel_trsm_kernel<true><<<nb, PT_ROWS, kPanelSmem, c.st>>>(D, ldd, Bp, ldb, m, w, alpha);
@@ -879,13 +876,7 @@ static size_t h2_shadow_bytes(int n) { return ((size_t)n * h2_ld(n) * 2 + 255) /
 static size_t h2_bytes_for(int n) { return (n >= H2_MIN_N && n % 8 == 0) ? h2_scale_bytes(n) + 4 * h2_shadow_bytes(n) : 0; }
 
 size_t potrf_workspace_bytes(int n) { return base_bytes(n, n) + tc_bytes_for(-1, n) + h2_bytes_for(n); }
-void set_presplit_engine(int on) { g_use_h2 = on ? 1 : 0; }
-int get_presplit_engine() { return g_use_h2; }
 
-void set_exact_below(int n) { g_exact_below = n < 0 ? 0 : n; }
-int get_exact_below() { return g_exact_below; }
-void set_panel_refinement(int mode) { g_panel_refine = (mode < 0 || mode > 3) ? 2 : mode; }
-int get_panel_refinement() { return g_panel_refine; }
 
 static int make_ctx(Ctx& c, int n, void* ws, size_t ws_bytes, int* err, cudaStream_t st) {
   if (ws_bytes < potrf_workspace_bytes(n) || !ws) return HB_ERR_WORKSPACE;

@@ -310,6 +310,7 @@ int hb_linop_prepare(const hb_linop_config* cfg, const float* A, void* ws, size_
 int hb_linop_elbo_local(const hb_linop_config* cfg, const float* A, const float* y, const float* params, const float* eps,
                         float* zbar_stats, void* ws, size_t ws_bytes, void* stream) {
   if (!cfg || !params || !zbar_stats) return HB_ERR_ARG;
+  OptScope scope(cfg->opt);
   const hb_linop_config c = *cfg;
   if (!cfg_ok(c) || (c.M > 0 && (!A || !y))) return HB_ERR_ARG;
   if (!eps && (c.offset & 3ull)) return HB_ERR_ARG;
@@ -343,12 +344,6 @@ int hb_linop_elbo_local(const hb_linop_config* cfg, const float* A, const float*
     HB_TRY(gemm(g, st));
   }
   HB_TRY(tril_logdet_kl(p_sq, n, (long long)n * n, n, 1, U, Z, (long long)Sn * n, Sn, kl, red, kReduceWsBytes, st));
-  // Experiment kept behind HB_LINOP_SWAP=1 (S = 64 only): the operator as the M operand of both products (sample-minor
-  // F^T [M, S] and Zbar^T [n, S]) on the engine's 128 x 64 tile, so that no MMA row is padding.  Correct (same tests),
-  // but SLOWER: local 3.78 ms against 3.04 ms -- per k-block the engine's cost is the staging/conversion of the 128-row
-  // operand tile, not the MMA, and this orientation doubles the number of tiles that stage A (profiles/README.md).
-  static const bool allow_swap = [] { const char* e = getenv("HB_LINOP_SWAP"); return e && e[0] == '1'; }();
-  const bool swapped = allow_swap && Sn == 64;       // the engine takes N >= 64 only (smaller S: samples stay the M operand)
   if (M > 0 && c.presplit) {
     // Both passes over the operator on the pre-split engine (csrc/gemm_h2.cu, 256 x 64 pair tiles): the operator's fp16
     // hi/lo shadow (hb_linop_prepare) is the M-side operand, K-major for F^T = A Z^T and MN-major for Zbar^T = A^T R^T, so
@@ -380,23 +375,6 @@ int hb_linop_elbo_local(const hb_linop_config* cfg, const float* A, const float*
       HB_TRY(gemm_h2(h, st));
     }
     HB_TRY(transpose2d(zbar_stats, n, Zbt, Sn, n, Sn, 1.f, st));
-  } else if (M > 0 && swapped) {
-    float* Zbt = reinterpret_cast<float*>(base + L.off_Zt);           // [n, S] scratch (free until the update call)
-    {  // F^T [M, S] = A Z^T
-      GemmParams g;
-      g.A = A; g.lda = n; g.B = Z; g.ldb = n; g.transB = 1;
-      g.C = F; g.ldc = Sn; g.M = M; g.N = Sn; g.K = n; g.ws = gws; g.ws_bytes = L.gemm_bytes;
-      HB_TRY(gemm(g, st));
-    }
-    // log-lik + R^T = (1/S) d ll / d F^T, in place (one y per row of S samples)
-    HB_TRY(gauss_loglik_fwd_ex(F, nullptr, y, (long long)Sn * M, M, Sn, sc, 1.f / (float)Sn, F, ll3, red, kReduceWsBytes, st));
-    {  // partial Zbar^T [n, S] = A^T R^T   (A consumed transposed in place; long K = M, split by whole waves)
-      GemmParams g;
-      g.A = A; g.lda = n; g.transA = 1; g.B = F; g.ldb = Sn; g.transB = 0;
-      g.C = Zbt; g.ldc = Sn; g.M = n; g.N = Sn; g.K = M; g.ws = gws; g.ws_bytes = L.gemm_bytes; g.hint_split_waves = 1;
-      HB_TRY(gemm(g, st));
-    }
-    HB_TRY(transpose2d(zbar_stats, n, Zbt, Sn, n, Sn, 1.f, st));     // -> [S, n], the layout the all-reduce and the update use
   } else if (M > 0) {
     {  // F [S, M] = Z A^T
       GemmParams g;

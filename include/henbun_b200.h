@@ -38,16 +38,37 @@ extern "C" {
 #define HB_ACT_RELU 2
 #define HB_ACT_TANH 3
 
+/* Behavioural switches travel WITH THE CALL (the library keeps no mutable configuration: two models with different accuracy
+ * settings can run side by side in one process).  Every entry point that reaches the level-3 engine takes a
+ * `const hb_options*` -- a trailing argument of the building blocks, the last field of the whole-step config structs --
+ * and NULL means hb_options_init()'s defaults.
+ *   gemm_engine      0 auto | 1 fp32 SIMT kernels only | 2 force tcgen05 (HB_ERR_ARG if the shape does not qualify) | 3 k-looped SIMT only
+ *   exact_below      factorisations (potrf / potrf_bwd / trsm) of order <= this run their products on the exact-fp32 SIMT
+ *                    kernels (default 2048: latency-bound sizes, where the notebook models live and where the split product's
+ *                    error shows on ill-conditioned inputs); 0 disables
+ *   panel_refinement panel solves multiply by explicit inverses of the 128 x 128 diagonal blocks; 0 inverse only, 1 one step of
+ *                    iterative refinement against the triangular block (LAPACK-grade on ill-conditioned matrices, two more
+ *                    short-K products per panel), 2 (default) refined for n <= 8192, 3 substitution kernel (no inverse)
+ *   presplit_engine  1 (default): factorisations of order >= 4096 (n % 8 == 0) keep fp16 hi/lo shadows of every finished panel
+ *                    of L and K-bar in their workspace and run their big products on csrc/gemm_h2.cu; 0: round-1 behaviour
+ *   small_gp_kernel  1: hb_gp_elbo_step runs n <= 128 as ONE persistent CTA (csrc/gp_small.cu); default 0 (measured slower)
+ *   tc_option        bit 2: no CTA pairs in the in-kernel-split engine, bit 3: three TF32 passes instead of TF32 + bf16 terms
+ *   lookahead        1 (default): leaf kernels of potrf / potrf_bwd run on a high-priority side stream */
+typedef struct hb_options {
+  int gemm_engine, exact_below, panel_refinement, presplit_engine, small_gp_kernel, tc_option, lookahead;
+} hb_options;
+void hb_options_init(hb_options* opt);
+
 /* library / bookkeeping */
 int hb_version(void);
 unsigned long long hb_launch_count(void);           /* kernels launched by this library so far */
 size_t hb_reduce_workspace_bytes(void);             /* workspace every reducing call needs */
-int hb_set_gemm_engine(int mode);                   /* 0 auto, 1 fp32 SIMT kernels only, 2 force tcgen05 3xTF32, 3 k-looped SIMT kernel only */
-int hb_get_gemm_engine(void);
 /* Optional instrumentation for bench.py: CUDA-event pairs around every GEMM launch on its stream.
  * hb_profile_end synchronises and fills a HOST array {launches, total ms, useful FLOP, 0}. */
 int hb_profile_begin(int max_gemm_launches);
 int hb_profile_end(double* out4_host);
+/* per-launch dump of the last profiled region (M,N,K,engine,useful FLOP,ms); call before the next hb_profile_begin */
+int hb_profile_dump_csv(const char* path_host);
 /* As hb_profile_end, plus the shares of the two CTA-pair tcgen05 kernels: out8 = {launches, ms, useful FLOP,
  * in-kernel-split pair kernel launches, ms, useful FLOP, pre-split (fp16 hi/lo) pair kernel ms, useful FLOP}. */
 int hb_profile_end_ex(double* out8_host);
@@ -180,33 +201,19 @@ int hb_rbf_gram_bwd(const float* G, long long ldg, long long strideG, const floa
                     float* g_ell, void* ws, size_t ws_bytes, void* stream);
 
 /* tf.cholesky (gp/kernels.py:101; gp/gp.py:135), batched, in place, lower. */
-/* Panel solves of potrf / potrf_bwd / trsm multiply by explicit inverses of the 128 x 128 diagonal blocks; one step of
- * iterative refinement against the triangular block restores LAPACK-grade accuracy on ill-conditioned matrices at the
- * price of two more short-K products per panel.  mode: 0 explicit inverse only, 1 refined, 2 (default) refined for n <= 8192, 3 no inverse: the panel is solved by
- * substitution against the triangular block (panel_trsm_kernel; as accurate as mode 1, slower at large n).  Returns
- * the mode set. */
-int hb_set_panel_refinement(int mode);
-/* Factorisations (potrf / potrf_bwd / trsm) of order <= n run their products on the exact-fp32 SIMT kernels instead of
- * the tensor-core split product (default n = 2048: latency-bound sizes, where the notebook models live and where the
- * split product's 1.5e-6 error shows on ill-conditioned inputs).  0 disables.  Returns the value set. */
-int hb_set_exact_below(int n);
-/* Factorisations of order >= 4096 (n % 8 == 0) keep fp16 hi/lo "shadow" copies of every finished panel of L and of K-bar
- * in their workspace and run their big products on the pre-split tcgen05 engine (csrc/gemm_h2.cu, see hb_gemm_presplit).
- * 0 turns that off (all products on the in-kernel-split engine, as in round 1).  Returns the value set. */
-int hb_set_presplit_engine(int on);
 size_t hb_potrf_workspace_bytes(int n);
 int hb_potrf_lower(float* A, long long lda, long long strideA, int n, int batch, int zero_upper, void* ws,
-                   size_t ws_bytes, int* err_flag, void* stream);
+                   size_t ws_bytes, int* err_flag, void* stream, const hb_options* opt);
 /* Reverse mode of tf.cholesky (TF's _CholeskyGrad, reached through Optimizer.compile, model.py:220).
  * In: G lower = dObj/dL.  Out: G lower = dObj/dK for the symmetric input (off-diagonals of a
  * symmetric perturbation count twice). */
 int hb_potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, long long ldg, long long strideG,
-                       int n, int batch, void* ws, size_t ws_bytes, void* stream);
+                       int n, int batch, void* ws, size_t ws_bytes, void* stream, const hb_options* opt);
 /* tf.matrix_triangular_solve from the right: X <- X L^{-T} (trans=1) or X L^{-1} (trans=0)
  * (gp/gp.py:162,169 and densities.py:84 use the transposed-left forms of the same solves). */
 size_t hb_trsm_workspace_bytes(int m, int n);
 int hb_trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int m, int n, int trans, void* ws,
-                        size_t ws_bytes, void* stream);
+                        size_t ws_bytes, void* stream, const hb_options* opt);
 
 /* tf.matmul (GaussianProcess.ipynb:144, gp/gp.py:50, nn.py:32, variationals.py:146) with the fused
  * MatBias epilogue clip(x w + b) -> activation (nn.py:32,83).
@@ -216,7 +223,7 @@ int hb_gemm(const float* A, long long lda, long long strideA, int transA, int a_
             long long strideB, int transB, int b_tri, float* C, long long ldc, long long strideC, int c_tri, int M,
             int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
             int clip, float clip_lo, float clip_hi, void* stream);
-/* hb_gemm with an optional scratch buffer.  Engine choice (hb_set_gemm_engine(0), the default):
+/* hb_gemm with an optional scratch buffer and options.  Engine choice (opt->gemm_engine == 0, the default):
  *   - K <= 256 and few output tiles          -> short-K fp32 SIMT kernel (whole K staged in one round trip)
  *   - batch 1, 16-byte aligned A/B, ld % 4 == 0, N >= 64, K >= 32 and M*N*K >= 256^3 (or K >= 512 with ws given)
  *                                            -> tcgen05 engine (gemm_tc2.cu): any transposition, triangular masks,
@@ -228,13 +235,10 @@ int hb_gemm(const float* A, long long lda, long long strideA, int transA, int a_
 int hb_gemm_ws(const float* A, long long lda, long long strideA, int transA, int a_tri, const float* B, long long ldb,
                long long strideB, int transB, int b_tri, float* C, long long ldc, long long strideC, int c_tri, int M,
                int N, int K, int batch, float alpha, float beta, const float* bias, long long strideBias, int act,
-               int clip, float clip_lo, float clip_hi, void* ws, size_t ws_bytes, void* stream);
+               int clip, float clip_lo, float clip_hi, void* ws, size_t ws_bytes, void* stream, const hb_options* opt);
 /* Force the tensor-core engine on C[M,N] = alpha*A[M,K]*B[N,K]^T + beta*C (both operands K-major); HB_ERR_ARG if the
- * operands do not qualify.  hb_set_tc_option bits (A/B experiments; also read once from the environment variable
- * HB_TC_OPTION): 1 = generation-1 engine writes explicit hi copies, 2 = use generation 1 (operand-preparation pass,
- * needs hb_gemm_tc_workspace_bytes of ws), 4 = no CTA pairs, 8 = three TF32 passes instead of TF32 + bf16 cross terms. */
+ * operands do not qualify. */
 size_t hb_gemm_tc_workspace_bytes(int M, int N, int K);
-int hb_set_tc_option(int v);
 int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int c_tri, int M,
                   int N, int K, float alpha, float beta, void* ws, size_t ws_bytes, void* stream);
 /* The engine behind the big products of hb_potrf_lower / hb_potrf_lower_bwd at n >= 4096 (csrc/gemm_h2.cu), standalone:
@@ -281,12 +285,13 @@ typedef struct {
   int q_fullrank;
   float jitter;
   unsigned long long seed, offset;
+  const hb_options* opt;   /* NULL = defaults */
 } hb_gp_config;
 size_t hb_gp_param_count(const hb_gp_config* cfg);
 /* Notebook-sized models (n <= hb_gp_small_max_n(0) = 128 in fp32, hb_gp_small_max_n(1) = 112 in fp64): the whole step --
  * Gram, Cholesky, sampler + KL, projection, log-likelihood, the complete backward and, when adam_m / adam_v are given,
  * the TF-1 Adam update -- is ONE persistent CTA with K / L / K-bar resident in shared memory (csrc/gp_small.cu).
- * hb_set_small_gp_kernel(1) makes hb_gp_elbo_step take this path for n <= 128 (default off: the one-CTA kernel runs
+ * opt->small_gp_kernel = 1 makes hb_gp_elbo_step take this path for n <= 128 (default off: the one-CTA kernel runs
  * level-2 column steps, 280 us per step at N = 100 against 239 us for the multi-kernel path with its blocked leaves).
  * The _f64 variant is the reference's float_type = float64 (henbunrc:7) for this graph: every pointer is double,
  * same packing.  adam: grad_scale = -1 minimises -ELBO; step counter read from *step_dev when non-NULL. */
@@ -296,7 +301,6 @@ typedef struct {
   int step_host;
 } hb_adam_config;
 int hb_gp_small_max_n(int f64);
-int hb_set_small_gp_kernel(int on);
 size_t hb_gp_small_workspace_bytes(const hb_gp_config* cfg, int f64);
 int hb_gp_small_step(const hb_gp_config* cfg, const float* X, const float* Y, float* params, const float* eps, float* grads,
                      float* out4, float* adam_m, float* adam_v, const hb_adam_config* adam, void* ws, size_t ws_bytes,
@@ -321,6 +325,7 @@ typedef struct {
   int n_enc, enc_nodes[HB_MAX_LAYERS + 1], enc_act[HB_MAX_LAYERS];
   int n_dec, dec_nodes[HB_MAX_LAYERS + 1], dec_act[HB_MAX_LAYERS];
   unsigned long long seed, offset;
+  const hb_options* opt;   /* NULL = defaults */
 } hb_amortised_config;
 size_t hb_amortised_param_count(const hb_amortised_config* cfg);
 size_t hb_amortised_workspace_bytes(const hb_amortised_config* cfg);
@@ -346,6 +351,7 @@ typedef struct {
   int presplit;          /* 1: both passes over A run on the pre-split tcgen05 engine from an fp16 hi/lo shadow of A that
                             hb_linop_prepare writes into the workspace once per operator (+ 4 bytes per element of A of
                             workspace; n % 8 == 0, M % 8 == 0).  0: A is consumed as fp32 (in-kernel split). */
+  const hb_options* opt; /* NULL = defaults */
 } hb_linop_config;
 size_t hb_linop_param_count(const hb_linop_config* cfg);
 size_t hb_linop_workspace_bytes(const hb_linop_config* cfg);

@@ -429,3 +429,32 @@ def test_gp_elbo_step_matches_oracle(lib, n, D, S, n_ell, full):
         assert e <= (tol if name not in ("lengthscales",) else 3 * tol), (name, e, got[off:off + 3], gref[off:off + 3])
         off += sz
     lib.hb_set_gemm_engine(0)
+
+
+def test_options_travel_with_the_call(lib):
+    """hb_options is a per-call argument (the library keeps no configuration): the same product with two different option
+    structs back to back takes two different engines, and forcing the tensor-core engine on a shape it cannot take is an
+    argument error for THAT call only."""
+    import ctypes as C
+    from henbun_b200 import _lib
+    g = torch.Generator("cuda").manual_seed(0)
+    M = N = K = 512
+    A = torch.randn(M, K, device="cuda", generator=g); B = torch.randn(K, N, device="cuda", generator=g)
+    ref = (A.double() @ B.double())
+    outs = {}
+    for name, engine in (("simt", 1), ("tc", 2), ("auto", 0)):
+        o = _lib.Options(); lib.hb_options_init(C.byref(o)); o.gemm_engine = engine
+        Cm = torch.zeros(M, N, device="cuda")
+        rc = lib.hb_gemm_ws(P(A), K, 0, 0, 0, P(B), N, 0, 0, 0, P(Cm), N, 0, 0, M, N, K, 1, 1.0, 0.0, None, 0, 0, 0, -50.0, 50.0, None, 0,
+                            ST(), C.byref(o))
+        assert rc == 0
+        outs[name] = Cm
+        assert (torch.linalg.norm(Cm.double() - ref) / torch.linalg.norm(ref)).item() < 3e-6
+    assert not torch.equal(outs["simt"], outs["tc"])              # different arithmetic paths really ran
+    o = _lib.Options(); lib.hb_options_init(C.byref(o)); o.gemm_engine = 2
+    A3 = torch.randn(8, 7, device="cuda", generator=g); B3 = torch.randn(7, 5, device="cuda", generator=g); C3 = torch.zeros(8, 5, device="cuda")
+    bad = lib.hb_gemm_ws(P(A3), 7, 0, 0, 0, P(B3), 5, 0, 0, 0, P(C3), 5, 0, 0, 8, 5, 7, 1, 1.0, 0.0, None, 0, 0, 0, -50.0, 50.0, None, 0, ST(),
+                         C.byref(o))
+    ok = lib.hb_gemm_ws(P(A3), 7, 0, 0, 0, P(B3), 5, 0, 0, 0, P(C3), 5, 0, 0, 8, 5, 7, 1, 1.0, 0.0, None, 0, 0, 0, -50.0, 50.0, None, 0, ST(),
+                        None)
+    assert bad == 1 and ok == 0

@@ -1,4 +1,4 @@
-"""Aggregate the per-launch GEMM CSV (HB_PROFILE_CSV) by size class."""
+"""Aggregate the per-launch GEMM CSV (bench.py --profile-csv) by size class."""
 import sys, csv, collections
 rows = list(csv.DictReader(open(sys.argv[1])))
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
