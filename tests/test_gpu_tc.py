@@ -273,6 +273,7 @@ def test_full_size_factorisation_properties(lib):
       * round trip: L (L^T V) == K V for 64 random probe vectors (relative, fp32-grade)
       * reverse mode is deterministic (bitwise, split-K included) and exactly homogeneous under a power-of-two scaling
       * the lower triangle of the result is finite and the strict upper triangle of L is untouched (zeroed on request)."""
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     n, D, S = 65536, 8, 64
     if free < 120 * (1 << 30):
