@@ -115,12 +115,19 @@ __device__ __forceinline__ void convert_tile(uint32_t raw, uint32_t lo, int ct, 
   }
 }
 
-template <int BN, bool AKM, bool BKM, bool BFX>
+// PERSIST (BN <= 128, no split-K): the CTA walks over output tiles blockIdx.x, blockIdx.x + gridDim.x, ... with the TMA ring,
+// the barrier phases and the two TMEM accumulators running straight through -- the next tile's loads and MMAs overlap the
+// current tile's epilogue (which then needs its own staging buffer instead of the idle pipeline memory) and the prologue
+// (barrier init, TMEM allocation) is paid once per SM instead of once per tile.  This is for the factorisations' tail:
+// thousands of tall, 128-wide, short-K products (panel solves, K = 128 updates) that are HBM-bound at ~8 us but took
+// ~30 us as 3.5 waves of one-tile CTAs (profiles/r2_gemm_classes_n65536.txt).
+template <int BN, bool AKM, bool BKM, bool BFX, bool PERSIST>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tc2Params p) {
   constexpr int B_TILE = BN * BK * 4;
   constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
   constexpr int HALF = BN / 2;                       // columns per epilogue warp
+  static_assert(!PERSIST || BN <= 128, "the persistent variant keeps a separate epilogue staging tile in shared memory");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + NSTAGE * STAGE_BYTES;
@@ -130,28 +137,37 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto tfull_bar = [&](int b) { return bars + 8u * (3 * NSTAGE + b); };
   auto tempty_bar = [&](int b) { return bars + 8u * (3 * NSTAGE + 2 + b); };
   const uint32_t tmem_ptr_addr = bars + 8u * (3 * NSTAGE + 4);
+  const uint32_t stage_tile = PERSIST ? bars + 256u : base;     // epilogue staging (store_tile)
 
-  constexpr int GROUP = 8;                            // grouped rasterisation: 8 row tiles share a B panel in L2
-  const int bid = blockIdx.x;
-  const int per_group = GROUP * p.tiles_n;
-  const int first_m = (bid / per_group) * GROUP;
-  const int gsz = min(p.tiles_m - first_m, GROUP);
-  const int tm = first_m + (bid % per_group) % gsz;
-  const int tn = (bid % per_group) / gsz;
-  const int m0 = tm * BM, n0 = tn * BN;
-  if (p.c_tri == 1 && n0 > m0 + BM - 1) return;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int kb_lo = 0, kb_hi = (p.K + BK - 1) / BK;
-  trim_range(p.a_mode, m0, BM, kb_lo, kb_hi);
-  trim_range(p.b_mode, n0, BN, kb_lo, kb_hi);
+  const int n_tiles = p.tiles_m * p.tiles_n;
+  const int tile_step = PERSIST ? (int)gridDim.x : n_tiles;    // one tile per CTA unless persistent
+  // geometry of one output tile; false = nothing to do (tile entirely above the diagonal of a triangular output)
+  auto geom = [&](int tile, int& m0, int& n0, int& kb_lo, int& num_k) -> bool {
+    constexpr int GROUP = 8;                          // grouped rasterisation: 8 row tiles share a B panel in L2
+    const int per_group = GROUP * p.tiles_n;
+    const int first_m = (tile / per_group) * GROUP;
+    const int gsz = min(p.tiles_m - first_m, GROUP);
+    const int tm = first_m + (tile % per_group) % gsz;
+    const int tn = (tile % per_group) / gsz;
+    m0 = tm * BM; n0 = tn * BN;
+    if (p.c_tri == 1 && n0 > m0 + BM - 1) return false;
+    int kb_hi = (p.K + BK - 1) / BK;
+    kb_lo = 0;
+    trim_range(p.a_mode, m0, BM, kb_lo, kb_hi);
+    trim_range(p.b_mode, n0, BN, kb_lo, kb_hi);
+    if (p.ksplit > 0) {
+      kb_lo = max(kb_lo, (int)blockIdx.y * p.ksplit);
+      kb_hi = min(kb_hi, ((int)blockIdx.y + 1) * p.ksplit);
+    }
+    num_k = max(kb_hi - kb_lo, 0);
+    return true;
+  };
   float* const Cout = p.C + (long long)blockIdx.y * p.csplit;   // split-K: this split's partial output
-  if (p.ksplit > 0) {
-    kb_lo = max(kb_lo, (int)blockIdx.y * p.ksplit);
-    kb_hi = min(kb_hi, ((int)blockIdx.y + 1) * p.ksplit);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (!PERSIST) {                                     // a skipped tile leaves before any barrier / TMEM is touched
+    int m0, n0, kb_lo, num_k;
+    if (!geom((int)blockIdx.x, m0, n0, kb_lo, num_k)) return;
   }
-  const int num_k = max(kb_hi - kb_lo, 0);
-  const int num_c = (num_k + CHK - 1) / CHK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 4); mbar_init(empty_bar(s), 1); }
@@ -172,23 +188,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {          // ---------------- TMA producer ----------------
       int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t st = base + s * STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), A_TILE + B_TILE);
-        const int k0 = (kb_lo + kb) * BK;
-        if (AKM) tma_load_2d(st, &tmA, full_bar(s), k0, m0);
-        else {
+      for (int tile = (int)blockIdx.x; tile < n_tiles; tile += tile_step) {
+        int m0, n0, kb_lo, num_k;
+        if (!geom(tile, m0, n0, kb_lo, num_k)) continue;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t st = base + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), A_TILE + B_TILE);
+          const int k0 = (kb_lo + kb) * BK;
+          if (AKM) tma_load_2d(st, &tmA, full_bar(s), k0, m0);
+          else {
 #pragma unroll
-          for (int i = 0; i < BM / 32; ++i) tma_load_2d(st + i * 2048, &tmA, full_bar(s), m0 + 32 * i, k0);
-        }
-        const uint32_t sb = st + 2 * A_TILE;
-        if (BKM) tma_load_2d(sb, &tmB, full_bar(s), k0, n0);
-        else {
+            for (int i = 0; i < BM / 32; ++i) tma_load_2d(st + i * 2048, &tmA, full_bar(s), m0 + 32 * i, k0);
+          }
+          const uint32_t sb = st + 2 * A_TILE;
+          if (BKM) tma_load_2d(sb, &tmB, full_bar(s), k0, n0);
+          else {
 #pragma unroll
-          for (int i = 0; i < BN / 32; ++i) tma_load_2d(sb + i * 2048, &tmB, full_bar(s), n0 + 32 * i, k0);
+            for (int i = 0; i < BN / 32; ++i) tma_load_2d(sb + i * 2048, &tmB, full_bar(s), n0 + 32 * i, k0);
+          }
+          if (++s == NSTAGE) { s = 0; ph ^= 1u; }
         }
-        if (++s == NSTAGE) { s = 0; ph ^= 1u; }
       }
     } else if (warp == 1 && lane == 0) {   // ---------------- MMA issuer ----------------
       // instruction descriptor: D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), major bits 15/16 (1 = MN-major),
@@ -202,40 +222,46 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       constexpr uint32_t ADV_A = AKM ? (32u >> 4) : (1024u >> 4);     // one K=8 step, in 16-byte units
       constexpr uint32_t ADV_B = BKM ? (32u >> 4) : (1024u >> 4);
       int s = 0; uint32_t ph = 0;
-      for (int c = 0; c < num_c; ++c) {
-        const int buf = c & 1;
-        mbar_wait(tempty_bar(buf), (uint32_t)(((c >> 1) & 1) ^ 1));
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        const int kb_end = min(num_k, (c + 1) * CHK);
-        for (int kb = c * CHK; kb < kb_end; ++kb) {
-          mbar_wait(conv_bar(s), ph);
+      int cg = 0;                          // accumulation chunks issued so far (TMEM buffer = cg & 1, across tiles)
+      for (int tile = (int)blockIdx.x; tile < n_tiles; tile += tile_step) {
+        int m0, n0, kb_lo, num_k;
+        if (!geom(tile, m0, n0, kb_lo, num_k)) continue;
+        const int num_c = (num_k + CHK - 1) / CHK;
+        for (int c = 0; c < num_c; ++c, ++cg) {
+          const int buf = cg & 1;
+          mbar_wait(tempty_bar(buf), (uint32_t)(((cg >> 1) & 1) ^ 1));
           tc_fence_after();
-          const uint32_t st = base + s * STAGE_BYTES;
-          const uint64_t a_hi = make_desc<AKM>(st), a_lo = make_desc<AKM>(st + A_TILE);
-          const uint64_t b_hi = make_desc<BKM>(st + 2 * A_TILE), b_lo = make_desc<BKM>(st + 2 * A_TILE + B_TILE);
-          const bool first_kb = (kb == c * CHK);
-          if (BFX) {
-            // cross products in bf16 (one K=16 MMA each), hi*hi in tf32 (two K=8 MMAs)
-            const uint32_t sa = st + A_TILE, sb = st + 2 * A_TILE + B_TILE;
-            tc_mma_bf16(d_tmem, make_desc_bf16<AKM>(sa + BM * 32), make_desc_bf16<BKM>(sb), idesc_bf, first_kb ? 0u : 1u);   // lo_a * hi_b
-            tc_mma_bf16(d_tmem, make_desc_bf16<AKM>(sa), make_desc_bf16<BKM>(sb + BN * 32), idesc_bf, 1u);                  // hi_a * lo_b
+          const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+          const int kb_end = min(num_k, (c + 1) * CHK);
+          for (int kb = c * CHK; kb < kb_end; ++kb) {
+            mbar_wait(conv_bar(s), ph);
+            tc_fence_after();
+            const uint32_t st = base + s * STAGE_BYTES;
+            const uint64_t a_hi = make_desc<AKM>(st), a_lo = make_desc<AKM>(st + A_TILE);
+            const uint64_t b_hi = make_desc<BKM>(st + 2 * A_TILE), b_lo = make_desc<BKM>(st + 2 * A_TILE + B_TILE);
+            const bool first_kb = (kb == c * CHK);
+            if (BFX) {
+              // cross products in bf16 (one K=16 MMA each), hi*hi in tf32 (two K=8 MMAs)
+              const uint32_t sa = st + A_TILE, sb = st + 2 * A_TILE + B_TILE;
+              tc_mma_bf16(d_tmem, make_desc_bf16<AKM>(sa + BM * 32), make_desc_bf16<BKM>(sb), idesc_bf, first_kb ? 0u : 1u);   // lo_a * hi_b
+              tc_mma_bf16(d_tmem, make_desc_bf16<AKM>(sa), make_desc_bf16<BKM>(sb + BN * 32), idesc_bf, 1u);                  // hi_a * lo_b
 #pragma unroll
-            for (int k2 = 0; k2 < BK / 8; ++k2)
-              tc_mma_tf32(d_tmem, a_hi + (uint64_t)(ADV_A * k2), b_hi + (uint64_t)(ADV_B * k2), idesc, 1u);
-          } else {
+              for (int k2 = 0; k2 < BK / 8; ++k2)
+                tc_mma_tf32(d_tmem, a_hi + (uint64_t)(ADV_A * k2), b_hi + (uint64_t)(ADV_B * k2), idesc, 1u);
+            } else {
 #pragma unroll
-          for (int k2 = 0; k2 < BK / 8; ++k2) {
-            const uint64_t da = (uint64_t)(ADV_A * k2), db = (uint64_t)(ADV_B * k2);
-            tc_mma_tf32(d_tmem, a_lo + da, b_hi + db, idesc, (first_kb && k2 == 0) ? 0u : 1u);   // small terms first
-            tc_mma_tf32(d_tmem, a_hi + da, b_lo + db, idesc, 1u);
-            tc_mma_tf32(d_tmem, a_hi + da, b_hi + db, idesc, 1u);
+              for (int k2 = 0; k2 < BK / 8; ++k2) {
+                const uint64_t da = (uint64_t)(ADV_A * k2), db = (uint64_t)(ADV_B * k2);
+                tc_mma_tf32(d_tmem, a_lo + da, b_hi + db, idesc, (first_kb && k2 == 0) ? 0u : 1u);   // small terms first
+                tc_mma_tf32(d_tmem, a_hi + da, b_lo + db, idesc, 1u);
+                tc_mma_tf32(d_tmem, a_hi + da, b_hi + db, idesc, 1u);
+              }
+            }
+            tc_commit(empty_bar(s));
+            if (++s == NSTAGE) { s = 0; ph ^= 1u; }
           }
-          }
-          tc_commit(empty_bar(s));
-          if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+          tc_commit(tfull_bar(buf));
         }
-        tc_commit(tfull_bar(buf));
       }
     }
   } else if (warp < 8) {
@@ -243,53 +269,64 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ---------------- converters ----------------
     const int ct = threadIdx.x - 128;
     int s = 0; uint32_t ph = 0;
-    for (int kb = 0; kb < num_k; ++kb) {
-      const int k0 = (kb_lo + kb) * BK;
-      mbar_wait(full_bar(s), ph);
-      const uint32_t st = base + s * STAGE_BYTES;
-      if (mask_crosses(p.a_mode, m0, BM, k0)) convert_tile<BM, AKM, true, BFX>(st, st + A_TILE, ct, p.a_mode, m0, k0);
-      else convert_tile<BM, AKM, false, BFX>(st, st + A_TILE, ct, 0, 0, 0);
-      if (mask_crosses(p.b_mode, n0, BN, k0)) convert_tile<BN, BKM, true, BFX>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ct, p.b_mode, n0, k0);
-      else convert_tile<BN, BKM, false, BFX>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ct, 0, 0, 0);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) mbar_arrive(conv_bar(s));
-      if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += tile_step) {
+      int m0, n0, kb_lo, num_k;
+      if (!geom(tile, m0, n0, kb_lo, num_k)) continue;
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int k0 = (kb_lo + kb) * BK;
+        mbar_wait(full_bar(s), ph);
+        const uint32_t st = base + s * STAGE_BYTES;
+        if (mask_crosses(p.a_mode, m0, BM, k0)) convert_tile<BM, AKM, true, BFX>(st, st + A_TILE, ct, p.a_mode, m0, k0);
+        else convert_tile<BM, AKM, false, BFX>(st, st + A_TILE, ct, 0, 0, 0);
+        if (mask_crosses(p.b_mode, n0, BN, k0)) convert_tile<BN, BKM, true, BFX>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ct, p.b_mode, n0, k0);
+        else convert_tile<BN, BKM, false, BFX>(st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, ct, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv_bar(s));
+        if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+      }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // ---------------- epilogue: warp (w & 3) owns TMEM lanes [32 (w&3), +32), column half (w - 8) / 4 ----------------
     const int q = warp & 3;
     const int half = (warp - 8) >> 2;
-    float acc[HALF];
+    int cg = 0;
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += tile_step) {
+      int m0, n0, kb_lo, num_k;
+      if (!geom(tile, m0, n0, kb_lo, num_k)) continue;
+      const int num_c = (num_k + CHK - 1) / CHK;
+      float acc[HALF];
 #pragma unroll
-    for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
-    for (int c = 0; c < num_c; ++c) {
-      const int buf = c & 1;
-      mbar_wait(tfull_bar(buf), (uint32_t)((c >> 1) & 1));
-      tc_fence_after();
+      for (int i = 0; i < HALF; ++i) acc[i] = 0.f;
+      for (int c = 0; c < num_c; ++c, ++cg) {
+        const int buf = cg & 1;
+        mbar_wait(tfull_bar(buf), (uint32_t)((cg >> 1) & 1));
+        tc_fence_after();
 #pragma unroll
-      for (int i = 0; i < HALF / 32; ++i) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF + i * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int i = 0; i < HALF / 32; ++i) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * HALF + i * 32);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[i * 32 + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) acc[i * 32 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(buf));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      store_tile<BN>(acc, p, p.alpha, Cout, stage_tile, m0, n0, warp - 8, lane);
+      if (PERSIST) asm volatile("bar.sync 1, 256;" ::: "memory");     // staging tile is reused by the next output tile
     }
-    store_tile<BN>(acc, p, p.alpha, Cout, base, m0, n0, warp - 8, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -530,16 +567,32 @@ int make_map2(CUtensorMap* map, const float* ptr, long long rows, long long K, l
 template <int BN, bool AKM, bool BKM, bool BFX>
 int launch4(const CUtensorMap& ta, const CUtensorMap& tb, Tc2Params tp, cudaStream_t st) {
   constexpr int SMEM = NSTAGE * (2 * A_TILE + 2 * BN * BK * 4) + 1024 + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(gemm_tc2_kernel<BN, AKM, BKM, BFX>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
-      return HB_ERR_CUDA;
-    attr_done = true;
-  }
   tp.tiles_m = cdiv(tp.M, BM);
   tp.tiles_n = cdiv(tp.N, BN);
   const int nsplit = tp.ksplit > 0 ? cdiv(cdiv(tp.K, BK), tp.ksplit) : 1;
-  gemm_tc2_kernel<BN, AKM, BKM, BFX><<<dim3((unsigned)(tp.tiles_m * tp.tiles_n), (unsigned)nsplit), NTHREADS, SMEM, st>>>(ta, tb, tp);
+  if constexpr (BN <= 128) {
+    // more than one wave of short products: one persistent CTA per SM walks over the tiles (see the kernel's header)
+    const long long tiles = (long long)tp.tiles_m * tp.tiles_n;
+    if (nsplit == 1 && tiles > 148 && tp.K <= 2048 && !(get_tc_option() & 16)) {
+      constexpr int SMEM_P = SMEM + 128 * (BN + 4) * 4;
+      static bool attr_p = false;
+      if (!attr_p) {
+        if (cudaFuncSetAttribute(gemm_tc2_kernel<BN, AKM, BKM, BFX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P) != cudaSuccess)
+          return HB_ERR_CUDA;
+        attr_p = true;
+      }
+      gemm_tc2_kernel<BN, AKM, BKM, BFX, true><<<148, NTHREADS, SMEM_P, st>>>(ta, tb, tp);
+      HB_CHECK_LAUNCH();
+      return HB_OK;
+    }
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(gemm_tc2_kernel<BN, AKM, BKM, BFX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess)
+      return HB_ERR_CUDA;
+    attr_done = true;
+  }
+  gemm_tc2_kernel<BN, AKM, BKM, BFX, false><<<dim3((unsigned)(tp.tiles_m * tp.tiles_n), (unsigned)nsplit), NTHREADS, SMEM, st>>>(ta, tb, tp);
   HB_CHECK_LAUNCH();
   return HB_OK;
 }

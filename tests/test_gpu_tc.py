@@ -76,6 +76,21 @@ LAYOUTS = [(0, 1), (0, 0), (1, 0), (1, 1)]
 
 
 @pytest.mark.parametrize("tA,tB", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", [(128 * 300, 128, 128), (128 * 149 + 5, 100, 272), (40000, 64, 1000), (128 * 200, 128, 16)])
+def test_tc_persistent_tile_walk(lib, M, N, K, tA, tB):
+    """More than 148 row tiles of a 128- (or 64-) wide short-K product: one persistent CTA per SM walks over the tiles
+    (ring, barrier phases and TMEM buffers run through; separate epilogue staging)."""
+    assert run(lib, M, N, K, tA, tB, alpha=-1.0, beta=1.0) < 3e-6
+    assert run(lib, M, N, K, tA, tB, alpha=0.5, beta=0.0, seed=3) < 3e-6
+
+
+@pytest.mark.parametrize("tri", [1, 2, 3, 4])
+def test_tc_persistent_tile_walk_masks(lib, tri):
+    assert run(lib, 128 * 170, 128, 256, 0, 0, b_tri=tri, alpha=-2.0, beta=1.0) < 3e-6
+    assert run(lib, 128 * 170, 128, 384, 0, 1, c_tri=1, alpha=-1.0, beta=1.0) < 3e-6
+
+
+@pytest.mark.parametrize("tA,tB", LAYOUTS)
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 384, 200), (300, 500, 100), (1000, 128, 336), (64, 1024, 512)])
 def test_tc_single_cta_layouts(lib, M, N, K, tA, tB):
     assert run(lib, M, N, K, tA, tB, alpha=-1.0, beta=1.0) < 3e-6
@@ -128,7 +143,7 @@ def test_tc_split_k(lib, M, N, K):
 
 
 @pytest.mark.parametrize("engine", [0, 1, 2])
-@pytest.mark.parametrize("m,k,trans", [(128, 128, 1), (1000, 128, 0), (5000, 96, 1), (20000, 128, 0)])
+@pytest.mark.parametrize("m,k,trans", [(128, 128, 1), (1000, 128, 0), (5000, 96, 1), (20000, 128, 0), (60000, 128, 1), (33333, 64, 0)])
 def test_in_place_panel_solve(lib, engine, m, k, trans):
     """X <- X * D (or D^T) with C aliasing A: the leaf step of the blocked triangular solves."""
     if engine == 2 and (k % 4 or (k + 8) % 4):
