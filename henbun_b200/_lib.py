@@ -111,7 +111,8 @@ SIGNATURES = {
     "hb_gemm_tc_workspace_bytes": (_sz, [_i, _i, _i]),
     "hb_gemm_tn_tc": (_i, [_c_f, _ll, _c_f, _ll, _c_f, _ll, _i, _i, _i, _i, _fl, _fl, _c_f, _sz, _c_f]),
     "hb_gemm_presplit_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "hb_gemm_presplit": (_i, [_c_f, _ll, _i, _c_f, _ll, _i, _c_f, _ll, _i, _i, _i, _i, _fl, _fl, _i, _i, _i, _c_f, _sz, _c_f]),
+    "hb_gemm_presplit": (_i, [_c_f, _ll, _i, _c_f, _ll, _i, _c_f, _ll, _i, _i, _i, _i, _fl, _fl, _i, _i, _i, _c_f, _sz, _c_f,
+                              C.POINTER(Options)]),
     "hb_act_bwd_colsum_workspace_bytes": (_sz, [_i, _i]),
     "hb_act_bwd_colsum_ws": (_i, [_c_f, _c_f, _c_f, _i, _i, _ll, _i, _i, _fl, _fl, _c_f, _c_f, _sz, _c_f]),
     "hb_act_bwd_colsum": (_i, [_c_f, _c_f, _c_f, _i, _i, _ll, _i, _i, _fl, _fl, _c_f, _c_f]),
@@ -172,7 +173,7 @@ def load() -> C.CDLL:
 
 
 # entry points whose LAST argument is `const hb_options*`, and whole-step entry points whose config struct carries it
-_TRAILING_OPT = ("hb_gemm_ws", "hb_potrf_lower", "hb_potrf_lower_bwd", "hb_trsm_right_lower")
+_TRAILING_OPT = ("hb_gemm_ws", "hb_potrf_lower", "hb_potrf_lower_bwd", "hb_trsm_right_lower", "hb_gemm_presplit")
 _CFG_OPT = ("hb_gp_elbo_step", "hb_linop_prepare", "hb_linop_elbo_local", "hb_linop_elbo_update", "hb_amortised_elbo_step")
 
 

@@ -506,7 +506,8 @@ size_t hb_gemm_presplit_workspace_bytes(int M, int N, int K, int transA, int tra
 }
 int hb_gemm_presplit(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
                      long long ldc, int c_tri, int M, int N, int K, float alpha, float beta, int a_bmode, int a_blockscale,
-                     int skip_split, void* ws, size_t ws_bytes, void* stream) {
+                     int skip_split, void* ws, size_t ws_bytes, void* stream, const hb_options* opt) {
+  OptScope scope(opt);
   if (M <= 0 || N <= 0 || K <= 0) return HB_OK;
   if (!A || !B || !C) return HB_ERR_ARG;
   size_t off[6];

@@ -71,6 +71,7 @@ __device__ __forceinline__ uint64_t make_desc_h(uint32_t saddr) {
 struct H2Params {
   Tc2Params t;
   int a_bmode;
+  int group;               // pair-tile rows per raster group (tiles of a group share their B panel in L2)
   const float* a_inv;
   const float* a_kinv;
   const float* a_dinv;
@@ -96,7 +97,7 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   const uint32_t tmem_ptr_addr = bars + 8u * (2 * H_NSTAGE + 4);
 
   const uint32_t rank = cluster_ctarank();
-  constexpr int GROUP = 8;
+  const int GROUP = hp.group;
   const int bid = blockIdx.x >> 1;
   const int per_group = GROUP * p.tiles_n;
   const int first_m = (bid / per_group) * GROUP;
@@ -445,6 +446,8 @@ int gemm_h2(const H2Gemm& g, cudaStream_t st) {
   tp.c_tri = g.c_tri; tp.a_mode = 0; tp.b_mode = 0; tp.tiles_m = 0; tp.tiles_n = 0;
   tp.vecC = aligned16(g.C) && (g.ldc % 4 == 0);
   tp.ksplit = 0; tp.csplit = 0; tp.bias = nullptr; tp.act = ACT_NONE; tp.clip = 0; tp.clip_lo = 0.f; tp.clip_hi = 0.f;
+  hp.group = (get_tc_option() >> 8) & 0xff;      // A/B experiments: hb_options.tc_option bits 8..15 override the raster group
+  if (hp.group <= 0) hp.group = 8;
   hp.a_bmode = g.a_bmode; hp.a_inv = g.a_inv; hp.a_kinv = g.a_kinv; hp.a_dinv = g.a_dinv ? g.a_dinv : g.a_kinv;
   hp.a_minv = g.a_minv; hp.b_inv = g.b_inv;
   if (narrow) return g.a_kmajor ? launch_h2<64, true, true>(m, hp, st) : launch_h2<64, false, true>(m, hp, st);

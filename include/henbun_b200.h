@@ -251,7 +251,7 @@ int hb_gemm_tn_tc(const float* A, long long lda, const float* B, long long ldb, 
 size_t hb_gemm_presplit_workspace_bytes(int M, int N, int K, int transA, int transB);
 int hb_gemm_presplit(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C,
                      long long ldc, int c_tri, int M, int N, int K, float alpha, float beta, int a_bmode, int a_blockscale,
-                     int skip_split, void* ws, size_t ws_bytes, void* stream);
+                     int skip_split, void* ws, size_t ws_bytes, void* stream, const hb_options* opt);
 /* Backward helper of MatBias: dz = dy * act'(y) (through the output y), dbias[c] = sum_r dz[r,c]. */
 /* Same with a scratch buffer of hb_act_bwd_colsum_workspace_bytes(rows, cols): full-grid kernel + deterministic partial
  * reduction (the scratch-free entry point uses one block per 32 columns).  Falls back to it when ws is NULL / too small. */
