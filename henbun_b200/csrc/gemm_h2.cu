@@ -447,7 +447,7 @@ int gemm_h2(const H2Gemm& g, cudaStream_t st) {
   tp.vecC = aligned16(g.C) && (g.ldc % 4 == 0);
   tp.ksplit = 0; tp.csplit = 0; tp.bias = nullptr; tp.act = ACT_NONE; tp.clip = 0; tp.clip_lo = 0.f; tp.clip_hi = 0.f;
   hp.group = (get_tc_option() >> 8) & 0xff;      // A/B experiments: hb_options.tc_option bits 8..15 override the raster group
-  if (hp.group <= 0) hp.group = 8;
+  if (hp.group <= 0) hp.group = 4;                  // measured (tools/h2_group_probe.py): 4 beats 8 by 5-8 % at the 32768-wide top-level products, equal at 16384
   hp.a_bmode = g.a_bmode; hp.a_inv = g.a_inv; hp.a_kinv = g.a_kinv; hp.a_dinv = g.a_dinv ? g.a_dinv : g.a_kinv;
   hp.a_minv = g.a_minv; hp.b_inv = g.b_inv;
   if (narrow) return g.a_kmajor ? launch_h2<64, true, true>(m, hp, st) : launch_h2<64, false, true>(m, hp, st);
