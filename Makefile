@@ -13,7 +13,7 @@ build/%.o: henbun_b200/csrc/%.cu $(wildcard henbun_b200/csrc/*.cuh) include/henb
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 
 $(LIB): $(OBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart -ldl
 
 clean:
 	rm -rf build $(LIB)

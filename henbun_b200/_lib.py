@@ -42,6 +42,11 @@ class GpConfig(C.Structure):
                 ("seed", _ull), ("offset", _ull), ("opt", C.POINTER(Options))]
 
 
+class Dist(C.Structure):
+    """hb_dist: this rank's place in a column-block-cyclic factorisation (comm from hb_comm_create; NULL when world == 1)."""
+    _fields_ = [("comm", C.c_void_p), ("rank", _i), ("world", _i), ("block", _i)]
+
+
 class AdamConfig(C.Structure):
     _fields_ = [("lr", C.c_double), ("b1", C.c_double), ("b2", C.c_double), ("eps", C.c_double), ("grad_scale", C.c_double),
                 ("step_dev", C.c_void_p),
@@ -139,6 +144,14 @@ SIGNATURES = {
     "hb_gp_param_count": (_sz, [C.POINTER(GpConfig)]),
     "hb_gp_elbo_workspace_bytes": (_sz, [C.POINTER(GpConfig)]),
     "hb_gp_elbo_step": (_i, [C.POINTER(GpConfig), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f, _c_f]),
+    "hb_comm_unique_id": (_i, [C.c_void_p]),
+    "hb_comm_create": (_i, [C.c_void_p, _i, _i, C.POINTER(C.c_void_p)]),
+    "hb_comm_destroy": (_i, [C.c_void_p]),
+    "hb_potrf_dist_workspace_bytes": (_sz, [_i, C.POINTER(Dist)]),
+    "hb_potrf_lower_dist": (_i, [_c_f, _ll, _i, C.POINTER(Dist), _c_f, _sz, _c_f, _c_f, C.POINTER(Options)]),
+    "hb_potrf_lower_bwd_dist": (_i, [_c_f, _ll, _c_f, _ll, _i, C.POINTER(Dist), _c_f, _sz, _c_f, C.POINTER(Options)]),
+    "hb_gp_elbo_dist_workspace_bytes": (_sz, [C.POINTER(GpConfig), C.POINTER(Dist)]),
+    "hb_gp_elbo_step_dist": (_i, [C.POINTER(GpConfig), C.POINTER(Dist), _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _c_f, _sz, _c_f, _c_f]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -173,8 +186,10 @@ def load() -> C.CDLL:
 
 
 # entry points whose LAST argument is `const hb_options*`, and whole-step entry points whose config struct carries it
-_TRAILING_OPT = ("hb_gemm_ws", "hb_potrf_lower", "hb_potrf_lower_bwd", "hb_trsm_right_lower", "hb_gemm_presplit")
-_CFG_OPT = ("hb_gp_elbo_step", "hb_linop_prepare", "hb_linop_elbo_local", "hb_linop_elbo_update", "hb_amortised_elbo_step")
+_TRAILING_OPT = ("hb_gemm_ws", "hb_potrf_lower", "hb_potrf_lower_bwd", "hb_trsm_right_lower", "hb_gemm_presplit",
+                 "hb_potrf_lower_dist", "hb_potrf_lower_bwd_dist")
+_CFG_OPT = ("hb_gp_elbo_step", "hb_gp_elbo_step_dist", "hb_linop_prepare", "hb_linop_elbo_local", "hb_linop_elbo_update",
+            "hb_amortised_elbo_step")
 
 
 def _install_option_plumbing(lib):

@@ -2,6 +2,7 @@
 #include "../../include/henbun_b200.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "comm.cuh"
 #include "gemm_h2.cuh"
 #include <vector>
 #include <cstdio>
@@ -176,7 +177,7 @@ struct GpLayout {
   size_t potrf_bytes;
 };
 
-GpLayout gp_layout(const hb_gp_config& c) {
+GpLayout gp_layout(const hb_gp_config& c, const DistEnv* d = nullptr) {
   GpLayout L{};
   const size_t nn = (size_t)c.n * c.n * sizeof(float), sn = (size_t)c.S * c.n * sizeof(float);
   size_t o = 0;
@@ -189,7 +190,7 @@ GpLayout gp_layout(const hb_gp_config& c) {
   L.off_U = o; o += align_up(c.q_fullrank ? sn : 0);
   L.off_sc = o; o += align_up((size_t)(16 + c.n_ell) * sizeof(float));
   L.off_red = o; o += align_up(kReduceWsBytes);
-  L.potrf_bytes = potrf_workspace_bytes(c.n);
+  L.potrf_bytes = d ? potrf_dist_workspace_bytes(c.n, *d) : potrf_workspace_bytes(c.n);
   L.off_potrf = o; o += align_up(L.potrf_bytes);
   L.total = o;
   return L;
@@ -626,14 +627,58 @@ size_t hb_gp_elbo_workspace_bytes(const hb_gp_config* c) {
   return gp_layout(*c).total + 256;
 }
 
+static DistEnv to_env(const hb_dist* d) {
+  DistEnv e;
+  e.comm = d->comm; e.rank = d->rank; e.world = d->world; e.block = d->block > 0 ? d->block : 2048;
+  return e;
+}
+
+int hb_comm_unique_id(void* out128_host) { return comm_unique_id(out128_host); }
+int hb_comm_create(const void* id128_host, int rank, int world, void** comm_out) { return comm_create(id128_host, rank, world, comm_out); }
+int hb_comm_destroy(void* comm) { return comm_destroy(comm); }
+
+size_t hb_potrf_dist_workspace_bytes(int n, const hb_dist* d) { return d ? potrf_dist_workspace_bytes(n, to_env(d)) : 0; }
+int hb_potrf_lower_dist(float* A, long long lda, int n, const hb_dist* d, void* ws, size_t ws_bytes, int* err_flag, void* stream,
+                        const hb_options* opt) {
+  if (!d) return HB_ERR_ARG;
+  OptScope scope(opt);
+  return potrf_lower_dist(A, lda, n, to_env(d), ws, ws_bytes, err_flag, S(stream));
+}
+int hb_potrf_lower_bwd_dist(const float* L, long long ldl, float* G, long long ldg, int n, const hb_dist* d, void* ws,
+                            size_t ws_bytes, void* stream, const hb_options* opt) {
+  if (!d) return HB_ERR_ARG;
+  OptScope scope(opt);
+  return potrf_lower_bwd_dist(L, ldl, G, ldg, n, to_env(d), ws, ws_bytes, S(stream), 0);
+}
+
+static int gp_elbo_step_impl(const hb_gp_config* cfg, const DistEnv* dist, const float* X, const float* Y, const float* params,
+                             const float* eps, float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream);
+
+size_t hb_gp_elbo_dist_workspace_bytes(const hb_gp_config* c, const hb_dist* d) {
+  if (!c || !d) return 0;
+  const DistEnv e = to_env(d);
+  return gp_layout(*c, &e).total + 256;
+}
+int hb_gp_elbo_step_dist(const hb_gp_config* cfg, const hb_dist* d, const float* X, const float* Y, const float* params,
+                         const float* eps, float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream) {
+  if (!d) return HB_ERR_ARG;
+  const DistEnv e = to_env(d);
+  return gp_elbo_step_impl(cfg, &e, X, Y, params, eps, grads, out4, ws, ws_bytes, err_flag, stream);
+}
 int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, const float* params, const float* eps,
                     float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream) {
+  return gp_elbo_step_impl(cfg, nullptr, X, Y, params, eps, grads, out4, ws, ws_bytes, err_flag, stream);
+}
+
+static int gp_elbo_step_impl(const hb_gp_config* cfg, const DistEnv* dist, const float* X, const float* Y, const float* params,
+                             const float* eps, float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream) {
   if (!cfg || !X || !Y || !params || !grads || !out4) return HB_ERR_ARG;
   OptScope scope(cfg->opt);
   const hb_gp_config c = *cfg;
   if (c.n <= 0 || c.D <= 0 || c.D > 32 || c.S <= 0 || (c.n_ell != 1 && c.n_ell != c.D)) return HB_ERR_ARG;
   if (!eps && (c.offset & 3ull)) return HB_ERR_ARG;
-  const GpLayout L = gp_layout(c);
+  if (dist && c.n <= 128) dist = nullptr;        // one leaf: nothing to schedule
+  const GpLayout L = gp_layout(c, dist);
   if (!ws || ws_bytes < L.total + 256) return HB_ERR_WORKSPACE;
   cudaStream_t st = S(stream);
   char* base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
@@ -681,7 +726,8 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
   // K = rbf(X) + jitter I (lower tiles), L = chol(K) in place
   HB_TRY(rbf_gram_fwd(X, nullptr, n, n, c.D, 0, 0, d_ell, c.n_ell, K, n, 0, 1, c.jitter, 1, 0, st));
   phase_mark(st);
-  HB_TRY(potrf_lower(K, n, 0, n, 1, 0, pws, L.potrf_bytes, err_flag, st));
+  if (dist) HB_TRY(potrf_lower_dist(K, n, n, *dist, pws, L.potrf_bytes, err_flag, st));
+  else HB_TRY(potrf_lower(K, n, 0, n, 1, 0, pws, L.potrf_bytes, err_flag, st));
   phase_mark(st);
 
   // sampler + KL
@@ -735,7 +781,8 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
     HB_TRY(gemm(g, st));
   }
   phase_mark(st);
-  HB_TRY(potrf_lower_bwd(K, n, 0, G, n, 0, n, 1, pws, L.potrf_bytes, st, /*l_shadow_valid=*/1));
+  if (dist) HB_TRY(potrf_lower_bwd_dist(K, n, G, n, n, *dist, pws, L.potrf_bytes, st, /*l_shadow_valid=*/1));
+  else HB_TRY(potrf_lower_bwd(K, n, 0, G, n, 0, n, 1, pws, L.potrf_bytes, st, /*l_shadow_valid=*/1));
   phase_mark(st);
   HB_TRY(rbf_gram_bwd(G, n, 0, X, nullptr, n, n, c.D, 0, 0, d_ell, c.n_ell, 1, 1, 0, d_a, g_ell, red, kReduceWsBytes, st));
   gp_scalar_bwd_kernel<<<1, 32, 0, st>>>(sc, ll3, kl, (long long)Sn * n, Sn, p_scale, p_ell, c.n_ell, p_kvar, p_var,

@@ -108,5 +108,12 @@ int potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, 
                     int n, int batch, void* ws, size_t ws_bytes, cudaStream_t st, int l_shadow_valid = 0);
 int trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int m, int n, int trans, void* ws,
                      size_t ws_bytes, cudaStream_t st);
+// right-looking schedule over column blocks, one GPU or a column-block-cyclic group (comm.cuh: DistEnv)
+struct DistEnv;
+size_t potrf_dist_workspace_bytes(int n, const DistEnv& d);
+int potrf_lower_dist(float* A, long long lda, int n, const DistEnv& d, void* ws, size_t ws_bytes, int* err_flag,
+                     cudaStream_t st);
+int potrf_lower_bwd_dist(const float* L, long long ldl, float* G, long long ldg, int n, const DistEnv& d, void* ws,
+                         size_t ws_bytes, cudaStream_t st, int l_shadow_valid = 0);
 
 }  // namespace hb

@@ -10,6 +10,7 @@
 #include "gemm.cuh"
 #include "gemm_h2.cuh"
 #include "kernels.cuh"
+#include "comm.cuh"
 #include <cstdlib>
 
 namespace hb {
@@ -858,6 +859,262 @@ int chol_rev_rec(const Ctx& c, const float* L, long long ldl, float* G, long lon
   return chol_rev_cols(c, L, ldl, G, ldg, 0, n, n);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Right-looking ("flat") schedule over column blocks of W columns, one GPU or a column-block-cyclic group of GPUs.
+//
+// The column recursion above runs its narrow steps (leaf kernels, panel solves, K <= 128 updates: ~150 us per 128 columns)
+// strictly between its big products, so on one GPU they are exposed time and on G GPUs they would be ALL of the time.
+// Here the same pieces are scheduled as two concurrent streams:
+//   chain (high priority):  F(p) = potrf_cols / chol_rev_cols of block p -- the existing recursion restricted to W columns --
+//                           preceded by the one update block p still lacks, U(p-1, p);
+//   main:                   U(p, j) for the blocks j after p+1 (before p-1 in the reverse mode) this rank owns, the block
+//                           the chain needs next first (event), then the far ones.
+// With G ranks block b belongs to rank b % G; the owner packs the finished panel (all rows below, W columns), ncclBroadcast
+// on a third stream carries it to the other ranks, which unpack it into their own copy of the matrix and rebuild its fp16
+// hi/lo shadow (and, for K-bar, the per-128-column scales) exactly as the owner did -- every rank ends with the complete
+// factor / gradient, bit-identical, so the rest of the step needs no further exchange.
+// ------------------------------------------------------------------------------------------------------------------
+
+// A[cj.., cj .. cj+wj) -= L[cj.., p0 .. p0+pw) L[cj .. cj+wj, p0 .. p0+pw)^T   (rows cj .. n-1, lower trapezoid)
+static int fwd_update(const Ctx& c, float* A, long long lda, int cj, int wj, int p0, int pw, int n) {
+  const int M = n - cj;
+  if (M <= 0 || wj <= 0 || pw <= 0) return HB_OK;
+  float* Cp = A + (long long)cj * lda + cj;
+  if (c.lh && gemm_h2_eligible(M, wj, pw)) {
+    H2Gemm h;
+    const long long o = (long long)cj * c.ldh + p0;
+    h.a_hi = c.lh + o; h.a_lo = c.ll + o; h.lda = c.ldh; h.a_kmajor = 1;
+    h.b_hi = c.lh + o; h.b_lo = c.ll + o; h.ldb = c.ldh; h.b_kmajor = 1;
+    h.C = Cp; h.ldc = lda; h.M = M; h.N = wj; h.K = pw; h.alpha = -1.f; h.beta = 1.f; h.c_tri = 1;
+    h.a_inv = c.lscale + 1; h.b_inv = c.lscale + 1;
+    return run_h2(c, h);
+  }
+  GemmParams g;
+  g.A = A + (long long)cj * lda + p0; g.lda = lda; g.B = g.A; g.ldb = lda; g.transB = 1;
+  g.C = Cp; g.ldc = lda; g.M = M; g.N = wj; g.K = pw; g.alpha = -1.f; g.beta = 1.f; g.c_tri = 1;
+  return gemm_ws(c, g);
+}
+
+// The three products that carry a finished K-bar panel `right` = columns/rows [r1, r1+w2) into the columns
+// left = [cj, cj+wj), cj + wj <= r1 (chol_rev_cols' inner node with a left part that need not be adjacent):
+//   G[R, left] -= 2 G[R, right] L[T, left];  G[T, left] -= 2 G[R, right]^T L[R, left];  G[T, left] -= 2 sym(G[T, right]) L[T, left]
+static int rev_update(const Ctx& c, const float* L, long long ldl, float* G, long long ldg, int cj, int wj, int r1, int w2,
+                      int n) {
+  if (wj <= 0 || w2 <= 0) return HB_OK;
+  const int rb = r1 + w2, nb = n - rb;
+  float* G_T_left = G + (long long)r1 * ldg + cj;
+  const float* L_T_left = L + (long long)r1 * ldl + cj;
+  const bool h2 = c.gh && c.lh && !(w2 % NB) && !(wj & 7) && !(cj & 7);
+  if (nb > 0) {
+    float* G_R_right = G + (long long)rb * ldg + r1;
+    float* G_R_left = G + (long long)rb * ldg + cj;
+    const float* L_R_left = L + (long long)rb * ldl + cj;
+    if (h2 && gemm_h2_eligible(nb, wj, w2)) {
+      H2Gemm h;
+      const long long oa = (long long)rb * c.ldh + r1, ob = (long long)r1 * c.ldh + cj;
+      h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 1; h.a_kinv = c.ginv + r1 / NB;
+      h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
+      h.C = G_R_left; h.ldc = ldg; h.M = nb; h.N = wj; h.K = w2; h.alpha = -2.f; h.beta = 1.f;
+      HB_TRY(run_h2(c, h));
+    } else {
+      GemmParams a;
+      a.A = G_R_right; a.lda = ldg; a.B = L_T_left; a.ldb = ldl; a.transB = 0;
+      a.C = G_R_left; a.ldc = ldg; a.M = nb; a.N = wj; a.K = w2; a.alpha = -2.f; a.beta = 1.f;
+      HB_TRY(gemm_ws(c, a));
+    }
+    if (h2 && gemm_h2_eligible(w2, wj, nb)) {
+      H2Gemm h;
+      const long long oa = (long long)rb * c.ldh + r1, ob = (long long)rb * c.ldh + cj;
+      h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 0; h.a_minv = c.ginv + r1 / NB;
+      h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
+      h.C = G_T_left; h.ldc = ldg; h.M = w2; h.N = wj; h.K = nb; h.alpha = -2.f; h.beta = 1.f;
+      HB_TRY(run_h2(c, h));
+    } else {
+      GemmParams b;
+      b.A = G_R_right; b.lda = ldg; b.transA = 1; b.B = L_R_left; b.ldb = ldl; b.transB = 0;
+      b.C = G_T_left; b.ldc = ldg; b.M = w2; b.N = wj; b.K = nb; b.alpha = -2.f; b.beta = 1.f;
+      b.hint_split_waves = 1;
+      HB_TRY(gemm_ws(c, b));
+    }
+  }
+  if (h2 && gemm_h2_eligible(w2, wj, w2)) {
+    H2Gemm h;
+    const long long oa = (long long)r1 * c.ldh + r1, ob = (long long)r1 * c.ldh + cj;
+    h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 1; h.a_bmode = 1;
+    h.a_kinv = c.ginv + r1 / NB; h.a_dinv = c.ginv + c.nblk + r1 / NB;
+    h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
+    h.C = G_T_left; h.ldc = ldg; h.M = w2; h.N = wj; h.K = w2; h.alpha = -2.f; h.beta = 1.f;
+    HB_TRY(run_h2(c, h));
+    h.a_kmajor = 0; h.a_bmode = 2; h.a_kinv = nullptr; h.a_dinv = nullptr; h.a_minv = c.ginv + r1 / NB;
+    return run_h2(c, h);
+  }
+  GemmParams g;
+  g.A = G + (long long)r1 * ldg + r1; g.lda = ldg; g.a_tri = 1; g.B = L_T_left; g.ldb = ldl; g.transB = 0;
+  g.C = G_T_left; g.ldc = ldg; g.M = w2; g.N = wj; g.K = w2; g.alpha = -2.f; g.beta = 1.f;
+  HB_TRY(gemm_ws(c, g));
+  g.transA = 1; g.a_tri = 3;
+  return gemm_ws(c, g);
+}
+
+// A received K-bar panel (columns [c0, c0+w), rows c0 .. n-1, fp32 already in place): rebuild what the owner's
+// chol_rev_cols left behind for the products above -- per 128-column block the maximum and the fp16 hi/lo shadow of the
+// rows below its diagonal block, and the diagonal block's own maximum and shadow.  Same data, same kernels: same bits.
+static int adopt_G_panel(const Ctx& c, const float* G, long long ldg, int c0, int w, int n) {
+  if (!c.gh) return HB_OK;
+  for (int s = c0; s < c0 + w; s += NB) {
+    const int ws = min(NB, c0 + w - s), below = n - (s + ws);
+    if (ws & 7) continue;
+    if (below > 0) {
+      const float* Gp = G + (long long)(s + ws) * ldg + s;
+      const int b = s / NB;
+      HB_TRY(h2_absmax(Gp, ldg, below, ws, 0, 0, c.gmax + b, c.st));
+      const long long o = (long long)(s + ws) * c.ldh + s;
+      HB_TRY(h2_split(Gp, ldg, below, ws, nullptr, c.gmax + b, c.ginv + b, 0, 0, c.gh + o, c.gl + o, c.ldh, c.st));
+    }
+    HB_TRY(split_G_diag(c, G, ldg, s, ws, c.st));
+  }
+  return HB_OK;
+}
+
+// Streams and events of the flat schedule, created once per device (a resource cache like g_side).
+struct FlatRes {
+  cudaStream_t chain = nullptr, comm = nullptr;
+  cudaEvent_t fork = nullptr, panel = nullptr, near_ = nullptr, packed = nullptr, arrived = nullptr, join = nullptr, join2 = nullptr;
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};
+  bool tried = false, ok = false;
+};
+static FlatRes g_flat[64];
+static FlatRes* flat_res() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  FlatRes& f = g_flat[dev];
+  if (!f.tried) {
+    f.tried = true;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    bool ok = cudaStreamCreateWithPriority(&f.chain, cudaStreamNonBlocking, hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&f.comm, cudaStreamNonBlocking, hi) == cudaSuccess;
+    cudaEvent_t* evs[] = {&f.fork, &f.panel, &f.near_, &f.packed, &f.arrived, &f.join, &f.join2, &f.stage_free[0], &f.stage_free[1]};
+    for (cudaEvent_t* e : evs) ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+    f.ok = ok;
+  }
+  return f.ok ? &f : nullptr;
+}
+
+static inline int bcast_wait(cudaStream_t waiter, cudaEvent_t ev, cudaStream_t recorder) {
+  if (cudaEventRecord(ev, recorder) != cudaSuccess || cudaStreamWaitEvent(waiter, ev, 0) != cudaSuccess) return HB_ERR_CUDA;
+  return HB_OK;
+}
+
+struct FlatPlan {
+  int n, W, P;
+  DistEnv d;
+  FlatRes* r;
+  float* stage[2];
+  bool mine(int b) const { return b >= 0 && b < P && (b % d.world) == d.rank; }
+  int c0(int b) const { return b * W; }
+  int bw(int b) const { return min(W, n - b * W); }
+};
+
+// owner: pack the finished panel and send it; others: receive, unpack (chain stream), `adopt` rebuilds the shadows
+template <class Adopt>
+static int exchange_panel(const FlatPlan& f, const Ctx& cc, float* M, long long ldm, int p, Adopt adopt) {
+  if (f.d.world <= 1) return HB_OK;
+  const int c0 = f.c0(p), wp = f.bw(p), rows = f.n - c0, s = p & 1;
+  float* stage = f.stage[s];
+  float* panel = M + (long long)c0 * ldm + c0;
+  const size_t count = (size_t)rows * wp;
+  if (f.mine(p)) {
+    if (cudaStreamWaitEvent(cc.st, f.r->stage_free[s], 0) != cudaSuccess) return HB_ERR_CUDA;   // the broadcast of p - 2 left this buffer
+    HB_TRY(copy2d(stage, wp, panel, ldm, rows, wp, 1.f, cc.st));
+    HB_TRY(bcast_wait(f.r->comm, f.r->packed, cc.st));
+    HB_TRY(comm_bcast_f32(f.d.comm, stage, count, p % f.d.world, f.r->comm));
+    if (cudaEventRecord(f.r->stage_free[s], f.r->comm) != cudaSuccess) return HB_ERR_CUDA;
+    return HB_OK;
+  }
+  if (cudaStreamWaitEvent(f.r->comm, f.r->stage_free[s], 0) != cudaSuccess) return HB_ERR_CUDA;   // panel p - 2 has been unpacked
+  HB_TRY(comm_bcast_f32(f.d.comm, stage, count, p % f.d.world, f.r->comm));
+  HB_TRY(bcast_wait(cc.st, f.r->arrived, f.r->comm));
+  HB_TRY(copy2d(panel, ldm, stage, wp, rows, wp, 1.f, cc.st));
+  if (cudaEventRecord(f.r->stage_free[s], cc.st) != cudaSuccess) return HB_ERR_CUDA;
+  return adopt(c0, wp);
+}
+
+static int potrf_flat(const Ctx& base, const FlatPlan& f, float* A, long long lda, void* chain_tcws) {
+  const int n = f.n, P = f.P;
+  Ctx cc = base;  cc.st = f.r->chain; cc.tcws = chain_tcws; cc.side_pending = false;     // panel chain (keeps the leaf look-ahead stream)
+  Ctx bc = base;  bc.side = nullptr; bc.side_pending = false;                            // trailing updates on the caller's stream
+  HB_TRY(bcast_wait(cc.st, f.r->fork, base.st));
+  if (f.d.world > 1 && cudaStreamWaitEvent(f.r->comm, f.r->fork, 0) != cudaSuccess) return HB_ERR_CUDA;
+  for (int p = 0; p < P; ++p) {
+    const int c0 = f.c0(p), wp = f.bw(p);
+    if (f.mine(p)) {
+      HB_TRY(potrf_cols(cc, A, lda, c0, wp, n));
+      join_side(cc);
+    }
+    HB_TRY(exchange_panel(f, cc, A, lda, p, [&](int q0, int w) { return split_L(cc, A, lda, q0, q0, n - q0, w); }));
+    if (p + 1 >= P) break;
+    if (cudaEventRecord(f.r->panel, cc.st) != cudaSuccess) return HB_ERR_CUDA;
+    if (f.mine(p + 1)) {                                 // the chain's own update: block p+1 lacks only panel p
+      if (p >= 1 && cudaStreamWaitEvent(cc.st, f.r->near_, 0) != cudaSuccess) return HB_ERR_CUDA;   // U(p-1, p+1) ran on main
+      HB_TRY(fwd_update(cc, A, lda, f.c0(p + 1), f.bw(p + 1), c0, wp, n));
+    }
+    if (p + 2 >= P) continue;
+    if (cudaStreamWaitEvent(bc.st, f.r->panel, 0) != cudaSuccess) return HB_ERR_CUDA;
+    if (f.mine(p + 2)) {
+      HB_TRY(fwd_update(bc, A, lda, f.c0(p + 2), f.bw(p + 2), c0, wp, n));
+      if (cudaEventRecord(f.r->near_, bc.st) != cudaSuccess) return HB_ERR_CUDA;
+    }
+    if (f.d.world == 1) {
+      if (p + 3 < P) HB_TRY(fwd_update(bc, A, lda, f.c0(p + 3), n - f.c0(p + 3), c0, wp, n));   // everything beyond, one trapezoid
+    } else {
+      for (int j = p + 3; j < P; ++j)
+        if (f.mine(j)) HB_TRY(fwd_update(bc, A, lda, f.c0(j), f.bw(j), c0, wp, n));
+    }
+  }
+  HB_TRY(bcast_wait(base.st, f.r->join, cc.st));
+  if (f.d.world > 1) HB_TRY(bcast_wait(base.st, f.r->join2, f.r->comm));
+  return HB_OK;
+}
+
+static int chol_rev_flat(const Ctx& base, const FlatPlan& f, const float* L, long long ldl, float* G, long long ldg,
+                         void* chain_tcws) {
+  const int n = f.n, P = f.P;
+  Ctx cc = base;  cc.st = f.r->chain; cc.tcws = chain_tcws; cc.side_pending = false;
+  Ctx bc = base;  bc.side = nullptr; bc.side_pending = false;
+  HB_TRY(bcast_wait(cc.st, f.r->fork, base.st));
+  if (f.d.world > 1 && cudaStreamWaitEvent(f.r->comm, f.r->fork, 0) != cudaSuccess) return HB_ERR_CUDA;
+  for (int p = P - 1; p >= 0; --p) {
+    const int c0 = f.c0(p), wp = f.bw(p);
+    if (f.mine(p)) {
+      HB_TRY(chol_rev_cols(cc, L, ldl, G, ldg, c0, wp, n));
+      join_side(cc);
+    }
+    HB_TRY(exchange_panel(f, cc, G, ldg, p, [&](int q0, int w) { return adopt_G_panel(cc, G, ldg, q0, w, n); }));
+    if (p == 0) break;
+    if (cudaEventRecord(f.r->panel, cc.st) != cudaSuccess) return HB_ERR_CUDA;
+    if (f.mine(p - 1)) {
+      if (p + 1 < P && cudaStreamWaitEvent(cc.st, f.r->near_, 0) != cudaSuccess) return HB_ERR_CUDA;   // V(p+1, p-1) ran on main
+      HB_TRY(rev_update(cc, L, ldl, G, ldg, f.c0(p - 1), f.bw(p - 1), c0, wp, n));
+    }
+    if (p < 2) continue;
+    if (cudaStreamWaitEvent(bc.st, f.r->panel, 0) != cudaSuccess) return HB_ERR_CUDA;
+    if (f.mine(p - 2)) {
+      HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(p - 2), f.bw(p - 2), c0, wp, n));
+      if (cudaEventRecord(f.r->near_, bc.st) != cudaSuccess) return HB_ERR_CUDA;
+    }
+    if (f.d.world == 1) {
+      if (p >= 3) HB_TRY(rev_update(bc, L, ldl, G, ldg, 0, f.c0(p - 2), c0, wp, n));           // all columns further left at once
+    } else {
+      for (int j = p - 3; j >= 0; --j)
+        if (f.mine(j)) HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(j), f.bw(j), c0, wp, n));
+    }
+  }
+  HB_TRY(bcast_wait(base.st, f.r->join, cc.st));
+  if (f.d.world > 1) HB_TRY(bcast_wait(base.st, f.r->join2, f.r->comm));
+  return HB_OK;
+}
+
 }  // namespace
 
 // The generation-2 tensor-core engine consumes operands in place, so the factorisations need no GEMM scratch
@@ -991,5 +1248,66 @@ int trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int
 }
 
 size_t trsm_workspace_bytes(int m, int n) { return base_bytes(m, n) + tc_bytes_for(m, n); }
+
+// ---- flat / column-block-cyclic entry points ------------------------------------------------------------------------
+// workspace = [ potrf_workspace_bytes(n) | split-K scratch of the chain stream | 2 panel staging buffers (world > 1) ]
+static size_t stage_bytes(int n, int block) { return ((size_t)n * block * sizeof(float) + 255) / 256 * 256; }
+size_t potrf_dist_workspace_bytes(int n, const DistEnv& d) {
+  return potrf_workspace_bytes(n) + tc_bytes_for(-1, n) + 256 + (d.world > 1 ? 2 * stage_bytes(n, d.block) : 0);
+}
+
+static int make_flat(FlatPlan& f, void*& chain_tcws, int n, const DistEnv& d, void* ws, size_t ws_bytes) {
+  if (d.world < 1 || d.rank < 0 || d.rank >= d.world || d.block < NB || (d.block % NB) || (d.world > 1 && !d.comm)) return HB_ERR_ARG;
+  if (!ws || ws_bytes < potrf_dist_workspace_bytes(n, d)) return HB_ERR_WORKSPACE;
+  f.n = n; f.W = d.block; f.P = (n + d.block - 1) / d.block; f.d = d;
+  f.r = flat_res();
+  if (!f.r) return HB_ERR_CUDA;
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + potrf_workspace_bytes(n) + 255) & ~uintptr_t(255));
+  chain_tcws = p; p += tc_bytes_for(-1, n);
+  f.stage[0] = reinterpret_cast<float*>(p);
+  f.stage[1] = reinterpret_cast<float*>(p + stage_bytes(n, d.block));
+  return HB_OK;
+}
+
+int potrf_lower_dist(float* A, long long lda, int n, const DistEnv& d, void* ws, size_t ws_bytes, int* err_flag,
+                     cudaStream_t st) {
+  if (n <= 0 || !A || lda < n) return HB_ERR_ARG;
+  HB_TRY(ensure_attrs());
+  FlatPlan f; void* ctws = nullptr;
+  HB_TRY(make_flat(f, ctws, n, d, ws, ws_bytes));
+  Ctx c;
+  HB_TRY(make_ctx(c, n, ws, potrf_workspace_bytes(n), err_flag, st));
+  attach_side(c);
+  if (c.lh) {
+    if (cudaMemsetAsync(c.lmax, 0, 16, st) != cudaSuccess) return HB_ERR_CUDA;
+    HB_TRY(h2_diag_absmax(A, lda, n, c.lmax, st));
+    HB_TRY(h2_scale_from_max(c.lmax, 1, c.lscale, st));
+  }
+  return potrf_flat(c, f, A, lda, ctws);
+}
+
+int potrf_lower_bwd_dist(const float* L, long long ldl, float* G, long long ldg, int n, const DistEnv& d, void* ws,
+                         size_t ws_bytes, cudaStream_t st, int l_shadow_valid) {
+  if (n <= 0 || !L || !G || ldl < n || ldg < n) return HB_ERR_ARG;
+  HB_TRY(ensure_attrs());
+  FlatPlan f; void* ctws = nullptr;
+  HB_TRY(make_flat(f, ctws, n, d, ws, ws_bytes));
+  Ctx c;
+  HB_TRY(make_ctx(c, n, ws, potrf_workspace_bytes(n), nullptr, st));
+  attach_side(c);
+  const int nblk = (n + NB - 1) / NB;
+  if (c.gh) {
+    if (cudaMemsetAsync(c.gmax, 0, (size_t)2 * c.nblk * 4, st) != cudaSuccess) return HB_ERR_CUDA;
+    if (!l_shadow_valid) {
+      if (cudaMemsetAsync(c.lmax, 0, 16, st) != cudaSuccess) return HB_ERR_CUDA;
+      HB_TRY(h2_absmax(L, ldl, n, n, 1, 0, c.lmax, st));
+      HB_TRY(h2_scale_from_max(c.lmax, 0, c.lscale, st));
+      HB_TRY(h2_split(L, ldl, n, n, c.lscale, nullptr, nullptr, 1, 0, c.lh, c.ll, c.ldh, st));
+    }
+  }
+  trinv_blocks_kernel<<<nblk, LEAF_THREADS, kLeafSmem3, st>>>(L, ldl, n, c.dinv);
+  HB_CHECK_LAUNCH();
+  return chol_rev_flat(c, f, L, ldl, G, ldg, ctws);
+}
 
 }  // namespace hb

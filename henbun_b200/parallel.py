@@ -41,3 +41,36 @@ def allreduce_sum_(flat: torch.Tensor) -> torch.Tensor:
     if w > 1:
         dist.all_reduce(flat)
     return flat
+
+
+# ---- column-block-cyclic factorisations (csrc/linalg.cu: potrf_flat / chol_rev_flat) --------------------------------
+_block_comm = {}
+
+
+def block_cyclic_env(block: int = 2048):
+    """``_lib.Dist`` describing this rank's place in a column-block-cyclic Cholesky / reverse mode over all ranks of the
+    default process group.  The library runs its own NCCL communicator (panel broadcasts on a dedicated stream): rank 0
+    draws the unique id, torch.distributed carries the 128 bytes to the other ranks, every rank joins with its current
+    CUDA device.  One communicator per process, created on first use."""
+    import ctypes as C
+    from . import _lib
+    w, r = world()
+    if w == 1:
+        return _lib.Dist(None, 0, 1, int(block))
+    comm = _block_comm.get("comm")
+    if comm is None:
+        lib = _lib.load()
+        ident = (C.c_ubyte * 128)()
+        if r == 0:
+            _lib.check(lib.hb_comm_unique_id(C.cast(ident, C.c_void_p)), "hb_comm_unique_id")
+        t = torch.tensor(list(ident), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().tolist())
+        buf = (C.c_ubyte * 128).from_buffer_copy(raw)
+        out = C.c_void_p()
+        _lib.check(lib.hb_comm_create(C.cast(buf, C.c_void_p), r, w, C.byref(out)), "hb_comm_create")
+        comm = out.value
+        _block_comm["comm"] = comm
+    return _lib.Dist(comm, r, w, int(block))

@@ -312,6 +312,37 @@ size_t hb_gp_elbo_workspace_bytes(const hb_gp_config* cfg);
 int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, const float* params, const float* eps,
                     float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream);
 
+/* ---- the same step with the factorisation and its reverse mode on a right-looking schedule over column blocks, on one GPU
+ * or SHARED BY A GROUP OF GPUs (strong scaling of BASELINE config 3; the reference has no multi-device path, SURVEY.md 8e:
+ * tf.cholesky, gp/kernels.py:100-101, and its gradient run on one device).
+ * Column blocks of `block` columns (a multiple of 128; 0 = 2048) are dealt round-robin: block b belongs to rank b % world.
+ * Its owner factors it (all rows below; the column recursion restricted to the block) on a high-priority "chain" stream while
+ * every rank applies the previous panels to the blocks it owns on the caller's stream; a finished panel travels to the other
+ * ranks by ncclBroadcast on a third stream and is unpacked into each rank's own copy of the matrix, fp16 hi/lo shadows and
+ * scales rebuilt bit-identically -- so after hb_potrf_lower_dist every rank holds the complete factor, after
+ * hb_potrf_lower_bwd_dist the complete gradient, and the rest of the step needs no further exchange.  world == 1
+ * (comm == NULL) is the same two-stream schedule on one GPU.
+ * hb_comm_*: a communicator of this library's own over the NCCL the process already carries (bound at run time; rank 0 calls
+ * hb_comm_unique_id, the 128 bytes travel to the other ranks by any means -- torch.distributed in the Python layer --, every
+ * rank calls hb_comm_create with its device current).  All ranks must make the same sequence of *_dist calls.
+ * err_flag is set on the rank that owns the failing block only: reduce it (max) across ranks before trusting a step. */
+typedef struct hb_dist {
+  void* comm;            /* from hb_comm_create; NULL when world == 1 */
+  int rank, world;
+  int block;             /* columns per block, multiple of 128; 0 = 2048 */
+} hb_dist;
+int hb_comm_unique_id(void* out128_host);
+int hb_comm_create(const void* id128_host, int rank, int world, void** comm_out);
+int hb_comm_destroy(void* comm);
+size_t hb_potrf_dist_workspace_bytes(int n, const hb_dist* d);
+int hb_potrf_lower_dist(float* A, long long lda, int n, const hb_dist* d, void* ws, size_t ws_bytes, int* err_flag, void* stream,
+                        const hb_options* opt);
+int hb_potrf_lower_bwd_dist(const float* L, long long ldl, float* G, long long ldg, int n, const hb_dist* d, void* ws,
+                            size_t ws_bytes, void* stream, const hb_options* opt);
+size_t hb_gp_elbo_dist_workspace_bytes(const hb_gp_config* cfg, const hb_dist* d);
+int hb_gp_elbo_step_dist(const hb_gp_config* cfg, const hb_dist* d, const float* X, const float* Y, const float* params,
+                         const float* eps, float* grads, float* out4, void* ws, size_t ws_bytes, int* err_flag, void* stream);
+
 /* ---- fused ELBO + gradient of the amortised local-variable model (BASELINE config 4) ----------------------------
  *   q_local = enc(X);  x_rec = dec(q_local);  ELBO = sum gaussian(X, x_rec, var) - KL(LOCAL),  S-sample mean
  * enc / dec = nn.NeuralNet (nn.py:34-87: hidden layers act(x w + b), last layer linear), q_local = LOCAL
