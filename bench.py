@@ -249,12 +249,16 @@ def ncu_traffic():
 class GpCabi:
     """Config 3 through the C ABI: hb_gp_elbo_step (+ all-reduce) + hb_adam_tf1 on caller-owned buffers."""
 
-    def __init__(self, d, n, D, S, seed_rank_offset=True):
+    def __init__(self, d, n, D, S, seed_rank_offset=True, shared=None, block=2048, batch=1):
+        """shared (default: whenever there is more than one rank): the ranks share ONE column-block-cyclic factorisation
+        and reverse mode (hb_gp_elbo_step_dist, shard_samples = 1); False: every rank factors K itself (round 1)."""
         import torch
-        from henbun_b200 import _lib
+        from henbun_b200 import _lib, parallel
         from henbun_b200.synthetic import make_gp_problem, pack_gp_params
         self.d, self.n, self.D, self.S = d, n, D, S
         self.lib = lib = _lib.load()
+        self.shared = (d.world > 1 and n >= 4096) if shared is None else bool(shared and d.world > 1)
+        self.env = parallel.block_cyclic_env(block, batch, shard_samples=True) if self.shared else None
         X, Y, p = make_gp_problem(n, D, S, seed=0, lengthscale=LENGTHSCALE)
         self.X, self.Y, self.p = X, Y, p
         params_h = pack_gp_params(p)
@@ -268,7 +272,8 @@ class GpCabi:
         self.step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
         self.out4 = torch.zeros(4, device=dev)
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.wsb = lib.hb_gp_elbo_workspace_bytes(C.byref(self.cfg))
+        self.wsb = (lib.hb_gp_elbo_dist_workspace_bytes(C.byref(self.cfg), C.byref(self.env)) if self.shared
+                    else lib.hb_gp_elbo_workspace_bytes(C.byref(self.cfg)))
         self.ws = torch.empty(self.wsb, dtype=torch.uint8, device=dev)
         self.Xd = torch.from_numpy(X).to(dev); self.Yd = torch.from_numpy(Y).to(dev)
         self.Xh = torch.from_numpy(X).pin_memory(); self.Yh = torch.from_numpy(Y).pin_memory()
@@ -284,9 +289,14 @@ class GpCabi:
         # ranks read disjoint windows of one Philox stream: the union over ranks is the single-GPU draw of S * world samples
         per_step = (self.S * d.world * self.n + 3) // 4 * 4
         self.cfg.offset = C.c_ulonglong(self.it * per_step + (d.rank * self.S * self.n) // 4 * 4)
-        _lib.check(lib.hb_gp_elbo_step(C.byref(self.cfg), _lib.ptr(self.Xd), _lib.ptr(self.Yd), _lib.ptr(self.params), None,
-                                       _lib.ptr(self.grads), _lib.ptr(self.out4), _lib.ptr(self.ws), self.wsb, _lib.ptr(self.err), st()),
-                   "hb_gp_elbo_step")
+        if self.shared:
+            _lib.check(lib.hb_gp_elbo_step_dist(C.byref(self.cfg), C.byref(self.env), _lib.ptr(self.Xd), _lib.ptr(self.Yd),
+                                                _lib.ptr(self.params), None, _lib.ptr(self.grads), _lib.ptr(self.out4), _lib.ptr(self.ws),
+                                                self.wsb, _lib.ptr(self.err), st()), "hb_gp_elbo_step_dist")
+        else:
+            _lib.check(lib.hb_gp_elbo_step(C.byref(self.cfg), _lib.ptr(self.Xd), _lib.ptr(self.Yd), _lib.ptr(self.params), None,
+                                           _lib.ptr(self.grads), _lib.ptr(self.out4), _lib.ptr(self.ws), self.wsb, _lib.ptr(self.err), st()),
+                       "hb_gp_elbo_step")
         if d.world > 1:
             d.dist.all_reduce(self.grads)          # one NCCL all-reduce of the packed gradient (sum); mean below
         _lib.check(lib.hb_increment_i32(_lib.ptr(self.step_ctr), st()), "hb_increment_i32")
@@ -299,6 +309,8 @@ class GpCabi:
     def check(self):
         self.d.barrier()
         elbo = self.out4[0].item()
+        if self.d.world > 1:                       # a failing block sets the flag on its owner only
+            self.d.dist.all_reduce(self.err, op=self.d.dist.ReduceOp.MAX)
         if self.err.item() != 0:
             raise RuntimeError(f"Cholesky failed: non-positive pivot at row {self.err.item() - 1}")
         if not math.isfinite(elbo):
@@ -382,10 +394,15 @@ def run_c3(d, a):
     ms_cabi_e2e = d.timed(lambda i: g.step(host_io=True), min(a.steps, 3)) / min(a.steps, 3)
     # separate, untimed passes for the evidence: per-launch GEMM events (roofline) and per-phase events
     d.barrier()
+    # the timed step overlaps the narrow steps of a block (chain stream) with the trailing updates (caller's stream);
+    # for per-launch durations the SAME launch sequence is issued on one stream (hb_options.lookahead = 0)
+    _lib.OPTIONS.lookahead = 0
+    g.step()
     lib.hb_profile_begin(200000)
     ms_prof = d.timed(lambda i: g.step(), 1)
     buf = (C.c_double * 8)()
     lib.hb_profile_end_ex(buf)
+    _lib.OPTIONS.lookahead = 1
     prof = list(buf)
     if a.profile_csv and d.rank == 0:
         lib.hb_profile_dump_csv(a.profile_csv.encode())
@@ -397,7 +414,30 @@ def run_c3(d, a):
     phases = {names[i] if i < len(names) else f"phase{i}": round(pbuf[i], 3) for i in range(max(npz, 0))}
     elbo = g.check()
     X, Y, p = g.X, g.Y, g.p
+    shared = g.shared
     g.free()
+
+    # strong scaling (same S in total, split over the ranks) and the round-1 path (every rank factors K itself)
+    multi = None
+    if d.world > 1 and shared:
+        multi = {}
+        if S % d.world == 0:
+            gs = GpCabi(d, n, D, S // d.world)
+            for _ in range(2):
+                gs.step()
+            gs.check()
+            k = min(a.steps, 3)
+            multi["strong"] = {"samples_total": S, "samples_per_rank": S // d.world, "ms_per_step": d.timed(lambda i: gs.step(), k) / k,
+                               "what": "the single-GPU job (S samples in total) on N ranks: shared factorisation, S / N samples per rank"}
+            gs.free()
+        gr = GpCabi(d, n, D, S, shared=False)
+        for _ in range(2):
+            gr.step()
+        gr.check()
+        k = min(a.steps, 3)
+        multi["replicated"] = {"samples_per_rank": S, "ms_per_step": d.timed(lambda i: gr.step(), k) / k,
+                               "what": "round-1 path: every rank factors K itself, samples sharded, one all-reduce"}
+        gr.free()
 
     # like-for-like pair at the CPU sample size (GPU side; the CPU side is cpu_baseline.sample_s_per_step)
     same_n = None
@@ -428,7 +468,11 @@ def run_c3(d, a):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": workload_string(n, D, S),
-            "parallelism": f"replicated factorisation, sample-sharded (weak scaling in S), {d.world} rank(s)",
+            "parallelism": (f"ONE column-block-cyclic factorisation + reverse mode shared by {d.world} ranks (panel broadcasts over "
+                            f"NCCL), samples sharded: S={S} per rank (weak scaling in S), one all-gather of Z/R + one all-reduce "
+                            f"of the packed gradient per step") if shared else
+                           f"sample-sharded (weak scaling in S), {d.world} rank(s), factorisation on every rank",
+            "schedule": "right-looking two-stream schedule over column blocks (hb_options.schedule = 0: auto)",
             "l2": "inputs larger than L2 (K/L and Lbar/Kbar are N^2 fp32 = %.1f GB each)" % (4.0 * n * n / 1e9),
             "eps": "device Philox-4x32-10, regenerated in the backward; ranks read disjoint windows of one stream",
             "gemm_engine": {0: "auto", 1: "simt-fp32", 2: "tcgen05", 3: "simt-kloop"}.get(eng, str(eng)),
@@ -461,10 +505,18 @@ def run_c3(d, a):
                      "multiplied as hi*hi + lo*hi + hi*lo = 3 tensor-pipe slots where a plain bf16 GEMM needs 1, i.e. frac <= 0.333 "
                      "against the bf16 peak for this formulation (round 1: tf32 + 2 bf16 terms = 4 slots, 0.25)"),
             "how": "CUDA-event pair around every GEMM launch of one extra (untimed) step on the launching stream; achieved = useful "
-                   "FLOP (trapezoid / block-mask shares counted, padding not) / summed launch time",
+                   "FLOP (trapezoid / block-mask shares counted, padding not) / summed launch time.  The timed steps run the block "
+                   "chain and the trailing updates on two concurrent streams; this pass issues the same launch sequence on ONE "
+                   "stream (hb_options.lookahead = 0) so that a launch's duration is its own",
+            "serialised_step_ms": ms_prof,
+            "step_level": {"what": "useful level-3 FLOP of the step / ms_per_step of the TIMED (two-stream) steps",
+                           "achieved": gemm_flop / (ms / a.steps * 1e-3) / 1e12 if ms > 0 else None,
+                           "frac": gemm_flop / (ms / a.steps * 1e-3) / 1e12 / peak if ms > 0 and peak else None},
         },
         "phases_ms": phases,
     }
+    if multi:
+        line["multi_gpu"] = multi
     if d.world == 1 and not a.no_cpu_baseline:
         cb = cpu_baseline(n, D, S, a.cpu_n)
         line["cpu_baseline"] = cb

@@ -29,12 +29,12 @@ _sz = C.c_size_t
 class Options(C.Structure):
     """hb_options (include/henbun_b200.h): behavioural switches that travel with every call."""
     _fields_ = [("gemm_engine", _i), ("exact_below", _i), ("panel_refinement", _i), ("presplit_engine", _i),
-                ("small_gp_kernel", _i), ("tc_option", _i), ("lookahead", _i)]
+                ("small_gp_kernel", _i), ("tc_option", _i), ("lookahead", _i), ("schedule", _i)]
 
 
 # The process-wide DEFAULT the Python layer passes when a caller gives no options of its own.  The C library itself keeps
 # no configuration; `lib.hb_set_*` below are Python-side conveniences that edit this object (tests, A/B runs).
-OPTIONS = Options(0, 2048, 2, 1, 0, 0, 1)
+OPTIONS = Options(0, 2048, 2, 1, 0, 0, 1, 0)
 
 
 class GpConfig(C.Structure):
@@ -44,7 +44,7 @@ class GpConfig(C.Structure):
 
 class Dist(C.Structure):
     """hb_dist: this rank's place in a column-block-cyclic factorisation (comm from hb_comm_create; NULL when world == 1)."""
-    _fields_ = [("comm", C.c_void_p), ("rank", _i), ("world", _i), ("block", _i)]
+    _fields_ = [("comm", C.c_void_p), ("rank", _i), ("world", _i), ("block", _i), ("shard_samples", _i), ("batch", _i)]
 
 
 class AdamConfig(C.Structure):
@@ -147,6 +147,8 @@ SIGNATURES = {
     "hb_comm_unique_id": (_i, [C.c_void_p]),
     "hb_comm_create": (_i, [C.c_void_p, _i, _i, C.POINTER(C.c_void_p)]),
     "hb_comm_destroy": (_i, [C.c_void_p]),
+    "hb_flat_trace_begin": (_i, []),
+    "hb_flat_trace_end": (_i, [C.POINTER(C.c_double), _i]),
     "hb_potrf_dist_workspace_bytes": (_sz, [_i, C.POINTER(Dist)]),
     "hb_potrf_lower_dist": (_i, [_c_f, _ll, _i, C.POINTER(Dist), _c_f, _sz, _c_f, _c_f, C.POINTER(Options)]),
     "hb_potrf_lower_bwd_dist": (_i, [_c_f, _ll, _c_f, _ll, _i, C.POINTER(Dist), _c_f, _sz, _c_f, C.POINTER(Options)]),
@@ -237,6 +239,7 @@ def _install_option_plumbing(lib):
     lib.hb_set_exact_below = set_field("exact_below", lambda v: max(0, int(v)))
     lib.hb_set_presplit_engine = set_field("presplit_engine", lambda v: 1 if v else 0)
     lib.hb_set_small_gp_kernel = set_field("small_gp_kernel", lambda v: 1 if v else 0)
+    lib.hb_set_schedule = set_field("schedule", int)
     lib.hb_set_tc_option = lambda v: (setattr(OPTIONS, "tc_option", int(v)), HB_OK)[1]
 
 

@@ -14,7 +14,7 @@ namespace hb {
 // The library keeps no mutable configuration.  Every extern "C" entry point that reaches the level-3 engine installs the
 // caller's hb_options for its own duration on the calling thread (OptScope) and the kernels' host code reads them through
 // the opt_*() accessors; outside any call, and for NULL, the defaults of hb_options_init apply.
-static const hb_options kDefaultOptions = {0, 2048, 2, 1, 0, 0, 1};
+static const hb_options kDefaultOptions = {0, 2048, 2, 1, 0, 0, 1, 0};
 static thread_local const hb_options* tl_options = nullptr;
 static inline const hb_options& cur_opt() { return tl_options ? *tl_options : kDefaultOptions; }
 int opt_gemm_engine() { const int e = cur_opt().gemm_engine; return (e < 0 || e > 3) ? 0 : e; }
@@ -24,6 +24,7 @@ int opt_presplit_engine() { return cur_opt().presplit_engine != 0; }
 int opt_small_gp_kernel() { return cur_opt().small_gp_kernel != 0; }
 int opt_tc_option() { return cur_opt().tc_option; }
 int opt_lookahead() { return cur_opt().lookahead != 0; }
+int opt_schedule() { return cur_opt().schedule; }
 OptScope::OptScope(const ::hb_options* o) : prev(tl_options) { if (o) tl_options = o; }
 OptScope::~OptScope() { tl_options = prev; }
 #define g_engine (opt_gemm_engine())
@@ -173,7 +174,7 @@ __global__ void gp_zbar_total_kernel(const float* __restrict__ wb, const float* 
 }
 
 struct GpLayout {
-  size_t off_K, off_G, off_Z, off_F, off_R, off_W, off_U, off_sc, off_red, off_potrf, total;
+  size_t off_K, off_G, off_Z, off_F, off_R, off_W, off_U, off_sc, off_red, off_potrf, off_ZA, off_RA, total;
   size_t potrf_bytes;
 };
 
@@ -192,6 +193,9 @@ GpLayout gp_layout(const hb_gp_config& c, const DistEnv* d = nullptr) {
   L.off_red = o; o += align_up(kReduceWsBytes);
   L.potrf_bytes = d ? potrf_dist_workspace_bytes(c.n, *d) : potrf_workspace_bytes(c.n);
   L.off_potrf = o; o += align_up(L.potrf_bytes);
+  const size_t gathered = (d && d->world > 1 && d->shard_samples) ? sn * d->world : 0;     // Z and R of every rank
+  L.off_ZA = o; o += align_up(gathered);
+  L.off_RA = o; o += align_up(gathered);
   L.total = o;
   return L;
 }
@@ -630,6 +634,8 @@ size_t hb_gp_elbo_workspace_bytes(const hb_gp_config* c) {
 static DistEnv to_env(const hb_dist* d) {
   DistEnv e;
   e.comm = d->comm; e.rank = d->rank; e.world = d->world; e.block = d->block > 0 ? d->block : 2048;
+  e.batch = d->batch > 0 ? d->batch : 1;
+  e.shard_samples = d->shard_samples ? 1 : 0;
   return e;
 }
 
@@ -637,6 +643,8 @@ int hb_comm_unique_id(void* out128_host) { return comm_unique_id(out128_host); }
 int hb_comm_create(const void* id128_host, int rank, int world, void** comm_out) { return comm_create(id128_host, rank, world, comm_out); }
 int hb_comm_destroy(void* comm) { return comm_destroy(comm); }
 
+int hb_flat_trace_begin(void) { return flat_trace_begin(); }
+int hb_flat_trace_end(double* out3_host, int capacity) { return flat_trace_end(out3_host, capacity); }
 size_t hb_potrf_dist_workspace_bytes(int n, const hb_dist* d) { return d ? potrf_dist_workspace_bytes(n, to_env(d)) : 0; }
 int hb_potrf_lower_dist(float* A, long long lda, int n, const hb_dist* d, void* ws, size_t ws_bytes, int* err_flag, void* stream,
                         const hb_options* opt) {
@@ -778,6 +786,15 @@ static int gp_elbo_step_impl(const hb_gp_config* cfg, const DistEnv* dist, const
     GemmParams g;
     g.A = R; g.lda = n; g.transA = 1; g.B = Z; g.ldb = n; g.transB = 0;
     g.C = G; g.ldc = n; g.c_tri = 1; g.M = n; g.N = n; g.K = Sn;
+    if (dist && dist->world > 1 && dist->shard_samples) {
+      // Sample-sharded ranks share ONE factorisation: its gradient is linear in L-bar, so the ranks' residuals and samples
+      // are gathered (2 x world x S x n floats) and every rank forms the L-bar of the rank-averaged objective itself.
+      float* ZA = reinterpret_cast<float*>(base + L.off_ZA);
+      float* RA = reinterpret_cast<float*>(base + L.off_RA);
+      HB_TRY(comm_allgather_f32(dist->comm, Z, ZA, (size_t)Sn * n, st));
+      HB_TRY(comm_allgather_f32(dist->comm, R, RA, (size_t)Sn * n, st));
+      g.A = RA; g.B = ZA; g.K = Sn * dist->world; g.alpha = 1.f / (float)dist->world;
+    }
     HB_TRY(gemm(g, st));
   }
   phase_mark(st);

@@ -21,7 +21,7 @@ typedef int (*fn_init_rank)(void** comm, int nranks, NcclId id, int rank);
 typedef int (*fn_destroy)(void* comm);
 typedef int (*fn_bcast)(const void* send, void* recv, size_t count, int dtype, int root, void* comm, cudaStream_t st);
 typedef int (*fn_allreduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, cudaStream_t st);
-typedef const char* (*fn_errstr)(int);
+typedef int (*fn_allgather)(const void* send, void* recv, size_t sendcount, int dtype, void* comm, cudaStream_t st);
 
 struct Nccl {
   void* h = nullptr;
@@ -30,6 +30,7 @@ struct Nccl {
   fn_destroy destroy = nullptr;
   fn_bcast bcast = nullptr;
   fn_allreduce allreduce = nullptr;
+  fn_allgather allgather = nullptr;
   bool tried = false;
 };
 Nccl g_nccl;      // resolved symbols of a shared library: a resource cache, not configuration
@@ -46,7 +47,8 @@ bool nccl_load() {
   g_nccl.destroy = (fn_destroy)dlsym(h, "ncclCommDestroy");
   g_nccl.bcast = (fn_bcast)dlsym(h, "ncclBroadcast");
   g_nccl.allreduce = (fn_allreduce)dlsym(h, "ncclAllReduce");
-  if (!g_nccl.get_id || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.bcast || !g_nccl.allreduce) return false;
+  g_nccl.allgather = (fn_allgather)dlsym(h, "ncclAllGather");
+  if (!g_nccl.get_id || !g_nccl.allgather || !g_nccl.init_rank || !g_nccl.destroy || !g_nccl.bcast || !g_nccl.allreduce) return false;
   g_nccl.h = h;
   return true;
 }
@@ -83,6 +85,13 @@ int comm_bcast_f32(void* comm, float* buf, size_t count, int root, cudaStream_t 
   if (!comm || !g_nccl.h) return HB_ERR_ARG;
   if (count == 0) return HB_OK;
   return g_nccl.bcast(buf, buf, count, /*ncclFloat*/ 7, root, comm, st) == 0 ? HB_OK : HB_ERR_CUDA;
+}
+
+// recv [world x count] <- every rank's send [count], in rank order
+int comm_allgather_f32(void* comm, const float* send, float* recv, size_t count, cudaStream_t st) {
+  if (!comm || !g_nccl.h) return HB_ERR_ARG;
+  if (count == 0) return HB_OK;
+  return g_nccl.allgather(send, recv, count, /*ncclFloat*/ 7, comm, st) == 0 ? HB_OK : HB_ERR_CUDA;
 }
 
 int comm_allreduce_f32(void* comm, float* buf, size_t count, int op_max, cudaStream_t st) {

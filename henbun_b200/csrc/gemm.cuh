@@ -52,6 +52,7 @@ int opt_presplit_engine();
 int opt_small_gp_kernel();
 int opt_tc_option();
 int opt_lookahead();
+int opt_schedule();
 struct OptScope {     // installs the caller's options for the duration of one extern "C" call (capi.cu)
   const ::hb_options* prev;
   explicit OptScope(const ::hb_options* o);

@@ -108,6 +108,8 @@ int potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, 
                     int n, int batch, void* ws, size_t ws_bytes, cudaStream_t st, int l_shadow_valid = 0);
 int trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int m, int n, int trans, void* ws,
                      size_t ws_bytes, cudaStream_t st);
+int flat_trace_begin();
+int flat_trace_end(double* out3, int capacity);
 // right-looking schedule over column blocks, one GPU or a column-block-cyclic group (comm.cuh: DistEnv)
 struct DistEnv;
 size_t potrf_dist_workspace_bytes(int n, const DistEnv& d);

@@ -12,6 +12,7 @@
 #include "kernels.cuh"
 #include "comm.cuh"
 #include <cstdlib>
+#include <vector>
 
 namespace hb {
 
@@ -1001,6 +1002,20 @@ static FlatRes* flat_res() {
   return f.ok ? &f : nullptr;
 }
 
+// Optional timeline of the schedule (hb_flat_trace_begin / _end): timing events at the stations of every block --
+// tag 0 chain: F(p) starts | 1 chain: F(p) done | 2 chain: panel p available (sent / received + unpacked) |
+// 3 chain: its own update U(p, p+-1) done | 4 main: U(p, .) may start | 5 main: U(p, .) all issued work done.
+struct TraceRow { int tag, p; cudaEvent_t ev; };
+static std::vector<TraceRow> g_trace;
+static bool g_trace_on = false;
+static inline void trace(int tag, int p, cudaStream_t st) {
+  if (!g_trace_on) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_trace.push_back({tag, p, e});
+}
+
 static inline int bcast_wait(cudaStream_t waiter, cudaEvent_t ev, cudaStream_t recorder) {
   if (cudaEventRecord(ev, recorder) != cudaSuccess || cudaStreamWaitEvent(waiter, ev, 0) != cudaSuccess) return HB_ERR_CUDA;
   return HB_OK;
@@ -1042,35 +1057,49 @@ static int exchange_panel(const FlatPlan& f, const Ctx& cc, float* M, long long 
 
 static int potrf_flat(const Ctx& base, const FlatPlan& f, float* A, long long lda, void* chain_tcws) {
   const int n = f.n, P = f.P;
-  Ctx cc = base;  cc.st = f.r->chain; cc.tcws = chain_tcws; cc.side_pending = false;     // panel chain (keeps the leaf look-ahead stream)
+  // hb_options.lookahead = 0: the same launches, all on the caller's stream (per-launch timing of the step's own kernels)
+  Ctx cc = base;  cc.st = opt_lookahead() ? f.r->chain : base.st; cc.tcws = chain_tcws; cc.side_pending = false;     // panel chain (keeps the leaf look-ahead stream)
   Ctx bc = base;  bc.side = nullptr; bc.side_pending = false;                            // trailing updates on the caller's stream
   HB_TRY(bcast_wait(cc.st, f.r->fork, base.st));
   if (f.d.world > 1 && cudaStreamWaitEvent(f.r->comm, f.r->fork, 0) != cudaSuccess) return HB_ERR_CUDA;
+  int pend = 0;                                            // first panel the far blocks have not received yet
   for (int p = 0; p < P; ++p) {
     const int c0 = f.c0(p), wp = f.bw(p);
     if (f.mine(p)) {
+      trace(0, p, cc.st);
       HB_TRY(potrf_cols(cc, A, lda, c0, wp, n));
       join_side(cc);
+      trace(1, p, cc.st);
     }
     HB_TRY(exchange_panel(f, cc, A, lda, p, [&](int q0, int w) { return split_L(cc, A, lda, q0, q0, n - q0, w); }));
+    trace(2, p, cc.st);
     if (p + 1 >= P) break;
     if (cudaEventRecord(f.r->panel, cc.st) != cudaSuccess) return HB_ERR_CUDA;
     if (f.mine(p + 1)) {                                 // the chain's own update: block p+1 lacks only panel p
       if (p >= 1 && cudaStreamWaitEvent(cc.st, f.r->near_, 0) != cudaSuccess) return HB_ERR_CUDA;   // U(p-1, p+1) ran on main
       HB_TRY(fwd_update(cc, A, lda, f.c0(p + 1), f.bw(p + 1), c0, wp, n));
+      trace(3, p, cc.st);
     }
     if (p + 2 >= P) continue;
     if (cudaStreamWaitEvent(bc.st, f.r->panel, 0) != cudaSuccess) return HB_ERR_CUDA;
+    trace(4, p, bc.st);
+    // Blocks from p+3 on are "far": they have every panel before `pend` applied and take the pending ones [pend, p] as ONE
+    // product with K = all their columns, `batch` panels at a time; block p+2 leaves the far set now and is brought up to date.
+    const int k0 = f.c0(pend), kw = c0 + wp - k0;
     if (f.mine(p + 2)) {
-      HB_TRY(fwd_update(bc, A, lda, f.c0(p + 2), f.bw(p + 2), c0, wp, n));
+      HB_TRY(fwd_update(bc, A, lda, f.c0(p + 2), f.bw(p + 2), k0, kw, n));
       if (cudaEventRecord(f.r->near_, bc.st) != cudaSuccess) return HB_ERR_CUDA;
     }
-    if (f.d.world == 1) {
-      if (p + 3 < P) HB_TRY(fwd_update(bc, A, lda, f.c0(p + 3), n - f.c0(p + 3), c0, wp, n));   // everything beyond, one trapezoid
-    } else {
-      for (int j = p + 3; j < P; ++j)
-        if (f.mine(j)) HB_TRY(fwd_update(bc, A, lda, f.c0(j), f.bw(j), c0, wp, n));
+    if (p + 3 < P && (p - pend + 1 >= f.d.batch || p + 4 >= P)) {
+      if (f.d.world == 1) {
+        HB_TRY(fwd_update(bc, A, lda, f.c0(p + 3), n - f.c0(p + 3), k0, kw, n));                 // everything beyond, one trapezoid
+      } else {
+        for (int j = p + 3; j < P; ++j)
+          if (f.mine(j)) HB_TRY(fwd_update(bc, A, lda, f.c0(j), f.bw(j), k0, kw, n));
+      }
+      pend = p + 1;
     }
+    trace(5, p, bc.st);
   }
   HB_TRY(bcast_wait(base.st, f.r->join, cc.st));
   if (f.d.world > 1) HB_TRY(bcast_wait(base.st, f.r->join2, f.r->comm));
@@ -1080,35 +1109,47 @@ static int potrf_flat(const Ctx& base, const FlatPlan& f, float* A, long long ld
 static int chol_rev_flat(const Ctx& base, const FlatPlan& f, const float* L, long long ldl, float* G, long long ldg,
                          void* chain_tcws) {
   const int n = f.n, P = f.P;
-  Ctx cc = base;  cc.st = f.r->chain; cc.tcws = chain_tcws; cc.side_pending = false;
+  Ctx cc = base;  cc.st = opt_lookahead() ? f.r->chain : base.st; cc.tcws = chain_tcws; cc.side_pending = false;
   Ctx bc = base;  bc.side = nullptr; bc.side_pending = false;
   HB_TRY(bcast_wait(cc.st, f.r->fork, base.st));
   if (f.d.world > 1 && cudaStreamWaitEvent(f.r->comm, f.r->fork, 0) != cudaSuccess) return HB_ERR_CUDA;
+  int pend = P - 1;                                        // last panel the far blocks have not received yet
   for (int p = P - 1; p >= 0; --p) {
     const int c0 = f.c0(p), wp = f.bw(p);
     if (f.mine(p)) {
+      trace(0, p, cc.st);
       HB_TRY(chol_rev_cols(cc, L, ldl, G, ldg, c0, wp, n));
       join_side(cc);
+      trace(1, p, cc.st);
     }
     HB_TRY(exchange_panel(f, cc, G, ldg, p, [&](int q0, int w) { return adopt_G_panel(cc, G, ldg, q0, w, n); }));
+    trace(2, p, cc.st);
     if (p == 0) break;
     if (cudaEventRecord(f.r->panel, cc.st) != cudaSuccess) return HB_ERR_CUDA;
     if (f.mine(p - 1)) {
       if (p + 1 < P && cudaStreamWaitEvent(cc.st, f.r->near_, 0) != cudaSuccess) return HB_ERR_CUDA;   // V(p+1, p-1) ran on main
       HB_TRY(rev_update(cc, L, ldl, G, ldg, f.c0(p - 1), f.bw(p - 1), c0, wp, n));
+      trace(3, p, cc.st);
     }
     if (p < 2) continue;
     if (cudaStreamWaitEvent(bc.st, f.r->panel, 0) != cudaSuccess) return HB_ERR_CUDA;
+    trace(4, p, bc.st);
+    // far blocks (up to p-3) have every panel after `pend` applied; the pending ones [p, pend] act as one right-hand range
+    const int r1 = c0, w2 = f.c0(pend) + f.bw(pend) - c0;
     if (f.mine(p - 2)) {
-      HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(p - 2), f.bw(p - 2), c0, wp, n));
+      HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(p - 2), f.bw(p - 2), r1, w2, n));
       if (cudaEventRecord(f.r->near_, bc.st) != cudaSuccess) return HB_ERR_CUDA;
     }
-    if (f.d.world == 1) {
-      if (p >= 3) HB_TRY(rev_update(bc, L, ldl, G, ldg, 0, f.c0(p - 2), c0, wp, n));           // all columns further left at once
-    } else {
-      for (int j = p - 3; j >= 0; --j)
-        if (f.mine(j)) HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(j), f.bw(j), c0, wp, n));
+    if (p >= 3 && (pend - p + 1 >= f.d.batch || p == 3)) {
+      if (f.d.world == 1) {
+        HB_TRY(rev_update(bc, L, ldl, G, ldg, 0, f.c0(p - 2), r1, w2, n));                       // all columns further left at once
+      } else {
+        for (int j = p - 3; j >= 0; --j)
+          if (f.mine(j)) HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(j), f.bw(j), r1, w2, n));
+      }
+      pend = p - 1;
     }
+    trace(5, p, bc.st);
   }
   HB_TRY(bcast_wait(base.st, f.r->join, cc.st));
   if (f.d.world > 1) HB_TRY(bcast_wait(base.st, f.r->join2, f.r->comm));
@@ -1132,11 +1173,24 @@ static size_t h2_scale_bytes(int n) { return ((size_t)(16 + 4 * ((n + NB - 1) / 
 static size_t h2_shadow_bytes(int n) { return ((size_t)n * h2_ld(n) * 2 + 255) / 256 * 256; }
 static size_t h2_bytes_for(int n) { return (n >= H2_MIN_N && n % 8 == 0) ? h2_scale_bytes(n) + 4 * h2_shadow_bytes(n) : 0; }
 
-size_t potrf_workspace_bytes(int n) { return base_bytes(n, n) + tc_bytes_for(-1, n) + h2_bytes_for(n); }
+static size_t core_bytes(int n) { return base_bytes(n, n) + tc_bytes_for(-1, n) + h2_bytes_for(n); }
+// Orders from which the right-looking two-stream schedule is available inside potrf_lower / potrf_lower_bwd: its chain
+// stream needs a split-K scratch of its own.
+constexpr int FLAT_MIN_N = 8192;
+static size_t chain_bytes(int n) { return n >= FLAT_MIN_N ? tc_bytes_for(-1, n) + 256 : 0; }
+size_t potrf_workspace_bytes(int n) { return core_bytes(n) + chain_bytes(n); }
+// block width of the schedule for one GPU: 0 = column recursion
+static int auto_block(int n) {
+  const int s = opt_schedule();
+  if (s == 1 || n < FLAT_MIN_N) return 0;
+  if (s >= NB) return s / NB * NB;
+  if (n < 32768) return 0;
+  return max(2048, n / 8 / NB * NB);
+}
 
 
 static int make_ctx(Ctx& c, int n, void* ws, size_t ws_bytes, int* err, cudaStream_t st) {
-  if (ws_bytes < potrf_workspace_bytes(n) || !ws) return HB_ERR_WORKSPACE;
+  if (ws_bytes < core_bytes(n) || !ws) return HB_ERR_WORKSPACE;
   const long long nblk = (n + NB - 1) / NB;
   c.st = st;
   c.dinv = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
@@ -1173,6 +1227,11 @@ int potrf_lower(float* A, long long lda, long long strideA, int n, int batch, in
     HB_CHECK_LAUNCH();
     return HB_OK;
   }
+  if (batch == 1 && auto_block(n) && ws_bytes >= potrf_workspace_bytes(n)) {
+    DistEnv d; d.block = auto_block(n);
+    HB_TRY(potrf_lower_dist(A, lda, n, d, ws, ws_bytes, err_flag, st));
+    return zero_upper ? zero_strict_upper(A, lda, n, st) : HB_OK;
+  }
   Ctx c;
   HB_TRY(make_ctx(c, n, ws, ws_bytes, err_flag, st));
   attach_side(c);
@@ -1201,6 +1260,10 @@ int potrf_lower_bwd(const float* L, long long ldl, long long strideL, float* G, 
     chol_rev_leaf_kernel<<<batch, LEAF_THREADS, kLeafSmem3, st>>>(L, ldl, strideL, G, ldg, strideG, n, nullptr, 0);
     HB_CHECK_LAUNCH();
     return HB_OK;
+  }
+  if (batch == 1 && auto_block(n) && ws_bytes >= potrf_workspace_bytes(n)) {
+    DistEnv d; d.block = auto_block(n);
+    return potrf_lower_bwd_dist(L, ldl, G, ldg, n, d, ws, ws_bytes, st, l_shadow_valid);
   }
   Ctx c;
   HB_TRY(make_ctx(c, n, ws, ws_bytes, nullptr, st));
@@ -1249,20 +1312,42 @@ int trsm_right_lower(const float* L, long long ldl, float* X, long long ldx, int
 
 size_t trsm_workspace_bytes(int m, int n) { return base_bytes(m, n) + tc_bytes_for(m, n); }
 
+int flat_trace_begin() {
+  for (auto& r : g_trace) cudaEventDestroy(r.ev);
+  g_trace.clear();
+  g_trace_on = true;
+  return HB_OK;
+}
+// rows of {tag, block, ms since the first station}; returns the number of stations recorded (synchronises)
+int flat_trace_end(double* out3, int capacity) {
+  g_trace_on = false;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  const int nrow = (int)g_trace.size();
+  for (int i = 0; i < nrow && i < capacity; ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_trace[0].ev, g_trace[i].ev);
+    out3[3 * i] = g_trace[i].tag; out3[3 * i + 1] = g_trace[i].p; out3[3 * i + 2] = ms;
+  }
+  for (auto& r : g_trace) cudaEventDestroy(r.ev);
+  g_trace.clear();
+  return nrow;
+}
+
 // ---- flat / column-block-cyclic entry points ------------------------------------------------------------------------
 // workspace = [ potrf_workspace_bytes(n) | split-K scratch of the chain stream | 2 panel staging buffers (world > 1) ]
 static size_t stage_bytes(int n, int block) { return ((size_t)n * block * sizeof(float) + 255) / 256 * 256; }
 size_t potrf_dist_workspace_bytes(int n, const DistEnv& d) {
-  return potrf_workspace_bytes(n) + tc_bytes_for(-1, n) + 256 + (d.world > 1 ? 2 * stage_bytes(n, d.block) : 0);
+  return core_bytes(n) + tc_bytes_for(-1, n) + 256 + (d.world > 1 ? 2 * stage_bytes(n, d.block) : 0);
 }
 
 static int make_flat(FlatPlan& f, void*& chain_tcws, int n, const DistEnv& d, void* ws, size_t ws_bytes) {
-  if (d.world < 1 || d.rank < 0 || d.rank >= d.world || d.block < NB || (d.block % NB) || (d.world > 1 && !d.comm)) return HB_ERR_ARG;
+  if (d.world < 1 || d.rank < 0 || d.rank >= d.world || d.block < NB || (d.block % NB) || d.batch < 1 || (d.world > 1 && !d.comm))
+    return HB_ERR_ARG;
   if (!ws || ws_bytes < potrf_dist_workspace_bytes(n, d)) return HB_ERR_WORKSPACE;
   f.n = n; f.W = d.block; f.P = (n + d.block - 1) / d.block; f.d = d;
   f.r = flat_res();
   if (!f.r) return HB_ERR_CUDA;
-  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + potrf_workspace_bytes(n) + 255) & ~uintptr_t(255));
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + core_bytes(n)) & ~uintptr_t(255));
   chain_tcws = p; p += tc_bytes_for(-1, n);
   f.stage[0] = reinterpret_cast<float*>(p);
   f.stage[1] = reinterpret_cast<float*>(p + stage_bytes(n, d.block));
@@ -1276,7 +1361,7 @@ int potrf_lower_dist(float* A, long long lda, int n, const DistEnv& d, void* ws,
   FlatPlan f; void* ctws = nullptr;
   HB_TRY(make_flat(f, ctws, n, d, ws, ws_bytes));
   Ctx c;
-  HB_TRY(make_ctx(c, n, ws, potrf_workspace_bytes(n), err_flag, st));
+  HB_TRY(make_ctx(c, n, ws, core_bytes(n), err_flag, st));
   attach_side(c);
   if (c.lh) {
     if (cudaMemsetAsync(c.lmax, 0, 16, st) != cudaSuccess) return HB_ERR_CUDA;
@@ -1293,7 +1378,7 @@ int potrf_lower_bwd_dist(const float* L, long long ldl, float* G, long long ldg,
   FlatPlan f; void* ctws = nullptr;
   HB_TRY(make_flat(f, ctws, n, d, ws, ws_bytes));
   Ctx c;
-  HB_TRY(make_ctx(c, n, ws, potrf_workspace_bytes(n), nullptr, st));
+  HB_TRY(make_ctx(c, n, ws, core_bytes(n), nullptr, st));
   attach_side(c);
   const int nblk = (n + NB - 1) / NB;
   if (c.gh) {

@@ -241,6 +241,8 @@ class GpElboBinding(object):
     def per_sample(self):
         return int(self.X.data.shape[0])
 
+    SHARED_MIN_N = 4096      # below this a factorisation is a handful of leaves: every rank keeps its own
+
     # notebook-sized models: the whole step, Adam included, is one persistent CTA (csrc/gp_small.cu)
     @property
     def fused_adam(self):
@@ -275,10 +277,17 @@ class GpElboBinding(object):
         cfg, key = self._cfg(opt, count, seed, offset)
         with_adam = world is not None
         f64 = with_adam and self._f64()
-        key = key + (with_adam, f64)
+        # More than one rank: the ranks share ONE column-block-cyclic factorisation and reverse mode (csrc/linalg.cu:
+        # potrf_flat / chol_rev_flat) instead of each factoring K itself; samples stay sharded (each rank its own Philox window).
+        nranks = parallel.world()[0]
+        shared = (not with_adam) and nranks > 1 and n >= self.SHARED_MIN_N and getattr(opt, '_shared_factorisation', True)
+        key = key + (with_adam, f64, shared)
         if self._key != key:
+            self._env = parallel.block_cyclic_env(2048, 1, shard_samples=True) if shared else None
             if with_adam:
                 self._wsb = int(self.lib.hb_gp_small_workspace_bytes(C.byref(cfg), 1 if f64 else 0))
+            elif shared:
+                self._wsb = int(self.lib.hb_gp_elbo_dist_workspace_bytes(C.byref(cfg), C.byref(self._env)))
             else:
                 self._wsb = int(self.lib.hb_gp_elbo_workspace_bytes(C.byref(cfg)))
             self._ws = torch.empty(self._wsb, dtype=torch.uint8, device=X.device)
@@ -288,6 +297,12 @@ class GpElboBinding(object):
         err = ops.err_flag(X.device)
         if not with_adam:
             e = self._eps(eps, count, n, X.device, torch.float32)
+            if shared:
+                check(self.lib.hb_gp_elbo_step_dist(C.byref(cfg), C.byref(self._env), ptr(X), ptr(Y), ptr(opt._flat), ptr(e),
+                                                    ptr(opt._flat_grad), ptr(self._out4), ptr(self._ws), self._wsb, ptr(err), stream()),
+                      "hb_gp_elbo_step_dist")
+                torch.distributed.all_reduce(err, op=torch.distributed.ReduceOp.MAX)    # a failing block flags its owner only
+                return self._out4[0]
             check(self.lib.hb_gp_elbo_step(C.byref(cfg), ptr(X), ptr(Y), ptr(opt._flat), ptr(e), ptr(opt._flat_grad), ptr(self._out4),
                                            ptr(self._ws), self._wsb, ptr(err), stream()), "hb_gp_elbo_step")
             return self._out4[0]

@@ -198,7 +198,7 @@ class Optimizer(object):
 
     # ---- compile: bind parameters to flat buffers, create Adam slots ----
     def compile(self, optimizer=None, collection=graph_key.VARIABLES, global_step=None, n_samples=1, seed=0,
-                verbose=True, shard=None, fused=True, device_index=True):
+                verbose=True, shard=None, fused=True, device_index=True, shared_factorisation=True):
         """``shard`` (multi-GPU, one process per GPU): 'samples' splits the n_samples draws over the ranks
         (contiguous windows of ONE Philox stream, so the union over ranks is the single-GPU draw), 'batch' keeps
         n_samples per rank and splits the minibatch (each rank draws its own indices and its own Philox window).
@@ -212,6 +212,7 @@ class Optimizer(object):
         self.global_step = global_step
         self._seed = int(seed)
         self._shard_mode = shard
+        self._shared_factorisation = bool(shared_factorisation)   # multi-GPU GP objective: one block-cyclic Cholesky for all ranks
         self._want_fused = bool(fused)
         self._fused = None
         self._device_index = bool(device_index)    # minibatch indices drawn on the device (False: numpy's global RNG, as upstream)

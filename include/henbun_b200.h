@@ -53,9 +53,13 @@ extern "C" {
  *                    of L and K-bar in their workspace and run their big products on csrc/gemm_h2.cu; 0: round-1 behaviour
  *   small_gp_kernel  1: hb_gp_elbo_step runs n <= 128 as ONE persistent CTA (csrc/gp_small.cu); default 0 (measured slower)
  *   tc_option        bit 2: no CTA pairs in the in-kernel-split engine, bit 3: three TF32 passes instead of TF32 + bf16 terms
- *   lookahead        1 (default): leaf kernels of potrf / potrf_bwd run on a high-priority side stream */
+ *   lookahead        1 (default): leaf kernels of potrf / potrf_bwd run on a high-priority side stream
+ *   schedule         order of the blocked factorisation and of its reverse mode.  0 (default): from n = 32768 on the
+ *                    right-looking two-stream schedule over n/8-column blocks (the narrow steps of a block on a high-priority
+ *                    stream next to the trailing updates of the previous one; see hb_potrf_lower_dist), below that the plain
+ *                    column recursion; 1: column recursion always; >= 128: right-looking with blocks of that many columns */
 typedef struct hb_options {
-  int gemm_engine, exact_below, panel_refinement, presplit_engine, small_gp_kernel, tc_option, lookahead;
+  int gemm_engine, exact_below, panel_refinement, presplit_engine, small_gp_kernel, tc_option, lookahead, schedule;
 } hb_options;
 void hb_options_init(hb_options* opt);
 
@@ -330,10 +334,23 @@ typedef struct hb_dist {
   void* comm;            /* from hb_comm_create; NULL when world == 1 */
   int rank, world;
   int block;             /* columns per block, multiple of 128; 0 = 2048 */
+  int shard_samples;     /* hb_gp_elbo_step_dist: 1 = every rank draws its OWN S samples (its own eps / Philox window) and the
+                            ranks share one factorisation: Z and the residuals are all-gathered (2 world S n floats) before
+                            L-bar is formed, K-bar and the lengthscale gradient come out as the rank-averaged ones on every
+                            rank, the remaining gradients are per-rank means to be averaged by the caller's all-reduce.
+                            0 = every rank evaluates the same samples (nothing to reduce afterwards) */
+  int batch;             /* blocks further than two from the current one take the finished panels `batch` at a time, as ONE
+                            product over all their columns (long-K products from narrow blocks); 0 = 1 */
 } hb_dist;
 int hb_comm_unique_id(void* out128_host);
 int hb_comm_create(const void* id128_host, int rank, int world, void** comm_out);
 int hb_comm_destroy(void* comm);
+/* Optional timeline of the schedule (instrumentation, like hb_profile_*): timing events at the stations of every block --
+ * tag 0 chain: factorisation of block p starts | 1 done | 2 panel p available on this rank (sent, or received + unpacked) |
+ * 3 chain: the update the next block still lacked is done | 4 main: updates with panel p may start | 5 main: done.
+ * hb_flat_trace_end synchronises the device, fills rows {tag, block, ms since the first station}, returns the row count. */
+int hb_flat_trace_begin(void);
+int hb_flat_trace_end(double* out3_host, int capacity);
 size_t hb_potrf_dist_workspace_bytes(int n, const hb_dist* d);
 int hb_potrf_lower_dist(float* A, long long lda, int n, const hb_dist* d, void* ws, size_t ws_bytes, int* err_flag, void* stream,
                         const hb_options* opt);
