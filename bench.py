@@ -395,7 +395,7 @@ def run_c3(d, a):
     # separate, untimed passes for the evidence: per-launch GEMM events (roofline) and per-phase events
     d.barrier()
     # the timed step overlaps the narrow steps of a block (chain stream) with the trailing updates (caller's stream);
-    # for per-launch durations the SAME launch sequence is issued on one stream (hb_options.lookahead = 0)
+    # for per-launch durations the same products are issued on one stream (hb_options.lookahead = 0)
     _lib.OPTIONS.lookahead = 0
     g.step()
     lib.hb_profile_begin(200000)
@@ -506,7 +506,7 @@ def run_c3(d, a):
                      "against the bf16 peak for this formulation (round 1: tf32 + 2 bf16 terms = 4 slots, 0.25)"),
             "how": "CUDA-event pair around every GEMM launch of one extra (untimed) step on the launching stream; achieved = useful "
                    "FLOP (trapezoid / block-mask shares counted, padding not) / summed launch time.  The timed steps run the block "
-                   "chain and the trailing updates on two concurrent streams; this pass issues the same launch sequence on ONE "
+                   "chain and the trailing updates on two concurrent streams; this pass issues the same products on ONE "
                    "stream (hb_options.lookahead = 0) so that a launch's duration is its own",
             "serialised_step_ms": ms_prof,
             "step_level": {"what": "useful level-3 FLOP of the step / ms_per_step of the TIMED (two-stream) steps",
