@@ -70,7 +70,19 @@ def block_cyclic_env(block: int = 2048, batch: int = 1, shard_samples: bool = Fa
         raw = bytes(t.cpu().tolist())
         buf = (C.c_ubyte * 128).from_buffer_copy(raw)
         out = C.c_void_p()
-        _lib.check(lib.hb_comm_create(C.cast(buf, C.c_void_p), r, w, C.byref(out)), "hb_comm_create")
+        # NCCL prints its version banner to stdout when a communicator is created: keep stdout clean for callers that print
+        # machine-readable lines there (bench.py) by pointing fd 1 at stderr for the duration of the call
+        import os
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            rc = lib.hb_comm_create(C.cast(buf, C.c_void_p), r, w, C.byref(out))
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        _lib.check(rc, "hb_comm_create")
         comm = out.value
         _block_comm["comm"] = comm
     return _lib.Dist(comm, r, w, int(block), 1 if shard_samples else 0, int(batch))
