@@ -114,8 +114,13 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
   const int t0 = pm0 >> 7;                            // first 128-row block of the pair tile
   if (hp.a_bmode == 1) kb_hi = min(kb_hi, H_CHS * (t0 + 2));          // k-blocks <= the pair tile's second row block
   else if (hp.a_bmode == 2) kb_lo = min(kb_hi, H_CHS * (t0 + 1));     // k-blocks > the pair tile's first row block
+  if (p.ksplit > 0) {                                 // split-K: blockIdx.y owns k-blocks [y * ksplit, (y + 1) * ksplit)
+    kb_lo = max(kb_lo, (int)blockIdx.y * p.ksplit);
+    kb_hi = min(kb_hi, ((int)blockIdx.y + 1) * p.ksplit);
+  }
   const int num_k = max(kb_hi - kb_lo, 0);
   const int num_c = (num_k + H_CHS - 1) / H_CHS;
+  float* const Cout = p.C + (long long)blockIdx.y * p.csplit;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < H_NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -244,7 +249,7 @@ gemm_h2_pair_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_const
     if (hp.a_inv) alpha *= __ldg(hp.a_inv);
     if (hp.b_inv) alpha *= __ldg(hp.b_inv);
     if (hp.a_minv) alpha *= __ldg(hp.a_minv + (m0 >> 7));
-    store_tile<BN>(acc, p, alpha, p.C, base, m0, n0, warp - 8, lane);
+    store_tile<BN>(acc, p, alpha, Cout, base, m0, n0, warp - 8, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -271,7 +276,7 @@ int make_map_h(CUtensorMap* map, const __half* ptr, long long rows, long long K,
 }
 
 template <int BN, bool AKM, bool BKM>
-int launch_h2(const CUtensorMap* m, H2Params hp, cudaStream_t st) {
+int launch_h2(const CUtensorMap* m, H2Params hp, cudaStream_t st, int nsplit = 1) {
   constexpr int SMEM = H2Geom<BN>::NSTAGE * H2Geom<BN>::STAGE + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
@@ -281,7 +286,7 @@ int launch_h2(const CUtensorMap* m, H2Params hp, cudaStream_t st) {
   }
   hp.t.tiles_m = cdiv(hp.t.M, 256);
   hp.t.tiles_n = cdiv(hp.t.N, BN);
-  gemm_h2_pair_kernel<BN, AKM, BKM><<<2 * hp.t.tiles_m * hp.t.tiles_n, NTHREADS, SMEM, st>>>(m[0], m[1], m[2], m[3], hp);
+  gemm_h2_pair_kernel<BN, AKM, BKM><<<dim3(2 * hp.t.tiles_m * hp.t.tiles_n, nsplit), NTHREADS, SMEM, st>>>(m[0], m[1], m[2], m[3], hp);
   HB_CHECK_LAUNCH();
   return HB_OK;
 }
@@ -421,6 +426,25 @@ inline int grid_rows(long long work, int threads) {
 
 }  // namespace
 
+// Split count for a product with `tiles` pair tiles and `kblocks` 64-wide k-blocks: the one with the best wave efficiency
+// (74 clusters per wave) among those that leave every split at least K = 1024.  0 = do not split.
+static int h2_split_count(long long tiles, int kblocks, size_t part_bytes, size_t ws_bytes) {
+  int best_ns = 0; double best = (double)tiles / (74.0 * (double)((tiles + 73) / 74));
+  for (int ns = 2; ns <= 32 && kblocks / ns >= 16; ++ns) {
+    if ((size_t)ns * part_bytes + 256 > ws_bytes) break;
+    const long long cl = tiles * ns;
+    const double eff = (double)cl / (74.0 * (double)((cl + 73) / 74));
+    if (eff > best + 0.05) { best = eff; best_ns = ns; }
+  }
+  return best_ns;
+}
+bool gemm_h2_splitk_eligible(int M, int N, int K, size_t ws_bytes) {
+  if (!(M > 128 && N > 128 && K >= 4096)) return false;
+  const long long tiles = (long long)cdiv(M, 256) * cdiv(N, 256);
+  if (tiles >= 32) return false;                      // the plain launch fills the GPU
+  return h2_split_count(tiles, cdiv(K, H_BK), (size_t)M * N * sizeof(float), ws_bytes) >= 2;
+}
+
 bool gemm_h2_eligible(int M, int N, int K) {
   // CTA-pair tiles of 256 x 256; worth it from 32 pair tiles on (fewer leave most of the 74 cluster slots empty) and
   // K >= 256 (prologue + epilogue of a tile cost about one K = 256 main loop)
@@ -451,8 +475,30 @@ int gemm_h2(const H2Gemm& g, cudaStream_t st) {
   hp.a_bmode = g.a_bmode; hp.a_inv = g.a_inv; hp.a_kinv = g.a_kinv; hp.a_dinv = g.a_dinv ? g.a_dinv : g.a_kinv;
   hp.a_minv = g.a_minv; hp.b_inv = g.b_inv;
   if (narrow) return g.a_kmajor ? launch_h2<64, true, true>(m, hp, st) : launch_h2<64, false, true>(m, hp, st);
-  if (g.a_kmajor) return g.b_kmajor ? launch_h2<256, true, true>(m, hp, st) : launch_h2<256, true, false>(m, hp, st);
-  return g.b_kmajor ? launch_h2<256, false, true>(m, hp, st) : launch_h2<256, false, false>(m, hp, st);
+  // long K, few output tiles (the tall reductions of the reverse mode inside a block): split along K into the caller's
+  // scratch, one deterministic reduction pass
+  int nsplit = 1;
+  float* part = nullptr;
+  const long long tiles = (long long)cdiv(g.M, 256) * cdiv(g.N, 256);
+  if (g.ws && !g.a_bmode && tiles < 32 && g.K >= 4096) {
+    const int kblocks = cdiv(g.K, H_BK);
+    const int ns = h2_split_count(tiles, kblocks, (size_t)g.M * g.N * sizeof(float), g.ws_bytes);
+    if (ns >= 2) {
+      int per = cdiv(kblocks, ns);
+      per = (per + H_CHS - 1) / H_CHS * H_CHS;          // whole K = 128 accumulation chunks (the per-chunk scales)
+      nsplit = cdiv(kblocks, per);
+      if (nsplit >= 2) {
+        part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(g.ws) + 255) & ~uintptr_t(255));
+        tp.C = part; tp.ldc = g.N; tp.beta = 0.f; tp.ksplit = per; tp.csplit = (long long)g.M * g.N;
+        tp.vecC = (g.N % 4 == 0);
+      } else nsplit = 1;
+    }
+  }
+  int rc;
+  if (g.a_kmajor) rc = g.b_kmajor ? launch_h2<256, true, true>(m, hp, st, nsplit) : launch_h2<256, true, false>(m, hp, st, nsplit);
+  else rc = g.b_kmajor ? launch_h2<256, false, true>(m, hp, st, nsplit) : launch_h2<256, false, false>(m, hp, st, nsplit);
+  if (rc != HB_OK || nsplit == 1) return rc;
+  return splitk_reduce(g.C, g.ldc, part, (long long)g.M * g.N, g.M, g.N, nsplit, g.beta, g.c_tri, st);
 }
 
 int h2_absmax(const float* A, long long ld, long long rows, int cols, int lower_only, long long diag_off, unsigned* out_bits,

@@ -21,8 +21,14 @@ struct H2Gemm {
   float alpha = 1.f, beta = 0.f;
   int c_tri = 0, a_bmode = 0;
   const float *a_inv = nullptr, *a_kinv = nullptr, *a_dinv = nullptr, *a_minv = nullptr, *b_inv = nullptr;
+  void* ws = nullptr;        // optional scratch: long-K products with few output tiles are split along K (partial tiles
+  size_t ws_bytes = 0;       // here, then one deterministic reduction pass)
 };
 bool gemm_h2_eligible(int M, int N, int K);
+// few 256 x 256 tiles but a long K: worth the pre-split engine when the caller can lend H2Gemm::ws (split-K)
+bool gemm_h2_splitk_eligible(int M, int N, int K, size_t ws_bytes);
+int splitk_reduce(float* C, long long ldc, const float* part, long long pstride, int M, int N, int nsplit, float beta, int c_tri,
+                  cudaStream_t st);
 int gemm_h2(const H2Gemm& g, cudaStream_t st);
 
 // atomicMax of |A| over a [rows x cols] block into *out_bits (bit pattern of a non-negative float; zero it first)

@@ -548,6 +548,18 @@ __global__ void splitk_reduce_kernel(float* C, long long ldc, const float* __res
   }
 }
 
+}  // namespace
+// deterministic reduction of split-K partial outputs (also used by the pre-split engine, gemm_h2.cu)
+int splitk_reduce(float* C, long long ldc, const float* part, long long pstride, int M, int N, int nsplit, float beta, int c_tri,
+                  cudaStream_t st) {
+  const long long tot = (long long)M * N;
+  int nb = (int)((tot + 255) / 256); if (nb > 148 * 8) nb = 148 * 8;
+  splitk_reduce_kernel<<<nb, 256, 0, st>>>(C, ldc, part, pstride, M, N, nsplit, beta, c_tri);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+namespace {
+
 // Tensor map of one operand.  K-major: stored [rows x K], box {16 k, box_rows} SWIZZLE_64B.
 //                              MN-major: stored [K x rows], box {32 rows, 16 k} SWIZZLE_128B_ATOM_32B.
 int make_map2(CUtensorMap* map, const float* ptr, long long rows, long long K, long long ld, bool kmajor, int box_rows) {

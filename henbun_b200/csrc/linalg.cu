@@ -817,8 +817,9 @@ int chol_rev_cols(const Ctx& c, const float* L, long long ldl, float* G, long lo
       a.C = G_R_left; a.ldc = ldg; a.M = nb; a.N = w1; a.K = w2; a.alpha = -2.f; a.beta = 1.f;
       HB_TRY(gemm_ws(c, a));
     }
-    if (h2 && gemm_h2_eligible(w2, w1, nb)) {
+    if (h2 && (gemm_h2_eligible(w2, w1, nb) || gemm_h2_splitk_eligible(w2, w1, nb, c.tcws_bytes))) {
       H2Gemm h;   // G[T, left] -= 2 G[R, right]^T L[R, left]: A MN-major (scales along M), B = L MN-major
+      h.ws = c.tcws; h.ws_bytes = c.tcws_bytes;             // small output, long K: split along K
       const long long oa = (long long)rb * c.ldh + r1, ob = (long long)rb * c.ldh + c0;
       h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 0; h.a_minv = c.ginv + r1 / NB;
       h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
@@ -923,8 +924,9 @@ static int rev_update(const Ctx& c, const float* L, long long ldl, float* G, lon
       a.C = G_R_left; a.ldc = ldg; a.M = nb; a.N = wj; a.K = w2; a.alpha = -2.f; a.beta = 1.f;
       HB_TRY(gemm_ws(c, a));
     }
-    if (h2 && gemm_h2_eligible(w2, wj, nb)) {
+    if (h2 && (gemm_h2_eligible(w2, wj, nb) || gemm_h2_splitk_eligible(w2, wj, nb, c.tcws_bytes))) {
       H2Gemm h;
+      h.ws = c.tcws; h.ws_bytes = c.tcws_bytes;
       const long long oa = (long long)rb * c.ldh + r1, ob = (long long)rb * c.ldh + cj;
       h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 0; h.a_minv = c.ginv + r1 / NB;
       h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
