@@ -636,6 +636,7 @@ static DistEnv to_env(const hb_dist* d) {
   e.comm = d->comm; e.rank = d->rank; e.world = d->world; e.block = d->block > 0 ? d->block : 2048;
   e.batch = d->batch > 0 ? d->batch : 1;
   e.shard_samples = d->shard_samples ? 1 : 0;
+  e.turn = d->turn > 0 ? d->turn : 1;
   return e;
 }
 

@@ -1028,7 +1028,8 @@ struct FlatPlan {
   DistEnv d;
   FlatRes* r;
   float* stage[2];
-  bool mine(int b) const { return b >= 0 && b < P && (b % d.world) == d.rank; }
+  int owner(int b) const { return (b / d.turn) % d.world; }          // `turn` consecutive blocks per rank, then the next rank
+  bool mine(int b) const { return b >= 0 && b < P && owner(b) == d.rank; }
   int c0(int b) const { return b * W; }
   int bw(int b) const { return min(W, n - b * W); }
 };
@@ -1045,12 +1046,12 @@ static int exchange_panel(const FlatPlan& f, const Ctx& cc, float* M, long long 
     if (cudaStreamWaitEvent(cc.st, f.r->stage_free[s], 0) != cudaSuccess) return HB_ERR_CUDA;   // the broadcast of p - 2 left this buffer
     HB_TRY(copy2d(stage, wp, panel, ldm, rows, wp, 1.f, cc.st));
     HB_TRY(bcast_wait(f.r->comm, f.r->packed, cc.st));
-    HB_TRY(comm_bcast_f32(f.d.comm, stage, count, p % f.d.world, f.r->comm));
+    HB_TRY(comm_bcast_f32(f.d.comm, stage, count, f.owner(p), f.r->comm));
     if (cudaEventRecord(f.r->stage_free[s], f.r->comm) != cudaSuccess) return HB_ERR_CUDA;
     return HB_OK;
   }
   if (cudaStreamWaitEvent(f.r->comm, f.r->stage_free[s], 0) != cudaSuccess) return HB_ERR_CUDA;   // panel p - 2 has been unpacked
-  HB_TRY(comm_bcast_f32(f.d.comm, stage, count, p % f.d.world, f.r->comm));
+  HB_TRY(comm_bcast_f32(f.d.comm, stage, count, f.owner(p), f.r->comm));
   HB_TRY(bcast_wait(cc.st, f.r->arrived, f.r->comm));
   HB_TRY(copy2d(panel, ldm, stage, wp, rows, wp, 1.f, cc.st));
   if (cudaEventRecord(f.r->stage_free[s], cc.st) != cudaSuccess) return HB_ERR_CUDA;
@@ -1343,7 +1344,7 @@ size_t potrf_dist_workspace_bytes(int n, const DistEnv& d) {
 }
 
 static int make_flat(FlatPlan& f, void*& chain_tcws, int n, const DistEnv& d, void* ws, size_t ws_bytes) {
-  if (d.world < 1 || d.rank < 0 || d.rank >= d.world || d.block < NB || (d.block % NB) || d.batch < 1 || (d.world > 1 && !d.comm))
+  if (d.world < 1 || d.rank < 0 || d.rank >= d.world || d.block < NB || (d.block % NB) || d.batch < 1 || d.turn < 1 || (d.world > 1 && !d.comm))
     return HB_ERR_ARG;
   if (!ws || ws_bytes < potrf_dist_workspace_bytes(n, d)) return HB_ERR_WORKSPACE;
   f.n = n; f.W = d.block; f.P = (n + d.block - 1) / d.block; f.d = d;

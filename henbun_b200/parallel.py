@@ -47,7 +47,7 @@ def allreduce_sum_(flat: torch.Tensor) -> torch.Tensor:
 _block_comm = {}
 
 
-def block_cyclic_env(block: int = 2048, batch: int = 1, shard_samples: bool = False):
+def block_cyclic_env(block: int = 2048, batch: int = 1, shard_samples: bool = False, turn: int = 1):
     """``_lib.Dist`` describing this rank's place in a column-block-cyclic Cholesky / reverse mode over all ranks of the
     default process group.  The library runs its own NCCL communicator (panel broadcasts on a dedicated stream): rank 0
     draws the unique id, torch.distributed carries the 128 bytes to the other ranks, every rank joins with its current
@@ -56,7 +56,7 @@ def block_cyclic_env(block: int = 2048, batch: int = 1, shard_samples: bool = Fa
     from . import _lib
     w, r = world()
     if w == 1:
-        return _lib.Dist(None, 0, 1, int(block), 0, int(batch))
+        return _lib.Dist(None, 0, 1, int(block), 0, int(batch), int(turn))
     comm = _block_comm.get("comm")
     if comm is None:
         lib = _lib.load()
@@ -85,4 +85,4 @@ def block_cyclic_env(block: int = 2048, batch: int = 1, shard_samples: bool = Fa
         _lib.check(rc, "hb_comm_create")
         comm = out.value
         _block_comm["comm"] = comm
-    return _lib.Dist(comm, r, w, int(block), 1 if shard_samples else 0, int(batch))
+    return _lib.Dist(comm, r, w, int(block), 1 if shard_samples else 0, int(batch), int(turn))

@@ -319,7 +319,7 @@ int hb_gp_elbo_step(const hb_gp_config* cfg, const float* X, const float* Y, con
 /* ---- the same step with the factorisation and its reverse mode on a right-looking schedule over column blocks, on one GPU
  * or SHARED BY A GROUP OF GPUs (strong scaling of BASELINE config 3; the reference has no multi-device path, SURVEY.md 8e:
  * tf.cholesky, gp/kernels.py:100-101, and its gradient run on one device).
- * Column blocks of `block` columns (a multiple of 128; 0 = 2048) are dealt round-robin: block b belongs to rank b % world.
+ * Column blocks of `block` columns (a multiple of 128; 0 = 2048) are dealt round-robin (`turn` at a time): block b belongs to rank (b / turn) % world.
  * Its owner factors it (all rows below; the column recursion restricted to the block) on a high-priority "chain" stream while
  * every rank applies the previous panels to the blocks it owns on the caller's stream; a finished panel travels to the other
  * ranks by ncclBroadcast on a third stream and is unpacked into each rank's own copy of the matrix, fp16 hi/lo shadows and
@@ -341,6 +341,9 @@ typedef struct hb_dist {
                             0 = every rank evaluates the same samples (nothing to reduce afterwards) */
   int batch;             /* blocks further than two from the current one take the finished panels `batch` at a time, as ONE
                             product over all their columns (long-K products from narrow blocks); 0 = 1 */
+  int turn;              /* consecutive blocks a rank owns before the next rank's turn: block b belongs to rank (b / turn) % world.
+                            Panels travel block by block, so with turn > 1 the broadcast of a block overlaps the factorisation
+                            of the owner's next one; 0 = 1 */
 } hb_dist;
 int hb_comm_unique_id(void* out128_host);
 int hb_comm_create(const void* id128_host, int rank, int world, void** comm_out);

@@ -42,7 +42,7 @@ def test_flat_schedule_vs_fp64(lib, n, block, batch):
     from henbun_b200 import _lib
     P, ST = _lib.ptr, _lib.stream
     A, G, Lref, Gref = _problem(n, n + block)
-    env = _lib.Dist(None, 0, 1, block, 0, batch)
+    env = _lib.Dist(None, 0, 1, block, 0, batch, 1)
     wsb = lib.hb_potrf_dist_workspace_bytes(n, C.byref(env))
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -96,16 +96,16 @@ def test_non_positive_pivot_is_flagged_by_the_flat_schedule(lib):
     P, ST = _lib.ptr, _lib.stream
     n = 1024
     A = -torch.eye(n, device="cuda")
-    env = _lib.Dist(None, 0, 1, 256, 0, 1)
+    env = _lib.Dist(None, 0, 1, 256, 0, 1, 1)
     wsb = lib.hb_potrf_dist_workspace_bytes(n, C.byref(env))
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     assert lib.hb_potrf_lower_dist(P(A), n, n, C.byref(env), P(ws), wsb, P(err), ST()) == 0
     torch.cuda.synchronize()
     assert err.item() == 1
-    bad = _lib.Dist(None, 0, 1, 200, 0, 1)                              # block must be a multiple of 128
+    bad = _lib.Dist(None, 0, 1, 200, 0, 1, 1)                              # block must be a multiple of 128
     assert lib.hb_potrf_lower_dist(P(A), n, n, C.byref(bad), P(ws), wsb, P(err), ST()) == _lib.HB_ERR_ARG
-    two = _lib.Dist(None, 0, 2, 256, 0, 1)                              # more than one rank needs a communicator
+    two = _lib.Dist(None, 0, 2, 256, 0, 1, 1)                              # more than one rank needs a communicator
     assert lib.hb_potrf_lower_dist(P(A), n, n, C.byref(two), P(ws), 1 << 40, P(err), ST()) == _lib.HB_ERR_ARG
 
 
@@ -130,8 +130,8 @@ K64 = torch.exp(-0.5 * torch.cdist(X, X) ** 2 / 0.25) + 1e-3 * torch.eye(n, devi
 Lbar = torch.tril(torch.randn(n, n, device="cuda", generator=g, dtype=torch.float64))
 Kr = K64.clone().requires_grad_(True); Lref = torch.linalg.cholesky(Kr); (Lref * Lbar).sum().backward()
 Gref = torch.tril(0.5 * (Kr.grad + Kr.grad.T)); Lref = Lref.detach()
-for block, batch in ((512, 1), (256, 3), (1024, 1)):
-    env = parallel.block_cyclic_env(block, batch)
+for block, batch, turn in ((512, 1, 1), (256, 3, 2), (1024, 1, 1), (128, 2, 3)):
+    env = parallel.block_cyclic_env(block, batch, turn=turn)
     A = K64.float().contiguous(); G = Lbar.float().contiguous()
     wsb = lib.hb_potrf_dist_workspace_bytes(n, C.byref(env)); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -147,7 +147,7 @@ for block, batch in ((512, 1), (256, 3), (1024, 1)):
             ref = T.clone(); dist.broadcast(ref, src=0)
             flag = torch.tensor([float(torch.equal(ref, T))], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             same = same and bool(flag.item())
-    out[f"chol_{block}x{batch}"] = [eL, eG, int(err.item()), same]
+    out[f"chol_{block}x{batch}x{turn}"] = [eL, eG, int(err.item()), same]
 del K64, Lbar, Kr, Lref, Gref, A, G, ws
 # (b) the API step: samples sharded, ONE factorisation shared by the ranks (n >= GpElboBinding.SHARED_MIN_N)
 rng = np.random.RandomState(0)

@@ -112,8 +112,8 @@ if world == 1:
     Ar, Gr = (A, G) if n <= 32768 else (None, None)
     del A, G
 for bb in blocks:
-    b, k = bb if len(bb) == 2 else (bb[0], 1)
-    env = parallel.block_cyclic_env(b, k)
+    b, k, tn = (tuple(bb) + (1, 1))[:3]                   # WxBATCHxTURN
+    env = parallel.block_cyclic_env(b, k, turn=tn)
     A, G, t, err = run(n, K0, G0, env, reps=2)
     msg = ""
     if world == 1 and Ar is not None:
@@ -121,6 +121,6 @@ for bb in blocks:
         dg = (torch.tril(G) - torch.tril(Gr)).norm() / torch.tril(Gr).norm()
         msg = f"  vs recursive: dL {dl:.2e} dG {dg:.2e}"
     if rank == 0:
-        print(f"n={n} flat W={b}x{k} world={world}: fwd {t[0]:.1f} ms  bwd {t[1]:.1f} ms  err={err}{msg}", flush=True)
+        print(f"n={n} flat W={b}x{k}x{tn} world={world}: fwd {t[0]:.1f} ms  bwd {t[1]:.1f} ms  err={err}{msg}", flush=True)
 if world > 1:
     dist.destroy_process_group()
