@@ -517,6 +517,10 @@ struct Ctx {
   float* lscale = nullptr;    // {s_L, 1 / s_L}
   unsigned* gmax = nullptr;   // [2 nblk]: panel maxima, then diagonal-block maxima
   float* ginv = nullptr;      // [2 nblk]: inverse scales of the K-bar panels, then of its diagonal blocks
+  // block-first reverse mode (rev_block): the rows of a column block BELOW its W-wide block are finished (and split) before
+  // the rows inside it, so the two parts carry separate maxima / scales; gmax / ginv then describe the in-block rows
+  unsigned* gpmax = nullptr;  // [nblk]
+  float* gpinv = nullptr;     // [nblk]
   int nblk = 0;
 };
 
@@ -766,7 +770,7 @@ int chol_rev_cols(const Ctx& c, const float* L, long long ldl, float* G, long lo
     if (below > 0) {
       float* Gp = GD + (long long)w * ldg;
       const float* Lp = LD + (long long)w * ldl;
-      HB_TRY(panel_solve(c, LD, ldl, c0, Gp, ldg, below, w, false, 0.5f, refine_on(n)));
+      HB_TRY(panel_solve(c, LD, ldl, c0, Gp, ldg, below, w, false, 0.5f, refine_on(c.n_total)));
       if (c.gh && !(w & 7)) {      // the panel of K-bar is final: scale by its own maximum, split into the shadow
         const int b = c0 / NB;
         HB_TRY(h2_absmax(Gp, ldg, below, w, 0, 0, c.gmax + b, c.st));
@@ -901,8 +905,9 @@ static int fwd_update(const Ctx& c, float* A, long long lda, int cj, int wj, int
 // left = [cj, cj+wj), cj + wj <= r1 (chol_rev_cols' inner node with a left part that need not be adjacent):
 //   G[R, left] -= 2 G[R, right] L[T, left];  G[T, left] -= 2 G[R, right]^T L[R, left];  G[T, left] -= 2 sym(G[T, right]) L[T, left]
 static int rev_update(const Ctx& c, const float* L, long long ldl, float* G, long long ldg, int cj, int wj, int r1, int w2,
-                      int n) {
+                      int n, bool panel_scales = false) {
   if (wj <= 0 || w2 <= 0) return HB_OK;
+  const float* rinv = panel_scales ? c.gpinv : c.ginv;     // scales of the rows BELOW the right-hand range
   const int rb = r1 + w2, nb = n - rb;
   float* G_T_left = G + (long long)r1 * ldg + cj;
   const float* L_T_left = L + (long long)r1 * ldl + cj;
@@ -914,7 +919,7 @@ static int rev_update(const Ctx& c, const float* L, long long ldl, float* G, lon
     if (h2 && gemm_h2_eligible(nb, wj, w2)) {
       H2Gemm h;
       const long long oa = (long long)rb * c.ldh + r1, ob = (long long)r1 * c.ldh + cj;
-      h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 1; h.a_kinv = c.ginv + r1 / NB;
+      h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 1; h.a_kinv = rinv + r1 / NB;
       h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
       h.C = G_R_left; h.ldc = ldg; h.M = nb; h.N = wj; h.K = w2; h.alpha = -2.f; h.beta = 1.f;
       HB_TRY(run_h2(c, h));
@@ -928,7 +933,7 @@ static int rev_update(const Ctx& c, const float* L, long long ldl, float* G, lon
       H2Gemm h;
       h.ws = c.tcws; h.ws_bytes = c.tcws_bytes;
       const long long oa = (long long)rb * c.ldh + r1, ob = (long long)rb * c.ldh + cj;
-      h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 0; h.a_minv = c.ginv + r1 / NB;
+      h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 0; h.a_minv = rinv + r1 / NB;
       h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
       h.C = G_T_left; h.ldc = ldg; h.M = w2; h.N = wj; h.K = nb; h.alpha = -2.f; h.beta = 1.f;
       HB_TRY(run_h2(c, h));
@@ -964,12 +969,20 @@ static int rev_update(const Ctx& c, const float* L, long long ldl, float* G, lon
 // rows below its diagonal block, and the diagonal block's own maximum and shadow.  Same data, same kernels: same bits.
 static int adopt_G_panel(const Ctx& c, const float* G, long long ldg, int c0, int w, int n) {
   if (!c.gh) return HB_OK;
+  const int rb = c0 + w;                                     // first row below the block (the owner ran rev_block)
   for (int s = c0; s < c0 + w; s += NB) {
-    const int ws = min(NB, c0 + w - s), below = n - (s + ws);
+    const int ws = min(NB, c0 + w - s);
     if (ws & 7) continue;
+    const int b = s / NB;
+    if (n > rb) {                                            // rows below the block: their own maximum / scale
+      const float* Gp = G + (long long)rb * ldg + s;
+      HB_TRY(h2_absmax(Gp, ldg, n - rb, ws, 0, 0, c.gpmax + b, c.st));
+      const long long o = (long long)rb * c.ldh + s;
+      HB_TRY(h2_split(Gp, ldg, n - rb, ws, nullptr, c.gpmax + b, c.gpinv + b, 0, 0, c.gh + o, c.gl + o, c.ldh, c.st));
+    }
+    const int below = rb - (s + ws);                         // rows inside the block
     if (below > 0) {
       const float* Gp = G + (long long)(s + ws) * ldg + s;
-      const int b = s / NB;
       HB_TRY(h2_absmax(Gp, ldg, below, ws, 0, 0, c.gmax + b, c.st));
       const long long o = (long long)(s + ws) * c.ldh + s;
       HB_TRY(h2_split(Gp, ldg, below, ws, nullptr, c.gmax + b, c.ginv + b, 0, 0, c.gh + o, c.gl + o, c.ldh, c.st));
@@ -977,6 +990,67 @@ static int adopt_G_panel(const Ctx& c, const float* G, long long ldg, int c0, in
     HB_TRY(split_G_diag(c, G, ldg, s, ws, c.st));
   }
   return HB_OK;
+}
+
+// Block-first reverse mode of one column block [c0, c0+W) with nb = n - (c0+W) rows below it.  chol_rev_cols walks the
+// block's 128-column leaves with ALL rows below in every step (a panel solve, an absmax, a split and a 128 x 128 x nb
+// reduction per leaf); here the rows below the block are finished first, as the reverse of  X = A_R L_DD^{-T}:
+//     Y = G_R L_DD^{-1} / 2          right-to-left blocked solve (rev_panel): leaf solves + products on the pre-split engine
+//     G_DD -= 2 tril(Y^T X)          ONE W x W x nb product
+// and only then the W x W diagonal block itself (chol_rev_cols with no rows below): its leaves touch <= W rows.
+static int rev_panel(const Ctx& c, const float* L, long long ldl, float* G, long long ldg, int s, int w, int rb, int n) {
+  const int nb = n - rb;
+  if (w <= NB) {
+    float* Gp = G + (long long)rb * ldg + s;
+    HB_TRY(panel_solve(c, L + (long long)s * ldl + s, ldl, s, Gp, ldg, nb, w, false, 0.5f, refine_on(c.n_total)));
+    if (c.gh && !(w & 7)) {
+      const int b = s / NB;
+      HB_TRY(h2_absmax(Gp, ldg, nb, w, 0, 0, c.gpmax + b, c.st));
+      const long long o = (long long)rb * c.ldh + s;
+      HB_TRY(h2_split(Gp, ldg, nb, w, nullptr, c.gpmax + b, c.gpinv + b, 0, 0, c.gh + o, c.gl + o, c.ldh, c.st));
+    }
+    return HB_OK;
+  }
+  const int w1 = split_point(w), w2 = w - w1, r1 = s + w1;
+  HB_TRY(rev_panel(c, L, ldl, G, ldg, r1, w2, rb, n));
+  // G[R, left] -= 2 Y[R, right] L[right rows, left]   (Y is final: half of the solved right part)
+  if (c.gh && c.lh && !(w2 % NB) && !(w1 & 7) && gemm_h2_eligible(nb, w1, w2)) {
+    H2Gemm h;
+    const long long oa = (long long)rb * c.ldh + r1, ob = (long long)r1 * c.ldh + s;
+    h.a_hi = c.gh + oa; h.a_lo = c.gl + oa; h.lda = c.ldh; h.a_kmajor = 1; h.a_kinv = c.gpinv + r1 / NB;
+    h.b_hi = c.lh + ob; h.b_lo = c.ll + ob; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
+    h.C = G + (long long)rb * ldg + s; h.ldc = ldg; h.M = nb; h.N = w1; h.K = w2; h.alpha = -2.f; h.beta = 1.f;
+    HB_TRY(run_h2(c, h));
+  } else {
+    GemmParams a;
+    a.A = G + (long long)rb * ldg + r1; a.lda = ldg; a.B = L + (long long)r1 * ldl + s; a.ldb = ldl; a.transB = 0;
+    a.C = G + (long long)rb * ldg + s; a.ldc = ldg; a.M = nb; a.N = w1; a.K = w2; a.alpha = -2.f; a.beta = 1.f;
+    HB_TRY(gemm_ws(c, a));
+  }
+  return rev_panel(c, L, ldl, G, ldg, s, w1, rb, n);
+}
+
+static int rev_block(const Ctx& c, const float* L, long long ldl, float* G, long long ldg, int c0, int W, int n) {
+  const int rb = c0 + W, nb = n - rb;
+  if (nb <= 0) return chol_rev_cols(c, L, ldl, G, ldg, c0, W, n);
+  HB_TRY(rev_panel(c, L, ldl, G, ldg, c0, W, rb, n));
+  float* GD = G + (long long)c0 * ldg + c0;
+  if (c.gh && c.lh && !(W % NB) &&
+      (gemm_h2_eligible(W, W, nb) || gemm_h2_splitk_eligible(W, W, nb, c.tcws_bytes))) {
+    H2Gemm h;                                          // A = Y MN-major (one scale per 128 columns = per row block of op(A))
+    const long long o = (long long)rb * c.ldh + c0;
+    h.a_hi = c.gh + o; h.a_lo = c.gl + o; h.lda = c.ldh; h.a_kmajor = 0; h.a_minv = c.gpinv + c0 / NB;
+    h.b_hi = c.lh + o; h.b_lo = c.ll + o; h.ldb = c.ldh; h.b_kmajor = 0; h.b_inv = c.lscale + 1;
+    h.C = GD; h.ldc = ldg; h.M = W; h.N = W; h.K = nb; h.alpha = -2.f; h.beta = 1.f; h.c_tri = 1;
+    h.ws = c.tcws; h.ws_bytes = c.tcws_bytes;
+    HB_TRY(run_h2(c, h));
+  } else {
+    GemmParams b;
+    b.A = G + (long long)rb * ldg + c0; b.lda = ldg; b.transA = 1; b.B = L + (long long)rb * ldl + c0; b.ldb = ldl; b.transB = 0;
+    b.C = GD; b.ldc = ldg; b.M = W; b.N = W; b.K = nb; b.alpha = -2.f; b.beta = 1.f; b.c_tri = 1; b.hint_split_waves = 1;
+    HB_TRY(gemm_ws(c, b));
+  }
+  return chol_rev_cols(c, L, ldl, G, ldg, c0, W, rb);   // the diagonal block: no rows below
 }
 
 // Streams and events of the flat schedule, created once per device (a resource cache like g_side).
@@ -1116,12 +1190,11 @@ static int chol_rev_flat(const Ctx& base, const FlatPlan& f, const float* L, lon
   Ctx bc = base;  bc.side = nullptr; bc.side_pending = false;
   HB_TRY(bcast_wait(cc.st, f.r->fork, base.st));
   if (f.d.world > 1 && cudaStreamWaitEvent(f.r->comm, f.r->fork, 0) != cudaSuccess) return HB_ERR_CUDA;
-  int pend = P - 1;                                        // last panel the far blocks have not received yet
   for (int p = P - 1; p >= 0; --p) {
     const int c0 = f.c0(p), wp = f.bw(p);
     if (f.mine(p)) {
       trace(0, p, cc.st);
-      HB_TRY(chol_rev_cols(cc, L, ldl, G, ldg, c0, wp, n));
+      HB_TRY(rev_block(cc, L, ldl, G, ldg, c0, wp, n));
       join_side(cc);
       trace(1, p, cc.st);
     }
@@ -1131,26 +1204,27 @@ static int chol_rev_flat(const Ctx& base, const FlatPlan& f, const float* L, lon
     if (cudaEventRecord(f.r->panel, cc.st) != cudaSuccess) return HB_ERR_CUDA;
     if (f.mine(p - 1)) {
       if (p + 1 < P && cudaStreamWaitEvent(cc.st, f.r->near_, 0) != cudaSuccess) return HB_ERR_CUDA;   // V(p+1, p-1) ran on main
-      HB_TRY(rev_update(cc, L, ldl, G, ldg, f.c0(p - 1), f.bw(p - 1), c0, wp, n));
+      HB_TRY(rev_update(cc, L, ldl, G, ldg, f.c0(p - 1), f.bw(p - 1), c0, wp, n, true));
       trace(3, p, cc.st);
     }
     if (p < 2) continue;
     if (cudaStreamWaitEvent(bc.st, f.r->panel, 0) != cudaSuccess) return HB_ERR_CUDA;
     trace(4, p, bc.st);
-    // far blocks (up to p-3) have every panel after `pend` applied; the pending ones [p, pend] act as one right-hand range
-    const int r1 = c0, w2 = f.c0(pend) + f.bw(pend) - c0;
+    // Every finished panel is applied on its own (hb_dist.batch concerns the forward pass only): the rows of a K-bar panel
+    // below its block and the rows inside it carry different scales (rev_block), which a right-hand range of several blocks
+    // would mix.
+    const int r1 = c0, w2 = wp;
     if (f.mine(p - 2)) {
-      HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(p - 2), f.bw(p - 2), r1, w2, n));
+      HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(p - 2), f.bw(p - 2), r1, w2, n, true));
       if (cudaEventRecord(f.r->near_, bc.st) != cudaSuccess) return HB_ERR_CUDA;
     }
-    if (p >= 3 && (pend - p + 1 >= f.d.batch || p == 3)) {
+    if (p >= 3) {
       if (f.d.world == 1) {
-        HB_TRY(rev_update(bc, L, ldl, G, ldg, 0, f.c0(p - 2), r1, w2, n));                       // all columns further left at once
+        HB_TRY(rev_update(bc, L, ldl, G, ldg, 0, f.c0(p - 2), r1, w2, n, true));                 // all columns further left at once
       } else {
         for (int j = p - 3; j >= 0; --j)
-          if (f.mine(j)) HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(j), f.bw(j), r1, w2, n));
+          if (f.mine(j)) HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(j), f.bw(j), r1, w2, n, true));
       }
-      pend = p - 1;
     }
     trace(5, p, bc.st);
   }
@@ -1172,7 +1246,7 @@ static size_t base_bytes(long long rows, int n) {
 }
 
 // fp16 hi/lo shadows of L and K-bar + their scales (orders >= H2_MIN_N only)
-static size_t h2_scale_bytes(int n) { return ((size_t)(16 + 4 * ((n + NB - 1) / NB)) * 4 + 255) / 256 * 256; }
+static size_t h2_scale_bytes(int n) { return ((size_t)(16 + 6 * ((n + NB - 1) / NB)) * 4 + 255) / 256 * 256; }
 static size_t h2_shadow_bytes(int n) { return ((size_t)n * h2_ld(n) * 2 + 255) / 256 * 256; }
 static size_t h2_bytes_for(int n) { return (n >= H2_MIN_N && n % 8 == 0) ? h2_scale_bytes(n) + 4 * h2_shadow_bytes(n) : 0; }
 
@@ -1188,7 +1262,7 @@ static int auto_block(int n) {
   if (s == 1 || n < FLAT_MIN_N) return 0;
   if (s >= NB) return s / NB * NB;
   if (n < 32768) return 0;
-  return max(2048, n / 8 / NB * NB);
+  return max(2048, n / 16 / NB * NB);      // measured at n = 65536: 4096-column blocks 738 ms (potrf + reverse), 8192: 755, 2048: 770
 }
 
 
@@ -1210,6 +1284,8 @@ static int make_ctx(Ctx& c, int n, void* ws, size_t ws_bytes, int* err, cudaStre
     c.lscale = reinterpret_cast<float*>(hb) + 4;
     c.gmax = reinterpret_cast<unsigned*>(hb) + 8;
     c.ginv = reinterpret_cast<float*>(hb) + 8 + 2 * nblk;
+    c.gpmax = reinterpret_cast<unsigned*>(hb) + 8 + 4 * nblk;
+    c.gpinv = reinterpret_cast<float*>(hb) + 8 + 5 * nblk;
     hb += h2_scale_bytes(n);
     const size_t sb = h2_shadow_bytes(n);
     c.lh = reinterpret_cast<__half*>(hb); c.ll = reinterpret_cast<__half*>(hb + sb);
@@ -1386,6 +1462,7 @@ int potrf_lower_bwd_dist(const float* L, long long ldl, float* G, long long ldg,
   const int nblk = (n + NB - 1) / NB;
   if (c.gh) {
     if (cudaMemsetAsync(c.gmax, 0, (size_t)2 * c.nblk * 4, st) != cudaSuccess) return HB_ERR_CUDA;
+    if (cudaMemsetAsync(c.gpmax, 0, (size_t)c.nblk * 4, st) != cudaSuccess) return HB_ERR_CUDA;
     if (!l_shadow_valid) {
       if (cudaMemsetAsync(c.lmax, 0, 16, st) != cudaSuccess) return HB_ERR_CUDA;
       HB_TRY(h2_absmax(L, ldl, n, n, 1, 0, c.lmax, st));

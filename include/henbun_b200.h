@@ -55,7 +55,7 @@ extern "C" {
  *   tc_option        bit 2: no CTA pairs in the in-kernel-split engine, bit 3: three TF32 passes instead of TF32 + bf16 terms
  *   lookahead        1 (default): leaf kernels of potrf / potrf_bwd run on a high-priority side stream
  *   schedule         order of the blocked factorisation and of its reverse mode.  0 (default): from n = 32768 on the
- *                    right-looking two-stream schedule over n/8-column blocks (the narrow steps of a block on a high-priority
+ *                    right-looking two-stream schedule over n/16-column blocks (the narrow steps of a block on a high-priority
  *                    stream next to the trailing updates of the previous one; see hb_potrf_lower_dist), below that the plain
  *                    column recursion; 1: column recursion always; >= 128: right-looking with blocks of that many columns */
 typedef struct hb_options {
