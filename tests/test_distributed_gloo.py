@@ -103,3 +103,50 @@ def test_linop_row_shards_sum_to_the_whole_operator():
     assert np.allclose(Zt.sum(0), g["q_mu"], rtol=1e-10)
     gL = np.tril(Zt.T @ U) + np.diag(1.0 / np.diag(p["q_sqrt"]))
     assert np.allclose(gL, g["q_sqrt"], rtol=1e-10, atol=1e-12)
+
+
+# ---- column-block-cyclic Cholesky + reverse mode: the algebra of the multi-rank path, on CPU -------------------------------
+def _bc_problem(n):
+    g = torch.Generator().manual_seed(n)
+    X = torch.randn(n, 3, dtype=torch.float64, generator=g)
+    K = torch.exp(-0.5 * torch.cdist(X, X) ** 2) + 1e-2 * torch.eye(n, dtype=torch.float64)
+    Lbar = torch.tril(torch.randn(n, n, dtype=torch.float64, generator=g))
+    return K, Lbar
+
+
+def _bc_worker(rank, world, port, out, n, block, turn):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.block_cyclic import potrf_block_cyclic, chol_rev_block_cyclic
+    K, Lbar = _bc_problem(n)
+    P = (n + block - 1) // block
+    mine = [b for b in range(P) if (b // turn) % world == rank]
+    # a rank starts from its OWN columns only: poison everything else, the broadcasts must fill it in
+    A = torch.full_like(K, float("nan")); G = torch.full_like(K, float("nan"))
+    for b in mine:
+        A[:, b * block:(b + 1) * block] = K[:, b * block:(b + 1) * block]
+        G[:, b * block:(b + 1) * block] = Lbar[:, b * block:(b + 1) * block]
+    L = torch.tril(potrf_block_cyclic(A, block, rank, world, turn))
+    Kbar = torch.tril(chol_rev_block_cyclic(L, G, block, rank, world, turn))
+    out[rank] = (L.numpy().copy(), Kbar.numpy().copy())
+    dist.destroy_process_group()
+
+
+def test_block_cyclic_cholesky_and_reverse_mode_world2():
+    """oracle/block_cyclic.py (the restatement of csrc/linalg.cu's potrf_flat / chol_rev_flat / rev_block) on two gloo ranks:
+    each starts from its own column blocks only and both end with the complete factor and the complete gradient, equal to
+    LAPACK's Cholesky and torch autograd's gradient of it, for plain and `turn`-wise ownership and a ragged last block."""
+    for n, block, turn in ((96, 16, 1), (100, 16, 2), (70, 32, 1)):
+        K, Lbar = _bc_problem(n)
+        Kr = K.clone().requires_grad_(True)
+        Lref = torch.linalg.cholesky(Kr)
+        (Lref * Lbar).sum().backward()
+        Gref = torch.tril(0.5 * (Kr.grad + Kr.grad.T)).numpy()
+        mgr = mp.Manager(); out = mgr.dict()
+        mp.spawn(_bc_worker, args=(2, _free_port(), out, n, block, turn), nprocs=2, join=True)
+        for r in (0, 1):
+            L, Kbar = out[r]
+            assert np.isfinite(L).all() and np.isfinite(Kbar).all()
+            assert np.allclose(L, Lref.detach().numpy(), rtol=1e-10, atol=1e-12), (n, block, turn, r)
+            assert np.allclose(Kbar, Gref, rtol=1e-8, atol=1e-10), (n, block, turn, r)
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])     # bit-identical on both ranks
