@@ -249,7 +249,7 @@ def ncu_traffic():
 class GpCabi:
     """Config 3 through the C ABI: hb_gp_elbo_step (+ all-reduce) + hb_adam_tf1 on caller-owned buffers."""
 
-    def __init__(self, d, n, D, S, seed_rank_offset=True, shared=None, block=2048, batch=1):
+    def __init__(self, d, n, D, S, seed_rank_offset=True, shared=None, block=None, batch=None):
         """shared (default: whenever there is more than one rank): the ranks share ONE column-block-cyclic factorisation
         and reverse mode (hb_gp_elbo_step_dist, shard_samples = 1); False: every rank factors K itself (round 1)."""
         import torch

@@ -969,20 +969,12 @@ static int rev_update(const Ctx& c, const float* L, long long ldl, float* G, lon
 // rows below its diagonal block, and the diagonal block's own maximum and shadow.  Same data, same kernels: same bits.
 static int adopt_G_panel(const Ctx& c, const float* G, long long ldg, int c0, int w, int n) {
   if (!c.gh) return HB_OK;
-  const int rb = c0 + w;                                     // first row below the block (the owner ran rev_block)
   for (int s = c0; s < c0 + w; s += NB) {
-    const int ws = min(NB, c0 + w - s);
+    const int ws = min(NB, c0 + w - s), below = n - (s + ws);
     if (ws & 7) continue;
-    const int b = s / NB;
-    if (n > rb) {                                            // rows below the block: their own maximum / scale
-      const float* Gp = G + (long long)rb * ldg + s;
-      HB_TRY(h2_absmax(Gp, ldg, n - rb, ws, 0, 0, c.gpmax + b, c.st));
-      const long long o = (long long)rb * c.ldh + s;
-      HB_TRY(h2_split(Gp, ldg, n - rb, ws, nullptr, c.gpmax + b, c.gpinv + b, 0, 0, c.gh + o, c.gl + o, c.ldh, c.st));
-    }
-    const int below = rb - (s + ws);                         // rows inside the block
     if (below > 0) {
       const float* Gp = G + (long long)(s + ws) * ldg + s;
+      const int b = s / NB;
       HB_TRY(h2_absmax(Gp, ldg, below, ws, 0, 0, c.gmax + b, c.st));
       const long long o = (long long)(s + ws) * c.ldh + s;
       HB_TRY(h2_split(Gp, ldg, below, ws, nullptr, c.gmax + b, c.ginv + b, 0, 0, c.gh + o, c.gl + o, c.ldh, c.st));
@@ -1190,11 +1182,17 @@ static int chol_rev_flat(const Ctx& base, const FlatPlan& f, const float* L, lon
   Ctx bc = base;  bc.side = nullptr; bc.side_pending = false;
   HB_TRY(bcast_wait(cc.st, f.r->fork, base.st));
   if (f.d.world > 1 && cudaStreamWaitEvent(f.r->comm, f.r->fork, 0) != cudaSuccess) return HB_ERR_CUDA;
+  // Block-first (rev_block) on one GPU, where the step is bound by GPU work and the single W x W x n product replaces 2 W / 128
+  // narrow reductions (-10 ms at N=65536).  Over several ranks the block chain is the critical path and rev_block's is the
+  // longer one (solve of all rows, then the big product, then the diagonal block: measured +20 ms at 8 GPUs), so the owner
+  // runs the column recursion on its block and the other ranks rebuild its single set of scales (adopt_G_panel).
+  const bool bf = f.d.world == 1;
   for (int p = P - 1; p >= 0; --p) {
     const int c0 = f.c0(p), wp = f.bw(p);
     if (f.mine(p)) {
       trace(0, p, cc.st);
-      HB_TRY(rev_block(cc, L, ldl, G, ldg, c0, wp, n));
+      if (bf) HB_TRY(rev_block(cc, L, ldl, G, ldg, c0, wp, n));
+      else HB_TRY(chol_rev_cols(cc, L, ldl, G, ldg, c0, wp, n));
       join_side(cc);
       trace(1, p, cc.st);
     }
@@ -1204,7 +1202,7 @@ static int chol_rev_flat(const Ctx& base, const FlatPlan& f, const float* L, lon
     if (cudaEventRecord(f.r->panel, cc.st) != cudaSuccess) return HB_ERR_CUDA;
     if (f.mine(p - 1)) {
       if (p + 1 < P && cudaStreamWaitEvent(cc.st, f.r->near_, 0) != cudaSuccess) return HB_ERR_CUDA;   // V(p+1, p-1) ran on main
-      HB_TRY(rev_update(cc, L, ldl, G, ldg, f.c0(p - 1), f.bw(p - 1), c0, wp, n, true));
+      HB_TRY(rev_update(cc, L, ldl, G, ldg, f.c0(p - 1), f.bw(p - 1), c0, wp, n, bf));
       trace(3, p, cc.st);
     }
     if (p < 2) continue;
@@ -1215,15 +1213,15 @@ static int chol_rev_flat(const Ctx& base, const FlatPlan& f, const float* L, lon
     // would mix.
     const int r1 = c0, w2 = wp;
     if (f.mine(p - 2)) {
-      HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(p - 2), f.bw(p - 2), r1, w2, n, true));
+      HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(p - 2), f.bw(p - 2), r1, w2, n, bf));
       if (cudaEventRecord(f.r->near_, bc.st) != cudaSuccess) return HB_ERR_CUDA;
     }
     if (p >= 3) {
       if (f.d.world == 1) {
-        HB_TRY(rev_update(bc, L, ldl, G, ldg, 0, f.c0(p - 2), r1, w2, n, true));                 // all columns further left at once
+        HB_TRY(rev_update(bc, L, ldl, G, ldg, 0, f.c0(p - 2), r1, w2, n, bf));                   // all columns further left at once
       } else {
         for (int j = p - 3; j >= 0; --j)
-          if (f.mine(j)) HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(j), f.bw(j), r1, w2, n, true));
+          if (f.mine(j)) HB_TRY(rev_update(bc, L, ldl, G, ldg, f.c0(j), f.bw(j), r1, w2, n, bf));
       }
     }
     trace(5, p, bc.st);

@@ -283,7 +283,7 @@ class GpElboBinding(object):
         shared = (not with_adam) and nranks > 1 and n >= self.SHARED_MIN_N and getattr(opt, '_shared_factorisation', True)
         key = key + (with_adam, f64, shared)
         if self._key != key:
-            self._env = parallel.block_cyclic_env(2048, 1, shard_samples=True) if shared else None
+            self._env = parallel.block_cyclic_env(shard_samples=True) if shared else None
             if with_adam:
                 self._wsb = int(self.lib.hb_gp_small_workspace_bytes(C.byref(cfg), 1 if f64 else 0))
             elif shared:

@@ -47,7 +47,14 @@ def allreduce_sum_(flat: torch.Tensor) -> torch.Tensor:
 _block_comm = {}
 
 
-def block_cyclic_env(block: int = 2048, batch: int = 1, shard_samples: bool = False, turn: int = 1):
+def default_block_cyclic(world_size: int):
+    """(block, batch, turn) measured best at N=65536 (tools/flat_probe.py, profiles/README.md): 2048-column blocks on 2 ranks
+    (each rank is busy ~95 % of the time; narrower blocks only add exchanges), 1024-column blocks dealt two at a time from 4
+    ranks on (the block chain is the critical path there: the broadcast of a block overlaps the owner's next one)."""
+    return (1024, 1, 2) if world_size >= 4 else (2048, 1, 1)
+
+
+def block_cyclic_env(block: int = None, batch: int = None, shard_samples: bool = False, turn: int = None):
     """``_lib.Dist`` describing this rank's place in a column-block-cyclic Cholesky / reverse mode over all ranks of the
     default process group.  The library runs its own NCCL communicator (panel broadcasts on a dedicated stream): rank 0
     draws the unique id, torch.distributed carries the 128 bytes to the other ranks, every rank joins with its current
@@ -55,6 +62,10 @@ def block_cyclic_env(block: int = 2048, batch: int = 1, shard_samples: bool = Fa
     import ctypes as C
     from . import _lib
     w, r = world()
+    dflt = default_block_cyclic(w)
+    block = dflt[0] if block is None else block
+    batch = dflt[1] if batch is None else batch
+    turn = dflt[2] if turn is None else turn
     if w == 1:
         return _lib.Dist(None, 0, 1, int(block), 0, int(batch), int(turn))
     comm = _block_comm.get("comm")
