@@ -210,3 +210,47 @@ def test_block_cyclic_factorisation_and_shared_step_on_two_gpus():
     for k in ("api_True", "api_False"):
         assert np.allclose(one[k], two[k], rtol=2e-4, atol=2e-6), k
     assert np.allclose(two["api_True"], two["api_False"], rtol=2e-4, atol=2e-6)
+
+
+def test_gp_step_on_the_right_looking_schedule_equals_the_recursive_step(lib):
+    """hb_gp_elbo_step_dist with world = 1 (the whole fused step over the right-looking schedule, any block width) against
+    hb_gp_elbo_step on the column recursion and against the fp64 oracle: ELBO and every gradient to 1e-5."""
+    from henbun_b200 import _lib
+    from henbun_b200.synthetic import make_gp_problem, pack_gp_params
+    from oracle import henbun_oracle as O
+    P, ST = _lib.ptr, _lib.stream
+    n, D, S = 4224, 8, 8
+    X, Y, p = make_gp_problem(n, D, S, seed=3, lengthscale=0.5)
+    U = np.random.RandomState(5).randn(S, n)
+    val, g = O.value_and_grads(O.gpr_elbo, {k: np.asarray(v, np.float64) for k, v in p.items()}, X.astype(np.float64),
+                               Y.astype(np.float64), U)
+    order = ("q_mu", "q_sqrt", "scale", "lengthscales", "k_var", "var")
+    ref = np.concatenate([np.asarray(g[k], np.float64).ravel() for k in order])
+    dev = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda()
+    Xd, Yd, Ud, params = dev(X), dev(Y), dev(U), dev(pack_gp_params(p))
+    cfg = _lib.GpConfig(n, D, S, 1, 0, 1e-5, 0, 0)
+    npar = lib.hb_gp_param_count(C.byref(cfg))
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    outs = {}
+    try:
+        lib.hb_set_schedule(1)                       # the reference run: column recursion
+        for name, env in (("recursion", None), ("flat512", _lib.Dist(None, 0, 1, 512, 0, 1, 1)), ("flat1024x2", _lib.Dist(None, 0, 1, 1024, 0, 2, 1))):
+            grads, out4 = torch.zeros(npar, device="cuda"), torch.zeros(4, device="cuda")
+            if env is None:
+                wsb = lib.hb_gp_elbo_workspace_bytes(C.byref(cfg)); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+                rc = lib.hb_gp_elbo_step(C.byref(cfg), P(Xd), P(Yd), P(params), P(Ud), P(grads), P(out4), P(ws), wsb, P(err), ST())
+            else:
+                wsb = lib.hb_gp_elbo_dist_workspace_bytes(C.byref(cfg), C.byref(env)); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+                rc = lib.hb_gp_elbo_step_dist(C.byref(cfg), C.byref(env), P(Xd), P(Yd), P(params), P(Ud), P(grads), P(out4), P(ws), wsb,
+                                              P(err), ST())
+            assert rc == 0
+            torch.cuda.synchronize()
+            assert err.item() == 0
+            outs[name] = (out4[0].item(), grads.cpu().numpy().astype(np.float64))
+            del ws
+    finally:
+        lib.hb_set_schedule(0)
+    for name, (elbo, gr) in outs.items():
+        assert abs(elbo - float(val)) <= 1e-5 * abs(float(val)), name
+        assert np.linalg.norm(gr - ref) <= 1e-5 * np.linalg.norm(ref), (name, np.linalg.norm(gr - ref) / np.linalg.norm(ref))
+    assert not np.array_equal(outs["recursion"][1], outs["flat512"][1])
