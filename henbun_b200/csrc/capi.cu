@@ -795,8 +795,18 @@ static int gp_elbo_step_impl(const hb_gp_config* cfg, const DistEnv* dist, const
       HB_TRY(comm_allgather_f32(dist->comm, Z, ZA, (size_t)Sn * n, st));
       HB_TRY(comm_allgather_f32(dist->comm, R, RA, (size_t)Sn * n, st));
       g.A = RA; g.B = ZA; g.K = Sn * dist->world; g.alpha = 1.f / (float)dist->world;
+      // ... and only for the column blocks it owns: the others arrive as finished K-bar panels before anything reads them
+      const int W = dist->block, nblocks = (n + W - 1) / W;
+      for (int b = 0; b < nblocks; ++b) {
+        if ((b / dist->turn) % dist->world != dist->rank) continue;
+        const int c0 = b * W, w = min(W, n - c0);
+        GemmParams q = g;
+        q.A = RA + c0; q.B = ZA + c0; q.C = G + (long long)c0 * n + c0; q.M = n - c0; q.N = w;
+        HB_TRY(gemm(q, st));
+      }
+    } else {
+      HB_TRY(gemm(g, st));
     }
-    HB_TRY(gemm(g, st));
   }
   phase_mark(st);
   if (dist) HB_TRY(potrf_lower_bwd_dist(K, n, G, n, n, *dist, pws, L.potrf_bytes, st, /*l_shadow_valid=*/1));

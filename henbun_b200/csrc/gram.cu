@@ -118,6 +118,18 @@ __global__ void __launch_bounds__(256) rbf_gram_bwd_kernel(const float* __restri
     const float* Xb = X + (long long)bz * sX;
     const float* Yb = X2 + (long long)bz * sX2;
     const float* Gb = G + (long long)bz * sG;
+    // this thread's four 16-byte pieces of G go in flight BEFORE the tile's X rows are staged: with 119 registers two CTAs
+    // share an SM, and a load issued right before its use left the 16 resident warps waiting on HBM most of the time
+    const bool vec = (DMAX <= 8) && (j0 + tx * 4 + 3 < n2 && (ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(Gb) & 15) == 0);
+    float4 gpre[4];
+    if (DMAX <= 8) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = i0 + ty + 16 * a;
+        const bool need = vec && i < n && !(sym_lower && j0 + tx * 4 > i);
+        gpre[a] = need ? __ldg(reinterpret_cast<const float4*>(Gb + (long long)i * ldg + j0 + tx * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     __syncthreads();
     for (int e = threadIdx.x; e < TILE * D; e += 256) {
       const int r = e / D, d = e % D;
@@ -141,10 +153,7 @@ __global__ void __launch_bounds__(256) rbf_gram_bwd_kernel(const float* __restri
       for (int a = 0; a < 4; ++a) {
         const int i = i0 + ty + 16 * a;
         if (i >= n) continue;
-        const float4 g4 = (j0 + tx * 4 + 3 < n2 && (ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(Gb) & 15) == 0)
-                              ? __ldg(reinterpret_cast<const float4*>(Gb + (long long)i * ldg + j0 + tx * 4))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool vec = (j0 + tx * 4 + 3 < n2 && (ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(Gb) & 15) == 0);
+        const float4 g4 = gpre[a];
         const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
