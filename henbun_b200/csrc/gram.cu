@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256) rbf_gram_fwd_kernel(const float* __restri
 }
 
 // Persistent over tiles; per-thread double accumulators per feature; one partial row per CTA.
-template <int DMAX>
+// ISO: one shared lengthscale (n_ell == 1) -- the gradient needs only sum_ij g K r^2, one FMA per element instead of D
+template <int DMAX, bool ISO = false>
 __global__ void __launch_bounds__(256) rbf_gram_bwd_kernel(const float* __restrict__ G, long long ldg, long long sG,
                                                            const float* __restrict__ X, const float* __restrict__ X2,
                                                            int n, int n2, int D, long long sX, long long sX2,
@@ -169,15 +170,21 @@ __global__ void __launch_bounds__(256) rbf_gram_bwd_kernel(const float* __restri
           for (int d = 0; d < DMAX; ++d) { df[d] = xr[a][d] - yr[b][d]; r2 = fmaf(df[d], df[d], r2); }
           const float g = w * (vec ? gv[b] : __ldg(Gb + (long long)i * ldg + j));
           const float gk = g * expf(-0.5f * r2);
+          if (ISO) facc[0] = fmaf(gk, r2, facc[0]);
+          else {
 #pragma unroll
-          for (int d = 0; d < DMAX; ++d) facc[d] = fmaf(gk * df[d], df[d], facc[d]);
+            for (int d = 0; d < DMAX; ++d) facc[d] = fmaf(gk * df[d], df[d], facc[d]);
+          }
           if (csym) {
             float sf[DMAX];
 #pragma unroll
             for (int d = 0; d < DMAX; ++d) { sf[d] = xr[a][d] + yr[b][d]; r2b = fmaf(sf[d], sf[d], r2b); }
             const float gkb = g * expf(-0.5f * r2b);
+            if (ISO) facc[0] = fmaf(gkb, r2b, facc[0]);
+            else {
 #pragma unroll
-            for (int d = 0; d < DMAX; ++d) facc[d] = fmaf(gkb * sf[d], sf[d], facc[d]);
+              for (int d = 0; d < DMAX; ++d) facc[d] = fmaf(gkb * sf[d], sf[d], facc[d]);
+            }
           }
         }
       }
@@ -221,8 +228,11 @@ __global__ void __launch_bounds__(256) rbf_gram_bwd_kernel(const float* __restri
       }
     }
     }
+    if (ISO) dacc[0] += (double)facc[0];
+    else {
 #pragma unroll
-    for (int d = 0; d < DMAX; ++d) dacc[d] += (double)facc[d];
+      for (int d = 0; d < DMAX; ++d) dacc[d] += (double)facc[d];
+    }
   }
   // block reduce, 8 features at a time
   for (int d0 = 0; d0 < DMAX; d0 += 8) {
@@ -354,7 +364,9 @@ int rbf_gram_bwd(const float* G, long long ldg, long long sG, const float* X, co
   if (nb == kReduceBlocks) nb = 148 * 6;
   double* partials = reinterpret_cast<double*>(ws);
   const int dmax = D <= 8 ? 8 : 32;
-  if (dmax == 8)
+  if (dmax == 8 && n_ell == 1)
+    rbf_gram_bwd_kernel<8, true><<<nb, 256, 0, st>>>(G, ldg, sG, X, Y, n, n2, D, sX, sY, ell, n_ell, batch, sym_lower, csym, partials);
+  else if (dmax == 8)
     rbf_gram_bwd_kernel<8><<<nb, 256, 0, st>>>(G, ldg, sG, X, Y, n, n2, D, sX, sY, ell, n_ell, batch, sym_lower, csym, partials);
   else
     rbf_gram_bwd_kernel<32><<<nb, 256, 0, st>>>(G, ldg, sG, X, Y, n, n2, D, sX, sY, ell, n_ell, batch, sym_lower, csym, partials);
