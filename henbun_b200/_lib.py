@@ -44,7 +44,7 @@ class GpConfig(C.Structure):
 
 class Dist(C.Structure):
     """hb_dist: this rank's place in a column-block-cyclic factorisation (comm from hb_comm_create; NULL when world == 1)."""
-    _fields_ = [("comm", C.c_void_p), ("rank", _i), ("world", _i), ("block", _i), ("shard_samples", _i), ("batch", _i), ("turn", _i)]
+    _fields_ = [("comm", C.c_void_p), ("rank", _i), ("world", _i), ("block", _i), ("shard_samples", _i), ("batch", _i), ("block_bwd", _i), ("turn", _i)]
 
 
 class AdamConfig(C.Structure):

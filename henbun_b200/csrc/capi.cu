@@ -191,7 +191,12 @@ GpLayout gp_layout(const hb_gp_config& c, const DistEnv* d = nullptr) {
   L.off_U = o; o += align_up(c.q_fullrank ? sn : 0);
   L.off_sc = o; o += align_up((size_t)(16 + c.n_ell) * sizeof(float));
   L.off_red = o; o += align_up(kReduceWsBytes);
-  L.potrf_bytes = d ? potrf_dist_workspace_bytes(c.n, *d) : potrf_workspace_bytes(c.n);
+  L.potrf_bytes = potrf_workspace_bytes(c.n);
+  if (d) {
+    DistEnv wide = *d;
+    wide.block = max(d->block, d->block_bwd);
+    L.potrf_bytes = potrf_dist_workspace_bytes(c.n, wide);
+  }
   L.off_potrf = o; o += align_up(L.potrf_bytes);
   const size_t gathered = (d && d->world > 1 && d->shard_samples) ? sn * d->world : 0;     // Z and R of every rank
   L.off_ZA = o; o += align_up(gathered);
@@ -637,6 +642,7 @@ static DistEnv to_env(const hb_dist* d) {
   e.batch = d->batch > 0 ? d->batch : 1;
   e.shard_samples = d->shard_samples ? 1 : 0;
   e.turn = d->turn > 0 ? d->turn : 1;
+  e.block_bwd = d->block_bwd > 0 ? d->block_bwd : 0;
   return e;
 }
 
@@ -796,7 +802,7 @@ static int gp_elbo_step_impl(const hb_gp_config* cfg, const DistEnv* dist, const
       HB_TRY(comm_allgather_f32(dist->comm, R, RA, (size_t)Sn * n, st));
       g.A = RA; g.B = ZA; g.K = Sn * dist->world; g.alpha = 1.f / (float)dist->world;
       // ... and only for the column blocks it owns: the others arrive as finished K-bar panels before anything reads them
-      const int W = dist->block, nblocks = (n + W - 1) / W;
+      const int W = dist->block_bwd > 0 ? dist->block_bwd : dist->block, nblocks = (n + W - 1) / W;   // the reverse mode's blocks
       for (int b = 0; b < nblocks; ++b) {
         if ((b / dist->turn) % dist->world != dist->rank) continue;
         const int c0 = b * W, w = min(W, n - c0);
@@ -809,7 +815,11 @@ static int gp_elbo_step_impl(const hb_gp_config* cfg, const DistEnv* dist, const
     }
   }
   phase_mark(st);
-  if (dist) HB_TRY(potrf_lower_bwd_dist(K, n, G, n, n, *dist, pws, L.potrf_bytes, st, /*l_shadow_valid=*/1));
+  if (dist) {
+    DistEnv rev = *dist;
+    if (dist->block_bwd > 0) rev.block = dist->block_bwd;
+    HB_TRY(potrf_lower_bwd_dist(K, n, G, n, n, rev, pws, L.potrf_bytes, st, /*l_shadow_valid=*/1));
+  }
   else HB_TRY(potrf_lower_bwd(K, n, 0, G, n, 0, n, 1, pws, L.potrf_bytes, st, /*l_shadow_valid=*/1));
   phase_mark(st);
   HB_TRY(rbf_gram_bwd(G, n, 0, X, nullptr, n, n, c.D, 0, 0, d_ell, c.n_ell, 1, 1, 0, d_a, g_ell, red, kReduceWsBytes, st));

@@ -18,6 +18,7 @@ struct DistEnv {
   int rank = 0, world = 1;
   int block = 2048;
   int shard_samples = 0;   // the GP step: every rank draws its own S samples; Z and R are all-gathered before L-bar is formed
+  int block_bwd = 0;   // the GP step: block width of the reverse mode (0 = block)
   int turn = 1;        // consecutive blocks per rank before the next rank's turn (exchange granularity = block, ownership = turn blocks)
   int batch = 1;       // far blocks take the finished panels `batch` at a time, as one product over all their columns
 };

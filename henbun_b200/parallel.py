@@ -48,13 +48,15 @@ _block_comm = {}
 
 
 def default_block_cyclic(world_size: int):
-    """(block, batch, turn) measured best at N=65536 (tools/flat_probe.py, profiles/README.md): 2048-column blocks on 2 ranks
-    (each rank is busy ~95 % of the time; narrower blocks only add exchanges), 1024-column blocks dealt two at a time from 4
-    ranks on (the block chain is the critical path there: the broadcast of a block overlaps the owner's next one)."""
-    return (1024, 1, 2) if world_size >= 4 else (2048, 1, 1)
+    """(block, batch, turn, block_bwd) measured best at N=65536 (tools/flat_probe.py, profiles/README.md): 2048-column blocks on 2
+    ranks (each rank is busy ~95 % of the time; narrower blocks only add exchanges).  From 4 ranks on the block chain is the
+    critical path: blocks are dealt two at a time (the broadcast of a block overlaps the owner's next one), 1024 columns wide
+    in the forward pass and 2048 in the reverse mode (potrf + reverse at 4 GPUs: 2048x1 151 + 253 ms, 1024x2 134 + 268,
+    2048x2 140 + 241)."""
+    return (1024, 1, 2, 2048) if world_size >= 4 else (2048, 1, 1, 0)
 
 
-def block_cyclic_env(block: int = None, batch: int = None, shard_samples: bool = False, turn: int = None):
+def block_cyclic_env(block: int = None, batch: int = None, shard_samples: bool = False, turn: int = None, block_bwd: int = None):
     """``_lib.Dist`` describing this rank's place in a column-block-cyclic Cholesky / reverse mode over all ranks of the
     default process group.  The library runs its own NCCL communicator (panel broadcasts on a dedicated stream): rank 0
     draws the unique id, torch.distributed carries the 128 bytes to the other ranks, every rank joins with its current
@@ -63,11 +65,13 @@ def block_cyclic_env(block: int = None, batch: int = None, shard_samples: bool =
     from . import _lib
     w, r = world()
     dflt = default_block_cyclic(w)
+    if block_bwd is None:                         # an explicit block width applies to both passes unless told otherwise
+        block_bwd = dflt[3] if block is None else 0
     block = dflt[0] if block is None else block
     batch = dflt[1] if batch is None else batch
     turn = dflt[2] if turn is None else turn
     if w == 1:
-        return _lib.Dist(None, 0, 1, int(block), 0, int(batch), int(turn))
+        return _lib.Dist(None, 0, 1, int(block), 0, int(batch), int(block_bwd), int(turn))
     comm = _block_comm.get("comm")
     if comm is None:
         lib = _lib.load()
@@ -96,4 +100,4 @@ def block_cyclic_env(block: int = None, batch: int = None, shard_samples: bool =
         _lib.check(rc, "hb_comm_create")
         comm = out.value
         _block_comm["comm"] = comm
-    return _lib.Dist(comm, r, w, int(block), 1 if shard_samples else 0, int(batch), int(turn))
+    return _lib.Dist(comm, r, w, int(block), 1 if shard_samples else 0, int(batch), int(block_bwd), int(turn))

@@ -341,6 +341,9 @@ typedef struct hb_dist {
                             0 = every rank evaluates the same samples (nothing to reduce afterwards) */
   int batch;             /* blocks further than two from the current one take the finished panels `batch` at a time, as ONE
                             product over all their columns (long-K products from narrow blocks); 0 = 1 */
+  int block_bwd;         /* hb_gp_elbo_step_dist: block width of the reverse mode when it should differ from the forward pass
+                            (every rank holds the complete factor in between, so the two distributions are independent; measured:
+                            the forward chain prefers 1024-column blocks, the reverse 2048); 0 = block */
   int turn;              /* consecutive blocks a rank owns before the next rank's turn: block b belongs to rank (b / turn) % world.
                             Panels travel block by block, so with turn > 1 the broadcast of a block overlaps the factorisation
                             of the owner's next one; 0 = 1 */

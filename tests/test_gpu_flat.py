@@ -42,7 +42,7 @@ def test_flat_schedule_vs_fp64(lib, n, block, batch):
     from henbun_b200 import _lib
     P, ST = _lib.ptr, _lib.stream
     A, G, Lref, Gref = _problem(n, n + block)
-    env = _lib.Dist(None, 0, 1, block, 0, batch, 1)
+    env = _lib.Dist(None, 0, 1, block, 0, batch, 0, 1)
     wsb = lib.hb_potrf_dist_workspace_bytes(n, C.byref(env))
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -96,16 +96,16 @@ def test_non_positive_pivot_is_flagged_by_the_flat_schedule(lib):
     P, ST = _lib.ptr, _lib.stream
     n = 1024
     A = -torch.eye(n, device="cuda")
-    env = _lib.Dist(None, 0, 1, 256, 0, 1, 1)
+    env = _lib.Dist(None, 0, 1, 256, 0, 1, 0, 1)
     wsb = lib.hb_potrf_dist_workspace_bytes(n, C.byref(env))
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     assert lib.hb_potrf_lower_dist(P(A), n, n, C.byref(env), P(ws), wsb, P(err), ST()) == 0
     torch.cuda.synchronize()
     assert err.item() == 1
-    bad = _lib.Dist(None, 0, 1, 200, 0, 1, 1)                              # block must be a multiple of 128
+    bad = _lib.Dist(None, 0, 1, 200, 0, 1, 0, 1)                              # block must be a multiple of 128
     assert lib.hb_potrf_lower_dist(P(A), n, n, C.byref(bad), P(ws), wsb, P(err), ST()) == _lib.HB_ERR_ARG
-    two = _lib.Dist(None, 0, 2, 256, 0, 1, 1)                              # more than one rank needs a communicator
+    two = _lib.Dist(None, 0, 2, 256, 0, 1, 0, 1)                              # more than one rank needs a communicator
     assert lib.hb_potrf_lower_dist(P(A), n, n, C.byref(two), P(ws), 1 << 40, P(err), ST()) == _lib.HB_ERR_ARG
 
 
@@ -234,7 +234,7 @@ def test_gp_step_on_the_right_looking_schedule_equals_the_recursive_step(lib):
     outs = {}
     try:
         lib.hb_set_schedule(1)                       # the reference run: column recursion
-        for name, env in (("recursion", None), ("flat512", _lib.Dist(None, 0, 1, 512, 0, 1, 1)), ("flat1024x2", _lib.Dist(None, 0, 1, 1024, 0, 2, 1))):
+        for name, env in (("recursion", None), ("flat512", _lib.Dist(None, 0, 1, 512, 0, 1, 0, 1)), ("flat1024x2_bwd256", _lib.Dist(None, 0, 1, 1024, 0, 2, 256, 1))):
             grads, out4 = torch.zeros(npar, device="cuda"), torch.zeros(4, device="cuda")
             if env is None:
                 wsb = lib.hb_gp_elbo_workspace_bytes(C.byref(cfg)); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")

@@ -94,7 +94,7 @@ if check_n > 0:
     Kbar = Kd.grad
     Kbar = torch.tril(Kbar + Kbar.T) - torch.diag(torch.diag(Kbar))       # lower triangle of the symmetric gradient, off-diagonals doubled
     ref_sym = torch.tril(0.5 * (Kd.grad + Kd.grad.T))                      # full-symmetric convention (what the library leaves)
-    for env in [None] + [parallel.block_cyclic_env(b, k) for b, k in ((256, 1), (512, 3), (256, 4), (1024, 2))]:
+    for env in [None] + [parallel.block_cyclic_env(b, k, turn=1, block_bwd=0) for b, k in ((256, 1), (512, 3), (256, 4), (1024, 2))]:
         A, G, t, err = run(check_n, K0, G0, env)
         eL = (torch.tril(A).double() - Ld.detach()).norm() / Ld.detach().norm()
         eG = (torch.tril(G).double() - ref_sym).norm() / ref_sym.norm()
@@ -113,7 +113,7 @@ if world == 1:
     del A, G
 for bb in blocks:
     b, k, tn = (tuple(bb) + (1, 1))[:3]                   # WxBATCHxTURN
-    env = parallel.block_cyclic_env(b, k, turn=tn)
+    env = parallel.block_cyclic_env(b, k, turn=tn, block_bwd=0)
     A, G, t, err = run(n, K0, G0, env, reps=2)
     msg = ""
     if world == 1 and Ar is not None:
