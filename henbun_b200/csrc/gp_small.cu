@@ -11,6 +11,7 @@
 // instantiation is the float_type = float64 path of the reference (henbunrc:7) for the 1-D notebook inputs, whose Gram
 // matrices (cond 1e6) put an fp32 factorisation 3 orders of magnitude away from the 1e-5 parity bar.
 #include "kernels.cuh"
+#include "leaf_smem.cuh"
 
 namespace hb {
 
@@ -318,6 +319,240 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_small_step_kernel(const Smal
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// fp32: the same step on the BLOCKED shared-memory building blocks of the 128 x 128 leaf kernels (leaf_smem.cuh) instead of
+// one-column-at-a-time loops -- 16-wide panels for the factorisation (3 barriers per panel instead of 2 per column) and the
+// closed form  K-bar = sym(L^-T Phi(L^T L-bar) L^-1)  for its reverse mode (a blocked triangular inverse + three masked 128^3
+// products, all level 3) in place of the level-2 reverse sweep.  Three 128 x 129 buffers (198 KB): B0 = K, then L;
+// B1 = staged q_sqrt, then L^-1; B2 = scratch, L-bar, K-bar.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GS_THREADS, 1) gp_leaf_step_kernel(const SmallArgs<float> a) {
+  using namespace leaf;
+  extern __shared__ __align__(16) unsigned char gs_smem[];
+  const int n = a.n, S = a.S, D = a.D, tid = threadIdx.x;
+  float* B0 = reinterpret_cast<float*>(gs_smem);
+  float* B1 = B0 + NB * LDS;
+  float* B2 = B1 + NB * LDS;
+  float* ell = B2 + NB * LDS;                            // [n_ell <= 32]
+  __shared__ double red[GS_THREADS / 32];
+
+  const size_t nq = a.q_fullrank ? (size_t)n * n : (size_t)n;
+  float* p_mu = a.params; float* p_sq = a.params + n; float* p_scale = p_sq + nq; float* p_ell = p_scale + 1;
+  float* p_kvar = p_ell + a.n_ell; float* p_var = p_kvar + 1;
+  float* g_mu = a.grads; float* g_sq = a.grads + n; float* g_scale = g_sq + nq; float* g_ell = g_scale + 1;
+  float* g_kvar = g_ell + a.n_ell; float* g_var = g_kvar + 1;
+  float* Z = a.ws; float* U = Z + (size_t)S * n; float* R = U + (size_t)S * n; float* Zb = R + (size_t)S * n;
+
+  const float s_q = t_softplus<float>(*p_scale) + 1e-6f;
+  const float kv = t_softplus<float>(*p_kvar) + 1e-6f;
+  const float var = t_softplus<float>(*p_var) + 1e-6f;
+  const float amp = sqrtf(kv) * s_q;
+  for (int d = tid; d < a.n_ell; d += GS_THREADS) ell[d] = t_softplus<float>(p_ell[d]) + 1e-6f;
+  __syncthreads();
+
+  // ---- K = rbf(X) + jitter I, lower triangle, identity padded to 128 x 128 ----
+  for (int e = tid; e < NB * NB; e += GS_THREADS) {
+    const int i = e >> 7, j = e & (NB - 1);
+    float val = (i == j) ? 1.f : 0.f;
+    if (i < n && j <= i) {
+      float r2 = 0.f;
+      for (int d = 0; d < D; ++d) {
+        const float df = (a.X[i * D + d] - a.X[j * D + d]) / ell[a.n_ell == 1 ? 0 : d];
+        r2 = fmaf(df, df, r2);
+      }
+      val = expf(-0.5f * r2) + (i == j ? a.jitter : 0.f);
+    } else if (i < n) {
+      val = 0.f;
+    }
+    B0[i * LDS + j] = val;
+  }
+  potrf_smem(B0, n, a.err_flag, 0);                      // blocked, in place; flags 1 + row of a non-positive pivot
+
+  // ---- sampler + one-sample KL ----
+  double kl_part = 0.0;
+  for (int e = tid; e < S * n; e += GS_THREADS)
+    U[e] = a.eps ? a.eps[e] : philox_normal_at(a.seed, a.offset, (unsigned long long)e);
+  if (a.q_fullrank)
+    for (int e = tid; e < n * n; e += GS_THREADS) B1[(e / n) * LDS + (e % n)] = p_sq[e];
+  __syncthreads();
+  for (int e = tid; e < S * n; e += GS_THREADS) {
+    const int s = e / n, i = e % n;
+    float z, logdet;
+    if (!a.q_fullrank) {
+      z = p_mu[i] + expf(p_sq[i]) * U[e];
+      logdet = 2.f * p_sq[i];
+    } else {
+      float acc = p_mu[i];
+      const float* lq = B1 + i * LDS;
+      const float* ur = U + (size_t)s * n;
+      for (int k = 0; k <= i; ++k) acc = fmaf(lq[k], ur[k], acc);
+      z = acc;
+      logdet = logf(lq[i] * lq[i]);
+    }
+    Z[e] = z;
+    const float u = U[e];
+    kl_part += (double)(logdet + u * u - z * z);
+  }
+  const double kl = -0.5 * block_sum_all(kl_part, red);
+  __syncthreads();
+
+  // ---- F = amp * Z L^T, log-likelihood, residual ----
+  double ll_part = 0.0, e2_part = 0.0, ef_part = 0.0;
+  const float inv_S = 1.f / (float)S;
+  for (int e = tid; e < S * n; e += GS_THREADS) {
+    const int s = e / n, i = e % n;
+    float acc = 0.f;
+    const float* zr = Z + (size_t)s * n;
+    for (int k = 0; k <= i; ++k) acc = fmaf(B0[i * LDS + k], zr[k], acc);
+    const float F = amp * acc;
+    const float E = a.Y[i] - F;
+    ll_part += (double)(-0.9189385332046727f - 0.5f * logf(var) - 0.5f * E * E / var);
+    e2_part += (double)(E * E);
+    ef_part += (double)(E * acc);
+    R[e] = E / var * inv_S;
+  }
+  const double ll = block_sum_all(ll_part, red);
+  const double sumE2 = block_sum_all(e2_part, red);
+  const double sumEFraw = block_sum_all(ef_part, red);
+  __syncthreads();
+
+  // ---- z-bar = amp * R L - Z / S ----
+  for (int e = tid; e < S * n; e += GS_THREADS) {
+    const int s = e / n, k = e % n;
+    float acc = 0.f;
+    const float* rr = R + (size_t)s * n;
+    for (int i = k; i < n; ++i) acc = fmaf(rr[i], B0[i * LDS + k], acc);
+    Zb[e] = amp * acc - Z[e] * inv_S;
+  }
+  __syncthreads();
+
+  // ---- sampler backward ----
+  for (int k = tid; k < n; k += GS_THREADS) {
+    float gm = 0.f, go = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float zt = Zb[s * n + k];
+      gm += zt;
+      if (!a.q_fullrank) go = fmaf(zt, U[s * n + k], go);
+    }
+    g_mu[k] = gm;
+    if (!a.q_fullrank) g_sq[k] = go * expf(p_sq[k]) + 1.f;
+  }
+  if (a.q_fullrank) {
+    for (int e = tid; e < n * n; e += GS_THREADS) {
+      const int i = e / n, k = e % n;
+      float acc = 0.f;
+      if (k <= i) {
+        for (int s = 0; s < S; ++s) acc = fmaf(Zb[s * n + i], U[s * n + k], acc);
+        if (k == i) acc += 1.f / B1[i * LDS + i];
+      }
+      g_sq[(size_t)i * n + k] = acc;
+    }
+  }
+  __syncthreads();
+
+  // ---- reverse-mode Cholesky, closed form on the blocked building blocks ----
+  trinv_smem(B0, B1, B2);                                // B1 = L^-1 (identity padded), B2 scratch
+  for (int e = tid; e < NB * NB; e += GS_THREADS) {      // B2 = L-bar = amp * tril(R^T Z), zero padded
+    const int i = e >> 7, k = e & (NB - 1);
+    float acc = 0.f;
+    if (i < n && k <= i) {
+      for (int s = 0; s < S; ++s) acc = fmaf(R[s * n + i], Z[s * n + k], acc);
+      acc *= amp;
+    }
+    B2[i * LDS + k] = acc;
+  }
+  __syncthreads();
+  mm_smem<true, false, 1>(B2, B0, B2);                   // P = L^T L-bar
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += GS_THREADS) {      // Phi: lower triangle, halved diagonal
+    const int i = e >> 7, j = e & (NB - 1);
+    float v = B2[i * LDS + j];
+    if (j > i) v = 0.f;
+    else if (j == i) v *= 0.5f;
+    B2[i * LDS + j] = v;
+  }
+  __syncthreads();
+  mm_smem<false, false, 2>(B0, B2, B1);                  // M1 = P L^-1        (L is dead: B0 receives M1)
+  __syncthreads();
+  mm_smem<true, false, 1>(B2, B1, B0);                   // S = L^-T M1;  dELBO/dK (symmetric) = (S + S^T) / 2
+  __syncthreads();
+
+  // ---- Gram backward: the stored lower entry (i, j) stands for both (i, j) and (j, i): weight S_ij + S_ji ----
+  {
+    double acc_e[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int d0 = 0; d0 < a.n_ell; d0 += 4) {
+      for (int q = 0; q < 4; ++q) acc_e[q] = 0.0;
+      for (int e = tid; e < n * n; e += GS_THREADS) {
+        const int i = e / n, j = e % n;
+        if (j >= i) continue;
+        float r2 = 0.f;
+        for (int d = 0; d < D; ++d) {
+          const float df = (a.X[i * D + d] - a.X[j * D + d]) / ell[a.n_ell == 1 ? 0 : d];
+          r2 = fmaf(df, df, r2);
+        }
+        const float gk = (B2[i * LDS + j] + B2[j * LDS + i]) * expf(-0.5f * r2);
+        if (a.n_ell == 1) {
+          acc_e[0] += (double)(gk * r2 / ell[0]);
+        } else {
+          for (int q = 0; q < 4 && d0 + q < a.n_ell; ++q) {
+            const float df = (a.X[i * D + d0 + q] - a.X[j * D + d0 + q]) / ell[d0 + q];
+            acc_e[q] += (double)(gk * df * df / ell[d0 + q]);
+          }
+        }
+      }
+      for (int q = 0; q < 4 && d0 + q < a.n_ell; ++q) {
+        const double t = block_sum_all(acc_e[q], red);
+        if (tid == 0) g_ell[d0 + q] = (float)t * t_sigmoid<float>(p_ell[d0 + q]);
+      }
+    }
+  }
+
+  if (tid == 0) {
+    const double v = (double)var, sq = (double)s_q, kvd = (double)kv;
+    const double invS = 1.0 / (double)S;
+    const double ga = invS * sumEFraw / v;
+    const double gv = invS * (-0.5 * (double)S * n / v + 0.5 * sumE2 / (v * v));
+    *g_scale = (float)(ga * sqrt(kvd) * (double)t_sigmoid<float>(*p_scale));
+    *g_kvar = (float)(ga * sq / (2.0 * sqrt(kvd)) * (double)t_sigmoid<float>(*p_kvar));
+    *g_var = (float)(gv * (double)t_sigmoid<float>(*p_var));
+    a.out4[0] = (float)((ll - kl) * invS); a.out4[1] = (float)ll; a.out4[2] = (float)kl; a.out4[3] = 0.f;
+  }
+
+  if (a.m) {                                             // optional TF-1 Adam on -ELBO (model.py:206,220)
+    __threadfence_block();
+    __syncthreads();
+    const int t = a.step_dev ? *a.step_dev : a.step_host;
+    const double lr_t = a.lr * sqrt(1.0 - pow(a.b2, (double)t)) / (1.0 - pow(a.b1, (double)t));
+    const size_t npar = (size_t)n + nq + 3 + a.n_ell;
+    for (size_t i = tid; i < npar; i += GS_THREADS) {
+      if (a.q_fullrank && i >= (size_t)n && i < (size_t)n + nq) {
+        const size_t q = i - n;
+        if (q % n > q / n) continue;
+      }
+      const float g = (float)a.grad_scale * a.grads[i];
+      const float mm = (float)a.b1 * a.m[i] + (float)(1.0 - a.b1) * g;
+      const float vv = (float)a.b2 * a.v[i] + (float)(1.0 - a.b2) * g * g;
+      a.m[i] = mm; a.v[i] = vv;
+      a.params[i] -= (float)lr_t * mm / (sqrtf(vv) + (float)a.eps_adam);
+    }
+  }
+}
+
+static int launch_leaf_step(const SmallArgs<float>& a, cudaStream_t st) {
+  if (a.n <= 0 || a.n > leaf::NB || a.D <= 0 || a.D > 32 || a.S <= 0 || (a.n_ell != 1 && a.n_ell != a.D)) return HB_ERR_ARG;
+  if (!a.X || !a.Y || !a.params || !a.grads || !a.out4 || !a.ws) return HB_ERR_ARG;
+  if (!a.eps && (a.offset & 3ull)) return HB_ERR_ARG;
+  const size_t smem = (size_t)(3 * leaf::NB * leaf::LDS + 32) * sizeof(float) + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gp_leaf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return HB_ERR_CUDA;
+    attr_set = true;
+  }
+  gp_leaf_step_kernel<<<1, GS_THREADS, smem, st>>>(a);
+  HB_CHECK_LAUNCH();
+  return HB_OK;
+}
+
 template <typename T>
 size_t small_smem_bytes(int n) {
   const size_t LD = (size_t)(n | 1);
@@ -354,7 +589,7 @@ int gp_small_step_f32(int n, int D, int S, int n_ell, int q_fullrank, float jitt
                       double eps_adam, double grad_scale, cudaStream_t st) {
   SmallArgs<float> a{n, D, S, n_ell, q_fullrank, jitter, seed, offset, X, Y, params, eps, grads, out4, ws, err_flag,
                      m, v, step_dev, step_host, lr, b1, b2, eps_adam, grad_scale};
-  return launch_small<float>(a, st);
+  return launch_leaf_step(a, st);      // blocked building blocks; the column-at-a-time template stays the fp64 route
 }
 
 int gp_small_step_f64(int n, int D, int S, int n_ell, int q_fullrank, double jitter, unsigned long long seed, unsigned long long offset,
