@@ -34,7 +34,7 @@ class Options(C.Structure):
 
 # The process-wide DEFAULT the Python layer passes when a caller gives no options of its own.  The C library itself keeps
 # no configuration; `lib.hb_set_*` below are Python-side conveniences that edit this object (tests, A/B runs).
-OPTIONS = Options(0, 2048, 2, 1, 0, 0, 1, 0)
+OPTIONS = Options(0, 2048, 2, 1, 1, 0, 1, 0)
 
 
 class GpConfig(C.Structure):

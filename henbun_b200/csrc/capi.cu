@@ -14,7 +14,7 @@ namespace hb {
 // The library keeps no mutable configuration.  Every extern "C" entry point that reaches the level-3 engine installs the
 // caller's hb_options for its own duration on the calling thread (OptScope) and the kernels' host code reads them through
 // the opt_*() accessors; outside any call, and for NULL, the defaults of hb_options_init apply.
-static const hb_options kDefaultOptions = {0, 2048, 2, 1, 0, 0, 1, 0};
+static const hb_options kDefaultOptions = {0, 2048, 2, 1, 1, 0, 1, 0};
 static thread_local const hb_options* tl_options = nullptr;
 static inline const hb_options& cur_opt() { return tl_options ? *tl_options : kDefaultOptions; }
 int opt_gemm_engine() { const int e = cur_opt().gemm_engine; return (e < 0 || e > 3) ? 0 : e; }

@@ -48,6 +48,7 @@ struct SmallArgs {
   int* err_flag;
   // optional fused Adam (m == nullptr: gradients only)
   T* m; T* v; const int* step_dev; int step_host; double lr, b1, b2, eps_adam, grad_scale;
+  int vec_smem = 0;      // gp_leaf_step_kernel: Z | U | R | Zbar in shared memory (set by the launcher)
 };
 
 // block-wide sum of one double per thread; result broadcast to every thread
@@ -341,13 +342,23 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_leaf_step_kernel(const Small
   float* p_kvar = p_ell + a.n_ell; float* p_var = p_kvar + 1;
   float* g_mu = a.grads; float* g_sq = a.grads + n; float* g_scale = g_sq + nq; float* g_ell = g_scale + 1;
   float* g_kvar = g_ell + a.n_ell; float* g_var = g_kvar + 1;
-  float* Z = a.ws; float* U = Z + (size_t)S * n; float* R = U + (size_t)S * n; float* Zb = R + (size_t)S * n;
+  // the S x n sample vectors live in shared memory when they fit (the notebook sizes do), else in the caller's workspace
+  float* vec = (a.vec_smem) ? (ell + 32) : a.ws;
+  float* Z = vec; float* U = Z + (size_t)S * n; float* R = U + (size_t)S * n; float* Zb = R + (size_t)S * n;
+  float* Xs = B1;                                        // X / ell, [n][D]: B1 is free until q_sqrt is staged
+  // instrumentation: cycles at the phase boundaries go to the 16 spare floats behind the caller's 4 S n workspace elements
+  float* stamps = a.ws + (size_t)4 * S * n;
+  const long long t_begin = clock64();
+  int stamp_i = 0;
+  auto stamp = [&]() { if (tid == 0 && stamp_i < 16) stamps[stamp_i] = (float)(clock64() - t_begin); ++stamp_i; };
 
   const float s_q = t_softplus<float>(*p_scale) + 1e-6f;
   const float kv = t_softplus<float>(*p_kvar) + 1e-6f;
   const float var = t_softplus<float>(*p_var) + 1e-6f;
   const float amp = sqrtf(kv) * s_q;
   for (int d = tid; d < a.n_ell; d += GS_THREADS) ell[d] = t_softplus<float>(p_ell[d]) + 1e-6f;
+  __syncthreads();
+  for (int e = tid; e < n * D; e += GS_THREADS) Xs[e] = a.X[e] / ell[a.n_ell == 1 ? 0 : e % D];
   __syncthreads();
 
   // ---- K = rbf(X) + jitter I, lower triangle, identity padded to 128 x 128 ----
@@ -357,7 +368,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_leaf_step_kernel(const Small
     if (i < n && j <= i) {
       float r2 = 0.f;
       for (int d = 0; d < D; ++d) {
-        const float df = (a.X[i * D + d] - a.X[j * D + d]) / ell[a.n_ell == 1 ? 0 : d];
+        const float df = Xs[i * D + d] - Xs[j * D + d];
         r2 = fmaf(df, df, r2);
       }
       val = expf(-0.5f * r2) + (i == j ? a.jitter : 0.f);
@@ -366,7 +377,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_leaf_step_kernel(const Small
     }
     B0[i * LDS + j] = val;
   }
+  stamp();   // 0: hyper-parameters + Gram
   potrf_smem(B0, n, a.err_flag, 0);                      // blocked, in place; flags 1 + row of a non-positive pivot
+  stamp();   // 1: potrf
 
   // ---- sampler + one-sample KL ----
   double kl_part = 0.0;
@@ -450,8 +463,10 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_leaf_step_kernel(const Small
   }
   __syncthreads();
 
+  stamp();   // 2: sampler, projection, log-likelihood, z-bar, sampler backward
   // ---- reverse-mode Cholesky, closed form on the blocked building blocks ----
   trinv_smem(B0, B1, B2);                                // B1 = L^-1 (identity padded), B2 scratch
+  stamp();   // 3: triangular inverse
   for (int e = tid; e < NB * NB; e += GS_THREADS) {      // B2 = L-bar = amp * tril(R^T Z), zero padded
     const int i = e >> 7, k = e & (NB - 1);
     float acc = 0.f;
@@ -462,6 +477,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_leaf_step_kernel(const Small
     B2[i * LDS + k] = acc;
   }
   __syncthreads();
+  stamp();   // 4: L-bar
   mm_smem<true, false, 1>(B2, B0, B2);                   // P = L^T L-bar
   __syncthreads();
   for (int e = tid; e < NB * NB; e += GS_THREADS) {      // Phi: lower triangle, halved diagonal
@@ -477,29 +493,35 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_leaf_step_kernel(const Small
   mm_smem<true, false, 1>(B2, B1, B0);                   // S = L^-T M1;  dELBO/dK (symmetric) = (S + S^T) / 2
   __syncthreads();
 
+  stamp();   // 5: three masked 128^3 products
   // ---- Gram backward: the stored lower entry (i, j) stands for both (i, j) and (j, i): weight S_ij + S_ji ----
   {
+    float* Xr = B0;                                      // X / ell again (M1 is dead)
+    for (int e = tid; e < n * D; e += GS_THREADS) Xr[e] = a.X[e] / ell[a.n_ell == 1 ? 0 : e % D];
+    __syncthreads();
     double acc_e[4] = {0.0, 0.0, 0.0, 0.0};
     for (int d0 = 0; d0 < a.n_ell; d0 += 4) {
       for (int q = 0; q < 4; ++q) acc_e[q] = 0.0;
+      float part[4] = {0.f, 0.f, 0.f, 0.f};              // a thread sums ~20 entries in fp32, the block reduction runs in fp64
       for (int e = tid; e < n * n; e += GS_THREADS) {
         const int i = e / n, j = e % n;
         if (j >= i) continue;
         float r2 = 0.f;
         for (int d = 0; d < D; ++d) {
-          const float df = (a.X[i * D + d] - a.X[j * D + d]) / ell[a.n_ell == 1 ? 0 : d];
+          const float df = Xr[i * D + d] - Xr[j * D + d];
           r2 = fmaf(df, df, r2);
         }
         const float gk = (B2[i * LDS + j] + B2[j * LDS + i]) * expf(-0.5f * r2);
         if (a.n_ell == 1) {
-          acc_e[0] += (double)(gk * r2 / ell[0]);
+          part[0] = fmaf(gk, r2, part[0]);
         } else {
           for (int q = 0; q < 4 && d0 + q < a.n_ell; ++q) {
-            const float df = (a.X[i * D + d0 + q] - a.X[j * D + d0 + q]) / ell[d0 + q];
-            acc_e[q] += (double)(gk * df * df / ell[d0 + q]);
+            const float df = Xr[i * D + d0 + q] - Xr[j * D + d0 + q];
+            part[q] = fmaf(gk * df, df, part[q]);
           }
         }
       }
+      for (int q = 0; q < 4; ++q) acc_e[q] = (double)part[q] / (double)ell[a.n_ell == 1 ? 0 : min(d0 + q, a.n_ell - 1)];
       for (int q = 0; q < 4 && d0 + q < a.n_ell; ++q) {
         const double t = block_sum_all(acc_e[q], red);
         if (tid == 0) g_ell[d0 + q] = (float)t * t_sigmoid<float>(p_ell[d0 + q]);
@@ -518,6 +540,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_leaf_step_kernel(const Small
     a.out4[0] = (float)((ll - kl) * invS); a.out4[1] = (float)ll; a.out4[2] = (float)kl; a.out4[3] = 0.f;
   }
 
+  stamp();   // 6: Gram backward + scalar gradients
   if (a.m) {                                             // optional TF-1 Adam on -ELBO (model.py:206,220)
     __threadfence_block();
     __syncthreads();
@@ -538,14 +561,18 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gp_leaf_step_kernel(const Small
   }
 }
 
-static int launch_leaf_step(const SmallArgs<float>& a, cudaStream_t st) {
+static int launch_leaf_step(SmallArgs<float> a, cudaStream_t st) {
   if (a.n <= 0 || a.n > leaf::NB || a.D <= 0 || a.D > 32 || a.S <= 0 || (a.n_ell != 1 && a.n_ell != a.D)) return HB_ERR_ARG;
   if (!a.X || !a.Y || !a.params || !a.grads || !a.out4 || !a.ws) return HB_ERR_ARG;
   if (!a.eps && (a.offset & 3ull)) return HB_ERR_ARG;
-  const size_t smem = (size_t)(3 * leaf::NB * leaf::LDS + 32) * sizeof(float) + 64;
+  const size_t base = (size_t)(3 * leaf::NB * leaf::LDS + 32) * sizeof(float) + 64;
+  const size_t vecs = (size_t)4 * a.S * a.n * sizeof(float);
+  constexpr size_t kBudget = 216 * 1024;                 // + 8.3 KB of static shared memory (panel staging, reductions) <= 227 KB
+  a.vec_smem = (base + vecs <= kBudget) ? 1 : 0;
+  const size_t smem = base + (a.vec_smem ? vecs : 0);
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gp_leaf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return HB_ERR_CUDA;
+    if (cudaFuncSetAttribute(gp_leaf_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBudget) != cudaSuccess) return HB_ERR_CUDA;
     attr_set = true;
   }
   gp_leaf_step_kernel<<<1, GS_THREADS, smem, st>>>(a);

@@ -51,7 +51,8 @@ extern "C" {
  *                    short-K products per panel), 2 (default) refined for n <= 8192, 3 substitution kernel (no inverse)
  *   presplit_engine  1 (default): factorisations of order >= 4096 (n % 8 == 0) keep fp16 hi/lo shadows of every finished panel
  *                    of L and K-bar in their workspace and run their big products on csrc/gemm_h2.cu; 0: round-1 behaviour
- *   small_gp_kernel  1: hb_gp_elbo_step runs n <= 128 as ONE persistent CTA (csrc/gp_small.cu); default 0 (measured slower)
+ *   small_gp_kernel  1 (default): hb_gp_elbo_step runs n <= 128 as ONE persistent CTA (csrc/gp_small.cu: 168 us per step at
+ *                    N = 100 against 239 us for the 23-kernel path); 0: the multi-kernel path
  *   tc_option        bit 2: no CTA pairs in the in-kernel-split engine, bit 3: three TF32 passes instead of TF32 + bf16 terms
  *   lookahead        1 (default): leaf kernels of potrf / potrf_bwd run on a high-priority side stream
  *   schedule         order of the blocked factorisation and of its reverse mode.  0 (default): from n = 32768 on the
@@ -295,8 +296,11 @@ size_t hb_gp_param_count(const hb_gp_config* cfg);
 /* Notebook-sized models (n <= hb_gp_small_max_n(0) = 128 in fp32, hb_gp_small_max_n(1) = 112 in fp64): the whole step --
  * Gram, Cholesky, sampler + KL, projection, log-likelihood, the complete backward and, when adam_m / adam_v are given,
  * the TF-1 Adam update -- is ONE persistent CTA with K / L / K-bar resident in shared memory (csrc/gp_small.cu).
- * opt->small_gp_kernel = 1 makes hb_gp_elbo_step take this path for n <= 128 (default off: the one-CTA kernel runs
- * level-2 column steps, 280 us per step at N = 100 against 239 us for the multi-kernel path with its blocked leaves).
+ * hb_gp_elbo_step takes this path for n <= 128 (opt->small_gp_kernel, default on).  fp32 runs on the blocked shared-memory
+ * building blocks of the 128 x 128 leaf kernels -- 16-wide panels for the factorisation, the closed form
+ * K-bar = sym(L^-T Phi(L^T L-bar) L^-1) as a blocked triangular inverse + three masked 128^3 products for its reverse mode:
+ * 168 us per step at N = 100, S = 10 against 239 us for the 23-kernel path (a first version with one column per step: 280 us);
+ * fp64 keeps the column-at-a-time form.
  * The _f64 variant is the reference's float_type = float64 (henbunrc:7) for this graph: every pointer is double,
  * same packing.  adam: grad_scale = -1 minimises -ELBO; step counter read from *step_dev when non-NULL. */
 typedef struct {

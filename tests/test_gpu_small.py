@@ -70,7 +70,7 @@ def run_small(lib, X, Y, p, U, jitter, full, dtype, adam=None, via_elbo_step=Fal
         try:
             rc = lib.hb_gp_elbo_step(C.byref(cfg), P(Xd), P(Yd), P(params), P(Ud), P(grads), P(out4), P(ws), wsb, P(err), ST())
         finally:
-            lib.hb_set_small_gp_kernel(0)
+            lib.hb_set_small_gp_kernel(1)                  # the default
         assert lib.hb_launch_count() - l0 == 1            # one kernel for the whole step
         m = v = None
     else:
