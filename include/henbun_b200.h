@@ -58,7 +58,9 @@ extern "C" {
  *   schedule         order of the blocked factorisation and of its reverse mode.  0 (default): from n = 32768 on the
  *                    right-looking two-stream schedule over n/16-column blocks (the narrow steps of a block on a high-priority
  *                    stream next to the trailing updates of the previous one; see hb_potrf_lower_dist), below that the plain
- *                    column recursion; 1: column recursion always; >= 128: right-looking with blocks of that many columns */
+ *                    column recursion; 1: column recursion always; >= 128: right-looking with blocks of that many columns
+ *                    (orders below 8192 always take the column recursion: their workspace carries no scratch for the second
+ *                    stream; hb_potrf_lower_dist / hb_gp_elbo_step_dist with world = 1 run the schedule at any order) */
 typedef struct hb_options {
   int gemm_engine, exact_below, panel_refinement, presplit_engine, small_gp_kernel, tc_option, lookahead, schedule;
 } hb_options;
