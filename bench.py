@@ -13,9 +13,11 @@ lengthscale gradient) -> Adam.  evals = S * N per step.
   e2e   : the SAME step through the Henbun API a user calls -- ``m.ELBO_gaussian().optimize(maxiter=1)`` on a model whose
           objective is the notebook's Python (Optimizer.compile traces it and binds it to the fused entry point) -- with
           X, Y re-fed from host memory every step and the ELBO read back.
-Multi-GPU: weak scaling in S (each rank draws its own window of one Philox stream and replicates the factorisation,
-SURVEY.md 8e), one NCCL all-reduce of the packed gradient per step.  The default line also carries short measurements of
-BASELINE configs 1, 4 and 5 (``other_workloads``; C4 minibatch-sharded and C5 row-sharded when N > 1).
+Multi-GPU: `value` is weak scaling in S (S samples per rank, each rank its own window of one Philox stream) on top of ONE
+column-block-cyclic factorisation + reverse mode shared by the ranks (hb_gp_elbo_step_dist: panel broadcasts over NCCL, one
+all-gather of Z / R, one all-reduce of the packed gradient per step); ``multi_gpu`` adds the strong-scaling figure (S in
+total) and the round-1 path (every rank factors K itself).  The default line also carries short measurements of BASELINE
+configs 1, 4 and 5 (``other_workloads``; C4 minibatch-sharded and C5 row-sharded when N > 1).
 """
 from __future__ import annotations
 
@@ -449,9 +451,13 @@ def run_c3(d, a):
         same_n = {"n": a.cpu_n, "gpu_ms_per_step": d.timed(lambda i: gs.step(), 5) / 5}
         gs.free()
 
-    api = None
+    api, api_error = None, None
     if not a.no_api_leg:
-        api = api_leg(d, a, X, Y, p)
+        try:
+            api = api_leg(d, a, X, Y, p)
+        except Exception as e:       # the main line must survive; e2e then falls back to the host-fed C-ABI step and says why
+            api_error = f"{type(e).__name__}: {e}"[:300]
+            torch.cuda.empty_cache()
 
     if d.rank != 0:
         return None
@@ -486,7 +492,8 @@ def run_c3(d, a):
                         "(compile() traced it and bound it to " + str(api and api["fused_entry"]) + "), X/Y re-assigned from host "
                         "arrays every step, ELBO read back") if api else
                        "hb_gp_elbo_step + hb_adam_tf1 through the C ABI, X/Y fed from pinned host memory every step",
-                "c_abi_ms_per_step": ms_cabi_e2e, "api_ms_per_step": api["ms_per_step"] if api else None},
+                "c_abi_ms_per_step": ms_cabi_e2e, "api_ms_per_step": api["ms_per_step"] if api else None,
+                **({"api_error": api_error} if api_error else {})},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {

@@ -320,15 +320,20 @@ class GpElboBinding(object):
             return self._out4[0]
         # float_type = float64 (henbunrc:7): fp64 master copies of parameters / moments live here, the Optimizer's fp32 flat
         # buffer mirrors them after every step (so .value, save() and the eager evaluation keep working)
-        if self._p64 is None or self._src64 is not (self.X.data, self.Y.data):
-            dev = X.device
+        dev = X.device
+        if self._src64 is None or self._src64[0] is not self.X.data or self._src64[1] is not self.Y.data:
             self._X64 = torch.as_tensor(np.ascontiguousarray(self.X.data, dtype=np.float64)).to(dev)
             self._Y64 = torch.as_tensor(np.ascontiguousarray(self.Y.data, dtype=np.float64)).to(dev).reshape(-1)
             self._src64 = (self.X.data, self.Y.data)
-            if self._p64 is None:
-                self._p64 = opt._flat[:npar].double()
-                self._g64 = torch.zeros(npar, dtype=torch.float64, device=dev)
-                self._m64 = opt._m[:npar].double(); self._v64 = opt._v[:npar].double()
+        if self._p64 is None:
+            self._p64 = opt._flat[:npar].double()
+            self._g64 = torch.zeros(npar, dtype=torch.float64, device=dev)
+            self._m64 = opt._m[:npar].double(); self._v64 = opt._v[:npar].double()
+        else:
+            # entries of the fp32 mirror that no longer equal the rounded master were edited from outside since the last
+            # step (an assignment, restore(), another Optimizer over the same variables): the master takes them
+            cur = opt._flat[:npar]
+            self._p64 = torch.where(cur != self._p64.float(), cur.double(), self._p64)
         e = self._eps(eps, count, n, X.device, torch.float64)
         check(self.lib.hb_gp_small_step_f64(C.byref(cfg), ptr(self._X64), ptr(self._Y64), ptr(self._p64), ptr(e), ptr(self._g64),
                                             ptr(self._out4), ptr(self._m64), ptr(self._v64), C.byref(adam), ptr(self._ws), self._wsb,

@@ -181,5 +181,11 @@ def test_config1_through_the_api_in_float64():
             for k in p:
                 p[k], mom[k], vel[k] = O.adam_tf1_step(p[k], -gr[k], mom[k], vel[k], t, lr=0.01)
         got = m.ELBO()._fused._p64.cpu().numpy()
+        mirror = m.q.q_mu._free_numpy().ravel().copy()
+        # a value assigned between steps (applied at the next run, Henbun/param.py:241-248) must reach the fp64 master copy
+        m.k_var = 7.5
+        m.ELBO().optimize(maxiter=1, eps={q: rng.randn(S, n, 1)})
+        k_var_after = float(np.ravel(m.k_var.value)[0])
     assert np.allclose(got, pack(p), rtol=1e-7, atol=1e-9)
-    assert np.allclose(m.q.q_mu._free_numpy().ravel(), p["q_mu"], rtol=1e-5, atol=1e-6)      # the fp32 mirror follows
+    assert np.allclose(mirror, p["q_mu"], rtol=1e-5, atol=1e-6)      # the fp32 mirror follows
+    assert abs(k_var_after - 7.5) < 0.2, k_var_after
