@@ -715,6 +715,28 @@ def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
+    # stdout carries exactly ONE line, the JSON: anything a library prints there meanwhile (NCCL's version banner when a
+    # communicator is created) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        d, line = measure(a)
+    finally:
+        sys.stdout.flush()
+        try:
+            C.CDLL(None).fflush(None)          # C stdio buffers too, before fd 1 is the real stdout again
+        except Exception:
+            pass
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if d.rank == 0 and line is not None:
+        print(json.dumps(line), flush=True)
+    if d.world > 1:
+        d.dist.destroy_process_group()
+
+
+def measure(a):
     d = Dist()
     line = None
     if a.workload == "c3":
@@ -743,10 +765,7 @@ def main():
                     "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                     "data": "synthetic", "config": {"workload": r["workload"]}, "e2e": dict(r["e2e"], unit=UNIT),
                     "roofline": r["roofline"], "gpu_launches": None}
-    if d.rank == 0 and line is not None:
-        print(json.dumps(line), flush=True)
-    if d.world > 1:
-        d.dist.destroy_process_group()
+    return d, line
 
 
 if __name__ == "__main__":

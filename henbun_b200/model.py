@@ -1,11 +1,15 @@
 """Driver: mirror of Henbun/model.py (Model :13-123, Indexer :126-153, AutoOptimize :155-188,
 Optimizer :190-269).
 
-The reference compiles the user's objective into one TF graph and loops ``session.run(optimize_op)``;
-here the objective is evaluated eagerly on device tensors every step (each heavy op is one of this
-package's CUDA kernels), torch's autograd tape drives the hand-written backward kernels, and the
-TF-1 Adam rule is applied by one fused kernel on a flat parameter buffer -- after a single NCCL
-all-reduce of the flat gradient when torch.distributed is initialised (one process per GPU).
+The reference compiles the user's objective into one TF graph and loops ``session.run(optimize_op)``.
+``Optimizer.compile`` traces the objective once (trace.py) and binds a recognised graph -- the notebook's
+variational GP regression, the linear-operator model, the amortised encoder/decoder model -- to its
+whole-step C entry point (fused.py): one C call per step writes the gradient into the flat buffer.  Any
+other objective is evaluated eagerly on device tensors every step (each heavy op is one of this package's
+CUDA kernels) with torch's autograd tape driving the hand-written backward kernels.  Either way the TF-1
+Adam rule is applied by one fused kernel on the flat parameter buffer -- after a single NCCL all-reduce
+of the flat gradient when torch.distributed is initialised (one process per GPU; the GP binding
+additionally shares ONE block-cyclic factorisation between the ranks).
 
 New, non-reference knobs: ``compile(n_samples=S, seed=...)`` and
 ``run/optimize(eps={variational: tensor})``.

@@ -1,7 +1,9 @@
 """Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the GPU box, gloo in
-the CPU tests).  The ELBO hot path needs exactly one collective per step -- an all-reduce of the packed
-gradient -- because the MC-sample axis is sharded and every other quantity is replicated
-(SURVEY.md 8e).  The reference has no distributed concept at all."""
+the CPU tests).  The model-level collective of a step is ONE all-reduce of the packed gradient: the
+MC-sample axis (or the minibatch, or the operator's rows) is sharded.  The dense-GP step
+additionally shares one column-block-cyclic Cholesky + reverse mode between the ranks; those panel
+broadcasts run inside the library on its own NCCL communicator (``block_cyclic_env`` below, csrc/comm.cu).
+The reference has no distributed concept at all."""
 from __future__ import annotations
 
 import torch
