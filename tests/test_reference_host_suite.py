@@ -273,3 +273,66 @@ def test_save_and_restore_by_long_name(tmp_path):
     assert np.allclose(m3.v.q_mu.value, 1.0) and not np.allclose(m3.p.value, 1.0)
     m3.initialize()
     assert np.allclose(m3.v.q_mu.value, 1.0)
+
+
+# ---------------------------------------------------------------------------------------------- test_variationals.py (host side)
+def test_variational_children_are_variables_even_in_tf_mode():            # test_variationals.py:56-67
+    for shape in ('fullrank', 'diagonal'):
+        m = hb.model.Model()
+        m.m = hb.variationals.Normal(10, n_layers=[3], q_shape=shape)
+        with m.tf_mode():
+            variables = m.get_variables()
+        v = object.__getattribute__(m, 'm')
+        assert any(x is v.q_mu for x in variables) and any(x is v.q_sqrt for x in variables)
+        assert v._parent is m
+
+
+def test_feeding_a_global_variational_does_nothing():                     # test_variationals.py:124-129
+    m = hb.model.Model()
+    m.m = hb.variationals.Normal(10, n_layers=[3])
+    ref = m.m._tensor
+    m.m.feed(np.ones(10))
+    assert m.m._tensor is ref
+
+
+def test_local_feed_size_is_the_same_inside_tf_mode():                    # test_variationals.py:166-180
+    for shape, want in (('diagonal', 20), ('fullrank', 110)):
+        m = hb.model.Model()
+        m.m = hb.variationals.Normal([10], n_layers=[3], q_shape=shape, collections=graph_key.LOCAL)
+        m.q = hb.variationals.Normal([10], n_layers=[3], n_batch=2, q_shape=shape)
+        with m.tf_mode():
+            inside = m.feed_size
+            local = m.get_variables(graph_key.LOCAL)
+        v = object.__getattribute__(m, 'm')
+        assert inside == m.feed_size == want
+        assert any(x is v.q_mu for x in local) and any(x is v.q_sqrt for x in local)
+        assert m.q.q_mu._host.shape == (3, 2, 10)                          # storage: n_layers + [n_batch] + shape
+
+
+def test_assigning_a_tensor_outside_tf_mode_replaces_the_attribute():     # test_variationals.py:224-234
+    m = hb.model.Model()
+    m.m = hb.variationals.Normal([10], n_layers=[3], collections=graph_key.LOCAL)
+    m.m = torch.zeros(3, 2, 20)
+    assert isinstance(m.m, torch.Tensor)
+
+
+def test_variational_model_tree():                                        # test_variationals.py:236-264
+    class VariationalModel(hb.model.Model):
+        def setUp(self):
+            self.q_global = hb.variationals.Normal(shape=[3])
+            self.q_local = hb.variationals.Normal(shape=[3], collections=graph_key.LOCAL)
+            self.x = hb.param.Variable(shape=[10, 6])
+
+    m = VariationalModel()
+    assert len(m.sorted_variables) == 3
+    assert m.feed_size == 6 and m.q_local.is_local and not m.q_global.is_local
+
+
+def test_scaled_families_accept_every_initialisation():                   # test_variationals.py:288-322 (construction part)
+    for cls in (hb.variationals.Gaussian, hb.variationals.Beta):
+        for mean, stddev in ((1.0, 0.5), (-1.0, 0.5), (0.0, 1.0)):
+            g = cls(shape=[3, 2], n_layers=[1, 2], n_batch=0, mean=mean, stddev=stddev, scale_shape=[3, 2], scale_n_layers=[1, 2])
+            assert g.q_mu._host.shape == (1, 2, 0, 6)                     # an EMPTY batch axis is legal upstream
+            assert g.size == 6
+    b = hb.variationals.Beta(shape=[3, 2], n_layers=[3], n_batch=2)       # test_variationals.py:349-356
+    assert b.alpha._host.shape == (1, 2, 1, 1) and b.q_mu._host.shape == (3, 2, 6)
