@@ -159,7 +159,10 @@ class Variational(Parameterized):
         lead = [self._S] if self._S > 1 else []
         if not self.is_local and self.n_batch is None:
             return clip(t.reshape(lead + self.n_layers + self._shape))
-        return clip(t.reshape(lead + self.n_layers + [-1] + self._shape))
+        # the batch axis is named, not inferred: an empty one (n_batch = 0, test_variationals.py:288-322) is legal upstream
+        # and torch refuses to infer a -1 for a tensor without elements
+        batch = int(t.shape[len(lead) + len(self.n_layers)])
+        return clip(t.reshape(lead + self.n_layers + [batch] + self._shape))
 
     def feed(self, x):
         """LOCAL: route the encoder output into q_mu / q_sqrt and sample (variationals.py:121-129)."""

@@ -336,3 +336,20 @@ def test_scaled_families_accept_every_initialisation():                   # test
             assert g.size == 6
     b = hb.variationals.Beta(shape=[3, 2], n_layers=[3], n_batch=2)       # test_variationals.py:349-356
     assert b.alpha._host.shape == (1, 2, 1, 1) and b.q_mu._host.shape == (3, 2, 6)
+
+
+def test_sample_view_names_the_batch_axis():
+    """Variational.tensor() views the flat sample as n_layers + [batch] + shape (variationals.py:112-119); an EMPTY batch
+    axis (n_batch = 0 in test_variationals.py:288-322) must survive the view.  The sample itself is a CUDA kernel: here the
+    drawn tensor is put in place by hand."""
+    def view(v, t, S):
+        v._tensor = t; v.transformed_tensor = t; v._S = S
+        return tuple(v.tensor().shape)
+
+    loc = hb.variationals.Normal([3, 2], n_layers=[2], collections=graph_key.LOCAL)
+    assert view(loc, torch.zeros(2, 7, 6), 1) == (2, 7, 3, 2)
+    assert view(loc, torch.zeros(4, 2, 7, 6), 4) == (4, 2, 7, 3, 2)                 # S samples: leading sample axis
+    empty = hb.variationals.Normal([3, 2], n_layers=[1, 2], n_batch=0)
+    assert view(empty, torch.zeros(1, 2, 0, 6), 1) == (1, 2, 0, 3, 2)
+    plain = hb.variationals.Normal([3, 2], n_layers=[2])
+    assert view(plain, torch.zeros(2, 6), 1) == (2, 3, 2)
